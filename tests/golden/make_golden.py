@@ -1,0 +1,162 @@
+#!/usr/bin/env python
+"""
+Regenerates tests/golden/ from the REFERENCE BINARY (oracle/_ref/pandepth_ref, built from
+/root/reference by `make -C oracle`).  Run in the build container only:
+
+    python tests/golden/make_golden.py
+
+Writes the input fixtures (SAM text, BED/GFF/GTF) and `expected.json`, which maps every case to the
+exact decompressed bytes the reference printed.  The SAM fixtures are run twice where stated: as SAM
+text (no index -> the reference's 18-bit SiteInfo path) and converted to BAM+.bai with
+oracle/_ref/bamgen -I (indexed -> uint32 windowed path, PanDepth.cpp:618-801).
+"""
+import gzip
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = os.path.join(ROOT, "oracle", "_ref", "pandepth_ref")
+BAMGEN = os.path.join(ROOT, "oracle", "_ref", "bamgen")
+
+K_SAM = (
+    "@HD\tVN:1.6\tSO:coordinate\n@SQ\tSN:k1\tLN:301\n@SQ\tSN:k2\tLN:1\n@SQ\tSN:k3\tLN:250\n"
+    "a\t0\tk1\t1\t60\t50M\t*\t0\t0\t*\t*\n"
+    "b\t16\tk1\t11\t0\t5S20M10D20M\t*\t0\t0\t*\t*\n"
+    "c\t0\tk1\t21\t30\t10=5X5I10M100N10M\t*\t0\t0\t*\t*\n"
+    "d\t1024\tk1\t30\t60\t50M\t*\t0\t0\t*\t*\n"
+    "e\t2048\tk1\t252\t60\t50M\t*\t0\t0\t*\t*\n"
+    "f\t0\tk3\t100\t5\t30M2D30M\t*\t0\t0\t*\t*\n"
+)
+K_BED3 = "k1\t1\t60\nk1\t40\t301\nk3\t90\t170\n#comment\nk9\t1\t5\nk1\t70\t60\n"
+K_BED4 = "k1\t1\t60\tx\nk1\t40\t301\ty\nk3\t90\t170\tx\nk1\t100\t120\tx\n"
+# region that starts on the last base of a contig: exercises the MeMEnd clip in PanDepth.cpp:299-308
+K_BEDEDGE = "k1\t10\t20\nk1\t301\t301\nk3\t250\t250\n"
+K_GFF = (
+    "##gff-version 3\n"
+    "k1\tsrc\tgene\t1\t300\t.\t+\t.\tID=g1\n"
+    "k1\tsrc\tmRNA\t1\t300\t.\t+\t.\tID=t1;Parent=g1\n"
+    "k1\tsrc\tCDS\t5\t60\t.\t+\t0\tID=c1;Parent=t1\n"
+    "k1\tsrc\tCDS\t100\t180\t.\t+\t0\tID=c2;Parent=t1\n"
+    "k1\tsrc\tCDS\t20\t40\t.\t+\t0\tID=c3;Parent=t2,t9\n"
+    "k1\tsrc\texon\t1\t300\t.\t+\t.\tID=e1;Parent=t1\n"
+    "k3\tsrc\tCDS\t80\t170\t.\t-\t0\tID=c4;Parent=t3\n"
+    "k3\tsrc\tCDS\t5\t10\t.\t-\t0\tParent=t1\n"
+    "zz\tsrc\tCDS\t5\t10\t.\t-\t0\tID=c5;Parent=t4\n"
+)
+K_GTF = (
+    'k1\tsrc\tCDS\t5\t60\t.\t+\t0\tgene_id "g1"; transcript_id "t1";\n'
+    'k1\tsrc\tCDS\t100\t180\t.\t+\t0\tgene_id "g1"; transcript_id "t1";\n'
+    'k1\tsrc\texon\t1\t300\t.\t+\t.\tgene_id "g1"; transcript_id "t1";\n'
+    'k3\tsrc\tCDS\t80\t170\t.\t-\t0\tgene_id "g2"; transcript_id "t3";\n'
+)
+
+MIX_CONTIGS = "cA:100001,cB:1001,cC:1,cD:2,cE:300"
+BIG_CONTIGS = "cF:10000001,cG:150"
+MIX_BED = "cA\t1\t5000\ncA\t4000\t9000\ncA\t50000\t50100\ncA\t99000\t100001\ncB\t1001\t1001\ncB\t5\t900\ncE\t10\t290\ncD\t1\t2\n"
+BIG_BED = "cF\t1\t150\ncF\t5000100\t5000400\ncF\t9999000\t10000001\ncG\t1\t150\n"
+
+
+def run_ref(inp, args, workdir, tag):
+    pre = os.path.join(workdir, tag)
+    cmd = [REF, "-i", inp, "-o", pre] + args
+    subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    res = {}
+    for fn in sorted(os.listdir(workdir)):
+        if fn.startswith(tag + ".") and fn.endswith(".gz"):
+            with gzip.open(os.path.join(workdir, fn), "rt") as fh:
+                res[fn[len(tag):]] = fh.read()
+    return res
+
+
+def compact(text, limit=65536):
+    """Outputs above `limit` bytes are stored as sha256 + size + head/tail instead of verbatim."""
+    if len(text) <= limit:
+        return text
+    import hashlib
+    return {"sha256": hashlib.sha256(text.encode()).hexdigest(), "n_bytes": len(text), "head": text[:2048], "tail": text[-512:]}
+
+
+def main():
+    if not (os.path.exists(REF) and os.path.exists(BAMGEN)):
+        sys.exit("build oracle/_ref first: make -C oracle")
+    w = lambda name, text: open(os.path.join(HERE, name), "w").write(text)
+    w("k.sam", K_SAM); w("k.bed3", K_BED3); w("k.bed4", K_BED4); w("k.bededge", K_BEDEDGE)
+    w("k.gff", K_GFF); w("k.gtf", K_GTF); w("mix.bed", MIX_BED); w("big.bed", BIG_BED)
+    subprocess.run([BAMGEN, "-o", os.path.join(HERE, "mix.sam"), "-c", MIX_CONTIGS, "-n", "3000", "-m", "mixed",
+                    "-s", "20260925", "-S"], check=True)
+    subprocess.run([BAMGEN, "-o", os.path.join(HERE, "big.sam"), "-c", BIG_CONTIGS, "-n", "1500", "-m", "mixed",
+                    "-s", "7", "-S"], check=True)
+
+    cases = []
+    def add(name, fixture, args, kinds=("sam", "bam")):
+        for k in kinds:
+            cases.append({"name": f"{name}.{k}", "fixture": fixture, "kind": k, "args": args})
+
+    g = lambda f: os.path.join(HERE, f)
+    add("k.default", "k.sam", [])
+    add("k.w100", "k.sam", ["-w", "100"])
+    add("k.w150", "k.sam", ["-w", "150"])
+    add("k.w7", "k.sam", ["-w", "7"])
+    add("k.q10d2", "k.sam", ["-q", "10", "-d", "2"])
+    add("k.x0", "k.sam", ["-x", "0"])
+    add("k.x16", "k.sam", ["-x", "16", "-q", "1"])
+    add("k.bed3", "k.sam", ["-b", "@k.bed3"])
+    add("k.bed4", "k.sam", ["-b", "@k.bed4"])
+    add("k.bededge", "k.sam", ["-b", "@k.bededge"])
+    add("k.gff", "k.sam", ["-g", "@k.gff"])
+    add("k.gffexon", "k.sam", ["-g", "@k.gff", "-f", "exon"])
+    add("k.gtf", "k.sam", ["-g", "@k.gtf"])
+    add("k.a", "k.sam", ["-a"])
+    add("k.a.w100", "k.sam", ["-a", "-w", "100"])
+    add("k.s", "k.sam", ["-s"], kinds=("bam",))
+    add("mix.default", "mix.sam", [])
+    add("mix.w100", "mix.sam", ["-w", "100"])
+    add("mix.w1000", "mix.sam", ["-w", "1000"])
+    add("mix.q20d3x3844", "mix.sam", ["-q", "20", "-d", "3", "-x", "3844"])
+    add("mix.bed", "mix.sam", ["-b", "@mix.bed"])
+    add("mix.bed.d2", "mix.sam", ["-b", "@mix.bed", "-d", "2"])
+    add("mix.w151", "mix.sam", ["-w", "151", "-d", "2"])
+    add("big.default", "big.sam", [])
+    add("big.w1000", "big.sam", ["-w", "1000"])
+    add("big.bed", "big.sam", ["-b", "@big.bed"])
+    # 18-bit wrap vector (SURVEY App. C `w.sam`): 262149 stacked 10M reads at pos 100 of a 1 kb contig
+    add("stack.default", "@stack", [])
+    add("stack.w100", "@stack", ["-w", "100"])
+    add("stack.w200", "@stack", ["-w", "200"])
+
+    out = {}
+    tmp = tempfile.mkdtemp(prefix="pdgold")
+    try:
+        stack = os.path.join(tmp, "stack.sam")
+        with open(stack, "w") as fh:
+            fh.write("@HD\tVN:1.6\tSO:coordinate\n@SQ\tSN:c\tLN:1000\n")
+            fh.write("r\t0\tc\t100\t60\t10M\t*\t0\t0\t*\t*\n" * 262149)
+        bams = {}
+        for c in cases:
+            sam = stack if c["fixture"] == "@stack" else g(c["fixture"])
+            if c["kind"] == "bam":
+                if sam not in bams:
+                    b = os.path.join(tmp, os.path.basename(sam) + ".bam")
+                    subprocess.run([BAMGEN, "-I", sam, "-o", b], check=True)
+                    bams[sam] = b
+                inp = bams[sam]
+            else:
+                inp = sam
+            args = [g(a[1:]) if a.startswith("@") else a for a in c["args"]]
+            res = run_ref(inp, args, tmp, c["name"])
+            res = {k: compact(v) for k, v in res.items()}
+            out[c["name"]] = {"fixture": c["fixture"], "kind": c["kind"], "args": c["args"], "outputs": res}
+            print(c["name"], {k: (len(v) if isinstance(v, str) else v["n_bytes"]) for k, v in res.items()})
+    finally:
+        shutil.rmtree(tmp)
+    with open(os.path.join(HERE, "expected.json"), "w") as fh:
+        json.dump(out, fh, indent=0, sort_keys=True)
+
+
+if __name__ == "__main__":
+    main()

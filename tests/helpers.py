@@ -1,0 +1,63 @@
+"""Shared helpers for the parity tests (golden-case plumbing)."""
+import hashlib
+import os
+
+import numpy as np
+
+from oracle import model
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+STACK_TARGETS = [("c", 1000)]
+
+
+def load_fixture(name):
+    """-> (targets, Records, sorted) for a golden fixture name ('k.sam', '@stack', ...)."""
+    if name == "@stack":
+        n = 262149
+        rec = model.Records(np.zeros(n, np.int32), np.full(n, 99, np.int32), np.zeros(n, np.uint16),
+                            np.full(n, 60, np.uint8), np.arange(n + 1, dtype=np.uint32),
+                            np.full(n, (10 << 4) | 0, np.uint32))
+        return STACK_TARGETS, rec, True
+    return model.parse_sam(os.path.join(GOLD, name))
+
+
+def options_from_args(args, kind):
+    """Translate a golden case's CLI args into model.Options (what bamCov_help01 would set, PanDepth.cpp:84-293)."""
+    o = model.Options()
+    o.indexed = (kind == "bam")
+    it = iter(args)
+    for a in it:
+        if a == "-w":
+            o.win = max(1, int(next(it)))
+        elif a == "-q":
+            o.min_mapq = int(next(it))
+        elif a == "-d":
+            o.min_dep = max(1, int(next(it)))
+        elif a == "-x":
+            o.xflags = int(next(it))
+        elif a == "-a":
+            o.site_output = True
+        elif a == "-s":
+            o.indexed = False
+        elif a == "-f":
+            o.feature = next(it)
+        elif a == "-g":
+            o.gff = os.path.join(GOLD, next(it)[1:])
+        elif a == "-b":
+            o.bed = os.path.join(GOLD, next(it)[1:])
+        else:
+            raise ValueError(a)
+    return o
+
+
+def assert_matches(expected_entry, text, what=""):
+    """Compare text with a golden output (verbatim string or compacted {sha256,...})."""
+    if isinstance(expected_entry, str):
+        assert text == expected_entry, f"{what}: output differs from the reference"
+    else:
+        assert len(text) == expected_entry["n_bytes"], f"{what}: size differs"
+        assert text[:2048] == expected_entry["head"], f"{what}: head differs"
+        assert text[-512:] == expected_entry["tail"], f"{what}: tail differs"
+        assert hashlib.sha256(text.encode()).hexdigest() == expected_entry["sha256"], f"{what}: sha256 differs"
