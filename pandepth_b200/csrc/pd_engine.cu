@@ -1,0 +1,552 @@
+// pd_engine.cu -- the engine behind include/pandepth_b200.h (C ABI, CUDA runtime only; no torch types).
+//
+// HBM layout (one engine = one GPU):
+//   depth   uint32[total]   all owned contigs back to back; contig t starts at off[t] (a multiple of 4096 elements) and is
+//                           followed by >= 1 element of padding, so a run's closing -1 at `len` never lands in a neighbour
+//   delta   uint32[total]   same geometry; +-1 run endpoints of the unsorted / far path; all-zero outside a pending scan
+//   seg_state uint8[total/1024]  0 = no batch has written this 1024-base segment yet (first write is a plain store)
+// 3 Gb genome: 12 GB + 12 GB + 3 MB of the 180 GB.
+#include "../../include/pandepth_b200.h"
+#include "pd_kernels.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+namespace {
+
+std::string g_create_error;
+
+constexpr uint64_t PAD_ELEMS = pdk::SCAN_TILE;           // contig offsets / total are multiples of this
+constexpr int64_t HOST_CHUNK_READS = 8 << 20;            // staging chunk for host-resident pushes
+constexpr int N_SLOTS = 2;
+
+enum KernelId { K_CUT = 0, K_TILE, K_SCATTER, K_SCAN, K_FILL, K_REDUCE, K_WINDOWS, K_COUNT };
+const char *const kKernelNames[K_COUNT] = {"k_cut", "k_tile_accumulate", "k_delta_scatter", "k_scan_add",
+                                           "k_fill_untouched", "k_reduce_units", "k_reduce_windows"};
+
+struct Slot {
+    int32_t *pos = nullptr; uint32_t *cigar = nullptr; uint32_t *cigar_off = nullptr;
+    uint16_t *flag = nullptr; uint8_t *mapq = nullptr;
+    size_t cap_reads = 0, cap_cigar = 0;
+    cudaEvent_t copied = nullptr, consumed = nullptr;
+    bool used = false;
+};
+
+}  // namespace
+
+struct pd_engine {
+    int device = 0;
+    int n_targets = 0;
+    std::vector<uint32_t> tlen;
+    std::vector<uint8_t> owned;
+    std::vector<uint64_t> off;       // element offset of contig t (valid when owned)
+    uint64_t total = 0;              // elements in depth/delta
+    uint64_t n_seg = 0;
+    uint32_t xflags = 1796; int min_mapq = -1;
+
+    uint32_t *d_depth = nullptr, *d_delta = nullptr;
+    uint8_t *d_seg_state = nullptr;
+    uint64_t *d_off = nullptr; uint32_t *d_tlen = nullptr;
+    uint32_t *d_lo = nullptr, *d_hi = nullptr; size_t cut_cap = 0;
+    uint32_t *d_L = nullptr;
+    int *d_flags = nullptr;          // [0] err bits, [1] delta_used
+    unsigned long long *d_desc = nullptr; unsigned int *d_counter = nullptr;
+
+    cudaStream_t own_stream = nullptr, copy_stream = nullptr, stream = nullptr;
+    Slot slot[N_SLOTS]; int next_slot = 0;
+
+    // reduce scratch
+    void *d_red = nullptr; size_t red_cap = 0;
+
+    bool finalized = false;
+    bool host_delta_used = false;    // a scatter-path batch was queued since the last scan
+    pd_stats stats{};
+    bool profiling = false;
+    struct Ev { int k; cudaEvent_t a, b; };
+    std::vector<Ev> pending;
+    double kms[K_COUNT] = {0}; uint64_t kcount[K_COUNT] = {0};
+    std::string err;
+};
+
+namespace {
+
+#define CK(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t _e = (call);                                                                      \
+        if (_e != cudaSuccess) {                                                                      \
+            char _b[512];                                                                             \
+            snprintf(_b, sizeof _b, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            e->err = _b;                                                                              \
+            return PD_ERR_CUDA;                                                                       \
+        }                                                                                             \
+    } while (0)
+
+int fail(pd_engine *e, int code, const char *msg) { if (e) e->err = msg; return code; }
+
+template <typename F>
+int launch(pd_engine *e, int k, F &&f)
+{
+    cudaEvent_t a = nullptr, b = nullptr;
+    if (e->profiling) {
+        CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+        CK(cudaEventRecord(a, e->stream));
+    }
+    f();
+    CK(cudaGetLastError());
+    if (e->profiling) { CK(cudaEventRecord(b, e->stream)); e->pending.push_back({k, a, b}); }
+    e->stats.kernel_launches++;
+    return PD_OK;
+}
+
+int drain_profile(pd_engine *e)
+{
+    for (auto &p : e->pending) {
+        CK(cudaEventSynchronize(p.b));
+        float ms = 0; CK(cudaEventElapsedTime(&ms, p.a, p.b));
+        e->kms[p.k] += ms; e->kcount[p.k]++;
+        cudaEventDestroy(p.a); cudaEventDestroy(p.b);
+    }
+    e->pending.clear();
+    return PD_OK;
+}
+
+int ensure_cut(pd_engine *e, size_t nseg)
+{
+    if (nseg <= e->cut_cap) return PD_OK;
+    if (e->d_lo) { CK(cudaStreamSynchronize(e->stream)); cudaFree(e->d_lo); cudaFree(e->d_hi); e->d_lo = e->d_hi = nullptr; }
+    size_t cap = nseg + nseg / 4 + 1024;
+    CK(cudaMalloc(&e->d_lo, cap * 4)); CK(cudaMalloc(&e->d_hi, cap * 4));
+    e->cut_cap = cap;
+    return PD_OK;
+}
+
+// Queue the kernels for one contig batch whose arrays are on the device.  seg range [seg_a, seg_b].
+int run_batch(pd_engine *e, int32_t tid, uint32_t n, const int32_t *pos, const uint16_t *flag, const uint8_t *mapq,
+              const uint32_t *cigar_off, const uint32_t *cigar, bool sorted, int64_t seg_a, int64_t seg_b)
+{
+    const uint64_t off = e->off[tid];
+    if (sorted) {
+        const int32_t nseg = (int32_t)(seg_b - seg_a + 1);
+        int rc = ensure_cut(e, (size_t)nseg); if (rc) return rc;
+        pdk::CutArgs c{pos, cigar, cigar_off, flag, mapq, n, (int32_t)seg_a, nseg, e->d_lo, e->d_hi, e->d_L, e->xflags, e->min_mapq};
+        rc = launch(e, K_CUT, [&] { pdk::k_cut<<<(nseg + 255) / 256, 256, 0, e->stream>>>(c); }); if (rc) return rc;
+        pdk::TileArgs t{pos, cigar, cigar_off, flag, mapq, e->d_lo, e->d_hi, e->d_L, (int32_t)seg_a, nseg, (int32_t)e->tlen[tid],
+                        e->d_depth + off, e->d_delta + off, e->d_seg_state + off / pdk::SEG, e->xflags, e->min_mapq,
+                        e->d_flags, e->d_flags + 1};
+        const size_t smem = (size_t)pdk::WPC * pdk::TILE_SMEM_WORDS * 4;
+        rc = launch(e, K_TILE, [&] { pdk::k_tile_accumulate<<<(nseg + pdk::WPC - 1) / pdk::WPC, pdk::WPC * 32, smem, e->stream>>>(t); });
+        if (rc) return rc;
+        e->stats.tile_path_batches++;
+    } else {
+        pdk::ScatterArgs s{pos, cigar, cigar_off, flag, mapq, n, (int32_t)e->tlen[tid], e->d_delta + off, e->xflags, e->min_mapq};
+        int rc = launch(e, K_SCATTER, [&] { pdk::k_delta_scatter<<<(n + 255) / 256, 256, 0, e->stream>>>(s); }); if (rc) return rc;
+        e->host_delta_used = true;
+        e->stats.delta_path_batches++;
+    }
+    e->stats.reads_pushed += n;
+    e->finalized = false;
+    return PD_OK;
+}
+
+int ensure_slot(pd_engine *e, Slot &s, size_t reads, size_t ncig, bool need_off, bool need_flag, bool need_mapq)
+{
+    if (!s.copied) { CK(cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&s.consumed, cudaEventDisableTiming)); }
+    if (reads > s.cap_reads) {
+        if (s.used) CK(cudaEventSynchronize(s.consumed));
+        cudaFree(s.pos); cudaFree(s.cigar_off); cudaFree(s.flag); cudaFree(s.mapq);
+        s.pos = nullptr; s.cigar_off = nullptr; s.flag = nullptr; s.mapq = nullptr;
+        size_t cap = reads + reads / 8 + 1024;
+        CK(cudaMalloc(&s.pos, cap * 4)); CK(cudaMalloc(&s.cigar_off, (cap + 1) * 4));
+        CK(cudaMalloc(&s.flag, cap * 2)); CK(cudaMalloc(&s.mapq, cap));
+        s.cap_reads = cap;
+        e->stats.hbm_bytes_allocated += cap * 11 + 4;
+    }
+    if (ncig > s.cap_cigar) {
+        if (s.used) CK(cudaEventSynchronize(s.consumed));
+        cudaFree(s.cigar); s.cigar = nullptr;
+        size_t cap = ncig + ncig / 8 + 1024;
+        CK(cudaMalloc(&s.cigar, cap * 4));
+        s.cap_cigar = cap;
+        e->stats.hbm_bytes_allocated += cap * 4;
+    }
+    (void)need_off; (void)need_flag; (void)need_mapq;
+    return PD_OK;
+}
+
+int check_device_flags(pd_engine *e)
+{
+    int h[2] = {0, 0};
+    CK(cudaMemcpyAsync(h, e->d_flags, sizeof h, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    if (h[0] & pdk::ERR_UNSORTED) return fail(e, PD_ERR_UNSORTED, "a batch pushed with PD_SORTED was not sorted by pos");
+    if (h[0] & pdk::ERR_RANGE) return fail(e, PD_ERR_UNSORTED, "a PD_SORTED batch had positions outside their segment (unsorted input)");
+    if (h[1]) e->host_delta_used = true;
+    return PD_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *pd_last_error(pd_engine *e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+
+void *pd_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+void pd_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+void pd_destroy(pd_engine *e)
+{
+    if (!e) return;
+    cudaSetDevice(e->device);
+    cudaDeviceSynchronize();
+    for (auto &p : e->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+    cudaFree(e->d_depth); cudaFree(e->d_delta); cudaFree(e->d_seg_state); cudaFree(e->d_off); cudaFree(e->d_tlen);
+    cudaFree(e->d_lo); cudaFree(e->d_hi); cudaFree(e->d_L); cudaFree(e->d_flags); cudaFree(e->d_desc); cudaFree(e->d_counter);
+    cudaFree(e->d_red);
+    for (auto &s : e->slot) {
+        cudaFree(s.pos); cudaFree(s.cigar); cudaFree(s.cigar_off); cudaFree(s.flag); cudaFree(s.mapq);
+        if (s.copied) cudaEventDestroy(s.copied);
+        if (s.consumed) cudaEventDestroy(s.consumed);
+    }
+    if (e->own_stream) cudaStreamDestroy(e->own_stream);
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+    delete e;
+}
+
+pd_engine *pd_create(int device, int n_targets, const uint32_t *target_len, const uint8_t *owned, uint32_t xflags, int min_mapq)
+{
+    if (n_targets <= 0 || !target_len) { g_create_error = "pd_create: bad arguments"; return nullptr; }
+    pd_engine *e = new pd_engine;
+    auto bail = [&](const char *what, cudaError_t ce) -> pd_engine * {
+        g_create_error = std::string("pd_create: ") + what + ": " + cudaGetErrorString(ce);
+        pd_destroy(e);
+        return nullptr;
+    };
+    e->device = device; e->n_targets = n_targets; e->xflags = xflags; e->min_mapq = min_mapq;
+    e->tlen.assign(target_len, target_len + n_targets);
+    e->owned.assign(n_targets, 1);
+    if (owned) e->owned.assign(owned, owned + n_targets);
+    e->off.assign(n_targets, 0);
+    uint64_t total = 0;
+    for (int t = 0; t < n_targets; ++t) {
+        if (!e->owned[t]) continue;
+        if (e->tlen[t] > 0x7fffffffu) { g_create_error = "pd_create: contig longer than 2^31-1"; delete e; return nullptr; }
+        e->off[t] = total;
+        total += ((uint64_t)e->tlen[t] + 1 + PAD_ELEMS - 1) / PAD_ELEMS * PAD_ELEMS;
+    }
+    if (total == 0) total = PAD_ELEMS;
+    e->total = total; e->n_seg = total / pdk::SEG;
+    cudaError_t ce;
+    if ((ce = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", ce);
+    if ((ce = cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", ce);
+    if ((ce = cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", ce);
+    e->stream = e->own_stream;
+    if ((ce = cudaMalloc(&e->d_depth, total * 4)) != cudaSuccess) return bail("cudaMalloc(depth)", ce);
+    if ((ce = cudaMalloc(&e->d_delta, total * 4)) != cudaSuccess) return bail("cudaMalloc(delta)", ce);
+    if ((ce = cudaMalloc(&e->d_seg_state, e->n_seg)) != cudaSuccess) return bail("cudaMalloc(seg_state)", ce);
+    if ((ce = cudaMalloc(&e->d_off, (size_t)n_targets * 8)) != cudaSuccess) return bail("cudaMalloc", ce);
+    if ((ce = cudaMalloc(&e->d_tlen, (size_t)n_targets * 4)) != cudaSuccess) return bail("cudaMalloc", ce);
+    if ((ce = cudaMalloc(&e->d_L, 4)) != cudaSuccess) return bail("cudaMalloc", ce);
+    if ((ce = cudaMalloc(&e->d_flags, 8)) != cudaSuccess) return bail("cudaMalloc", ce);
+    if ((ce = cudaMalloc(&e->d_desc, (total / pdk::SCAN_TILE) * 8)) != cudaSuccess) return bail("cudaMalloc", ce);
+    if ((ce = cudaMalloc(&e->d_counter, 4)) != cudaSuccess) return bail("cudaMalloc", ce);
+    e->stats.hbm_bytes_allocated = total * 8 + e->n_seg + (total / pdk::SCAN_TILE) * 8;
+    if ((ce = cudaMemcpy(e->d_off, e->off.data(), (size_t)n_targets * 8, cudaMemcpyHostToDevice)) != cudaSuccess) return bail("memcpy", ce);
+    if ((ce = cudaMemcpy(e->d_tlen, e->tlen.data(), (size_t)n_targets * 4, cudaMemcpyHostToDevice)) != cudaSuccess) return bail("memcpy", ce);
+    if ((ce = cudaMemsetAsync(e->d_delta, 0, total * 4, e->stream)) != cudaSuccess) return bail("memset", ce);
+    if ((ce = cudaMemsetAsync(e->d_seg_state, 0, e->n_seg, e->stream)) != cudaSuccess) return bail("memset", ce);
+    if ((ce = cudaMemsetAsync(e->d_flags, 0, 8, e->stream)) != cudaSuccess) return bail("memset", ce);
+    if ((ce = cudaFuncSetAttribute(pdk::k_tile_accumulate, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   pdk::WPC * pdk::TILE_SMEM_WORDS * 4)) != cudaSuccess) return bail("cudaFuncSetAttribute", ce);
+    if ((ce = cudaStreamSynchronize(e->stream)) != cudaSuccess) return bail("sync", ce);
+    return e;
+}
+
+int pd_set_stream(pd_engine *e, void *cuda_stream)
+{
+    if (!e) return PD_ERR_ARG;
+    CK(cudaSetDevice(e->device));
+    CK(cudaStreamSynchronize(e->stream));
+    e->stream = cuda_stream ? (cudaStream_t)cuda_stream : e->own_stream;
+    return PD_OK;
+}
+
+int pd_reset(pd_engine *e)
+{
+    if (!e) return PD_ERR_ARG;
+    CK(cudaSetDevice(e->device));
+    CK(cudaStreamSynchronize(e->copy_stream));
+    (void)check_device_flags(e);          // picks up far-run deltas queued on the device; stale errors are dropped
+    e->err.clear();
+    CK(cudaMemsetAsync(e->d_seg_state, 0, e->n_seg, e->stream));
+    CK(cudaMemsetAsync(e->d_flags, 0, 8, e->stream));
+    if (e->host_delta_used) CK(cudaMemsetAsync(e->d_delta, 0, e->total * 4, e->stream));
+    e->host_delta_used = false;
+    e->finalized = false;
+    uint64_t keep = e->stats.hbm_bytes_allocated;
+    e->stats = pd_stats{};
+    e->stats.hbm_bytes_allocated = keep;
+    return PD_OK;
+}
+
+int pd_push_contig(pd_engine *e, int32_t tid, int64_t n_reads, const int32_t *pos, const uint16_t *flag, const uint8_t *mapq,
+                   const uint32_t *cigar_off, const uint32_t *cigar, uint32_t flags)
+{
+    if (!e) return PD_ERR_ARG;
+    if (tid < 0 || tid >= e->n_targets || n_reads < 0 || (n_reads > 0 && (!pos || !cigar))) return fail(e, PD_ERR_ARG, "pd_push_contig: bad arguments");
+    if (!e->owned[tid] || n_reads == 0 || e->tlen[tid] == 0) return PD_OK;
+    CK(cudaSetDevice(e->device));
+    const bool sorted = (flags & PD_SORTED) != 0;
+    const int64_t max_seg = ((int64_t)e->tlen[tid]) / pdk::SEG;      // segment of the padding element
+
+    if (flags & PD_DEVICE) {
+        for (int64_t b = 0; b < n_reads; b += 0x7fff0000ll) {
+            const uint32_t n = (uint32_t)std::min<int64_t>(0x7fff0000ll, n_reads - b);
+            if (cigar_off && b) return fail(e, PD_ERR_ARG, "pd_push_contig: device batches with cigar_off must have < 2^31 reads");
+            int rc = run_batch(e, tid, n, pos + b, flag ? flag + b : nullptr, mapq ? mapq + b : nullptr, cigar_off,
+                               cigar_off ? cigar : cigar + b, sorted, 0, max_seg);
+            if (rc) return rc;
+        }
+        return PD_OK;
+    }
+
+    // host-resident batch: stage through device slots in chunks, copy stream overlapping the compute stream
+    for (int64_t b = 0; b < n_reads; b += HOST_CHUNK_READS) {
+        const int64_t n = std::min<int64_t>(HOST_CHUNK_READS, n_reads - b);
+        const uint32_t cg0 = cigar_off ? cigar_off[b] : 0;
+        const size_t ncig = cigar_off ? (size_t)(cigar_off[b + n] - cg0) : (size_t)n;
+        Slot &s = e->slot[e->next_slot]; e->next_slot = (e->next_slot + 1) % N_SLOTS;
+        int rc = ensure_slot(e, s, (size_t)n, ncig, cigar_off != nullptr, flag != nullptr, mapq != nullptr); if (rc) return rc;
+        if (s.used) CK(cudaStreamWaitEvent(e->copy_stream, s.consumed, 0));
+        CK(cudaMemcpyAsync(s.pos, pos + b, (size_t)n * 4, cudaMemcpyHostToDevice, e->copy_stream));
+        CK(cudaMemcpyAsync(s.cigar, cigar_off ? cigar + cg0 : cigar + b, ncig * 4, cudaMemcpyHostToDevice, e->copy_stream));
+        e->stats.h2d_bytes += (uint64_t)n * 4 + ncig * 4;
+        if (cigar_off) { CK(cudaMemcpyAsync(s.cigar_off, cigar_off + b, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, e->copy_stream)); e->stats.h2d_bytes += (uint64_t)(n + 1) * 4; }
+        if (flag) { CK(cudaMemcpyAsync(s.flag, flag + b, (size_t)n * 2, cudaMemcpyHostToDevice, e->copy_stream)); e->stats.h2d_bytes += (uint64_t)n * 2; }
+        if (mapq) { CK(cudaMemcpyAsync(s.mapq, mapq + b, (size_t)n, cudaMemcpyHostToDevice, e->copy_stream)); e->stats.h2d_bytes += (uint64_t)n; }
+        CK(cudaEventRecord(s.copied, e->copy_stream));
+        CK(cudaStreamWaitEvent(e->stream, s.copied, 0));
+        int64_t seg_a = 0, seg_b = max_seg;
+        if (sorted) {
+            // sorted => first/last positions bound the segments this chunk can touch (+HALO of look-ahead for the halo readers)
+            int64_t p0 = pos[b], p1 = pos[b + n - 1];
+            if (p0 < 0) p0 = 0;
+            if (p1 < 0) p1 = 0;
+            seg_a = std::min<int64_t>(p0 / pdk::SEG, max_seg);
+            seg_b = std::min<int64_t>((p1 + pdk::HALO) / pdk::SEG, max_seg);
+            if (seg_b < seg_a) seg_b = seg_a;
+        }
+        // cigar offsets on the device are absolute: rebase the cigar pointer instead of rewriting them
+        const uint32_t *d_cig = cigar_off ? s.cigar - cg0 : s.cigar;
+        rc = run_batch(e, tid, (uint32_t)n, s.pos, flag ? s.flag : nullptr, mapq ? s.mapq : nullptr,
+                       cigar_off ? s.cigar_off : nullptr, d_cig, sorted, seg_a, seg_b);
+        if (rc) return rc;
+        CK(cudaEventRecord(s.consumed, e->stream));
+        s.used = true;
+    }
+    if (!(flags & PD_ASYNC)) CK(cudaStreamSynchronize(e->copy_stream));
+    return PD_OK;
+}
+
+int pd_push(pd_engine *e, int64_t n_reads, const int32_t *tid, const int32_t *pos, const uint16_t *flag, const uint8_t *mapq,
+            const uint32_t *cigar_off, const uint32_t *cigar, uint32_t flags)
+{
+    if (!e) return PD_ERR_ARG;
+    if (flags & PD_DEVICE) return fail(e, PD_ERR_ARG, "pd_push: per-record tid arrays must be host pointers (use pd_push_contig for device batches)");
+    if (n_reads < 0 || (n_reads > 0 && (!tid || !pos || !cigar))) return fail(e, PD_ERR_ARG, "pd_push: bad arguments");
+    int64_t b = 0;
+    while (b < n_reads) {
+        const int32_t t = tid[b];
+        int64_t end;
+        if (flags & PD_SORTED) end = std::upper_bound(tid + b, tid + n_reads, t) - tid;     // tids are non-decreasing
+        else { end = b + 1; while (end < n_reads && tid[end] == t) ++end; }
+        if (t >= 0 && t < e->n_targets) {
+            // cigar_off is absolute into `cigar`: pass the sub-array of offsets, the full cigar base
+            int rc = pd_push_contig(e, t, end - b, pos + b, flag ? flag + b : nullptr, mapq ? mapq + b : nullptr,
+                                    cigar_off ? cigar_off + b : nullptr, cigar_off ? cigar : cigar + b, flags);
+            if (rc) return rc;
+        }
+        b = end;
+    }
+    return PD_OK;
+}
+
+int pd_sync(pd_engine *e)
+{
+    if (!e) return PD_ERR_ARG;
+    CK(cudaSetDevice(e->device));
+    CK(cudaStreamSynchronize(e->copy_stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return check_device_flags(e);
+}
+
+int pd_finalize(pd_engine *e)
+{
+    if (!e) return PD_ERR_ARG;
+    CK(cudaSetDevice(e->device));
+    if (e->finalized) return PD_OK;
+    int rc = check_device_flags(e); if (rc) return rc;
+    rc = launch(e, K_FILL, [&] { pdk::k_fill_untouched<<<(unsigned)((e->n_seg + 7) / 8), 256, 0, e->stream>>>(e->d_depth, e->d_seg_state, e->n_seg); });
+    if (rc) return rc;
+    if (e->host_delta_used) {
+        const uint64_t n_tiles = e->total / pdk::SCAN_TILE;
+        CK(cudaMemsetAsync(e->d_desc, 0, n_tiles * 8, e->stream));
+        CK(cudaMemsetAsync(e->d_counter, 0, 4, e->stream));
+        rc = launch(e, K_SCAN, [&] { pdk::k_scan_add<<<(unsigned)n_tiles, pdk::SCAN_THREADS, 0, e->stream>>>(e->d_depth, e->d_delta, e->total, e->d_desc, e->d_counter); });
+        if (rc) return rc;
+        CK(cudaMemsetAsync(e->d_flags + 1, 0, 4, e->stream));
+        e->host_delta_used = false;
+        e->stats.scan_passes++;
+    }
+    e->finalized = true;
+    return PD_OK;
+}
+
+static int ensure_red(pd_engine *e, size_t bytes)
+{
+    if (bytes <= e->red_cap) return PD_OK;
+    if (e->d_red) { CK(cudaStreamSynchronize(e->stream)); cudaFree(e->d_red); e->d_red = nullptr; }
+    size_t cap = bytes + bytes / 4 + 4096;
+    CK(cudaMalloc(&e->d_red, cap));
+    e->red_cap = cap;
+    return PD_OK;
+}
+
+int pd_reduce(pd_engine *e, int64_t n_iv, const int32_t *tid, const int32_t *start0, const int32_t *end0_excl,
+              uint32_t min_dep, uint32_t depth_mask, uint64_t *cov, uint64_t *sum, uint32_t flags)
+{
+    if (!e) return PD_ERR_ARG;
+    if (n_iv < 0 || (n_iv > 0 && (!tid || !start0 || !end0_excl || !cov || !sum))) return fail(e, PD_ERR_ARG, "pd_reduce: bad arguments");
+    if (flags & PD_DEVICE) return fail(e, PD_ERR_ARG, "pd_reduce: interval tables are host pointers");
+    CK(cudaSetDevice(e->device));
+    int rc = pd_finalize(e); if (rc) return rc;
+    if (n_iv == 0) return PD_OK;
+    // unit list: one warp per (interval, 8192-base chunk); intervals of contigs this engine does not own yield 0
+    std::vector<uint2> units;
+    units.reserve((size_t)n_iv);
+    for (int64_t i = 0; i < n_iv; ++i) {
+        const int32_t t = tid[i];
+        if (t < 0 || t >= e->n_targets) return fail(e, PD_ERR_ARG, "pd_reduce: tid out of range");
+        if (!e->owned[t]) continue;
+        int64_t s = std::max<int64_t>(start0[i], 0), en = std::min<int64_t>(end0_excl[i], e->tlen[t]);
+        if (s >= en) continue;
+        const int64_t nchunk = (en - s + pdk::REDUCE_CHUNK - 1) / pdk::REDUCE_CHUNK;
+        for (int64_t c = 0; c < nchunk; ++c) units.push_back(make_uint2((unsigned)i, (unsigned)c));
+    }
+    const size_t iv_bytes = (size_t)n_iv * 4;
+    const size_t a_tid = 0, a_s = a_tid + ((iv_bytes + 15) & ~15ull), a_e = a_s + ((iv_bytes + 15) & ~15ull);
+    const size_t a_units = a_e + ((iv_bytes + 15) & ~15ull);
+    const size_t a_cov = a_units + ((units.size() * 8 + 15) & ~15ull), a_sum = a_cov + (size_t)n_iv * 8;
+    const size_t need = a_sum + (size_t)n_iv * 8;
+    rc = ensure_red(e, need); if (rc) return rc;
+    char *base = (char *)e->d_red;
+    CK(cudaMemcpyAsync(base + a_tid, tid, iv_bytes, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(base + a_s, start0, iv_bytes, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(base + a_e, end0_excl, iv_bytes, cudaMemcpyHostToDevice, e->stream));
+    if (!units.empty()) CK(cudaMemcpyAsync(base + a_units, units.data(), units.size() * 8, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemsetAsync(base + a_cov, 0, (size_t)n_iv * 16, e->stream));
+    e->stats.h2d_bytes += iv_bytes * 3 + units.size() * 8;
+    if (!units.empty()) {
+        pdk::ReduceArgs r{e->d_depth, e->d_off, e->d_tlen, (const int32_t *)(base + a_tid), (const int32_t *)(base + a_s),
+                          (const int32_t *)(base + a_e), (const uint2 *)(base + a_units), (uint64_t)units.size(), min_dep, depth_mask,
+                          (unsigned long long *)(base + a_cov), (unsigned long long *)(base + a_sum)};
+        rc = launch(e, K_REDUCE, [&] { pdk::k_reduce_units<<<(unsigned)((units.size() + 7) / 8), 256, 0, e->stream>>>(r); });
+        if (rc) return rc;
+    }
+    CK(cudaMemcpyAsync(cov, base + a_cov, (size_t)n_iv * 8, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(sum, base + a_sum, (size_t)n_iv * 8, cudaMemcpyDeviceToHost, e->stream));
+    e->stats.d2h_bytes += (uint64_t)n_iv * 16;
+    CK(cudaStreamSynchronize(e->stream));
+    return PD_OK;
+}
+
+int pd_reduce_windows(pd_engine *e, int32_t tid, int32_t start0, int32_t win, int64_t n_win, uint32_t min_dep, uint32_t depth_mask,
+                      uint32_t *cov, uint64_t *sum, uint32_t flags)
+{
+    if (!e) return PD_ERR_ARG;
+    if (tid < 0 || tid >= e->n_targets || win < 1 || start0 < 0 || n_win < 0 || (n_win > 0 && (!cov || !sum))) return fail(e, PD_ERR_ARG, "pd_reduce_windows: bad arguments");
+    CK(cudaSetDevice(e->device));
+    int rc = pd_finalize(e); if (rc) return rc;
+    if (n_win == 0) return PD_OK;
+    const bool dev = (flags & PD_DEVICE) != 0;
+    if (!e->owned[tid]) {
+        if (dev) { CK(cudaMemsetAsync(cov, 0, (size_t)n_win * 4, e->stream)); CK(cudaMemsetAsync(sum, 0, (size_t)n_win * 8, e->stream)); }
+        else { memset(cov, 0, (size_t)n_win * 4); memset(sum, 0, (size_t)n_win * 8); }
+        return PD_OK;
+    }
+    uint32_t *d_cov = cov; unsigned long long *d_sum = (unsigned long long *)sum;
+    if (!dev) {
+        const size_t a_sum = ((size_t)n_win * 4 + 15) & ~15ull;
+        rc = ensure_red(e, a_sum + (size_t)n_win * 8); if (rc) return rc;
+        d_cov = (uint32_t *)e->d_red; d_sum = (unsigned long long *)((char *)e->d_red + a_sum);
+    }
+    pdk::WindowArgs w{e->d_depth + e->off[tid], (int64_t)e->tlen[tid], start0, win, n_win, min_dep, depth_mask, d_cov, d_sum};
+    const int64_t warps_needed = win >= 32 ? n_win : (n_win + 31) / 32;
+    const unsigned grid = (unsigned)std::min<int64_t>((warps_needed + 7) / 8, 148 * 64);
+    rc = launch(e, K_WINDOWS, [&] { pdk::k_reduce_windows<<<grid, 256, 0, e->stream>>>(w); }); if (rc) return rc;
+    if (!dev) {
+        CK(cudaMemcpyAsync(cov, d_cov, (size_t)n_win * 4, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaMemcpyAsync(sum, d_sum, (size_t)n_win * 8, cudaMemcpyDeviceToHost, e->stream));
+        e->stats.d2h_bytes += (uint64_t)n_win * 12;
+        CK(cudaStreamSynchronize(e->stream));
+    }
+    return PD_OK;
+}
+
+int pd_depth_read(pd_engine *e, int32_t tid, int32_t start0, int32_t n, uint32_t *out, uint32_t flags)
+{
+    if (!e) return PD_ERR_ARG;
+    if (tid < 0 || tid >= e->n_targets || start0 < 0 || n < 0 || (n > 0 && !out)) return fail(e, PD_ERR_ARG, "pd_depth_read: bad arguments");
+    if ((int64_t)start0 + n > (int64_t)e->tlen[tid]) return fail(e, PD_ERR_ARG, "pd_depth_read: range beyond the contig");
+    CK(cudaSetDevice(e->device));
+    int rc = pd_finalize(e); if (rc) return rc;
+    if (n == 0) return PD_OK;
+    const bool dev = (flags & PD_DEVICE) != 0;
+    if (!e->owned[tid]) {
+        if (dev) CK(cudaMemsetAsync(out, 0, (size_t)n * 4, e->stream)); else memset(out, 0, (size_t)n * 4);
+        return PD_OK;
+    }
+    CK(cudaMemcpyAsync(out, e->d_depth + e->off[tid] + start0, (size_t)n * 4, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, e->stream));
+    if (!dev) { e->stats.d2h_bytes += (uint64_t)n * 4; CK(cudaStreamSynchronize(e->stream)); }
+    return PD_OK;
+}
+
+int pd_get_stats(pd_engine *e, pd_stats *out)
+{
+    if (!e || !out) return PD_ERR_ARG;
+    *out = e->stats;
+    return PD_OK;
+}
+
+int pd_profile_enable(pd_engine *e, int on)
+{
+    if (!e) return PD_ERR_ARG;
+    CK(cudaSetDevice(e->device));
+    int rc = drain_profile(e); if (rc) return rc;
+    e->profiling = on != 0;
+    if (on) { for (int k = 0; k < K_COUNT; ++k) { e->kms[k] = 0; e->kcount[k] = 0; } }
+    return PD_OK;
+}
+
+int pd_profile_get(pd_engine *e, pd_kernel_time *out, int cap)
+{
+    if (!e) return PD_ERR_ARG;
+    CK(cudaSetDevice(e->device));
+    int rc = drain_profile(e); if (rc) return rc;
+    for (int k = 0; k < K_COUNT && k < cap; ++k) {
+        memset(out[k].name, 0, sizeof out[k].name);
+        strncpy(out[k].name, kKernelNames[k], sizeof out[k].name - 1);
+        out[k].launches = e->kcount[k]; out[k].ms = e->kms[k];
+    }
+    return K_COUNT;
+}
+
+}  // extern "C"

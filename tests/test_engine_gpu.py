@@ -1,0 +1,285 @@
+"""
+GPU parity tests: the CUDA engine, called through its C ABI (include/pandepth_b200.h), against the oracle
+(oracle/pd_oracle.c restatement, itself pinned to the reference binary) and against the reference's own printed
+outputs (tests/golden/expected.json).  Integer work: every comparison is bit-exact.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import model
+from tests.helpers import GOLD, assert_matches, load_fixture, options_from_args
+
+pytestmark = pytest.mark.gpu
+
+with open(os.path.join(GOLD, "expected.json")) as _fh:
+    _CASES = json.load(_fh)
+
+
+def _engine(tlen, **kw):
+    import pandepth_b200 as pd
+    return pd.Engine(tlen, **kw)
+
+
+def _sorted_order(rec):
+    return np.lexsort((rec.pos, rec.tid))
+
+
+def _push_all(eng, rec, sorted_flag=True, chunks=1):
+    """Push a Records batch through pd_push in `chunks` consecutive pieces."""
+    import pandepth_b200 as pd
+    n = rec.n
+    edges = np.linspace(0, n, chunks + 1).astype(np.int64)
+    for a, b in zip(edges[:-1], edges[1:]):
+        if b <= a:
+            continue
+        sub = rec.select(np.arange(a, b))
+        eng.push(sub.tid, sub.pos, sub.cigar, flag=sub.flag, mapq=sub.mapq, cigar_off=sub.cigar_off,
+                 flags=pd.PD_SORTED if sorted_flag else 0)
+
+
+def _check_depth(eng, tlen, want):
+    for t, w in enumerate(want):
+        if tlen[t] == 0:
+            continue
+        got = eng.depth(t)
+        assert got.shape == w.shape
+        if not np.array_equal(got, w):
+            bad = np.flatnonzero(got != w)
+            raise AssertionError(f"contig {t}: {bad.size} bases differ, first at {bad[0]}: got {got[bad[0]]} want {w[bad[0]]}")
+
+
+# ------------------------------------------------------------------------------------------------------
+# golden fixtures: per-base depth, interval reduce and the final printed text
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("fixture", ["k.sam", "mix.sam", "big.sam"])
+@pytest.mark.parametrize("path", ["sorted", "sorted_chunked", "unsorted"])
+def test_depth_matches_oracle_on_fixtures(fixture, path):
+    targets, rec, _ = load_fixture(fixture)
+    tlen = np.array([t[1] for t in targets], np.uint32)
+    for xflags, q in ((1796, -1), (0, 20), (3844, 5)):
+        want = model.accumulate(tlen, rec, xflags, q)
+        with _engine(tlen, xflags=xflags, min_mapq=q) as eng:
+            if path == "unsorted":
+                perm = np.random.default_rng(1).permutation(rec.n)
+                _push_all(eng, rec.select(perm), sorted_flag=False, chunks=3)
+            else:
+                r = rec.select(_sorted_order(rec))
+                _push_all(eng, r, sorted_flag=True, chunks=1 if path == "sorted" else 7)
+            eng.finalize()
+            _check_depth(eng, tlen, want)
+            st = eng.stats()
+            assert st["kernel_launches"] > 0
+
+
+@pytest.mark.parametrize("case", sorted(_CASES))
+def test_printed_output_matches_reference(case):
+    """Engine depth + engine reduce -> the exact text the reference binary printed for this case."""
+    c = _CASES[case]
+    targets, rec, _ = load_fixture(c["fixture"])
+    opts = options_from_args(c["args"], c["kind"])
+    tlen = np.array([t[1] for t in targets], np.uint32)
+    r = rec.select(_sorted_order(rec))
+    with _engine(tlen, xflags=opts.xflags, min_mapq=opts.min_mapq) as eng:
+        _push_all(eng, r, sorted_flag=True, chunks=2)
+        eng.finalize()
+        depth = [eng.depth(t) if tlen[t] else np.zeros(0, np.uint32) for t in range(len(targets))]
+        res = model.run_model(targets, rec, opts, depth_override=depth)
+        assert_matches(c["outputs"][res["suffix"]], res["stat"], case)
+        # and the device-side reducers against the oracle's on the same depth
+        whole = (not opts.indexed) or opts.site_output or res["mode"] == 6
+        mask = 0x3FFFF if whole else 0xFFFFFFFF
+        for t, (nm, ln) in enumerate(targets):
+            if ln < 2:
+                continue
+            a, b = model.tile_contig(ln, 97)
+            cov_o, sum_o = model.reduce_intervals(depth[t], a - 1, b, opts.min_dep, mask)
+            cov_g, sum_g = eng.reduce(np.full(a.size, t, np.int32), a - 1, b, opts.min_dep, mask)
+            assert np.array_equal(cov_o, cov_g) and np.array_equal(sum_o, sum_g)
+            for win in (7, 100, 1000):
+                s0, e0 = model.mode6_windows(ln, win)
+                cov_o, sum_o = model.reduce_intervals(depth[t], s0, e0, opts.min_dep, mask)
+                cov_w, sum_w = eng.reduce_windows(t, 0, win, s0.size, opts.min_dep, mask)
+                assert np.array_equal(cov_o, cov_w.astype(np.uint64)) and np.array_equal(sum_o, sum_w)
+
+
+# ------------------------------------------------------------------------------------------------------
+# seeded synthetic batches (SURVEY 8d shapes, scaled so the oracle finishes in seconds)
+# ------------------------------------------------------------------------------------------------------
+def _uniform_reads(rng, length, n, readlen=150):
+    pos = np.sort(rng.integers(0, max(1, length - readlen + 1), n)).astype(np.int32)
+    cig = np.full(n, (readlen << 4) | 0, np.uint32)
+    return pos, cig
+
+
+def test_cfg1_shape_sorted_150M():
+    """BASELINE config 1 shape: one 10 Mb contig, 1 M sorted 150M reads (seed 12345)."""
+    rng = np.random.default_rng(12345)
+    L = 10_000_000
+    pos, cig = _uniform_reads(rng, L, 1_000_000)
+    tlen = np.array([L], np.uint32)
+    rec = model.Records(np.zeros(pos.size, np.int32), pos, np.zeros(pos.size, np.uint16), np.full(pos.size, 60, np.uint8),
+                        np.arange(pos.size + 1, dtype=np.uint32), cig)
+    want = model.accumulate(tlen, rec)
+    import pandepth_b200 as pd
+    with _engine(tlen) as eng:
+        eng.push_contig(0, pos, cig, flags=pd.PD_SORTED)
+        eng.finalize()
+        _check_depth(eng, tlen, want)
+        a, b = model.tile_contig(L, 10_000_000)
+        cov, tot = eng.reduce(np.zeros(a.size, np.int32), a - 1, b)
+        assert int(tot.sum()) == 150 * pos.size            # every aligned base counted once
+        co, so = model.reduce_intervals(want[0], a - 1, b)
+        assert np.array_equal(cov, co) and np.array_equal(tot, so)
+        st = eng.stats()
+        assert st["tile_path_batches"] == 1 and st["delta_path_batches"] == 0 and st["scan_passes"] == 0
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_random_mixed_cigars_all_paths(seed):
+    """Random CIGARs over MIDNSHP=X with long N skips (far runs), random flags/mapq, duplicates, three push styles."""
+    rng = np.random.default_rng(seed)
+    lens = [300_001, 1, 5000, 70_000, 2]
+    names = [f"c{i}" for i in range(len(lens))]
+    rows = []
+    for t, ln in enumerate(lens):
+        n = 0 if ln < 10 else int(ln * (0.5 if t else 0.2))
+        starts = np.sort(rng.integers(0, ln, n))
+        if n:
+            starts[rng.integers(0, n, n // 10)] = starts[n // 2]          # a pile-up at one position
+            starts = np.sort(starts)
+        for p in starts.tolist():
+            k = rng.integers(0, 10)
+            if k < 5:
+                cs = "150M"
+            elif k == 5:
+                cs = f"{rng.integers(1, 40)}S{rng.integers(1, 120)}M"
+            elif k == 6:
+                cs = f"{rng.integers(1, 80)}M{rng.integers(1, 5000)}N{rng.integers(1, 80)}M"
+            elif k == 7:
+                cs = f"{rng.integers(1, 60)}={rng.integers(1, 9)}I{rng.integers(1, 60)}X{rng.integers(1, 30)}D{rng.integers(1, 60)}M2H"
+            elif k == 8:
+                cs = f"3D{rng.integers(1, 100)}M1P{rng.integers(1, 100)}M"
+            else:
+                cs = f"{rng.integers(1, 300)}M"
+            fl = int(rng.choice([0, 0, 0, 16, 1024, 256, 4, 2048, 512]))
+            rows.append((fl, t, p + 1, int(rng.integers(0, 61)), cs))
+    rec = model.records_from_tuples(rows, names)
+    tlen = np.array(lens, np.uint32)
+    for xflags, q in ((1796, -1), (0, 30)):
+        want = model.accumulate(tlen, rec, xflags, q)
+        for style in ("sorted", "chunked", "unsorted", "half_half"):
+            with _engine(tlen, xflags=xflags, min_mapq=q) as eng:
+                if style == "sorted":
+                    _push_all(eng, rec, True, 1)
+                elif style == "chunked":
+                    _push_all(eng, rec, True, 13)
+                elif style == "unsorted":
+                    _push_all(eng, rec.select(rng.permutation(rec.n)), False, 2)
+                else:                                   # depth is additive across batches and paths
+                    half = rec.n // 2
+                    _push_all(eng, rec.select(np.arange(0, half)), True, 2)
+                    _push_all(eng, rec.select(rng.permutation(np.arange(half, rec.n))), False, 1)
+                eng.finalize()
+                _check_depth(eng, tlen, want)
+
+
+def test_other_read_lengths_and_no_common_span():
+    """Read lengths above the modelled span (L > HALO) and batches with no dominant span fall back to corrections."""
+    rng = np.random.default_rng(9)
+    L = 400_000
+    tlen = np.array([L], np.uint32)
+    import pandepth_b200 as pd
+    for readlen in (36, 250, 256, 257, 300, 1000, 5000):
+        pos, cig = _uniform_reads(rng, L, 40_000, readlen)
+        rec = model.Records(np.zeros(pos.size, np.int32), pos, np.zeros(pos.size, np.uint16), np.zeros(pos.size, np.uint8),
+                            np.arange(pos.size + 1, dtype=np.uint32), cig)
+        want = model.accumulate(tlen, rec)
+        with _engine(tlen) as eng:
+            eng.push_contig(0, pos, cig, flags=pd.PD_SORTED)
+            eng.finalize()
+            _check_depth(eng, tlen, want)
+    # every read a different length
+    pos = np.sort(rng.integers(0, L - 400, 50_000)).astype(np.int32)
+    cig = ((rng.integers(1, 400, pos.size).astype(np.uint32)) << 4) | np.uint32(0)
+    rec = model.Records(np.zeros(pos.size, np.int32), pos, np.zeros(pos.size, np.uint16), np.zeros(pos.size, np.uint8),
+                        np.arange(pos.size + 1, dtype=np.uint32), cig)
+    want = model.accumulate(tlen, rec)
+    with _engine(tlen) as eng:
+        eng.push_contig(0, pos, cig, flags=pd.PD_SORTED)
+        eng.finalize()
+        _check_depth(eng, tlen, want)
+
+
+def test_18bit_wrap_and_uint32_paths():
+    """SURVEY App. C `w.sam`: 262149 stacked reads; mask 0x3FFFF reproduces the SiteInfo bit-field."""
+    targets, rec, _ = load_fixture("@stack")
+    tlen = np.array([1000], np.uint32)
+    import pandepth_b200 as pd
+    with _engine(tlen) as eng:
+        eng.push_contig(0, rec.pos, rec.cigar, flags=pd.PD_SORTED)
+        cov, tot = eng.reduce([0], [0], [1000], 1, 0xFFFFFFFF)
+        assert (int(cov[0]), int(tot[0])) == (10, 2621490)
+        cov, tot = eng.reduce([0], [0], [1000], 1, 0x3FFFF)
+        assert (int(cov[0]), int(tot[0])) == (10, 50)
+        cov, tot = eng.reduce_windows(0, 0, 100, 10, 1, 0x3FFFF)
+        assert cov.tolist()[:2] == [1, 9] and tot.tolist()[:2] == [5, 45]
+
+
+def test_empty_ragged_and_reset():
+    import pandepth_b200 as pd
+    tlen = np.array([5000, 0, 1, 123456], np.uint32)
+    with _engine(tlen) as eng:
+        eng.finalize()                                            # no input at all
+        assert not eng.depth(0).any() and not eng.depth(3).any()
+        cov, tot = eng.reduce([0, 3, 2], [0, -5, 0], [5000, 999999, 1])
+        assert cov.tolist() == [0, 0, 0] and tot.tolist() == [0, 0, 0]
+        eng.push_contig(3, np.array([], np.int32), np.array([], np.uint32), flags=pd.PD_SORTED)   # empty batch
+        eng.push_contig(3, np.array([10, 10, 123400], np.int32), np.array([(100 << 4), (100 << 4) | 7, (100 << 4) | 8], np.uint32),
+                        flags=pd.PD_SORTED)
+        d = eng.depth(3)
+        assert d[10:110].tolist() == [2] * 100 and d[110] == 0 and d[123400:].tolist() == [1] * 56   # clipped at the contig end
+        eng.reset()
+        assert not eng.depth(3).any()
+        eng.push_contig(0, np.array([4990], np.int32), np.array([(5 << 4) | 4], np.uint32), flags=0)   # soft clip only
+        assert not eng.depth(0).any()
+
+
+def test_unsorted_batch_declared_sorted_is_reported():
+    import pandepth_b200 as pd
+    tlen = np.array([100_000], np.uint32)
+    pos = np.array([5000, 100, 90_000, 7], np.int32)
+    cig = np.full(4, (50 << 4), np.uint32)
+    with _engine(tlen) as eng:
+        eng.push_contig(0, pos, cig, flags=pd.PD_SORTED)
+        with pytest.raises(pd.PDError) as ei:
+            eng.finalize()
+        assert ei.value.code == 4
+
+
+def test_contig_sharding_two_engines():
+    """Contig sharding: two engines that each own a subset reproduce the single-engine triples."""
+    rng = np.random.default_rng(5)
+    lens = [200_000, 150_000, 90_000, 10_000]
+    tlen = np.array(lens, np.uint32)
+    import pandepth_b200 as pd
+    batches = [_uniform_reads(rng, ln, ln // 5) for ln in lens]
+    tid = np.arange(4, dtype=np.int32)
+    s0 = np.zeros(4, np.int32); e0 = np.array(lens, np.int32)
+    with _engine(tlen) as eng:
+        for t, (p, c) in enumerate(batches):
+            eng.push_contig(t, p, c, flags=pd.PD_SORTED)
+        full = eng.reduce(tid, s0, e0)
+    from pandepth_b200.shard import assign_contigs
+    owner = assign_contigs(lens, 2)
+    parts = []
+    for r in range(2):
+        own = (np.array(owner) == r).astype(np.uint8)
+        with _engine(tlen, owned=own) as eng:
+            for t, (p, c) in enumerate(batches):
+                eng.push_contig(t, p, c, flags=pd.PD_SORTED)       # not-owned contigs are ignored by the engine
+            parts.append(eng.reduce(tid, s0, e0))
+    cov = parts[0][0] + parts[1][0]; tot = parts[0][1] + parts[1][1]
+    assert np.array_equal(cov, full[0]) and np.array_equal(tot, full[1])
