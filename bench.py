@@ -36,7 +36,7 @@ N_CONTIGS = 9
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--genome", type=float, default=3.0e9, help="bases per GPU (cfg2: 3e9)")
@@ -267,11 +267,12 @@ def ours(args):
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     # ---- device-resident arm (value) with per-kernel timing --------------------------------------------------
+    if sampler:
+        sampler.start()
+        time.sleep(0.5)              # nvidia-smi needs a moment before its first sample
     for _ in range(args.warmup):
         step_device()
     eng.profile_enable(True)
-    if sampler:
-        sampler.start()
     ms_dev, (cov, tot) = timed(step_device, args.steps, 0)
     clocks = sampler.stop() if sampler else None
     prof = eng.profile()

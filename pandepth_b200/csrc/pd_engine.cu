@@ -51,8 +51,7 @@ struct pd_engine {
     uint32_t *d_depth = nullptr, *d_delta = nullptr;
     uint8_t *d_seg_state = nullptr;
     uint64_t *d_off = nullptr; uint32_t *d_tlen = nullptr;
-    uint32_t *d_lo = nullptr, *d_hi = nullptr; size_t cut_cap = 0;
-    uint32_t *d_L = nullptr;
+    uint32_t *d_lo = nullptr, *d_hi = nullptr, *d_coarse = nullptr; size_t cut_cap = 0;
     int *d_flags = nullptr;          // [0] err bits, [1] delta_used
     unsigned long long *d_desc = nullptr; unsigned int *d_counter = nullptr;
 
@@ -117,9 +116,9 @@ int drain_profile(pd_engine *e)
 int ensure_cut(pd_engine *e, size_t nseg)
 {
     if (nseg <= e->cut_cap) return PD_OK;
-    if (e->d_lo) { CK(cudaStreamSynchronize(e->stream)); cudaFree(e->d_lo); cudaFree(e->d_hi); e->d_lo = e->d_hi = nullptr; }
+    if (e->d_lo) { CK(cudaStreamSynchronize(e->stream)); cudaFree(e->d_lo); cudaFree(e->d_hi); cudaFree(e->d_coarse); e->d_lo = e->d_hi = e->d_coarse = nullptr; }
     size_t cap = nseg + nseg / 4 + 1024;
-    CK(cudaMalloc(&e->d_lo, cap * 4)); CK(cudaMalloc(&e->d_hi, cap * 4));
+    CK(cudaMalloc(&e->d_lo, cap * 4)); CK(cudaMalloc(&e->d_hi, cap * 4)); CK(cudaMalloc(&e->d_coarse, (cap / pdk::CUT_COARSE + 2) * 4));
     e->cut_cap = cap;
     return PD_OK;
 }
@@ -132,13 +131,24 @@ int run_batch(pd_engine *e, int32_t tid, uint32_t n, const int32_t *pos, const u
     if (sorted) {
         const int32_t nseg = (int32_t)(seg_b - seg_a + 1);
         int rc = ensure_cut(e, (size_t)nseg); if (rc) return rc;
-        pdk::CutArgs c{pos, cigar, cigar_off, flag, mapq, n, (int32_t)seg_a, nseg, e->d_lo, e->d_hi, e->d_L, e->xflags, e->min_mapq};
-        rc = launch(e, K_CUT, [&] { pdk::k_cut<<<(nseg + 255) / 256, 256, 0, e->stream>>>(c); }); if (rc) return rc;
-        pdk::TileArgs t{pos, cigar, cigar_off, flag, mapq, e->d_lo, e->d_hi, e->d_L, (int32_t)seg_a, nseg, (int32_t)e->tlen[tid],
+        pdk::CutArgs c{pos, n, (int32_t)seg_a, nseg, e->d_lo, e->d_hi};
+        const int32_t ncoarse = (nseg + pdk::CUT_COARSE - 1) / pdk::CUT_COARSE;
+        rc = launch(e, K_CUT, [&] {
+            pdk::k_cut_coarse<<<(ncoarse + 127) / 128, 128, 0, e->stream>>>(c, e->d_coarse, ncoarse);
+            pdk::k_cut<<<(nseg + 255) / 256, 256, 0, e->stream>>>(c, e->d_coarse, ncoarse);
+        });
+        if (rc) return rc;
+        e->stats.kernel_launches++;
+        pdk::TileArgs t{pos, cigar, cigar_off, flag, mapq, e->d_lo, e->d_hi, n, (int32_t)seg_a, nseg, (int32_t)e->tlen[tid],
                         e->d_depth + off, e->d_delta + off, e->d_seg_state + off / pdk::SEG, e->xflags, e->min_mapq,
                         e->d_flags, e->d_flags + 1};
         const size_t smem = (size_t)pdk::WPC * pdk::TILE_SMEM_WORDS * 4;
-        rc = launch(e, K_TILE, [&] { pdk::k_tile_accumulate<<<(nseg + pdk::WPC - 1) / pdk::WPC, pdk::WPC * 32, smem, e->stream>>>(t); });
+        const unsigned grid = (nseg + pdk::WPC - 1) / pdk::WPC, blk = pdk::WPC * 32;
+        const bool has_off = cigar_off != nullptr, has_filter = flag != nullptr || mapq != nullptr;
+        rc = launch(e, K_TILE, [&] {
+            if (has_off) { if (has_filter) pdk::k_tile_accumulate<true, true><<<grid, blk, smem, e->stream>>>(t); else pdk::k_tile_accumulate<true, false><<<grid, blk, smem, e->stream>>>(t); }
+            else { if (has_filter) pdk::k_tile_accumulate<false, true><<<grid, blk, smem, e->stream>>>(t); else pdk::k_tile_accumulate<false, false><<<grid, blk, smem, e->stream>>>(t); }
+        });
         if (rc) return rc;
         e->stats.tile_path_batches++;
     } else {
@@ -209,7 +219,7 @@ void pd_destroy(pd_engine *e)
     cudaDeviceSynchronize();
     for (auto &p : e->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     cudaFree(e->d_depth); cudaFree(e->d_delta); cudaFree(e->d_seg_state); cudaFree(e->d_off); cudaFree(e->d_tlen);
-    cudaFree(e->d_lo); cudaFree(e->d_hi); cudaFree(e->d_L); cudaFree(e->d_flags); cudaFree(e->d_desc); cudaFree(e->d_counter);
+    cudaFree(e->d_lo); cudaFree(e->d_hi); cudaFree(e->d_coarse); cudaFree(e->d_flags); cudaFree(e->d_desc); cudaFree(e->d_counter);
     cudaFree(e->d_red);
     for (auto &s : e->slot) {
         cudaFree(s.pos); cudaFree(s.cigar); cudaFree(s.cigar_off); cudaFree(s.flag); cudaFree(s.mapq);
@@ -254,7 +264,6 @@ pd_engine *pd_create(int device, int n_targets, const uint32_t *target_len, cons
     if ((ce = cudaMalloc(&e->d_seg_state, e->n_seg)) != cudaSuccess) return bail("cudaMalloc(seg_state)", ce);
     if ((ce = cudaMalloc(&e->d_off, (size_t)n_targets * 8)) != cudaSuccess) return bail("cudaMalloc", ce);
     if ((ce = cudaMalloc(&e->d_tlen, (size_t)n_targets * 4)) != cudaSuccess) return bail("cudaMalloc", ce);
-    if ((ce = cudaMalloc(&e->d_L, 4)) != cudaSuccess) return bail("cudaMalloc", ce);
     if ((ce = cudaMalloc(&e->d_flags, 8)) != cudaSuccess) return bail("cudaMalloc", ce);
     if ((ce = cudaMalloc(&e->d_desc, (total / pdk::SCAN_TILE) * 8)) != cudaSuccess) return bail("cudaMalloc", ce);
     if ((ce = cudaMalloc(&e->d_counter, 4)) != cudaSuccess) return bail("cudaMalloc", ce);
@@ -264,8 +273,13 @@ pd_engine *pd_create(int device, int n_targets, const uint32_t *target_len, cons
     if ((ce = cudaMemsetAsync(e->d_delta, 0, total * 4, e->stream)) != cudaSuccess) return bail("memset", ce);
     if ((ce = cudaMemsetAsync(e->d_seg_state, 0, e->n_seg, e->stream)) != cudaSuccess) return bail("memset", ce);
     if ((ce = cudaMemsetAsync(e->d_flags, 0, 8, e->stream)) != cudaSuccess) return bail("memset", ce);
-    if ((ce = cudaFuncSetAttribute(pdk::k_tile_accumulate, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   pdk::WPC * pdk::TILE_SMEM_WORDS * 4)) != cudaSuccess) return bail("cudaFuncSetAttribute", ce);
+    {
+        const int smem = pdk::WPC * pdk::TILE_SMEM_WORDS * 4;
+        if ((ce = cudaFuncSetAttribute(pdk::k_tile_accumulate<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return bail("cudaFuncSetAttribute", ce);
+        if ((ce = cudaFuncSetAttribute(pdk::k_tile_accumulate<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return bail("cudaFuncSetAttribute", ce);
+        if ((ce = cudaFuncSetAttribute(pdk::k_tile_accumulate<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return bail("cudaFuncSetAttribute", ce);
+        if ((ce = cudaFuncSetAttribute(pdk::k_tile_accumulate<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return bail("cudaFuncSetAttribute", ce);
+    }
     if ((ce = cudaStreamSynchronize(e->stream)) != cudaSuccess) return bail("sync", ce);
     return e;
 }
@@ -283,8 +297,10 @@ int pd_reset(pd_engine *e)
 {
     if (!e) return PD_ERR_ARG;
     CK(cudaSetDevice(e->device));
-    CK(cudaStreamSynchronize(e->copy_stream));
-    (void)check_device_flags(e);          // picks up far-run deltas queued on the device; stale errors are dropped
+    if (!e->finalized) {                  // un-finalized pushes may have queued far-run deltas on the device
+        CK(cudaStreamSynchronize(e->copy_stream));
+        (void)check_device_flags(e);      // stale errors are dropped
+    }
     e->err.clear();
     CK(cudaMemsetAsync(e->d_seg_state, 0, e->n_seg, e->stream));
     CK(cudaMemsetAsync(e->d_flags, 0, 8, e->stream));
@@ -338,6 +354,7 @@ int pd_push_contig(pd_engine *e, int32_t tid, int64_t n_reads, const int32_t *po
         if (sorted) {
             // sorted => first/last positions bound the segments this chunk can touch (+HALO of look-ahead for the halo readers)
             int64_t p0 = pos[b], p1 = pos[b + n - 1];
+            if (p1 < p0) return fail(e, PD_ERR_UNSORTED, "a batch pushed with PD_SORTED was not sorted by pos (last < first)");
             if (p0 < 0) p0 = 0;
             if (p1 < 0) p1 = 0;
             seg_a = std::min<int64_t>(p0 / pdk::SEG, max_seg);
@@ -429,36 +446,38 @@ int pd_reduce(pd_engine *e, int64_t n_iv, const int32_t *tid, const int32_t *sta
     CK(cudaSetDevice(e->device));
     int rc = pd_finalize(e); if (rc) return rc;
     if (n_iv == 0) return PD_OK;
-    // unit list: one warp per (interval, 8192-base chunk); intervals of contigs this engine does not own yield 0
-    std::vector<uint2> units;
-    units.reserve((size_t)n_iv);
+    // one warp per unit = (interval, 8192-base chunk); unit_prefix[i] = units before interval i.
+    // intervals of contigs this engine does not own (or empty after clipping) have no units and yield 0
+    std::vector<uint64_t> prefix((size_t)n_iv + 1);
+    uint64_t n_units = 0;
     for (int64_t i = 0; i < n_iv; ++i) {
+        prefix[i] = n_units;
         const int32_t t = tid[i];
         if (t < 0 || t >= e->n_targets) return fail(e, PD_ERR_ARG, "pd_reduce: tid out of range");
         if (!e->owned[t]) continue;
         int64_t s = std::max<int64_t>(start0[i], 0), en = std::min<int64_t>(end0_excl[i], e->tlen[t]);
         if (s >= en) continue;
-        const int64_t nchunk = (en - s + pdk::REDUCE_CHUNK - 1) / pdk::REDUCE_CHUNK;
-        for (int64_t c = 0; c < nchunk; ++c) units.push_back(make_uint2((unsigned)i, (unsigned)c));
+        n_units += (uint64_t)((en - s + pdk::REDUCE_CHUNK - 1) / pdk::REDUCE_CHUNK);
     }
+    prefix[n_iv] = n_units;
     const size_t iv_bytes = (size_t)n_iv * 4;
     const size_t a_tid = 0, a_s = a_tid + ((iv_bytes + 15) & ~15ull), a_e = a_s + ((iv_bytes + 15) & ~15ull);
     const size_t a_units = a_e + ((iv_bytes + 15) & ~15ull);
-    const size_t a_cov = a_units + ((units.size() * 8 + 15) & ~15ull), a_sum = a_cov + (size_t)n_iv * 8;
+    const size_t a_cov = a_units + ((prefix.size() * 8 + 15) & ~15ull), a_sum = a_cov + (size_t)n_iv * 8;
     const size_t need = a_sum + (size_t)n_iv * 8;
     rc = ensure_red(e, need); if (rc) return rc;
     char *base = (char *)e->d_red;
     CK(cudaMemcpyAsync(base + a_tid, tid, iv_bytes, cudaMemcpyHostToDevice, e->stream));
     CK(cudaMemcpyAsync(base + a_s, start0, iv_bytes, cudaMemcpyHostToDevice, e->stream));
     CK(cudaMemcpyAsync(base + a_e, end0_excl, iv_bytes, cudaMemcpyHostToDevice, e->stream));
-    if (!units.empty()) CK(cudaMemcpyAsync(base + a_units, units.data(), units.size() * 8, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(base + a_units, prefix.data(), prefix.size() * 8, cudaMemcpyHostToDevice, e->stream));
     CK(cudaMemsetAsync(base + a_cov, 0, (size_t)n_iv * 16, e->stream));
-    e->stats.h2d_bytes += iv_bytes * 3 + units.size() * 8;
-    if (!units.empty()) {
+    e->stats.h2d_bytes += iv_bytes * 3 + prefix.size() * 8;
+    if (n_units) {
         pdk::ReduceArgs r{e->d_depth, e->d_off, e->d_tlen, (const int32_t *)(base + a_tid), (const int32_t *)(base + a_s),
-                          (const int32_t *)(base + a_e), (const uint2 *)(base + a_units), (uint64_t)units.size(), min_dep, depth_mask,
+                          (const int32_t *)(base + a_e), (const uint64_t *)(base + a_units), (uint64_t)n_iv, n_units, min_dep, depth_mask,
                           (unsigned long long *)(base + a_cov), (unsigned long long *)(base + a_sum)};
-        rc = launch(e, K_REDUCE, [&] { pdk::k_reduce_units<<<(unsigned)((units.size() + 7) / 8), 256, 0, e->stream>>>(r); });
+        rc = launch(e, K_REDUCE, [&] { pdk::k_reduce_units<<<(unsigned)((n_units + 7) / 8), 256, 0, e->stream>>>(r); });
         if (rc) return rc;
     }
     CK(cudaMemcpyAsync(cov, base + a_cov, (size_t)n_iv * 8, cudaMemcpyDeviceToHost, e->stream));
@@ -540,7 +559,7 @@ int pd_profile_get(pd_engine *e, pd_kernel_time *out, int cap)
 {
     if (!e) return PD_ERR_ARG;
     CK(cudaSetDevice(e->device));
-    int rc = drain_profile(e); if (rc) return rc;
+    int rc = drain_profile(e); if (rc) return -rc;
     for (int k = 0; k < K_COUNT && k < cap; ++k) {
         memset(out[k].name, 0, sizeof out[k].name);
         strncpy(out[k].name, kKernelNames[k], sizeof out[k].name - 1);

@@ -16,16 +16,26 @@
 
 namespace pdk {
 
-constexpr int SEG = 1024;   // bases owned by one warp of k_tile_accumulate (4 KB of depth)
+#ifndef PD_SEG
+#define PD_SEG 2048
+#endif
+#ifndef PD_TILE_UNROLL
+#define PD_TILE_UNROLL 16
+#endif
+#ifndef PD_TILE_MIN_CTAS
+#define PD_TILE_MIN_CTAS 3
+#endif
+constexpr int SEG = PD_SEG;   // bases owned by one warp of k_tile_accumulate (8 KB of depth at 2048)
 constexpr int HALO = 256;   // look-back window in bases; also the largest "common span" L the fast path models
 constexpr int WPC = 8;      // warps per CTA in k_tile_accumulate
-constexpr int TILE_SMEM_WORDS = 2 * SEG + HALO;   // per warp: H[SEG+HALO] start counts, D[SEG] corrections
+constexpr int TILE_SMEM_WORDS = SEG;   // per warp: E[SEG], +-count per base of the segment (4 KB)
+constexpr int TILE_MIN_CTAS = PD_TILE_MIN_CTAS;   // resident CTAs per SM k_tile_accumulate is compiled for (register cap)
 constexpr unsigned FULL = 0xffffffffu;
 
 enum { ERR_UNSORTED = 1, ERR_RANGE = 2 };
 
-__device__ __forceinline__ bool is_match_op(uint32_t op) { return op == 0u || op == 7u || op == 8u; }   // M = X  (:745-747)
-__device__ __forceinline__ bool is_skip_op(uint32_t op) { return op == 2u || op == 3u; }                  // D N    (:754-755)
+__device__ __forceinline__ bool is_match_op(uint32_t op) { return (0x181u >> op) & 1u; }               // M = X  (:745-747)
+__device__ __forceinline__ bool is_skip_op(uint32_t op) { return (0x00cu >> op) & 1u; }                // D N    (:754-755)
 
 __device__ __forceinline__ int32_t ldg_i32(const int32_t *p) { return __ldg(p); }
 __device__ __forceinline__ uint32_t ldg_u32(const uint32_t *p) { return __ldg(p); }
@@ -37,8 +47,7 @@ __device__ __forceinline__ void red_add_u32(uint32_t *addr, uint32_t v)
 
 // ---------------------------------------------------------------------------------------------------------------
 // k_cut: for segment j (bases [s0, s0+SEG)) of a pos-sorted batch: lo[j] = first read with pos >= s0-HALO,
-// hi[j] = first read with pos >= s0+SEG.  Warp 0 of block 0 also samples 32 reads and publishes the most common
-// single-run span L (0 if none dominates or L > HALO).
+// hi[j] = first read with pos >= s0+SEG.
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t lower_bound_pos(const int32_t *pos, uint32_t n, int64_t key)
 {
@@ -51,68 +60,64 @@ __device__ __forceinline__ uint32_t lower_bound_pos(const int32_t *pos, uint32_t
 }
 
 struct CutArgs {
-    const int32_t *pos; const uint32_t *cigar; const uint32_t *cigar_off;
-    const uint16_t *flag; const uint8_t *mapq;
+    const int32_t *pos;
     uint32_t n; int32_t seg0; int32_t nseg;
-    uint32_t *lo; uint32_t *hi; uint32_t *L;
-    uint32_t xflags; int32_t min_mapq;
+    uint32_t *lo; uint32_t *hi;
 };
 
-__global__ void __launch_bounds__(256) k_cut(CutArgs a)
+constexpr int CUT_COARSE = 64;   // segments per coarse search key
+
+// pass A: one thread per CUT_COARSE segments: coarse[k] = lower_bound(pos, (seg0 + k*CUT_COARSE)*SEG - HALO)
+__global__ void __launch_bounds__(128) k_cut_coarse(CutArgs a, uint32_t *coarse, int32_t ncoarse)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= ncoarse) return;
+    const int64_t key = (int64_t)(a.seg0 + (int64_t)k * CUT_COARSE) * SEG - HALO;
+    coarse[k] = lower_bound_pos(a.pos, a.n, key);
+}
+
+// pass B: lo[j] inside its coarse bracket, hi[j] by a short search to the right of lo[j].
+__global__ void __launch_bounds__(256) k_cut(CutArgs a, const uint32_t *coarse, int32_t ncoarse)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j < a.nseg) {
         const int64_t s0 = (int64_t)(a.seg0 + j) * SEG;
-        const uint32_t l = lower_bound_pos(a.pos, a.n, s0 - HALO);
-        // hi >= lo always; search the tail only
-        const uint32_t h = l + lower_bound_pos(a.pos + l, a.n - l, s0 + SEG);
-        a.lo[j] = l;
-        a.hi[j] = h;
-    }
-    if (blockIdx.x == 0 && threadIdx.x < 32) {
-        const int lane = threadIdx.x;
-        uint32_t span = 0;
-        if (a.n > 0) {
-            const uint32_t i = (uint32_t)(((uint64_t)a.n * (uint32_t)lane) / 32u);
-            uint32_t c, nops;
-            if (a.cigar_off) { uint32_t c0 = a.cigar_off[i]; nops = a.cigar_off[i + 1] - c0; c = nops ? a.cigar[c0] : 0u; }
-            else { nops = 1; c = a.cigar[i]; }
-            bool pass = true;
-            if (a.flag && (a.flag[i] & a.xflags)) pass = false;
-            if (a.mapq && (int)a.mapq[i] < a.min_mapq) pass = false;
-            if (pass && nops == 1 && is_match_op(c & 15u)) span = c >> 4;
+        const int k = j / CUT_COARSE;
+        const uint32_t ca = coarse[k];
+        const uint32_t cb = (k + 1 < ncoarse) ? coarse[k + 1] : a.n;
+        const uint32_t l = ca + lower_bound_pos(a.pos + ca, cb - ca, s0 - HALO);
+        // hi: first read with pos >= s0+SEG; gallop right from l (the distance is ~ (SEG+HALO) x read density)
+        const int64_t key = s0 + SEG;
+        uint32_t step = 256, lo_i = l, hi_i = l;
+        while (true) {
+            hi_i = (a.n - lo_i > step) ? lo_i + step : a.n;
+            if (hi_i == a.n || (int64_t)ldg_i32(a.pos + hi_i) >= key) break;
+            lo_i = hi_i; step <<= 1;
         }
-        const unsigned same = __match_any_sync(FULL, span);
-        int votes = __popc(same);
-        if (span == 0 || span > (uint32_t)HALO) votes = 0;
-        int best = votes;
-        for (int o = 16; o; o >>= 1) best = max(best, __shfl_xor_sync(FULL, best, o));
-        const unsigned who = __ballot_sync(FULL, votes == best && best >= 8);
-        uint32_t L = 0;
-        if (who) L = __shfl_sync(FULL, span, __ffs(who) - 1);
-        if (lane == 0) *a.L = L;
+        a.lo[j] = l;
+        a.hi[j] = lo_i + lower_bound_pos(a.pos + lo_i, hi_i - lo_i, key);
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // k_tile_accumulate: one warp per SEG-base segment of one contig.
 //
-// The warp sees every read whose pos lies in [s0-HALO, s0+SEG) (lo/hi from k_cut).  Per-base depth of the segment is
-//     depth(b) = #{reads: pos in (b-L, b]}            "every read is one run of the common span L"   (table H)
-//              + prefix-sum of corrections D(b)        for reads that are not (filtered / other CIGARs) (table D)
-// H is filled with plain (non-atomic) read-modify-writes: reads are sorted, so within a 32-read chunk equal positions
-// are adjacent and one lane per distinct position adds the group size; chunks are processed sequentially by the same
-// warp and H is private to it.  D takes shared-memory atomics, but only for the uncommon reads.  With L = 0 (no
-// common span) every read goes through D: the plain "scatter +-1 deltas into a shared tile" scheme.
-// Runs that reach past the segments that see the read (pos + HALO) are "far": the owner segment scatters them as
-// +-1 deltas into the global delta array, folded in by k_scan_add at finalize.
-// The segment is then scanned once (warp shuffles) and written with coalesced 16-byte stores: a plain streaming
-// store if no earlier batch touched the segment (zero-initialisation is fused away), else load+add+store.
+// The warp sees every read whose pos lies in [s0-HALO, s0+SEG) (lo/hi from k_cut) and builds, in its private 4 KB of
+// shared memory, E[b] = (runs starting at b) - (runs ending at b) for the bases of its segment with shared-memory atomics
+// (warp-private table, so the only contention is equal positions inside one 32-read chunk); every +-1 that lands left of
+// s0 goes to a per-lane register carry instead.  Loads of TILE_UNROLL chunks are issued together before any is consumed.
+// Runs that reach past the segments that see the read (pos + HALO) are "far": the owner segment scatters them as +-1
+// deltas into the global delta array, folded in by k_scan_add at finalize.
+// The segment is then prefix-summed (warp shuffles) and written with coalesced 16-byte stores: a plain streaming store if
+// no earlier batch touched the segment (zero-initialisation is fused away), else load+add+store.
+// (Measured alternative, dropped: modelling reads as one common span and applying group counts with plain two-phase
+// read-modify-writes was 15% slower than the atomics on B200 -- see DESIGN.md.)
 // ---------------------------------------------------------------------------------------------------------------
 struct TileArgs {
     const int32_t *pos; const uint32_t *cigar; const uint32_t *cigar_off;
     const uint16_t *flag; const uint8_t *mapq;
-    const uint32_t *lo; const uint32_t *hi; const uint32_t *L;
+    const uint32_t *lo; const uint32_t *hi;
+    uint32_t n;
     int32_t seg0; int32_t nseg; int32_t contig_len;
     uint32_t *depth;      // contig base
     uint32_t *delta;      // contig base (global delta array)
@@ -121,82 +126,139 @@ struct TileArgs {
     int *err; int *delta_used;
 };
 
-__global__ void __launch_bounds__(WPC * 32) k_tile_accumulate(TileArgs a)
+constexpr int TILE_UNROLL = PD_TILE_UNROLL;   // 32-read chunks whose loads are issued together (memory-level parallelism)
+
+template <bool HAS_OFF, bool HAS_FILTER>
+__global__ void __launch_bounds__(WPC * 32, TILE_MIN_CTAS) k_tile_accumulate(TileArgs a)
 {
     extern __shared__ __align__(16) uint32_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int j = blockIdx.x * WPC + warp;
     if (j >= a.nseg) return;
     const uint32_t i_lo = a.lo[j], i_hi = a.hi[j];
-    if (i_lo >= i_hi) return;
-
-    uint32_t *H = smem + warp * TILE_SMEM_WORDS;
-    uint32_t *D = H + SEG + HALO;
     const int64_t s0 = (int64_t)(a.seg0 + j) * SEG;
     const int64_t hbase = s0 - HALO;
     const int64_t send = s0 + SEG;
-    const int L = (int)*a.L;
-    const int64_t clen = a.contig_len;
+    // PD_SORTED is verified on everything the kernel touches.  The cut must be consistent with its neighbours: reads left
+    // of lo are before the window, the read at hi is beyond it, and the next window starts inside ours.  The loads are
+    // issued here and checked at the very end, off the critical path.
+    int32_t chk_l = INT32_MIN, chk_r = INT32_MAX; uint32_t chk_n = 0;
+    bool bad = i_lo > i_hi || i_hi > a.n;
+    if (lane == 0 && !bad) {
+        if (i_lo > 0) chk_l = ldg_i32(a.pos + i_lo - 1);
+        if (i_hi < a.n) chk_r = ldg_i32(a.pos + i_hi);
+        if (j + 1 < a.nseg) chk_n = a.lo[j + 1];
+    }
+    if (i_lo >= i_hi || bad) {
+        if (lane == 0 && (bad || (int64_t)chk_l >= hbase || (int64_t)chk_r < send || chk_n > i_hi)) atomicOr(a.err, ERR_UNSORTED);
+        return;
+    }
 
+    uint32_t *E = smem + warp * TILE_SMEM_WORDS;     // (runs starting at b) - (runs ending at b) for b in [s0, s0+SEG)
+    const int64_t clen = a.contig_len;
     {
         const uint4 z = make_uint4(0, 0, 0, 0);
-        uint4 *H4 = reinterpret_cast<uint4 *>(H);
+        uint4 *E4 = reinterpret_cast<uint4 *>(E);
 #pragma unroll
-        for (int k = lane; k < TILE_SMEM_WORDS / 4; k += 32) H4[k] = z;
+        for (int k = lane; k < TILE_SMEM_WORDS / 4; k += 32) E4[k] = z;
     }
     __syncwarp();
 
+    uint32_t carry_reg = 0;        // per-lane part of "depth just left of the segment": every +-1 that lands before s0
     int32_t carry_p = INT32_MIN;   // last position of the previous chunk (sortedness check)
-    for (uint32_t base = i_lo; base < i_hi; base += 32) {
-        const uint32_t i = base + lane;
-        const bool valid = i < i_hi;
-        const int32_t p = valid ? ldg_i32(a.pos + i) : INT32_MAX;
-        uint32_t c = 0, c0 = i, nops = 1;
-        bool pass = valid;
-        if (valid) {
-            if (a.cigar_off) { c0 = ldg_u32(a.cigar_off + i); nops = ldg_u32(a.cigar_off + i + 1) - c0; c = nops ? ldg_u32(a.cigar + c0) : 0u; }
-            else c = ldg_u32(a.cigar + i);
-            if (a.flag && (a.flag[i] & a.xflags)) pass = false;          // :732
-            if (a.mapq && (int)a.mapq[i] < a.min_mapq) pass = false;     // :733
-            if (p < 0) pass = false;
+    // all coordinates below are relative to s0 (32-bit): a read seen by this warp has rel in [-HALO, SEG)
+    const int32_t s0i = (int32_t)s0;
+    const int32_t clen_rel = (int32_t)(clen - s0);
+    // delta v applies to every base >= x (x relative to s0)
+    auto emit = [&](int64_t x, uint32_t v) {
+        if (x < 0) carry_reg += v;
+        else if (x < SEG) atomicAdd(&E[(int)x], v);
+    };
+    for (uint32_t base = i_lo; base < i_hi; base += 32 * TILE_UNROLL) {
+        // issue every load of TILE_UNROLL chunks before consuming any of them
+        int32_t pv[TILE_UNROLL]; uint32_t cv[TILE_UNROLL]; uint32_t ov[TILE_UNROLL]; uint32_t nv[TILE_UNROLL];
+        uint32_t failm = 0;        // bit u: fails the record filter
+        const uint32_t left = i_hi - base;                    // reads left in this and later chunks (>= 1)
+#pragma unroll
+        for (int u = 0; u < TILE_UNROLL; ++u) {
+            const uint32_t i = base + u * 32 + lane;
+            const bool valid = (uint32_t)(u * 32 + lane) < left;
+            pv[u] = valid ? ldg_i32(a.pos + i) : INT32_MAX;
+            ov[u] = 0; nv[u] = 1; cv[u] = 0;
+            if (HAS_OFF) {
+                ov[u] = valid ? ldg_u32(a.cigar_off + i) : 0u;
+                nv[u] = valid ? ldg_u32(a.cigar_off + i + 1) : 0u;
+            } else {
+                cv[u] = valid ? ldg_u32(a.cigar + i) : 0u;
+            }
+            if (HAS_FILTER) {
+                if (valid) {
+                    if (a.flag && (__ldg(a.flag + i) & a.xflags)) failm |= 1u << u;           // :732
+                    if (a.mapq && (int)__ldg(a.mapq + i) < a.min_mapq) failm |= 1u << u;      // :733
+                }
+            }
         }
-        int32_t pp = __shfl_up_sync(FULL, p, 1);
-        const int32_t pn = __shfl_down_sync(FULL, p, 1);
-        if (lane == 0) pp = carry_p;
-        if (valid && p < pp) atomicOr(a.err, ERR_UNSORTED);
-        carry_p = __shfl_sync(FULL, p, 31);
-        const bool first = (lane == 0) || (p != pp);
-        const bool last = (lane == 31) || (p != pn);
-        const unsigned mf = __ballot_sync(FULL, first);
-        if (valid && last) {
-            const int fl = 31 - __clz(mf & (FULL >> (31 - lane)));
-            const uint32_t idx = (uint32_t)((int64_t)p - hbase);
-            if (idx < (uint32_t)(SEG + HALO)) H[idx] += (uint32_t)(lane - fl + 1);
-            else atomicOr(a.err, ERR_RANGE);
+        if (HAS_OFF) {
+#pragma unroll
+            for (int u = 0; u < TILE_UNROLL; ++u) {
+                nv[u] -= ov[u];
+                cv[u] = nv[u] ? ldg_u32(a.cigar + ov[u]) : 0u;
+            }
         }
-        const bool common = pass && nops == 1 && L > 0 && (c >> 4) == (uint32_t)L && is_match_op(c & 15u);
-        if (valid && !common) {
-            // corrections: cancel the modelled run [p, p+L), then add the real runs
-            auto emit = [&](int64_t x, uint32_t v) {
-                if (x < send) atomicAdd(&D[x <= s0 ? 0 : (int)(x - s0)], v);
-            };
-            bool cancel_start = (L > 0);
-            if (L > 0) emit((int64_t)p + L, 1u);
-            if (pass) {
-                const bool owner = (int64_t)p >= s0;
-                const int64_t far_lo = (((int64_t)p + HALO) / SEG + 1) * SEG;
-                int64_t q = p, rs = -1, re = -1;
+        // sortedness of everything just loaded: one rotate-shuffle per chunk (lane l gets lane l-1; lane 0 gets lane 31,
+        // which it compares with the NEXT chunk's first read).  Invalid lanes hold INT32_MAX and sort last.
+        {
+            int32_t prev_last = carry_p;
+#pragma unroll
+            for (int u = 0; u < TILE_UNROLL; ++u) {
+                const int32_t r = __shfl_sync(FULL, pv[u], (lane + 31) & 31);
+                bad |= pv[u] < (lane == 0 ? prev_last : r);
+                prev_last = r;                                 // meaningful in lane 0 only
+            }
+            carry_p = prev_last;
+        }
+#pragma unroll
+        for (int u = 0; u < TILE_UNROLL; ++u) {
+            if ((uint32_t)(u * 32) >= left) break;            // warp-uniform
+            const bool valid = (uint32_t)(u * 32 + lane) < left;
+            const int32_t p = pv[u];
+            const uint32_t c = cv[u];
+            const uint32_t nops = HAS_OFF ? nv[u] : 1u;
+            bool pass = valid && p >= 0;
+            if (HAS_FILTER && ((failm >> u) & 1u)) pass = false;
+            if (!pass) continue;
+            const int32_t rel = p - s0i;
+            if ((uint32_t)(rel + HALO) >= (uint32_t)(SEG + HALO)) { bad = true; continue; }
+            // first base (relative) that no segment seeing this read owns: segments see reads up to HALO to their left
+            const int32_t far_rel = (rel + HALO >= SEG) ? 2 * SEG : SEG;
+            if (nops == 1) {
+                // one CIGAR op (the common case): M/=/X is one run [p, p+len)                      :745-752
+                if ((0x181u >> (c & 15u)) & 1u) {
+                    const int32_t e = min(rel + (int32_t)(c >> 4), clen_rel);     // len < 2^28: no overflow
+                    if (e > rel) {
+                        if (rel < 0) carry_reg += 1u; else atomicAdd(&E[rel], 1u);
+                        if (e < 0) carry_reg -= 1u; else if (e < SEG) atomicAdd(&E[e], 0xffffffffu);
+                        if (e > far_rel && rel >= 0) {
+                            red_add_u32(a.delta + s0 + far_rel, 1u);
+                            red_add_u32(a.delta + s0 + e, 0xffffffffu);
+                            *a.delta_used = 1;
+                        }
+                    }
+                }
+            } else {
+                const uint32_t c0 = HAS_OFF ? ov[u] : (base + u * 32 + lane);
+                const bool owner = rel >= 0;
+                int64_t q = rel, rs = INT64_MIN, re = INT64_MIN;
                 auto flush = [&]() {
-                    if (rs < 0) return;
-                    int64_t s = rs < 0 ? 0 : rs, e = re > clen ? clen : re;
+                    if (rs == INT64_MIN) return;
+                    const int64_t s = rs, e = re > (int64_t)clen_rel ? (int64_t)clen_rel : re;
                     if (s >= e) return;
-                    if (s == (int64_t)p && cancel_start) cancel_start = false;   // +1 and the cancelling -1 meet at p
-                    else emit(s, 1u);
+                    emit(s, 1u);
                     emit(e, 0xffffffffu);
-                    if (owner && e > far_lo) {
-                        const int64_t gs = s > far_lo ? s : far_lo;
-                        red_add_u32(a.delta + gs, 1u);
-                        red_add_u32(a.delta + e, 0xffffffffu);
+                    if (owner && e > far_rel) {
+                        const int64_t gs = s > far_rel ? s : far_rel;
+                        red_add_u32(a.delta + s0 + gs, 1u);
+                        red_add_u32(a.delta + s0 + e, 0xffffffffu);
                         *a.delta_used = 1;
                     }
                 };
@@ -204,40 +266,30 @@ __global__ void __launch_bounds__(WPC * 32) k_tile_accumulate(TileArgs a)
                     const uint32_t w = (k == 0) ? c : ldg_u32(a.cigar + c0 + k);
                     const uint32_t op = w & 15u;
                     const int64_t n = w >> 4;
-                    if (is_match_op(op)) {
-                        if (rs >= 0 && re == q) re = q + n; else { flush(); rs = q; re = q + n; }
+                    if (is_match_op(op)) {                                     // :745-752  adjacent M/=/X merge into one run
+                        if (re == q && rs != INT64_MIN) re = q + n; else { flush(); rs = q; re = q + n; }
                         q += n;
-                    } else if (is_skip_op(op)) q += n;
+                    } else if (is_skip_op(op)) q += n;                         // :754-757
                 }
                 flush();
             }
-            if (cancel_start) emit((int64_t)p, 0xffffffffu);
         }
-        __syncwarp();
     }
+    __syncwarp();
 
-    // depth just left of the segment under the common-span model: reads with pos in [s0-L, s0)
-    uint32_t carry = 0;
-    if (L > 0) {
-        uint32_t part = 0;
-        for (int k = HALO - L + lane; k < HALO; k += 32) part += H[k];
-        for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(FULL, part, o);
-        carry = part;
-    }
+    // depth just left of the segment
+    uint32_t carry = carry_reg;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) carry += __shfl_xor_sync(FULL, carry, o);
+
     uint8_t *st_ptr = a.seg_state + (a.seg0 + j);
     const bool fresh = (*st_ptr == 0);
     uint32_t *out = a.depth + s0;
-#pragma unroll 2
+#pragma unroll 4
     for (int r = 0; r < SEG / 128; ++r) {
         const int b = r * 128 + lane * 4;
-        const uint4 h = *reinterpret_cast<const uint4 *>(H + HALO + b);
-        const uint4 d = *reinterpret_cast<const uint4 *>(D + b);
-        uint32_t x0 = h.x + d.x, x1 = h.y + d.y, x2 = h.z + d.z, x3 = h.w + d.w;
-        if (L > 0) {
-            const uint32_t *hl = H + HALO + b - L;
-            x0 -= hl[0]; x1 -= hl[1]; x2 -= hl[2]; x3 -= hl[3];
-        }
-        x1 += x0; x2 += x1; x3 += x2;
+        const uint4 d = *reinterpret_cast<const uint4 *>(E + b);
+        uint32_t x0 = d.x, x1 = d.y + x0, x2 = d.z + x1, x3 = d.w + x2;
         uint32_t t = x3;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -256,6 +308,8 @@ __global__ void __launch_bounds__(WPC * 32) k_tile_accumulate(TileArgs a)
         }
     }
     if (fresh && lane == 0) *st_ptr = 1;
+    bad = __any_sync(FULL, bad);
+    if (lane == 0 && (bad || (int64_t)chk_l >= hbase || (int64_t)chk_r < send || chk_n > i_hi)) atomicOr(a.err, ERR_UNSORTED);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -426,8 +480,8 @@ struct ReduceArgs {
     const uint64_t *contig_off;      // per tid, element offset
     const uint32_t *contig_len;      // per tid
     const int32_t *tid; const int32_t *start0; const int32_t *end0;
-    const uint2 *units;              // (interval index, chunk index)
-    uint64_t n_units;
+    const uint64_t *unit_prefix;     // n_iv+1: units before interval i (one unit = REDUCE_CHUNK bases)
+    uint64_t n_iv; uint64_t n_units;
     uint32_t min_dep, mask;
     unsigned long long *cov; unsigned long long *sum;
 };
@@ -468,7 +522,13 @@ __global__ void __launch_bounds__(256) k_reduce_units(ReduceArgs a)
     const uint64_t u = (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (u >= a.n_units) return;
     const int lane = threadIdx.x & 31;
-    const uint2 un = a.units[u];
+    // interval of this unit: last i with unit_prefix[i] <= u
+    uint64_t lo_i = 0, hi_i = a.n_iv;
+    while (hi_i - lo_i > 1) {
+        const uint64_t m = (lo_i + hi_i) >> 1;
+        if (__ldg(a.unit_prefix + m) <= u) lo_i = m; else hi_i = m;
+    }
+    uint2 un; un.x = (unsigned)lo_i; un.y = (unsigned)(u - __ldg(a.unit_prefix + lo_i));
     const int32_t t = a.tid[un.x];
     int64_t s = a.start0[un.x], e = a.end0[un.x];
     const int64_t len = a.contig_len[t];

@@ -28,7 +28,8 @@ class _KTime(ctypes.Structure):
 
 
 def lib_path() -> str:
-    return os.path.join(_HERE, "libpandepth_b200.so")
+    # PANDEPTH_B200_LIB selects another build of the same CUDA library (kernel tuning experiments)
+    return os.environ.get("PANDEPTH_B200_LIB") or os.path.join(_HERE, "libpandepth_b200.so")
 
 
 def load_library() -> ctypes.CDLL:
@@ -78,7 +79,14 @@ def _p(a):
 
 
 def _arr(a, dt):
-    return None if a is None else np.ascontiguousarray(a, dtype=dt)
+    """Contiguous array of dtype dt; same-width integer arrays are reinterpreted in place (no copy, stays pinned)."""
+    if a is None:
+        return None
+    a = np.asarray(a)
+    dt = np.dtype(dt)
+    if a.dtype != dt and a.dtype.kind in "iu" and a.dtype.itemsize == dt.itemsize and a.flags.c_contiguous:
+        return a.view(dt)
+    return np.ascontiguousarray(a, dtype=dt)
 
 
 class Engine:

@@ -253,8 +253,18 @@ def test_unsorted_batch_declared_sorted_is_reported():
     pos = np.array([5000, 100, 90_000, 7], np.int32)
     cig = np.full(4, (50 << 4), np.uint32)
     with _engine(tlen) as eng:
-        eng.push_contig(0, pos, cig, flags=pd.PD_SORTED)
         with pytest.raises(pd.PDError) as ei:
+            eng.push_contig(0, pos, cig, flags=pd.PD_SORTED)
+            eng.finalize()
+        assert ei.value.code == 4
+    # sorted except for two swapped reads in the middle: first <= last, so only the device can see it
+    rng = np.random.default_rng(3)
+    pos = np.sort(rng.integers(0, 99_000, 20_000)).astype(np.int32)
+    pos[5000], pos[15000] = pos[15000], pos[5000]
+    cig = np.full(pos.size, (150 << 4), np.uint32)
+    with _engine(tlen) as eng:
+        with pytest.raises(pd.PDError) as ei:
+            eng.push_contig(0, pos, cig, flags=pd.PD_SORTED)
             eng.finalize()
         assert ei.value.code == 4
 
