@@ -131,6 +131,7 @@ constexpr int TILE_UNROLL = PD_TILE_UNROLL;   // 32-read chunks whose loads are 
 template <bool HAS_OFF, bool HAS_FILTER>
 __global__ void __launch_bounds__(WPC * 32, TILE_MIN_CTAS) k_tile_accumulate(TileArgs a)
 {
+    constexpr int U = HAS_OFF ? (TILE_UNROLL > 8 ? 8 : TILE_UNROLL) : TILE_UNROLL;   // offsets cost two more registers per chunk
     extern __shared__ __align__(16) uint32_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int j = blockIdx.x * WPC + warp;
@@ -174,13 +175,13 @@ __global__ void __launch_bounds__(WPC * 32, TILE_MIN_CTAS) k_tile_accumulate(Til
         if (x < 0) carry_reg += v;
         else if (x < SEG) atomicAdd(&E[(int)x], v);
     };
-    for (uint32_t base = i_lo; base < i_hi; base += 32 * TILE_UNROLL) {
+    for (uint32_t base = i_lo; base < i_hi; base += 32 * U) {
         // issue every load of TILE_UNROLL chunks before consuming any of them
-        int32_t pv[TILE_UNROLL]; uint32_t cv[TILE_UNROLL]; uint32_t ov[TILE_UNROLL]; uint32_t nv[TILE_UNROLL];
+        int32_t pv[U]; uint32_t cv[U]; uint32_t ov[U]; uint32_t nv[U];
         uint32_t failm = 0;        // bit u: fails the record filter
         const uint32_t left = i_hi - base;                    // reads left in this and later chunks (>= 1)
 #pragma unroll
-        for (int u = 0; u < TILE_UNROLL; ++u) {
+        for (int u = 0; u < U; ++u) {
             const uint32_t i = base + u * 32 + lane;
             const bool valid = (uint32_t)(u * 32 + lane) < left;
             pv[u] = valid ? ldg_i32(a.pos + i) : INT32_MAX;
@@ -200,7 +201,7 @@ __global__ void __launch_bounds__(WPC * 32, TILE_MIN_CTAS) k_tile_accumulate(Til
         }
         if (HAS_OFF) {
 #pragma unroll
-            for (int u = 0; u < TILE_UNROLL; ++u) {
+            for (int u = 0; u < U; ++u) {
                 nv[u] -= ov[u];
                 cv[u] = nv[u] ? ldg_u32(a.cigar + ov[u]) : 0u;
             }
@@ -210,7 +211,7 @@ __global__ void __launch_bounds__(WPC * 32, TILE_MIN_CTAS) k_tile_accumulate(Til
         {
             int32_t prev_last = carry_p;
 #pragma unroll
-            for (int u = 0; u < TILE_UNROLL; ++u) {
+            for (int u = 0; u < U; ++u) {
                 const int32_t r = __shfl_sync(FULL, pv[u], (lane + 31) & 31);
                 bad |= pv[u] < (lane == 0 ? prev_last : r);
                 prev_last = r;                                 // meaningful in lane 0 only
@@ -218,7 +219,7 @@ __global__ void __launch_bounds__(WPC * 32, TILE_MIN_CTAS) k_tile_accumulate(Til
             carry_p = prev_last;
         }
 #pragma unroll
-        for (int u = 0; u < TILE_UNROLL; ++u) {
+        for (int u = 0; u < U; ++u) {
             if ((uint32_t)(u * 32) >= left) break;            // warp-uniform
             const bool valid = (uint32_t)(u * 32 + lane) < left;
             const int32_t p = pv[u];

@@ -1,0 +1,67 @@
+// pd_host.hpp -- C++ host around the CUDA engine: the `pandepth` command line (same flags, same output files as the
+// reference), the region model, the htslib feeder and the report writer.  New code; behaviour follows
+// /root/reference/src/PanDepth.cpp (cited per function as :line).
+#pragma once
+#include <cstdint>
+#include <map>
+#include <string>
+#include <utility>
+#include <vector>
+
+namespace pdh {
+
+// In3str1v (include/DataClass.h:22-59) with the defaults main() applies (:3444).
+struct Options {
+    std::string input;                 // -i
+    std::string out_arg;               // -o as given
+    std::string gff;                   // -g
+    std::string bed;                   // -b
+    std::string feature = "CDS";       // -f
+    std::string reference;             // -r (CRAM decode)
+    bool site_output = false;          // -a
+    bool use_index = true;             // cleared by the undocumented -s (:223-226)
+    uint32_t xflags = 1796;            // -x
+    int min_mapq = -1;                 // -q  (InInt preset to -1 at :3444)
+    int min_dep = 1;                   // -d  (clamped >= 1, :233)
+    int win = 0;                       // -w  (clamped >= 1 when given, :211-215)
+    int threads = 3;                   // -t
+    int region_mode = 0;               // InInt2: 0 chr, 1 gff, 2 gtf, 3 bed3, 4 bed4, 5 window>=150, 6 window<150
+    bool gc = false;                   // -c (not supported by this build; reported)
+    bool help = false;
+};
+
+// Returns 0 = run, 1 = exit quietly with status 0 (help / usage error, like the reference's `return 0`).
+int parse_args(int argc, char **argv, Options &o);
+void print_help();
+
+// GeneInfo (include/DataClass.h:62-80)
+struct Gene {
+    int start = 0, end = 0;
+    uint64_t length = 0;
+    std::vector<std::pair<int, int>> cds;   // 1-based closed
+    int64_t cover = 0;                      // int GeneCover in the reference
+    uint64_t depth = 0;
+};
+using GeneMap = std::map<int, std::map<std::string, Gene>>;     // tid -> GeneID -> Gene   (:3543)
+
+struct Target { std::string name; uint32_t len; };
+
+// :3547-3905 (GFF/GTF/BED parsers), :3975-4051 (pseudo-gene tiling).  Sets o.region_mode.
+bool build_regions(Options &o, const std::vector<Target> &targets, GeneMap &genes, std::string &err);
+// :3919-3972
+std::vector<std::pair<int, int>> merge_regions(const std::map<std::string, Gene> &genes);
+// How often ProDealChrBambai's windowing (:695-784) hands each gene to StatChrDepthWin (:299-308): 1, or 0 for a gene that
+// starts on/after the contig-clipped window end.
+std::map<std::string, int> indexed_window_counts(const std::vector<std::pair<int, int>> &regions,
+                                                 const std::map<std::string, Gene> &genes, int chr_len);
+
+// output naming :4057-4090
+std::string output_prefix(const std::string &out_arg);
+const char *stat_suffix(int mode);
+const char *stat_header(int mode);
+
+// fixed/setprecision(2) of cov*100.0/len and sum*1.0/len (:5023-5024)
+std::string fmt_ratio_pct(double cov, double len);
+std::string fmt_ratio(double sum, double len);
+
+}  // namespace pdh

