@@ -45,6 +45,19 @@ __device__ __forceinline__ void red_add_u32(uint32_t *addr, uint32_t v)
     asm volatile("red.global.add.u32 [%0], %1;" ::"l"(addr), "r"(v) : "memory");
 }
 
+// one Kogge-Stone step of a warp inclusive scan: t += (lane >= o) ? shfl_up(t, o) : 0, using the predicate shfl.up
+// itself produces (2 instructions instead of shuffle + compare + select + add)
+__device__ __forceinline__ uint32_t scan_step_up(uint32_t t, int o)
+{
+    uint32_t r;
+    asm volatile("{ .reg .u32 y; .reg .pred p;\n\t"
+                 "shfl.sync.up.b32 y|p, %1, %2, 0, 0xffffffff;\n\t"
+                 "@p add.u32 y, y, %1;\n\t"
+                 "@!p mov.u32 y, %1;\n\t"
+                 "mov.u32 %0, y; }" : "=r"(r) : "r"(t), "r"(o));
+    return r;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // k_cut: for segment j (bases [s0, s0+SEG)) of a pos-sorted batch: lo[j] = first read with pos >= s0-HALO,
 // hi[j] = first read with pos >= s0+SEG.
@@ -180,20 +193,22 @@ __global__ void __launch_bounds__(WPC * 32, TILE_MIN_CTAS) k_tile_accumulate(Til
         int32_t pv[U]; uint32_t cv[U]; uint32_t ov[U]; uint32_t nv[U];
         uint32_t failm = 0;        // bit u: fails the record filter
         const uint32_t left = i_hi - base;                    // reads left in this and later chunks (>= 1)
+        const int32_t *ppos = a.pos + base + lane;
+        const uint32_t *pcig = HAS_OFF ? a.cigar_off + base + lane : a.cigar + base + lane;
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const uint32_t i = base + u * 32 + lane;
             const bool valid = (uint32_t)(u * 32 + lane) < left;
-            pv[u] = valid ? ldg_i32(a.pos + i) : INT32_MAX;
+            pv[u] = valid ? ldg_i32(ppos + u * 32) : INT32_MAX;
             ov[u] = 0; nv[u] = 1; cv[u] = 0;
             if (HAS_OFF) {
-                ov[u] = valid ? ldg_u32(a.cigar_off + i) : 0u;
-                nv[u] = valid ? ldg_u32(a.cigar_off + i + 1) : 0u;
+                ov[u] = valid ? ldg_u32(pcig + u * 32) : 0u;
+                nv[u] = valid ? ldg_u32(pcig + u * 32 + 1) : 0u;
             } else {
-                cv[u] = valid ? ldg_u32(a.cigar + i) : 0u;
+                cv[u] = valid ? ldg_u32(pcig + u * 32) : 0u;
             }
             if (HAS_FILTER) {
                 if (valid) {
+                    const uint32_t i = base + u * 32 + lane;
                     if (a.flag && (__ldg(a.flag + i) & a.xflags)) failm |= 1u << u;           // :732
                     if (a.mapq && (int)__ldg(a.mapq + i) < a.min_mapq) failm |= 1u << u;      // :733
                 }
@@ -227,27 +242,29 @@ __global__ void __launch_bounds__(WPC * 32, TILE_MIN_CTAS) k_tile_accumulate(Til
             const uint32_t nops = HAS_OFF ? nv[u] : 1u;
             bool pass = valid && p >= 0;
             if (HAS_FILTER && ((failm >> u) & 1u)) pass = false;
-            if (!pass) continue;
-            const int32_t rel = p - s0i;
-            if ((uint32_t)(rel + HALO) >= (uint32_t)(SEG + HALO)) { bad = true; continue; }
+            const int32_t rel = p - s0i;                       // in [-HALO, SEG) for a consistent cut
+            const bool in_win = (uint32_t)(rel + HALO) < (uint32_t)(SEG + HALO);
+            bad |= pass && !in_win;
+            pass = pass && in_win;
             // first base (relative) that no segment seeing this read owns: segments see reads up to HALO to their left
             const int32_t far_rel = (rel + HALO >= SEG) ? 2 * SEG : SEG;
-            if (nops == 1) {
+            if (!HAS_OFF || nops == 1) {
                 // one CIGAR op (the common case): M/=/X is one run [p, p+len)                      :745-752
-                if ((0x181u >> (c & 15u)) & 1u) {
-                    const int32_t e = min(rel + (int32_t)(c >> 4), clen_rel);     // len < 2^28: no overflow
-                    if (e > rel) {
-                        if (rel < 0) carry_reg += 1u; else atomicAdd(&E[rel], 1u);
-                        if (e < 0) carry_reg -= 1u; else if (e < SEG) atomicAdd(&E[e], 0xffffffffu);
-                        if (e > far_rel && rel >= 0) {
-                            red_add_u32(a.delta + s0 + far_rel, 1u);
-                            red_add_u32(a.delta + s0 + e, 0xffffffffu);
-                            *a.delta_used = 1;
-                        }
-                    }
+                // written branch-free: predicated atomics, arithmetic carry
+                const int32_t e = min(rel + (int32_t)(c >> 4), clen_rel);         // len < 2^28: no overflow
+                const bool ok = pass && ((0x181u >> (c & 15u)) & 1u) && e > rel;
+                const bool s_in = ok && rel >= 0;
+                const bool e_in = ok && e >= 0 && e < SEG;
+                carry_reg += (uint32_t)(ok && rel < 0) - (uint32_t)(ok && e < 0);
+                if (s_in) atomicAdd(&E[rel], 1u);
+                if (e_in) atomicAdd(&E[e], 0xffffffffu);
+                if (s_in && e > far_rel) {                                          // rare: run longer than HALO
+                    red_add_u32(a.delta + s0 + far_rel, 1u);
+                    red_add_u32(a.delta + s0 + e, 0xffffffffu);
+                    *a.delta_used = 1;
                 }
-            } else {
-                const uint32_t c0 = HAS_OFF ? ov[u] : (base + u * 32 + lane);
+            } else if (pass) {
+                const uint32_t c0 = ov[u];
                 const bool owner = rel >= 0;
                 int64_t q = rel, rs = INT64_MIN, re = INT64_MIN;
                 auto flush = [&]() {
@@ -286,24 +303,29 @@ __global__ void __launch_bounds__(WPC * 32, TILE_MIN_CTAS) k_tile_accumulate(Til
     uint8_t *st_ptr = a.seg_state + (a.seg0 + j);
     const bool fresh = (*st_ptr == 0);
     uint32_t *out = a.depth + s0;
-#pragma unroll 4
-    for (int r = 0; r < SEG / 128; ++r) {
-        const int b = r * 128 + lane * 4;
+    auto scan_row = [&](int b) -> uint4 {
         const uint4 d = *reinterpret_cast<const uint4 *>(E + b);
-        uint32_t x0 = d.x, x1 = d.y + x0, x2 = d.z + x1, x3 = d.w + x2;
+        const uint32_t x0 = d.x, x1 = d.y + x0, x2 = d.z + x1, x3 = d.w + x2;
         uint32_t t = x3;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t y = __shfl_up_sync(FULL, t, o);
-            if (lane >= o) t += y;
-        }
+        for (int o = 1; o < 32; o <<= 1) t = scan_step_up(t, o);
         const uint32_t ex = t - x3 + carry;
         carry += __shfl_sync(FULL, t, 31);
-        uint4 v = make_uint4(x0 + ex, x1 + ex, x2 + ex, x3 + ex);
-        uint4 *dst = reinterpret_cast<uint4 *>(out + b);
-        if (fresh) __stcs(dst, v);
-        else {
+        return make_uint4(x0 + ex, x1 + ex, x2 + ex, x3 + ex);
+    };
+    if (fresh) {
+#pragma unroll 4
+        for (int r = 0; r < SEG / 128; ++r) {
+            const int b = r * 128 + lane * 4;
+            __stcs(reinterpret_cast<uint4 *>(out + b), scan_row(b));
+        }
+    } else {
+#pragma unroll 2
+        for (int r = 0; r < SEG / 128; ++r) {
+            const int b = r * 128 + lane * 4;
+            uint4 *dst = reinterpret_cast<uint4 *>(out + b);
             const uint4 old = *dst;
+            uint4 v = scan_row(b);
             v.x += old.x; v.y += old.y; v.z += old.z; v.w += old.w;
             *dst = v;
         }
