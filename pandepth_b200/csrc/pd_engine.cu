@@ -130,12 +130,12 @@ int run_batch(pd_engine *e, int32_t tid, uint32_t n, const int32_t *pos, const u
     const uint64_t off = e->off[tid];
     if (sorted) {
         const int32_t nseg = (int32_t)(seg_b - seg_a + 1);
-        int rc = ensure_cut(e, (size_t)nseg); if (rc) return rc;
+        int rc = ensure_cut(e, (size_t)nseg + 1); if (rc) return rc;
         pdk::CutArgs c{pos, n, (int32_t)seg_a, nseg, e->d_lo, e->d_hi};
         const int32_t ncoarse = (nseg + pdk::CUT_COARSE - 1) / pdk::CUT_COARSE;
         rc = launch(e, K_CUT, [&] {
             pdk::k_cut_coarse<<<(ncoarse + 127) / 128, 128, 0, e->stream>>>(c, e->d_coarse, ncoarse);
-            pdk::k_cut<<<(nseg + 255) / 256, 256, 0, e->stream>>>(c, e->d_coarse, ncoarse);
+            pdk::k_cut<<<(nseg + 1 + 255) / 256, 256, 0, e->stream>>>(c, e->d_coarse, ncoarse);
         });
         if (rc) return rc;
         e->stats.kernel_launches++;
@@ -411,17 +411,20 @@ int pd_finalize(pd_engine *e)
     CK(cudaSetDevice(e->device));
     if (e->finalized) return PD_OK;
     int rc = check_device_flags(e); if (rc) return rc;
-    rc = launch(e, K_FILL, [&] { pdk::k_fill_untouched<<<(unsigned)((e->n_seg + 7) / 8), 256, 0, e->stream>>>(e->d_depth, e->d_seg_state, e->n_seg); });
-    if (rc) return rc;
     if (e->host_delta_used) {
+        // the scan visits every element: it also zero-fills (plain store) the segments no tile batch wrote
         const uint64_t n_tiles = e->total / pdk::SCAN_TILE;
         CK(cudaMemsetAsync(e->d_desc, 0, n_tiles * 8, e->stream));
         CK(cudaMemsetAsync(e->d_counter, 0, 4, e->stream));
-        rc = launch(e, K_SCAN, [&] { pdk::k_scan_add<<<(unsigned)n_tiles, pdk::SCAN_THREADS, 0, e->stream>>>(e->d_depth, e->d_delta, e->total, e->d_desc, e->d_counter); });
+        rc = launch(e, K_SCAN, [&] { pdk::k_scan_add<<<(unsigned)n_tiles, pdk::SCAN_THREADS, 0, e->stream>>>(e->d_depth, e->d_delta, e->total, e->d_desc, e->d_counter, e->d_seg_state); });
         if (rc) return rc;
+        CK(cudaMemsetAsync(e->d_seg_state, 1, e->n_seg, e->stream));
         CK(cudaMemsetAsync(e->d_flags + 1, 0, 4, e->stream));
         e->host_delta_used = false;
         e->stats.scan_passes++;
+    } else {
+        rc = launch(e, K_FILL, [&] { pdk::k_fill_untouched<<<(unsigned)((e->n_seg + 7) / 8), 256, 0, e->stream>>>(e->d_depth, e->d_seg_state, e->n_seg); });
+        if (rc) return rc;
     }
     e->finalized = true;
     return PD_OK;

@@ -60,7 +60,7 @@ __device__ __forceinline__ uint32_t scan_step_up(uint32_t t, int o)
 
 // ---------------------------------------------------------------------------------------------------------------
 // k_cut: for segment j (bases [s0, s0+SEG)) of a pos-sorted batch: lo[j] = first read with pos >= s0-HALO,
-// hi[j] = first read with pos >= s0+SEG.
+// hi[j] = first read with pos >= s0 (so segment j's reads end at hi[j+1]).
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t lower_bound_pos(const int32_t *pos, uint32_t n, int64_t key)
 {
@@ -89,27 +89,45 @@ __global__ void __launch_bounds__(128) k_cut_coarse(CutArgs a, uint32_t *coarse,
     coarse[k] = lower_bound_pos(a.pos, a.n, key);
 }
 
-// pass B: lo[j] inside its coarse bracket, hi[j] by a short search to the right of lo[j].
+// lower_bound(pos, n, key) found by galloping outwards from a guess, then bisecting the bracket: O(log distance) probes,
+// all close to the answer (the plain bisection touches ~30 different 32-byte sectors per key).
+__device__ __forceinline__ uint32_t lower_bound_near(const int32_t *pos, uint32_t n, int64_t key, uint32_t g)
+{
+    if (g > n) g = n;
+    uint32_t a, b, step = 32;
+    if (g < n && (int64_t)ldg_i32(pos + g) < key) {            // answer in (g, n]
+        a = g + 1;
+        while (true) {
+            b = (n - a > step) ? a + step : n;
+            if (b == n || (int64_t)ldg_i32(pos + b) >= key) break;
+            a = b + 1; step <<= 1;
+        }
+    } else {                                                   // answer in [0, g]
+        b = g;
+        while (true) {
+            if (b == 0) { a = 0; break; }
+            a = (b > step) ? b - step : 0;
+            if ((int64_t)ldg_i32(pos + a) < key) { a = a + 1; break; }
+            b = a; step <<= 1;
+        }
+    }
+    return a + lower_bound_pos(pos + a, b - a, key);
+}
+
+// pass B: thread j < nseg: lo[j] = lower_bound(s0_j - HALO) from an interpolated guess inside its coarse bracket, and
+// mid[j] = lower_bound(s0_j) a few reads to its right; thread nseg: mid[nseg].  Segment j's reads are [lo[j], mid[j+1]).
 __global__ void __launch_bounds__(256) k_cut(CutArgs a, const uint32_t *coarse, int32_t ncoarse)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < a.nseg) {
-        const int64_t s0 = (int64_t)(a.seg0 + j) * SEG;
-        const int k = j / CUT_COARSE;
-        const uint32_t ca = coarse[k];
-        const uint32_t cb = (k + 1 < ncoarse) ? coarse[k + 1] : a.n;
-        const uint32_t l = ca + lower_bound_pos(a.pos + ca, cb - ca, s0 - HALO);
-        // hi: first read with pos >= s0+SEG; gallop right from l (the distance is ~ (SEG+HALO) x read density)
-        const int64_t key = s0 + SEG;
-        uint32_t step = 256, lo_i = l, hi_i = l;
-        while (true) {
-            hi_i = (a.n - lo_i > step) ? lo_i + step : a.n;
-            if (hi_i == a.n || (int64_t)ldg_i32(a.pos + hi_i) >= key) break;
-            lo_i = hi_i; step <<= 1;
-        }
-        a.lo[j] = l;
-        a.hi[j] = lo_i + lower_bound_pos(a.pos + lo_i, hi_i - lo_i, key);
-    }
+    if (j > a.nseg) return;
+    const int64_t s0 = (int64_t)(a.seg0 + j) * SEG;
+    int k = j / CUT_COARSE; if (k >= ncoarse) k = ncoarse - 1;
+    const uint32_t ca = coarse[k];
+    const uint32_t cb = (k + 1 < ncoarse) ? coarse[k + 1] : a.n;
+    const uint32_t g = ca + (uint32_t)(((uint64_t)(cb - ca) * (uint32_t)(j - k * CUT_COARSE)) / CUT_COARSE);
+    const uint32_t l = lower_bound_near(a.pos, a.n, s0 - HALO, g);
+    if (j < a.nseg) a.lo[j] = l;
+    a.hi[j] = lower_bound_near(a.pos, a.n, s0, l);             // "mid": nseg+1 entries
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -149,7 +167,7 @@ __global__ void __launch_bounds__(WPC * 32, TILE_MIN_CTAS) k_tile_accumulate(Til
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int j = blockIdx.x * WPC + warp;
     if (j >= a.nseg) return;
-    const uint32_t i_lo = a.lo[j], i_hi = a.hi[j];
+    const uint32_t i_lo = a.lo[j], i_hi = a.hi[j + 1];        // hi[] holds lower_bound(s0_j): nseg+1 entries
     const int64_t s0 = (int64_t)(a.seg0 + j) * SEG;
     const int64_t hbase = s0 - HALO;
     const int64_t send = s0 + SEG;
@@ -379,16 +397,18 @@ __global__ void __launch_bounds__(256) k_delta_scatter(ScatterArgs a)
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// k_scan_add: depth[i] += inclusive_prefix_sum(delta)[i]; delta[i] = 0.  Single pass, decoupled look-back
+// k_scan_add: depth[i] (+)= inclusive_prefix_sum(delta)[i]; delta[i] = 0.  Single pass, decoupled look-back
 // (tile aggregates published through 64-bit {status,value} descriptors), dynamic tile ids for forward progress.
 // Every contig's deltas sum to zero before its padding ends, so one scan over the whole array needs no resets.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 16;                           // uint32 per thread (4 x uint4)
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;     // 4096 elements = one 16 KB tile
+static_assert(SEG % 512 == 0 && SCAN_TILE % SEG == 0 || SEG % SCAN_TILE == 0, "a scan warp (512 elements) must lie inside one segment");
 
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_add(uint32_t *__restrict__ depth, uint32_t *__restrict__ delta,
-                                                           uint64_t n_elems, unsigned long long *desc, unsigned int *counter)
+                                                           uint64_t n_elems, unsigned long long *desc, unsigned int *counter,
+                                                           const uint8_t *__restrict__ seg_state)
 {
     __shared__ uint32_t s_tile;
     __shared__ uint32_t s_warp_tot[SCAN_THREADS / 32];
@@ -464,14 +484,18 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_add(uint32_t *__restrict_
     __syncthreads();
     const uint32_t add = s_prefix + woff;
     const uint4 z = make_uint4(0, 0, 0, 0);
+    // a warp's 512 elements lie inside one segment (SEG is a multiple of 512): segments no tile batch has written yet
+    // take a plain store (the engine marks every segment written after this kernel)
+    const bool fresh = seg_state[wbase / SEG] == 0;
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
         const uint64_t e = wbase + r * 128 + lane * 4;
         uint4 *dp = reinterpret_cast<uint4 *>(depth + e);
-        uint4 o = *dp;
+        uint4 o = make_uint4(0, 0, 0, 0);
+        if (!fresh) o = *dp;
         o.x += v[r].x + add; o.y += v[r].y + add; o.z += v[r].z + add; o.w += v[r].w + add;
-        *dp = o;
-        *reinterpret_cast<uint4 *>(delta + e) = z;
+        __stcs(dp, o);
+        __stcs(reinterpret_cast<uint4 *>(delta + e), z);
     }
 }
 
