@@ -17,6 +17,8 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <future>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -28,52 +30,65 @@ using namespace pdh;
 
 namespace {
 
-struct GzOut {
-    gzFile fp = nullptr;
-    std::string buf;
-    bool open(const std::string &path) { fp = gzopen(path.c_str(), "wb"); if (fp) gzbuffer(fp, 1 << 20); buf.reserve(1 << 22); return fp != nullptr; }
-    void put(const std::string &s) { buf += s; if (buf.size() > (1u << 22)) flush(); }
-    void put(const char *s, size_t n) { buf.append(s, n); if (buf.size() > (1u << 22)) flush(); }
-    void flush() { if (!buf.empty()) { gzwrite(fp, buf.data(), (unsigned)buf.size()); buf.clear(); } }
-    void close() { if (fp) { flush(); gzclose(fp); fp = nullptr; } }
+// gzip member of one text chunk (RFC 1952; concatenated members are one valid .gz stream -- parity is on decompressed bytes)
+std::string gz_member(const std::string &in)
+{
+    z_stream zs;
+    memset(&zs, 0, sizeof zs);
+    if (deflateInit2(&zs, Z_DEFAULT_COMPRESSION, Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY) != Z_OK) return std::string();
+    std::string out;
+    out.resize(deflateBound(&zs, (uLong)in.size()) + 64);
+    zs.next_in = (Bytef *)in.data(); zs.avail_in = (uInt)in.size();
+    zs.next_out = (Bytef *)&out[0]; zs.avail_out = (uInt)out.size();
+    deflate(&zs, Z_FINISH);
+    out.resize(out.size() - zs.avail_out);
+    deflateEnd(&zs);
+    return out;
+}
+
+// Ordered output file whose chunks are formatted and compressed by a pool of threads (the reference formats and
+// compresses every row on one thread, PanDepth.cpp:4384 / :4280 -- that is where its -w / -a time goes).
+struct GzWriter {
+    FILE *fp = nullptr;
+    int threads = 1;
+    bool wrote = false;
+    bool open(const std::string &path, int nthreads) { fp = fopen(path.c_str(), "wb"); threads = std::max(1, nthreads); return fp != nullptr; }
+    void put(const std::string &text) { if (text.empty()) return; std::string z = gz_member(text); fwrite(z.data(), 1, z.size(), fp); wrote = true; }
+    // chunks 0..n-1, text of chunk k = produce(k); chunks must be < 2 GiB each
+    template <typename F> void put_chunks(size_t n, F &&produce)
+    {
+        const size_t wave = (size_t)threads * 2;
+        std::vector<std::string> z(wave);
+        for (size_t base = 0; base < n; base += wave) {
+            const size_t m = std::min(wave, n - base);
+            std::atomic<size_t> next{0};
+            auto work = [&] { for (;;) { size_t k = next.fetch_add(1); if (k >= m) break; std::string t = produce(base + k); z[k] = t.empty() ? std::string() : gz_member(t); } };
+            std::vector<std::thread> th;
+            const size_t nt = std::min<size_t>((size_t)threads, m);
+            for (size_t i = 1; i < nt; i++) th.emplace_back(work);
+            work();
+            for (auto &t : th) t.join();
+            for (size_t k = 0; k < m; k++) if (!z[k].empty()) { fwrite(z[k].data(), 1, z[k].size(), fp); wrote = true; }
+        }
+    }
+    void close() { if (!fp) return; if (!wrote) { std::string z = gz_member(std::string()); fwrite(z.data(), 1, z.size(), fp); } fclose(fp); fp = nullptr; }
 };
 
-// growable pinned SoA batch of one contig's records
+// SoA batch of one contig's records in plain (pageable) host memory: workers can fill it before the CUDA context exists
 struct Batch {
-    int32_t *pos = nullptr; uint32_t *cigar = nullptr; uint32_t *off = nullptr;
-    size_t cap_r = 0, cap_c = 0, n = 0, nc = 0;
+    std::vector<int32_t> pos; std::vector<uint32_t> cigar, off;
+    size_t n = 0;
     bool single_op = true;
-    ~Batch() { pd_host_free(pos); pd_host_free(cigar); pd_host_free(off); }
-    bool reserve_reads(size_t want)
-    {
-        if (want <= cap_r) return true;
-        size_t cap = std::max<size_t>(want, cap_r ? cap_r * 2 : (1u << 20));
-        int32_t *p = (int32_t *)pd_host_alloc(cap * 4); uint32_t *o = (uint32_t *)pd_host_alloc((cap + 1) * 4);
-        if (!p || !o) return false;
-        if (n) { memcpy(p, pos, n * 4); memcpy(o, off, (n + 1) * 4); }
-        pd_host_free(pos); pd_host_free(off); pos = p; off = o; cap_r = cap;
-        return true;
-    }
-    bool reserve_cigar(size_t want)
-    {
-        if (want <= cap_c) return true;
-        size_t cap = std::max<size_t>(want, cap_c ? cap_c * 2 : (1u << 20));
-        uint32_t *c = (uint32_t *)pd_host_alloc(cap * 4);
-        if (!c) return false;
-        if (nc) memcpy(c, cigar, nc * 4);
-        pd_host_free(cigar); cigar = c; cap_c = cap;
-        return true;
-    }
-    void clear() { n = 0; nc = 0; single_op = true; }
+    Batch() { pos.reserve(1u << 20); cigar.reserve(1u << 20); off.reserve((1u << 20) + 1); off.push_back(0); }
+    void clear() { pos.clear(); cigar.clear(); off.clear(); off.push_back(0); n = 0; single_op = true; }
     bool add(const bam1_t *b)
     {
         const uint32_t k = b->core.n_cigar;
-        if (!reserve_reads(n + 1) || !reserve_cigar(nc + k)) return false;
-        pos[n] = (int32_t)b->core.pos;                      // hts_pos_t truncated to int32 like :736
-        off[n] = (uint32_t)nc;
-        memcpy(cigar + nc, bam_get_cigar(b), (size_t)k * 4);
-        nc += k; n++;
-        off[n] = (uint32_t)nc;
+        pos.push_back((int32_t)b->core.pos);                  // hts_pos_t truncated to int32 like :736
+        const uint32_t *c = bam_get_cigar(b);
+        cigar.insert(cigar.end(), c, c + k);
+        off.push_back((uint32_t)cigar.size());
+        n++;
         if (k != 1) single_op = false;
         return true;
     }
@@ -83,7 +98,8 @@ struct WorkItem { int tid; int64_t beg, end, prev_end; int r0, r1; };   // 0-bas
 
 struct Feeder {
     const Options &o;
-    pd_engine *eng;
+    pd_engine *eng = nullptr;
+    std::shared_future<pd_engine *> eng_future;          // the CUDA context is created while the first ranges decode
     std::mutex eng_mu;
     std::atomic<size_t> next{0};
     std::atomic<bool> failed{false};
@@ -93,21 +109,62 @@ struct Feeder {
     const std::map<int, std::vector<std::pair<int, int>>> &merged;   // per tid, 1-based closed, modes 1-4 only
     bool filter_by_region;
     std::atomic<uint64_t> reads_pushed{0};
+    hts_idx_t *shared_idx = nullptr;                     // loaded once, read-only, shared by all workers
+    // PANDEPTH_TIMING diagnostics (summed over workers, seconds); PANDEPTH_DRY=1 decodes without pushing
+    std::atomic<uint64_t> ns_decode{0}, ns_wait{0}, ns_push{0}, n_push{0};
+    bool dry = getenv("PANDEPTH_DRY") != nullptr;
+    struct Pending { int tid; bool sorted; Batch b; };
+    std::vector<Pending> pending;                        // batches decoded before the CUDA context was ready
 
-    Feeder(const Options &oo, pd_engine *e, const std::map<int, std::vector<std::pair<int, int>>> &m, bool f)
-        : o(oo), eng(e), merged(m), filter_by_region(f) {}
+    Feeder(const Options &oo, std::shared_future<pd_engine *> e, const std::map<int, std::vector<std::pair<int, int>>> &m, bool f)
+        : o(oo), eng_future(e), merged(m), filter_by_region(f) {}
 
     void fail(const std::string &m) { std::lock_guard<std::mutex> g(err_mu); if (!failed.exchange(true)) err = m; }
 
     bool push(int tid, Batch &b, bool sorted)
     {
         if (b.n == 0) return true;
+        if (dry) { reads_pushed += b.n; b.clear(); return true; }
+        const auto w0 = std::chrono::steady_clock::now();
         std::lock_guard<std::mutex> g(eng_mu);
-        int rc = pd_push_contig(eng, tid, (int64_t)b.n, b.pos, nullptr, nullptr, b.single_op ? nullptr : b.off, b.cigar, sorted ? PD_SORTED : 0u);
-        if (rc != PD_OK) { fail(std::string("pd_push_contig: ") + pd_last_error(eng)); return false; }
-        reads_pushed += b.n;
+        const auto w1 = std::chrono::steady_clock::now();
+        ns_wait += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(w1 - w0).count();
+        struct Done { Feeder *f; std::chrono::steady_clock::time_point t; ~Done() { f->ns_push += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t).count(); f->n_push++; } } done{this, w1};
+        if (!eng) {
+            // keep decoding while the CUDA context comes up: park the batch instead of blocking (never wait under the mutex)
+            if (eng_future.wait_for(std::chrono::seconds(0)) != std::future_status::ready) {
+                pending.push_back(Pending{tid, sorted, std::move(b)});
+                b = Batch();
+                return true;
+            }
+            eng = eng_future.get();
+            if (!eng) { fail(std::string("Error: ") + pd_last_error(nullptr)); return false; }
+        }
+        if (!flush_pending_locked()) return false;
+        if (!push_locked(tid, b, sorted)) return false;
         b.clear();
         return true;
+    }
+
+    bool push_locked(int tid, Batch &b, bool sorted)
+    {
+        int rc = pd_push_contig(eng, tid, (int64_t)b.n, b.pos.data(), nullptr, nullptr, b.single_op ? nullptr : b.off.data(), b.cigar.data(), sorted ? PD_SORTED : 0u);
+        if (rc != PD_OK) { fail(std::string("pd_push_contig: ") + pd_last_error(eng)); return false; }
+        reads_pushed += b.n;
+        return true;
+    }
+    bool flush_pending_locked()
+    {
+        for (auto &p : pending) if (!push_locked(p.tid, p.b, p.sorted)) return false;
+        pending.clear();
+        return true;
+    }
+    // after the workers are done: push whatever is still parked
+    bool finish()
+    {
+        std::lock_guard<std::mutex> g(eng_mu);
+        if (!eng) { eng = eng_future.get(); if (!eng) { fail(std::string("Error: ") + pd_last_error(nullptr)); return false; } }
+        return flush_pending_locked();
     }
 
     htsFile *open_input(sam_hdr_t **hdr, int nthreads)
@@ -131,11 +188,13 @@ struct Feeder {
     {
         sam_hdr_t *hdr = nullptr;
         htsFile *fp = open_input(&hdr, 0);
-        hts_idx_t *idx = fp ? sam_index_load(fp, o.input.c_str()) : nullptr;
+        hts_idx_t *idx = shared_idx;
         if (!fp || !idx) { fail("Error: Failed to open the index file or BAM/CRAM file: " + o.input); if (fp) hts_close(fp); return; }
         bam1_t *b = bam_init1();
         Batch batch;
         const uint32_t xf = o.xflags;
+        const auto t_begin = std::chrono::steady_clock::now();
+        struct Tot { Feeder *f; std::chrono::steady_clock::time_point t; ~Tot() { f->ns_decode += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t).count(); } } tot{this, t_begin};
         while (!failed) {
             const size_t k = next.fetch_add(1);
             if (k >= items.size()) break;
@@ -162,14 +221,13 @@ struct Feeder {
                     }
                     if (!hit) continue;
                 }
-                if (!batch.add(b)) { fail("out of pinned host memory"); break; }
-                if (batch.n >= (4u << 20)) { if (!push(w.tid, batch, true)) break; }
+                batch.add(b);
+                if (batch.n >= (1u << 20)) { if (!push(w.tid, batch, true)) break; }
             }
             hts_itr_destroy(it);
             if (!push(w.tid, batch, true)) break;
         }
         bam_destroy1(b);
-        hts_idx_destroy(idx);
         sam_hdr_destroy(hdr);
         hts_close(fp);
     }
@@ -189,8 +247,8 @@ struct Feeder {
             const int t = b->core.tid;
             if (t < 0) continue;
             if (t != cur) { if (!push(cur, batch, sorted)) break; cur = t; }
-            if (!batch.add(b)) { fail("out of pinned host memory"); break; }
-            if (batch.n >= (4u << 20)) { if (!push(cur, batch, sorted)) break; }
+            batch.add(b);
+            if (batch.n >= (1u << 20)) { if (!push(cur, batch, sorted)) break; }
         }
         if (!failed) push(cur, batch, sorted);
         bam_destroy1(b);
@@ -202,12 +260,27 @@ struct Feeder {
 
 bool file_exists(const std::string &p) { return access(p.c_str(), 0) == 0; }
 
+// PANDEPTH_TIMING=1: phase wall times on stderr
+struct Timer {
+    bool on = getenv("PANDEPTH_TIMING") != nullptr;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now(), last = t0;
+    void mark(const char *what)
+    {
+        if (!on) return;
+        auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[timing] %-22s %8.3f s  (total %.3f s)\n", what, std::chrono::duration<double>(now - last).count(),
+                std::chrono::duration<double>(now - t0).count());
+        last = now;
+    }
+};
+
 }  // namespace
 
 int main(int argc, char **argv)
 {
     Options o;
     if (parse_args(argc, argv, o) != 0) return 0;
+    Timer tm;
 
     std::string ext = o.input.substr(o.input.rfind('.') == std::string::npos ? o.input.size() : o.input.rfind('.') + 1);
     if (ext == "gz") {
@@ -239,10 +312,20 @@ int main(int argc, char **argv)
     if (!build_regions(o, targets, genes, err)) { std::cerr << err << std::endl; return 1; }
     const int mode = o.region_mode;
 
+    // the CUDA context (~0.5 s) is created in the background while the host threads already decode
+    int device = 0;
+    if (const char *d = getenv("PANDEPTH_DEVICE")) device = atoi(d);
+    std::vector<uint32_t> tlen(targets.size());
+    std::vector<uint8_t> owned(targets.size(), 0);
+    for (size_t t = 0; t < targets.size(); t++) { tlen[t] = targets[t].len; owned[t] = genes.count((int)t) ? 1 : 0; }
+    std::shared_future<pd_engine *> eng_future = std::async(std::launch::async, [&]() -> pd_engine * {
+        return pd_create(device, (int)targets.size(), tlen.data(), owned.data(), o.xflags, o.min_mapq);
+    }).share();
+
     const std::string prefix = output_prefix(o.out_arg);
-    GzOut out;
+    GzWriter out;
     const std::string stat_path = prefix + stat_suffix(mode);
-    if (!out.open(stat_path)) { std::cerr << "open OUT File error: " << stat_path << std::endl; return 0; }
+    if (!out.open(stat_path, o.threads)) { std::cerr << "open OUT File error: " << stat_path << std::endl; eng_future.wait(); return 0; }
 
     const bool have_index = file_exists(o.input + ".bai") || file_exists(o.input + ".crai") || file_exists(o.input + ".csi");   // :4121-4124
     const bool indexed = have_index && o.use_index;
@@ -253,20 +336,16 @@ int main(int argc, char **argv)
     // merged regions per contig (RegionMerger, :3912-3972)
     std::map<int, std::vector<std::pair<int, int>>> merged;
     for (const auto &kv : genes) merged[kv.first] = merge_regions(kv.second);
-
-    int device = 0;
-    if (const char *d = getenv("PANDEPTH_DEVICE")) device = atoi(d);
-    std::vector<uint32_t> tlen(targets.size());
-    std::vector<uint8_t> owned(targets.size(), 0);
-    for (size_t t = 0; t < targets.size(); t++) { tlen[t] = targets[t].len; owned[t] = genes.count((int)t) ? 1 : 0; }
-    pd_engine *eng = pd_create(device, (int)targets.size(), tlen.data(), owned.data(), o.xflags, o.min_mapq);
-    if (!eng) { std::cerr << "Error: " << pd_last_error(nullptr) << std::endl; return 1; }
+    tm.mark("header+regions");
 
     // ---- feed ---------------------------------------------------------------------------------------------------
     const bool region_modes = mode >= 1 && mode <= 4;
-    Feeder feeder(o, eng, merged, indexed && region_modes);
+    Feeder feeder(o, eng_future, merged, indexed && region_modes);
     if (indexed) {
-        const int64_t RANGE = 4 << 20;                       // bases per work item when tiling a whole contig
+        int64_t total_len = 0;
+        for (const auto &kv : merged) total_len += tlen[kv.first];
+        // bases per work item: ~6 items per thread, but never so small that BGZF blocks are decoded twice at every boundary
+        const int64_t RANGE = std::max<int64_t>(1 << 20, std::min<int64_t>(8 << 20, total_len / (6 * (int64_t)o.threads) + 1));
         const int64_t GAP = 64 << 10;                        // merged regions closer than this share one index query
         for (const auto &kv : merged) {
             const int tid = kv.first;
@@ -288,42 +367,59 @@ int main(int argc, char **argv)
                 }
             }
         }
+        {
+            htsFile *ifp = hts_open(o.input.c_str(), "r");
+            if (ifp) { feeder.shared_idx = sam_index_load(ifp, o.input.c_str()); hts_close(ifp); }
+        }
         const int nthreads = (int)std::max<size_t>(1, std::min<size_t>((size_t)o.threads, feeder.items.size()));
         std::vector<std::thread> th;
         for (int i = 0; i < nthreads; i++) th.emplace_back([&] { feeder.indexed_worker(); });
         for (auto &t : th) t.join();
+        if (feeder.shared_idx) hts_idx_destroy(feeder.shared_idx);
     } else {
         if (sorted_hdr) std::cout << "Warning: PanDepth will run in No Index mode: " << o.input << std::endl;                       // :4606
         else std::cout << "Warning: Can't find index file of input BAM/CRAM. PanDepth will run in No Index mode: " << o.input << std::endl;   // :4677
         feeder.stream_all(sorted_hdr);
     }
+    feeder.finish();
+    if (tm.on) fprintf(stderr, "[timing] workers: total %.3f thread-s, of which mutex wait %.3f s, inside push %.3f s (%llu pushes, %llu reads)\n",
+                       feeder.ns_decode / 1e9, feeder.ns_wait / 1e9, feeder.ns_push / 1e9, (unsigned long long)feeder.n_push.load(), (unsigned long long)feeder.reads_pushed.load());
+    pd_engine *eng = eng_future.get();
+    if (!eng) { std::cerr << "Error: " << pd_last_error(nullptr) << std::endl; return 1; }
+    tm.mark("decode+push");
     if (feeder.failed) { std::cerr << feeder.err << std::endl; pd_destroy(eng); return 1; }
     if (pd_finalize(eng) != PD_OK) { std::cerr << "Error: " << pd_last_error(eng) << std::endl; pd_destroy(eng); return 1; }
     std::cout << "INFO: Input data read done" << std::endl;                                                                        // :4879
 
-    // ---- -a per-site dump (:4264-4284) ---------------------------------------------------------------------------
+    // ---- -a per-site dump (:4264-4284): D2H in 4 M-base pieces, rows formatted + compressed by the thread pool -------
     if (o.site_output) {
-        GzOut site;
-        if (site.open(prefix + ".SiteDepth.gz")) {
-            std::vector<uint32_t> d;
-            const int32_t CH = 4 << 20;
+        GzWriter site;
+        if (site.open(prefix + ".SiteDepth.gz", o.threads)) {
+            const int32_t CH = 4 << 20, SUB = 1 << 18;
+            std::vector<uint32_t> d((size_t)CH);
             for (size_t t = 0; t < targets.size(); t++) {
                 if (!genes.count((int)t)) continue;
                 const std::string &nm = targets[t].name;
                 for (int64_t s = 0; s < (int64_t)tlen[t]; s += CH) {
                     const int32_t n = (int32_t)std::min<int64_t>(CH, (int64_t)tlen[t] - s);
-                    d.resize((size_t)n);
                     if (pd_depth_read(eng, (int32_t)t, (int32_t)s, n, d.data(), 0) != PD_OK) { std::cerr << "Error: " << pd_last_error(eng) << std::endl; return 1; }
-                    char line[96];
-                    for (int32_t j = 0; j < n; j++) {
-                        int m = snprintf(line, sizeof line, "\t%lld\t%u\n", (long long)(s + j), d[j] & 0x3FFFFu);
-                        site.put(nm); site.put(line, (size_t)m);
-                    }
+                    site.put_chunks((size_t)((n + SUB - 1) / SUB), [&](size_t k) {
+                        std::string text;
+                        const int32_t a = (int32_t)k * SUB, b = std::min<int32_t>(n, a + SUB);
+                        text.reserve((size_t)(b - a) * (nm.size() + 16));
+                        char line[64];
+                        for (int32_t j = a; j < b; j++) {
+                            int m = snprintf(line, sizeof line, "\t%lld\t%u\n", (long long)(s + j), d[(size_t)j] & 0x3FFFFu);
+                            text += nm; text.append(line, (size_t)m);
+                        }
+                        return text;
+                    });
                 }
             }
             site.close();
         }
     }
+    tm.mark("finalize(+site dump)");
 
     // ---- reduce + report -----------------------------------------------------------------------------------------
     uint64_t SS_Len = 0, SS_Cov = 0, SS_TotalD = 0;
@@ -339,15 +435,27 @@ int main(int argc, char **argv)
             if (n_win && pd_reduce_windows(eng, (int32_t)t, 0, (int32_t)W, n_win, (uint32_t)o.min_dep, 0x3FFFFu, cov.data(), sum.data(), 0) != PD_OK) {
                 std::cerr << "Error: " << pd_last_error(eng) << std::endl; return 1;
             }
+            const char *nm = targets[t].name.c_str();
+            const int64_t SUB = 1 << 16;
+            out.put_chunks((size_t)((n_win + SUB - 1) / SUB), [&](size_t c) {
+                std::string text;
+                const int64_t a = (int64_t)c * SUB, b = std::min(n_win, a + SUB);
+                text.reserve((size_t)(b - a) * 48);
+                char r[256];
+                for (int64_t k = a; k < b; k++) {
+                    const int64_t j = 1 + k * W;
+                    const int64_t End = std::min(j - 1 + W, CC);
+                    const int GeneLength = (int)(End - j + 1), GeneCover = (int)cov[(size_t)k], GeneDepth = (int)sum[(size_t)k];   // ints (:4364)
+                    const double Coverage = GeneCover * 100.0 / GeneLength, MeanDepth = GeneDepth * 1.0 / GeneLength;
+                    int m = snprintf(r, sizeof r, "%s\t%lld\t%lld\t%d\t%d\t%d\t%.2f\t%.2f\n", nm, (long long)j, (long long)End, GeneLength, GeneCover, GeneDepth, Coverage, MeanDepth);
+                    text.append(r, (size_t)m);
+                }
+                return text;
+            });
             for (int64_t k = 0; k < n_win; k++) {
                 const int64_t j = 1 + k * W;
                 const int64_t End = std::min(j - 1 + W, CC);
-                const int GeneLength = (int)(End - j + 1), GeneCover = (int)cov[k], GeneDepth = (int)sum[k];   // ints (:4364)
-                const double Coverage = GeneCover * 100.0 / GeneLength, MeanDepth = GeneDepth * 1.0 / GeneLength;
-                int m = snprintf(row, sizeof row, "%s\t%lld\t%lld\t%d\t%d\t%d\t%.2f\t%.2f\n", targets[t].name.c_str(), (long long)j, (long long)End,
-                                 GeneLength, GeneCover, GeneDepth, Coverage, MeanDepth);
-                out.put(row, (size_t)m);
-                SS_Cov += (uint64_t)(int64_t)GeneCover; SS_Len += (uint64_t)(int64_t)GeneLength; SS_TotalD += (uint64_t)(int64_t)GeneDepth;
+                SS_Cov += (uint64_t)(int64_t)(int)cov[(size_t)k]; SS_Len += (uint64_t)(int64_t)(int)(End - j + 1); SS_TotalD += (uint64_t)(int64_t)(int)sum[(size_t)k];
             }
         }
     } else {
@@ -368,43 +476,52 @@ int main(int argc, char **argv)
         }
         for (size_t i = 0; i < iv_g.size(); i++) { iv_g[i]->cover += (int64_t)cov[i]; iv_g[i]->depth += sum[i]; }
 
-        for (auto &kv : genes) {
-            const std::string &chr = targets[kv.first].name;
+        std::vector<int> tids;
+        for (auto &kv : genes) tids.push_back(kv.first);
+        std::vector<uint64_t> pL(tids.size(), 0), pC(tids.size(), 0), pD(tids.size(), 0);
+        out.put_chunks(tids.size(), [&](size_t ci) {                                         // one chunk per contig, rows in order
+            auto &gm = genes[tids[ci]];
+            const std::string &chr = targets[(size_t)tids[ci]].name;
+            std::string text;
+            char num[256];
             if (mode == 0) {                                                                   // :5051-5079
                 uint64_t L = 0, C = 0, D = 0;
-                for (auto &gk : kv.second) { L += gk.second.length; C += (uint64_t)(int64_t)(int)gk.second.cover; D += gk.second.depth; }
-                SS_Len += L; SS_Cov += C; SS_TotalD += D;
-                int m = snprintf(row, sizeof row, "%s\t%llu\t%llu\t%llu\t%s\t%s\n", chr.c_str(), (unsigned long long)L, (unsigned long long)C,
+                for (auto &gk : gm) { L += gk.second.length; C += (uint64_t)(int64_t)(int)gk.second.cover; D += gk.second.depth; }
+                pL[ci] = L; pC[ci] = C; pD[ci] = D;
+                int m = snprintf(num, sizeof num, "%s\t%llu\t%llu\t%llu\t%s\t%s\n", chr.c_str(), (unsigned long long)L, (unsigned long long)C,
                                  (unsigned long long)D, fmt_ratio_pct((double)C, (double)L).c_str(), fmt_ratio((double)D, (double)L).c_str());
-                out.put(row, (size_t)m);
+                text.append(num, (size_t)m);
             } else {                                                                           // :5011-5050 / :5080-5118
                 std::map<int, std::string> by_start;                                           // rows by GeneStart; ties in GeneID order
-                for (auto &gk : kv.second) {
+                for (auto &gk : gm) {
                     const Gene &g = gk.second;
                     const int GeneCover = (int)g.cover;
-                    SS_Cov += (uint64_t)(int64_t)GeneCover; SS_Len += g.length; SS_TotalD += g.depth;
+                    pC[ci] += (uint64_t)(int64_t)GeneCover; pL[ci] += g.length; pD[ci] += g.depth;
                     const double Coverage = GeneCover * 100.0 / g.length, MeanDepth = g.depth * 1.0 / g.length;
                     std::string line = chr + "\t" + std::to_string(g.start) + "\t" + std::to_string(g.end) + "\t";
                     if (mode != 5) line += gk.first + "\t";
-                    char num[160];
                     snprintf(num, sizeof num, "%llu\t%d\t%llu\t%.2f\t%.2f", (unsigned long long)g.length, GeneCover, (unsigned long long)g.depth, Coverage, MeanDepth);
                     line += num;
                     auto it = by_start.find(g.start);
                     if (it == by_start.end()) by_start.emplace(g.start, line);
                     else { it->second += "\n"; it->second += line; }
                 }
-                for (auto &r : by_start) { out.put(r.second); out.put("\n", 1); }
+                for (auto &r : by_start) { text += r.second; text += "\n"; }
             }
-        }
+            return text;
+        });
+        for (size_t ci = 0; ci < tids.size(); ci++) { SS_Len += pL[ci]; SS_Cov += pC[ci]; SS_TotalD += pD[ci]; }
     }
     {
         const double Coverage = SS_Cov * 100.0 / SS_Len, MeanDepth = SS_TotalD * 1.0 / SS_Len;   // :5119-5122
         int m = snprintf(row, sizeof row, "##RegionLength: %llu\tCoveredSite: %llu\tCoverage(%%): %.2f\tMeanDepth: %.2f\n",
                          (unsigned long long)SS_Len, (unsigned long long)SS_Cov, Coverage, MeanDepth);
-        out.put(row, (size_t)m);
+        out.put(std::string(row, (size_t)m));
     }
     out.close();
+    tm.mark("reduce+report");
     pd_destroy(eng);
     sam_hdr_destroy(hdr);
+    tm.mark("pd_destroy");
     return 0;
 }
