@@ -7,6 +7,7 @@
 // Decode parallelism is by genomic range through the BAI/CSI index (any number of threads on one contig), not by contig
 // as in the reference (:4415-4523).
 #include "pd_host.hpp"
+#include "fastbam.hpp"
 #include "../../include/pandepth_b200.h"
 
 #include <zlib.h>
@@ -92,6 +93,28 @@ struct Batch {
         if (k != 1) single_op = false;
         return true;
     }
+    void add_raw(const RawRead &r)
+    {
+        pos.push_back(r.pos);
+        const size_t at = cigar.size();
+        cigar.resize(at + r.n_cigar);
+        if (r.n_cigar) memcpy(&cigar[at], r.cigar, (size_t)r.n_cigar * 4);
+        off.push_back((uint32_t)cigar.size());
+        n++;
+        if (r.n_cigar != 1) single_op = false;
+    }
+    // order-independent digest of the batch (PANDEPTH_DRY diagnostics: compare decode paths without a GPU)
+    uint64_t digest(int tid) const
+    {
+        auto mix = [](uint64_t x) { x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33; return x; };
+        uint64_t sum = 0;
+        for (size_t i = 0; i < n; i++) {
+            uint64_t h = mix(((uint64_t)(uint32_t)tid << 32) | (uint32_t)pos[i]);
+            for (uint32_t k = off[i]; k < off[i + 1]; k++) h = mix(h ^ cigar[k]);
+            sum += h;
+        }
+        return sum;
+    }
 };
 
 struct WorkItem { int tid; int64_t beg, end, prev_end; int r0, r1; };   // 0-based [beg,end); merged regions [r0,r1) of the contig (modes 1-4)
@@ -111,7 +134,8 @@ struct Feeder {
     std::atomic<uint64_t> reads_pushed{0};
     hts_idx_t *shared_idx = nullptr;                     // loaded once, read-only, shared by all workers
     // PANDEPTH_TIMING diagnostics (summed over workers, seconds); PANDEPTH_DRY=1 decodes without pushing
-    std::atomic<uint64_t> ns_decode{0}, ns_wait{0}, ns_push{0}, n_push{0};
+    std::atomic<uint64_t> ns_decode{0}, ns_wait{0}, ns_push{0}, n_push{0}, dry_digest{0};
+    const BaiLinear *bai = nullptr;                      // non-null: scan raw BAM records directly (fastbam.hpp)
     bool dry = getenv("PANDEPTH_DRY") != nullptr;
     struct Pending { int tid; bool sorted; Batch b; };
     std::vector<Pending> pending;                        // batches decoded before the CUDA context was ready
@@ -124,7 +148,7 @@ struct Feeder {
     bool push(int tid, Batch &b, bool sorted)
     {
         if (b.n == 0) return true;
-        if (dry) { reads_pushed += b.n; b.clear(); return true; }
+        if (dry) { reads_pushed += b.n; dry_digest += b.digest(tid); b.clear(); return true; }
         const auto w0 = std::chrono::steady_clock::now();
         std::lock_guard<std::mutex> g(eng_mu);
         const auto w1 = std::chrono::steady_clock::now();
@@ -232,6 +256,52 @@ struct Feeder {
         hts_close(fp);
     }
 
+    // indexed path for sorted BAM + .bai: raw record scan, no htslib in the loop
+    void fast_worker()
+    {
+        BamRangeScanner sc;
+        if (!sc.open(o.input)) { fail("Error: Failed to open the BAM/CRAM file: " + o.input); return; }
+        Batch batch;
+        const uint32_t xf = o.xflags;
+        const auto t_begin = std::chrono::steady_clock::now();
+        struct Tot { Feeder *f; std::chrono::steady_clock::time_point t; ~Tot() { f->ns_decode += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t).count(); } } tot{this, t_begin};
+        while (!failed) {
+            const size_t k = next.fetch_add(1);
+            if (k >= items.size()) break;
+            const WorkItem &w = items[k];
+            const uint64_t voff = bai->start_voffset(w.tid, w.beg);
+            if (!voff) continue;
+            const std::vector<std::pair<int, int>> *regs = nullptr;
+            if (filter_by_region) { auto f = merged.find(w.tid); if (f != merged.end()) regs = &f->second; }
+            int rcur = w.r0;
+            bool ok_push = true;
+            const bool ok = sc.scan(voff, w.tid, w.end, [&](const RawRead &r) {
+                if (!ok_push) return;
+                if (r.flag & xf) return;                                      // :732
+                if ((int)r.mapq < o.min_mapq) return;                         // :733
+                const int64_t p = r.pos;
+                if (p < w.prev_end) return;                                   // an earlier range already took this read
+                if (regs) {
+                    int64_t rlen = 0;                                         // bam_endpos(): unmapped or no reference-consuming op -> 1
+                    if (!(r.flag & 4)) for (uint32_t c = 0; c < r.n_cigar; c++) { const uint32_t wd = r.word(c); if ((0x18du >> (wd & 15u)) & 1u) rlen += wd >> 4; }
+                    const int64_t e = p + (rlen ? rlen : 1);
+                    while (rcur < w.r1 && (int64_t)(*regs)[rcur].second + 1 <= p) rcur++;
+                    bool hit = false;
+                    for (int q = rcur; q < w.r1; q++) {
+                        const int64_t wb = std::max<int64_t>((int64_t)(*regs)[q].first - 1, 1) - 1;
+                        if (wb >= e) break;
+                        if ((int64_t)(*regs)[q].second + 1 > p) { hit = true; break; }
+                    }
+                    if (!hit) return;
+                }
+                batch.add_raw(r);
+                if (batch.n >= (1u << 20)) ok_push = push(w.tid, batch, true);
+            });
+            if (!ok) { fail("Error: malformed BAM while scanning " + o.input + ": " + sc.error()); break; }
+            if (!ok_push || !push(w.tid, batch, true)) break;
+        }
+    }
+
     // no-index path (:4604-4713): one pass over the file, batches split at contig changes
     bool stream_all(bool sorted)
     {
@@ -294,6 +364,7 @@ int main(int argc, char **argv)
     hts_set_log_level(HTS_LOG_OFF);
     if (!in) { std::cerr << "Error: Failed to open the BAM/CRAM file: " << o.input << std::endl; return 1; }
     if (in->format.format == cram) hts_set_fai_filename(in, o.reference.c_str());
+    const bool is_bam = in->format.format == bam;
     sam_hdr_t *hdr = sam_hdr_read(in);
     if (!hdr) { std::cerr << "Error: Failed to read the header for the BAM/CRAM file: " << o.input << std::endl; return 1; }
     std::vector<Target> targets((size_t)hdr->n_targets);
@@ -318,7 +389,9 @@ int main(int argc, char **argv)
     std::vector<uint32_t> tlen(targets.size());
     std::vector<uint8_t> owned(targets.size(), 0);
     for (size_t t = 0; t < targets.size(); t++) { tlen[t] = targets[t].len; owned[t] = genes.count((int)t) ? 1 : 0; }
+    const bool dry = getenv("PANDEPTH_DRY") != nullptr;      // decode only: no GPU is touched (diagnostics)
     std::shared_future<pd_engine *> eng_future = std::async(std::launch::async, [&]() -> pd_engine * {
+        if (dry) return nullptr;
         return pd_create(device, (int)targets.size(), tlen.data(), owned.data(), o.xflags, o.min_mapq);
     }).share();
 
@@ -367,19 +440,29 @@ int main(int argc, char **argv)
                 }
             }
         }
-        {
+        // sorted BAM + .bai: raw-record scanner; anything else (CRAM, .csi only, PANDEPTH_HTS_ITER=1): htslib iterators
+        BaiLinear bai;
+        if (is_bam && !getenv("PANDEPTH_HTS_ITER") && file_exists(o.input + ".bai") && bai.load(o.input + ".bai") && bai.refs.size() == targets.size())
+            feeder.bai = &bai;
+        if (!feeder.bai) {
             htsFile *ifp = hts_open(o.input.c_str(), "r");
             if (ifp) { feeder.shared_idx = sam_index_load(ifp, o.input.c_str()); hts_close(ifp); }
         }
         const int nthreads = (int)std::max<size_t>(1, std::min<size_t>((size_t)o.threads, feeder.items.size()));
         std::vector<std::thread> th;
-        for (int i = 0; i < nthreads; i++) th.emplace_back([&] { feeder.indexed_worker(); });
+        for (int i = 0; i < nthreads; i++) th.emplace_back([&] { if (feeder.bai) feeder.fast_worker(); else feeder.indexed_worker(); });
         for (auto &t : th) t.join();
         if (feeder.shared_idx) hts_idx_destroy(feeder.shared_idx);
     } else {
         if (sorted_hdr) std::cout << "Warning: PanDepth will run in No Index mode: " << o.input << std::endl;                       // :4606
         else std::cout << "Warning: Can't find index file of input BAM/CRAM. PanDepth will run in No Index mode: " << o.input << std::endl;   // :4677
         feeder.stream_all(sorted_hdr);
+    }
+    if (dry) {
+        tm.mark("decode (dry)");
+        std::cout << "dry: reads=" << feeder.reads_pushed.load() << " digest=" << feeder.dry_digest.load() << " path=" << (feeder.bai ? "fastbam" : "htslib") << std::endl;
+        if (feeder.failed) { std::cerr << feeder.err << std::endl; return 1; }
+        return 0;
     }
     feeder.finish();
     if (tm.on) fprintf(stderr, "[timing] workers: total %.3f thread-s, of which mutex wait %.3f s, inside push %.3f s (%llu pushes, %llu reads)\n",

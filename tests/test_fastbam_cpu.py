@@ -1,0 +1,58 @@
+"""
+CPU: the raw-record BAM scanner (pandepth_b200/host/fastbam.*) must hand the engine exactly the reads the htslib
+iterator path does.  `PANDEPTH_DRY=1` makes the CLI decode without touching a GPU and print an order-independent digest
+of every (tid, pos, cigar) it would push; `PANDEPTH_HTS_ITER=1` forces the htslib path.
+"""
+import os
+import re
+import subprocess
+
+import pytest
+
+from tests.helpers import GOLD, ROOT
+
+CLI = os.path.join(ROOT, "pandepth_b200", "bin", "pandepth")
+BAMGEN = os.path.join(ROOT, "oracle", "_ref", "bamgen")
+
+pytestmark = pytest.mark.skipif(not (os.path.exists(CLI) and os.path.exists(BAMGEN)), reason="host binary / bamgen not built")
+
+
+def _digest(bam, opts, hts):
+    env = dict(os.environ, PANDEPTH_DRY="1")
+    if hts:
+        env["PANDEPTH_HTS_ITER"] = "1"
+    r = subprocess.run([CLI, "-i", bam, "-o", bam + ".out"] + opts, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+    m = re.search(r"dry: reads=(\d+) digest=(\d+) path=(\w+)", r.stdout)
+    assert r.returncode == 0 and m, (r.stdout, r.stderr)
+    return int(m.group(1)), int(m.group(2)), m.group(3)
+
+
+@pytest.fixture(scope="module")
+def bams(tmp_path_factory):
+    d = tmp_path_factory.mktemp("fastbam")
+    out = {}
+    for fx in ("k", "mix", "big"):
+        out[fx] = str(d / f"{fx}.bam")
+        subprocess.run([BAMGEN, "-I", os.path.join(GOLD, fx + ".sam"), "-o", out[fx]], check=True)
+    out["r1"] = str(d / "r1.bam")
+    subprocess.run([BAMGEN, "-o", out["r1"], "-c", "a:300001,b:1,c:5000,d:70000,e:2,f:1001", "-n", "60000", "-m", "mixed", "-s", "11"], check=True)
+    out["r2"] = str(d / "r2.bam")     # with SEQ/QUAL: records span BGZF blocks
+    subprocess.run([BAMGEN, "-o", out["r2"], "-c", "chrA:2000001,chrB:999999", "-n", "150000", "-m", "mixed", "-s", "12", "-q"], check=True)
+    bed = str(d / "r.bed")
+    with open(bed, "w") as fh:
+        for nm, ln in (("a", 300001), ("c", 5000), ("d", 70000), ("f", 1001), ("chrA", 2000001), ("chrB", 999999), ("cA", 100001), ("cB", 1001), ("k1", 301)):
+            step = max(ln // 50, 150)
+            for s in range(1, ln - 100, step):
+                fh.write(f"{nm}\t{s}\t{min(ln, s + step // 3)}\n")
+            fh.write(f"{nm}\t{ln}\t{ln}\n")
+    out["bed"] = bed
+    return out
+
+
+@pytest.mark.parametrize("name", ["k", "mix", "big", "r1", "r2"])
+def test_scanner_feeds_the_same_reads_as_htslib(name, bams):
+    for opts in ([], ["-w", "100"], ["-b", bams["bed"]], ["-x", "0"], ["-q", "20"], ["-x", "3844", "-q", "3", "-t", "7"], ["-t", "1"]):
+        fast = _digest(bams[name], opts, hts=False)
+        slow = _digest(bams[name], opts, hts=True)
+        assert fast[2] == "fastbam" and slow[2] == "htslib"
+        assert fast[:2] == slow[:2], (name, opts, fast, slow)
