@@ -211,6 +211,7 @@ def ours(args):
     stream = torch.cuda.current_stream()
     eng = pd.Engine(tlen, device=local_rank, owned=owned_mask(owner, rank))
     eng.set_stream(stream.cuda_stream)
+    eng.set_reduce_hint(1, 0xFFFFFFFF)          # -d 1, uint32 path: known before the reads arrive, as in the CLI
 
     # synthetic sorted reads, generated on the device (seeded), one (pos, cigar) pair of arrays per owned contig
     gen = torch.Generator(device=dev); gen.manual_seed(7 + rank)

@@ -54,6 +54,13 @@ const char *pd_last_error(pd_engine *e);
 /* Use the caller's CUDA stream (a cudaStream_t) for all kernels and copies; NULL restores the engine's own. */
 int pd_set_stream(pd_engine *e, void *cuda_stream);
 
+/* Optional: announce the (min_dep, depth_mask) pair pd_reduce will be called with (-d and the depth width are known before
+ * the BAM is read).  While a segment of depth is written for the first time the engine then also records its
+ * CoveredSite/TotalDepth, and pd_reduce with the same pair takes whole, written-once segments from those partials instead
+ * of re-reading depth (per-chr / large-interval modes: the 4 B/base reduce pass disappears).  Purely an optimisation:
+ * results are identical with or without it.  Call before the first push after pd_create / pd_reset. */
+int pd_set_reduce_hint(pd_engine *e, uint32_t min_dep, uint32_t depth_mask);
+
 /* Forget all accumulated depth (start a new BAM) without reallocating. */
 int pd_reset(pd_engine *e);
 

@@ -53,6 +53,9 @@ struct pd_engine {
     uint64_t *d_off = nullptr; uint32_t *d_tlen = nullptr;
     uint32_t *d_lo = nullptr, *d_hi = nullptr, *d_coarse = nullptr; size_t cut_cap = 0;
     int *d_flags = nullptr;          // [0] err bits, [1] delta_used
+    uint32_t *d_part_cov = nullptr; unsigned long long *d_part_sum = nullptr;   // per-segment reduce partials (hint)
+    bool hint_on = false; uint32_t hint_min_dep = 1, hint_mask = 0xFFFFFFFFu;
+    bool pushed_since_reset = false;
     unsigned long long *d_desc = nullptr; unsigned int *d_counter = nullptr;
 
     cudaStream_t own_stream = nullptr, copy_stream = nullptr, stream = nullptr;
@@ -141,7 +144,8 @@ int run_batch(pd_engine *e, int32_t tid, uint32_t n, const int32_t *pos, const u
         e->stats.kernel_launches++;
         pdk::TileArgs t{pos, cigar, cigar_off, flag, mapq, e->d_lo, e->d_hi, n, (int32_t)seg_a, nseg, (int32_t)e->tlen[tid],
                         e->d_depth + off, e->d_delta + off, e->d_seg_state + off / pdk::SEG, e->xflags, e->min_mapq,
-                        e->d_flags, e->d_flags + 1};
+                        e->d_flags, e->d_flags + 1,
+                        e->hint_on ? 1u : 0u, e->hint_min_dep, e->hint_mask, e->d_part_cov + off / pdk::SEG, e->d_part_sum + off / pdk::SEG};
         const size_t smem = (size_t)pdk::WPC * pdk::TILE_SMEM_WORDS * 4;
         const unsigned grid = (nseg + pdk::WPC - 1) / pdk::WPC, blk = pdk::WPC * 32;
         const bool has_off = cigar_off != nullptr, has_filter = flag != nullptr || mapq != nullptr;
@@ -159,6 +163,7 @@ int run_batch(pd_engine *e, int32_t tid, uint32_t n, const int32_t *pos, const u
     }
     e->stats.reads_pushed += n;
     e->finalized = false;
+    e->pushed_since_reset = true;
     return PD_OK;
 }
 
@@ -220,7 +225,7 @@ void pd_destroy(pd_engine *e)
     for (auto &p : e->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     cudaFree(e->d_depth); cudaFree(e->d_delta); cudaFree(e->d_seg_state); cudaFree(e->d_off); cudaFree(e->d_tlen);
     cudaFree(e->d_lo); cudaFree(e->d_hi); cudaFree(e->d_coarse); cudaFree(e->d_flags); cudaFree(e->d_desc); cudaFree(e->d_counter);
-    cudaFree(e->d_red);
+    cudaFree(e->d_red); cudaFree(e->d_part_cov); cudaFree(e->d_part_sum);
     for (auto &s : e->slot) {
         cudaFree(s.pos); cudaFree(s.cigar); cudaFree(s.cigar_off); cudaFree(s.flag); cudaFree(s.mapq);
         if (s.copied) cudaEventDestroy(s.copied);
@@ -267,7 +272,9 @@ pd_engine *pd_create(int device, int n_targets, const uint32_t *target_len, cons
     if ((ce = cudaMalloc(&e->d_flags, 8)) != cudaSuccess) return bail("cudaMalloc", ce);
     if ((ce = cudaMalloc(&e->d_desc, (total / pdk::SCAN_TILE) * 8)) != cudaSuccess) return bail("cudaMalloc", ce);
     if ((ce = cudaMalloc(&e->d_counter, 4)) != cudaSuccess) return bail("cudaMalloc", ce);
-    e->stats.hbm_bytes_allocated = total * 8 + e->n_seg + (total / pdk::SCAN_TILE) * 8;
+    if ((ce = cudaMalloc(&e->d_part_cov, e->n_seg * 4)) != cudaSuccess) return bail("cudaMalloc", ce);
+    if ((ce = cudaMalloc(&e->d_part_sum, e->n_seg * 8)) != cudaSuccess) return bail("cudaMalloc", ce);
+    e->stats.hbm_bytes_allocated = total * 8 + e->n_seg * 13 + (total / pdk::SCAN_TILE) * 8;
     if ((ce = cudaMemcpy(e->d_off, e->off.data(), (size_t)n_targets * 8, cudaMemcpyHostToDevice)) != cudaSuccess) return bail("memcpy", ce);
     if ((ce = cudaMemcpy(e->d_tlen, e->tlen.data(), (size_t)n_targets * 4, cudaMemcpyHostToDevice)) != cudaSuccess) return bail("memcpy", ce);
     if ((ce = cudaMemsetAsync(e->d_delta, 0, total * 4, e->stream)) != cudaSuccess) return bail("memset", ce);
@@ -293,6 +300,15 @@ int pd_set_stream(pd_engine *e, void *cuda_stream)
     return PD_OK;
 }
 
+int pd_set_reduce_hint(pd_engine *e, uint32_t min_dep, uint32_t depth_mask)
+{
+    if (!e) return PD_ERR_ARG;
+    if (e->pushed_since_reset) return fail(e, PD_ERR_STATE, "pd_set_reduce_hint must be called before the first push (after pd_create or pd_reset)");
+    e->hint_on = min_dep >= 1;          // with min_dep 0 every base counts, including never-written ones: no partials
+    e->hint_min_dep = min_dep; e->hint_mask = depth_mask;
+    return PD_OK;
+}
+
 int pd_reset(pd_engine *e)
 {
     if (!e) return PD_ERR_ARG;
@@ -307,6 +323,7 @@ int pd_reset(pd_engine *e)
     if (e->host_delta_used) CK(cudaMemsetAsync(e->d_delta, 0, e->total * 4, e->stream));
     e->host_delta_used = false;
     e->finalized = false;
+    e->pushed_since_reset = false;
     uint64_t keep = e->stats.hbm_bytes_allocated;
     e->stats = pd_stats{};
     e->stats.hbm_bytes_allocated = keep;
@@ -418,12 +435,12 @@ int pd_finalize(pd_engine *e)
         CK(cudaMemsetAsync(e->d_counter, 0, 4, e->stream));
         rc = launch(e, K_SCAN, [&] { pdk::k_scan_add<<<(unsigned)n_tiles, pdk::SCAN_THREADS, 0, e->stream>>>(e->d_depth, e->d_delta, e->total, e->d_desc, e->d_counter, e->d_seg_state); });
         if (rc) return rc;
-        CK(cudaMemsetAsync(e->d_seg_state, 1, e->n_seg, e->stream));
+        CK(cudaMemsetAsync(e->d_seg_state, 2, e->n_seg, e->stream));     // written, partials (if any) no longer valid
         CK(cudaMemsetAsync(e->d_flags + 1, 0, 4, e->stream));
         e->host_delta_used = false;
         e->stats.scan_passes++;
     } else {
-        rc = launch(e, K_FILL, [&] { pdk::k_fill_untouched<<<(unsigned)((e->n_seg + 7) / 8), 256, 0, e->stream>>>(e->d_depth, e->d_seg_state, e->n_seg); });
+        rc = launch(e, K_FILL, [&] { pdk::k_fill_untouched<<<(unsigned)((e->n_seg + 7) / 8), 256, 0, e->stream>>>(e->d_depth, e->d_seg_state, e->n_seg, e->hint_on ? 1u : 0u, e->d_part_cov, e->d_part_sum); });
         if (rc) return rc;
     }
     e->finalized = true;
@@ -460,7 +477,7 @@ int pd_reduce(pd_engine *e, int64_t n_iv, const int32_t *tid, const int32_t *sta
         if (!e->owned[t]) continue;
         int64_t s = std::max<int64_t>(start0[i], 0), en = std::min<int64_t>(end0_excl[i], e->tlen[t]);
         if (s >= en) continue;
-        n_units += (uint64_t)((en - s + pdk::REDUCE_CHUNK - 1) / pdk::REDUCE_CHUNK);
+        n_units += (uint64_t)((en - 1) / pdk::REDUCE_CHUNK - s / pdk::REDUCE_CHUNK + 1);      // REDUCE_CHUNK-aligned pieces
     }
     prefix[n_iv] = n_units;
     const size_t iv_bytes = (size_t)n_iv * 4;
@@ -479,7 +496,8 @@ int pd_reduce(pd_engine *e, int64_t n_iv, const int32_t *tid, const int32_t *sta
     if (n_units) {
         pdk::ReduceArgs r{e->d_depth, e->d_off, e->d_tlen, (const int32_t *)(base + a_tid), (const int32_t *)(base + a_s),
                           (const int32_t *)(base + a_e), (const uint64_t *)(base + a_units), (uint64_t)n_iv, n_units, min_dep, depth_mask,
-                          (unsigned long long *)(base + a_cov), (unsigned long long *)(base + a_sum)};
+                          (unsigned long long *)(base + a_cov), (unsigned long long *)(base + a_sum),
+                          (e->hint_on && min_dep == e->hint_min_dep && depth_mask == e->hint_mask) ? 1u : 0u, e->d_seg_state, e->d_part_cov, e->d_part_sum};
         rc = launch(e, K_REDUCE, [&] { pdk::k_reduce_units<<<(unsigned)((n_units + 7) / 8), 256, 0, e->stream>>>(r); });
         if (rc) return rc;
     }

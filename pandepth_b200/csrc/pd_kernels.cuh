@@ -152,9 +152,12 @@ struct TileArgs {
     int32_t seg0; int32_t nseg; int32_t contig_len;
     uint32_t *depth;      // contig base
     uint32_t *delta;      // contig base (global delta array)
-    uint8_t *seg_state;   // contig base: 0 = never written
+    uint8_t *seg_state;   // contig base: 0 = never written, 1 = written once and part_* valid, 2 = written (read depth)
     uint32_t xflags; int32_t min_mapq;
     int *err; int *delta_used;
+    // reduce hint (pd_set_reduce_hint): per-segment CoveredSite/TotalDepth partials for segments written exactly once
+    uint32_t hint_on, hint_min_dep, hint_mask;
+    uint32_t *part_cov; unsigned long long *part_sum;     // contig base, one entry per segment
 };
 
 constexpr int TILE_UNROLL = PD_TILE_UNROLL;   // 32-read chunks whose loads are issued together (memory-level parallelism)
@@ -331,12 +334,32 @@ __global__ void __launch_bounds__(WPC * 32, TILE_MIN_CTAS) k_tile_accumulate(Til
         carry += __shfl_sync(FULL, t, 31);
         return make_uint4(x0 + ex, x1 + ex, x2 + ex, x3 + ex);
     };
-    if (fresh) {
+    // partials only for a first write of a segment that lies completely inside the contig
+    const bool do_part = fresh && a.hint_on && send <= clen;
+    if (do_part) {
+        const uint32_t md = a.hint_min_dep, mk = a.hint_mask;
+        uint32_t pc = 0; unsigned long long ps = 0;
+#pragma unroll 4
+        for (int r = 0; r < SEG / 128; ++r) {
+            const int b = r * 128 + lane * 4;
+            const uint4 v = scan_row(b);
+            __stcs(reinterpret_cast<uint4 *>(out + b), v);
+            uint32_t x;                                              // if (depth >= minDep) { Cover++; Depth += depth; }  :319-323
+            x = v.x & mk; if (x >= md) { pc++; ps += x; }
+            x = v.y & mk; if (x >= md) { pc++; ps += x; }
+            x = v.z & mk; if (x >= md) { pc++; ps += x; }
+            x = v.w & mk; if (x >= md) { pc++; ps += x; }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) { pc += __shfl_xor_sync(FULL, pc, o); ps += __shfl_xor_sync(FULL, ps, o); }
+        if (lane == 0) { a.part_cov[a.seg0 + j] = pc; a.part_sum[a.seg0 + j] = ps; *st_ptr = 1; }
+    } else if (fresh) {
 #pragma unroll 4
         for (int r = 0; r < SEG / 128; ++r) {
             const int b = r * 128 + lane * 4;
             __stcs(reinterpret_cast<uint4 *>(out + b), scan_row(b));
         }
+        if (lane == 0) *st_ptr = 2;
     } else {
 #pragma unroll 2
         for (int r = 0; r < SEG / 128; ++r) {
@@ -347,8 +370,8 @@ __global__ void __launch_bounds__(WPC * 32, TILE_MIN_CTAS) k_tile_accumulate(Til
             v.x += old.x; v.y += old.y; v.z += old.z; v.w += old.w;
             *dst = v;
         }
+        if (lane == 0) *st_ptr = 2;
     }
-    if (fresh && lane == 0) *st_ptr = 1;
     bad = __any_sync(FULL, bad);
     if (lane == 0 && (bad || (int64_t)chk_l >= hbase || (int64_t)chk_r < send || chk_n > i_hi)) atomicOr(a.err, ERR_UNSORTED);
 }
@@ -502,7 +525,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_add(uint32_t *__restrict_
 // ---------------------------------------------------------------------------------------------------------------
 // k_fill_untouched: one warp per segment; segments never written by a batch become zeros.
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_fill_untouched(uint32_t *depth, uint8_t *seg_state, uint64_t n_seg)
+__global__ void __launch_bounds__(256) k_fill_untouched(uint32_t *depth, uint8_t *seg_state, uint64_t n_seg,
+                                                        uint32_t hint_on, uint32_t *part_cov, unsigned long long *part_sum)
 {
     const uint64_t s = (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (s >= n_seg) return;
@@ -513,7 +537,10 @@ __global__ void __launch_bounds__(256) k_fill_untouched(uint32_t *depth, uint8_t
 #pragma unroll
     for (int k = lane; k < SEG / 4; k += 32) p[k] = z;
     __syncwarp();
-    if (lane == 0) seg_state[s] = 1;
+    if (lane == 0) {
+        if (hint_on) { part_cov[s] = 0; part_sum[s] = 0; seg_state[s] = 1; }     // min_dep >= 1: zero depth covers nothing
+        else seg_state[s] = 2;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -521,23 +548,25 @@ __global__ void __launch_bounds__(256) k_fill_untouched(uint32_t *depth, uint8_t
 // 64-bit atomic pair per unit.   if (depth >= minDep) { Cover++; Depth += depth; }   (:319-323, :340-344)
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int REDUCE_CHUNK = 8192;
+static_assert(REDUCE_CHUNK % SEG == 0, "reduce chunks are whole segments");
 
 struct ReduceArgs {
     const uint32_t *depth;           // array base
-    const uint64_t *contig_off;      // per tid, element offset
+    const uint64_t *contig_off;      // per tid, element offset (multiple of SCAN_TILE, hence of SEG)
     const uint32_t *contig_len;      // per tid
     const int32_t *tid; const int32_t *start0; const int32_t *end0;
-    const uint64_t *unit_prefix;     // n_iv+1: units before interval i (one unit = REDUCE_CHUNK bases)
-    uint64_t n_iv; uint64_t n_units;
+    const uint64_t *unit_prefix;     // n_iv+1: units before interval i; unit c of an interval is its part inside the
+    uint64_t n_iv; uint64_t n_units; //   REDUCE_CHUNK-aligned chunk floor(start/REDUCE_CHUNK)+c of the contig
     uint32_t min_dep, mask;
     unsigned long long *cov; unsigned long long *sum;
+    // partials written by k_tile_accumulate for (hint_min_dep, hint_mask); used when use_part (the caller asked for the same pair)
+    uint32_t use_part; const uint8_t *seg_state; const uint32_t *part_cov; const unsigned long long *part_sum;
 };
 
 __device__ __forceinline__ void warp_reduce_range(const uint32_t *__restrict__ d, int64_t a, int64_t b, uint32_t min_dep,
                                                   uint32_t mask, int lane, uint32_t &cov, unsigned long long &sum)
 {
-    // d + a .. d + b, any alignment.  head to 16-byte alignment, vector body, tail.
-    cov = 0; sum = 0;
+    // per-lane partial sums over d[a..b), any alignment: head to 16-byte alignment, vector body, tail.  NOT yet warp-reduced.
     if (a >= b) return;
     const uint32_t *p = d + a;
     int64_t n = b - a;
@@ -558,10 +587,6 @@ __device__ __forceinline__ void warp_reduce_range(const uint32_t *__restrict__ d
     }
     const int64_t done = nv << 2;
     if (lane < n - done) { const uint32_t x = __ldg(p + done + lane) & mask; if (x >= min_dep) { cov++; sum += x; } }
-    for (int o = 16; o; o >>= 1) {
-        cov += __shfl_xor_sync(FULL, cov, o);
-        sum += __shfl_xor_sync(FULL, sum, o);
-    }
 }
 
 __global__ void __launch_bounds__(256) k_reduce_units(ReduceArgs a)
@@ -575,19 +600,34 @@ __global__ void __launch_bounds__(256) k_reduce_units(ReduceArgs a)
         const uint64_t m = (lo_i + hi_i) >> 1;
         if (__ldg(a.unit_prefix + m) <= u) lo_i = m; else hi_i = m;
     }
-    uint2 un; un.x = (unsigned)lo_i; un.y = (unsigned)(u - __ldg(a.unit_prefix + lo_i));
-    const int32_t t = a.tid[un.x];
-    int64_t s = a.start0[un.x], e = a.end0[un.x];
+    const uint64_t iv = lo_i;
+    const int64_t c = (int64_t)(u - __ldg(a.unit_prefix + iv));
+    const int32_t t = a.tid[iv];
+    int64_t s = a.start0[iv], e = a.end0[iv];
     const int64_t len = a.contig_len[t];
     if (s < 0) s = 0;
     if (e > len) e = len;
-    int64_t lo = s + (int64_t)un.y * REDUCE_CHUNK, hi = lo + REDUCE_CHUNK;
-    if (hi > e) hi = e;
-    uint32_t cov; unsigned long long sum;
-    warp_reduce_range(a.depth + a.contig_off[t], lo, hi, a.min_dep, a.mask, lane, cov, sum);
+    const int64_t chunk0 = (s / REDUCE_CHUNK + c) * REDUCE_CHUNK;
+    const int64_t lo = s > chunk0 ? s : chunk0;
+    const int64_t hi = e < chunk0 + REDUCE_CHUNK ? e : chunk0 + REDUCE_CHUNK;
+    const uint64_t off = a.contig_off[t];
+    uint32_t cov = 0; unsigned long long sum = 0;
+    if (a.use_part) {
+        // segment by segment: a whole, written-once segment contributes its partial; anything else reads depth
+        for (int64_t q = chunk0; q < chunk0 + REDUCE_CHUNK && q < hi; q += SEG) {
+            const int64_t qa = lo > q ? lo : q, qb = hi < q + SEG ? hi : q + SEG;
+            if (qa >= qb) continue;
+            const uint64_t sg = (off + (uint64_t)q) / SEG;
+            if (qb - qa == SEG && a.seg_state[sg] == 1) {
+                if (lane == 0) { cov += a.part_cov[sg]; sum += a.part_sum[sg]; }
+            } else warp_reduce_range(a.depth + off, qa, qb, a.min_dep, a.mask, lane, cov, sum);
+        }
+    } else warp_reduce_range(a.depth + off, lo, hi, a.min_dep, a.mask, lane, cov, sum);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { cov += __shfl_xor_sync(FULL, cov, o); sum += __shfl_xor_sync(FULL, sum, o); }
     if (lane == 0 && (cov | (sum != 0))) {
-        atomicAdd(a.cov + un.x, (unsigned long long)cov);
-        atomicAdd(a.sum + un.x, sum);
+        atomicAdd(a.cov + iv, (unsigned long long)cov);
+        atomicAdd(a.sum + iv, sum);
     }
 }
 
@@ -611,8 +651,10 @@ __global__ void __launch_bounds__(256) k_reduce_windows(WindowArgs a)
         for (int64_t k = warp; k < a.n_win; k += nwarps) {
             const int64_t lo = a.start0 + k * a.win;
             int64_t hi = lo + a.win; if (hi > a.len) hi = a.len;
-            uint32_t cov; unsigned long long sum;
+            uint32_t cov = 0; unsigned long long sum = 0;
             warp_reduce_range(a.depth, lo, hi, a.min_dep, a.mask, lane, cov, sum);
+#pragma unroll
+            for (int o = 16; o; o >>= 1) { cov += __shfl_xor_sync(FULL, cov, o); sum += __shfl_xor_sync(FULL, sum, o); }
             if (lane == 0) { a.cov[k] = cov; a.sum[k] = sum; }
         }
     } else {

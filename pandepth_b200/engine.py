@@ -48,6 +48,7 @@ def load_library() -> ctypes.CDLL:
     L.pd_last_error.restype = ctypes.c_char_p; L.pd_last_error.argtypes = [vp]
     L.pd_set_stream.restype = ctypes.c_int; L.pd_set_stream.argtypes = [vp, vp]
     L.pd_reset.restype = ctypes.c_int; L.pd_reset.argtypes = [vp]
+    L.pd_set_reduce_hint.restype = ctypes.c_int; L.pd_set_reduce_hint.argtypes = [vp, u32, u32]
     L.pd_push_contig.restype = ctypes.c_int
     L.pd_push_contig.argtypes = [vp, i32, i64, vp, vp, vp, vp, vp, u32]
     L.pd_push.restype = ctypes.c_int
@@ -127,6 +128,9 @@ class Engine:
 
     def reset(self):
         self._ck(self._L.pd_reset(self._h))
+
+    def set_reduce_hint(self, min_dep: int = 1, mask: int = 0xFFFFFFFF):
+        self._ck(self._L.pd_set_reduce_hint(self._h, min_dep, mask))
 
     def push_contig(self, tid: int, pos, cigar, flag=None, mapq=None, cigar_off=None, flags: int = 0, n: Optional[int] = None):
         """Arrays are numpy (host) or, with PD_DEVICE, integer device pointers (then pass n)."""

@@ -390,9 +390,15 @@ int main(int argc, char **argv)
     std::vector<uint8_t> owned(targets.size(), 0);
     for (size_t t = 0; t < targets.size(); t++) { tlen[t] = targets[t].len; owned[t] = genes.count((int)t) ? 1 : 0; }
     const bool dry = getenv("PANDEPTH_DRY") != nullptr;      // decode only: no GPU is touched (diagnostics)
+    // -d and the depth width are known before the first read: let the engine keep per-segment partials for pd_reduce
+    const bool idx_early = (file_exists(o.input + ".bai") || file_exists(o.input + ".crai") || file_exists(o.input + ".csi")) && o.use_index;
+    const uint32_t hint_mask = (!idx_early || o.site_output || mode == 6) ? 0x3FFFFu : 0xFFFFFFFFu;
+    const bool hint_reduce = mode != 6;
     std::shared_future<pd_engine *> eng_future = std::async(std::launch::async, [&]() -> pd_engine * {
         if (dry) return nullptr;
-        return pd_create(device, (int)targets.size(), tlen.data(), owned.data(), o.xflags, o.min_mapq);
+        pd_engine *e = pd_create(device, (int)targets.size(), tlen.data(), owned.data(), o.xflags, o.min_mapq);
+        if (e && hint_reduce) pd_set_reduce_hint(e, (uint32_t)o.min_dep, hint_mask);
+        return e;
     }).share();
 
     const std::string prefix = output_prefix(o.out_arg);

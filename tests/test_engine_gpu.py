@@ -293,3 +293,55 @@ def test_contig_sharding_two_engines():
             parts.append(eng.reduce(tid, s0, e0))
     cov = parts[0][0] + parts[1][0]; tot = parts[0][1] + parts[1][1]
     assert np.array_equal(cov, full[0]) and np.array_equal(tot, full[1])
+
+
+@pytest.mark.parametrize("style", ["one_push", "chunked", "unsorted", "mixed_paths", "spliced_far_runs"])
+def test_reduce_hint_partials_give_identical_results(style):
+    """pd_set_reduce_hint is purely an optimisation: whole written-once segments come from partials recorded by the tile
+    kernel, everything else (edges, re-written segments, scan path, other (min_dep, mask) pairs) still reads depth."""
+    import pandepth_b200 as pd
+    rng = np.random.default_rng(21)
+    lens = [1_000_003, 40_000, 4096, 2048, 300]
+    tlen = np.array(lens, np.uint32)
+    rows = []
+    for t, ln in enumerate(lens):
+        n = ln // 3
+        starts = np.sort(rng.integers(0, max(1, ln - 150), n))
+        for p in starts.tolist():
+            if style == "spliced_far_runs" and rng.integers(0, 4) == 0:
+                cs = f"{rng.integers(20, 80)}M{rng.integers(300, 20000)}N{rng.integers(20, 80)}M"
+            else:
+                cs = "150M" if rng.integers(0, 5) else f"{rng.integers(1, 149)}M"
+            rows.append((0, t, p + 1, 60, cs))
+    rec = model.records_from_tuples(rows, [f"c{i}" for i in range(len(lens))])
+    want = model.accumulate(tlen, rec)
+    # intervals: whole contigs, 10 kb tiles, odd-aligned pieces, tiny pieces
+    iv = []
+    for t, ln in enumerate(lens):
+        iv.append((t, 0, ln))
+        for s in range(0, ln, 10_000):
+            iv.append((t, s, min(ln, s + 10_000)))
+        iv += [(t, 1, ln - 1), (t, 2047, min(ln, 2049 + 4096)), (t, ln // 2, ln // 2 + 1), (t, -5, ln + 99)]
+    it = np.array([x[0] for x in iv], np.int32); s0 = np.array([x[1] for x in iv], np.int32); e0 = np.array([x[2] for x in iv], np.int32)
+    for (hd, hm), (md, mk) in (((1, 0xFFFFFFFF), (1, 0xFFFFFFFF)), ((3, 0x3FFFF), (3, 0x3FFFF)), ((1, 0xFFFFFFFF), (2, 0xFFFFFFFF)), ((0, 0xFFFFFFFF), (0, 0xFFFFFFFF))):
+        with _engine(tlen) as eng:
+            eng.set_reduce_hint(hd, hm)
+            if style in ("one_push", "spliced_far_runs"):
+                _push_all(eng, rec, True, 1)
+            elif style == "chunked":
+                _push_all(eng, rec, True, 9)
+            elif style == "unsorted":
+                _push_all(eng, rec.select(rng.permutation(rec.n)), False, 2)
+            else:
+                half = rec.n // 2
+                _push_all(eng, rec.select(np.arange(0, half)), True, 1)
+                _push_all(eng, rec.select(rng.permutation(np.arange(half, rec.n))), False, 1)
+            cov, tot = eng.reduce(it, s0, e0, md, mk)
+            for k, (t, a, b) in enumerate(iv):
+                co, so = model.reduce_intervals(want[t], [a], [b], md, mk)
+                assert (int(cov[k]), int(tot[k])) == (int(co[0]), int(so[0])), (style, (hd, hm), (md, mk), iv[k])
+            _check_depth(eng, tlen, want)
+            with pytest.raises(pd.PDError):                   # the hint must precede the first push
+                eng.set_reduce_hint(1, 0xFFFFFFFF)
+            eng.reset()
+            eng.set_reduce_hint(1, 0xFFFFFFFF)
