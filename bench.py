@@ -328,6 +328,16 @@ def ours(args):
         alg_per_launch = alg_bytes_per_step * args.steps / n_launch
         achieved = alg_per_launch / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
         value = R_local * world * args.steps / (ms_dev * 1e-3) / 1e6
+        # dram traffic of one k_tile_accumulate launch from the committed ncu --set full capture (same workload only)
+        traffic = None
+        try:
+            import glob
+            for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json"))):
+                tj = json.load(open(f))["kernels"].get("k_tile_accumulate")
+                if tj and args.genome == 3.0e9 and args.coverage == 50.0:
+                    traffic = tj["dram_bytes_per_launch"]
+        except Exception:
+            traffic = None
         line = {
             "metric": "Mreads/s depth-accumulated", "value": value, "unit": "Mreads/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -339,7 +349,7 @@ def ours(args):
                        "l2": "inputs (8 GB/GPU) and the depth array (12 GB/GPU) are far larger than the 126 MB L2; no flush needed",
                        "timing": "CUDA events on the engine's stream, max over ranks"},
             "roofline": {"bound": "hbm", "kernel": "k_tile_accumulate", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak if peak else None, "traffic": None,
+                         "frac": achieved / peak if peak else None, "traffic": traffic,
                          "algorithmic_bytes_per_launch": alg_per_launch, "avg_launch_ms": avg_ms, "launches": kt["launches"],
                          "peak_source": peak_src,
                          "kernel_share_of_step": kt["ms"] / ms_dev if ms_dev else None},

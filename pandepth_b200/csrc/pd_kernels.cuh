@@ -339,16 +339,28 @@ __global__ void __launch_bounds__(WPC * 32, TILE_MIN_CTAS) k_tile_accumulate(Til
     if (do_part) {
         const uint32_t md = a.hint_min_dep, mk = a.hint_mask;
         uint32_t pc = 0; unsigned long long ps = 0;
+        if (md == 1u && mk == 0xffffffffu) {
+            // default -d 1 on the uint32 path: covered == non-zero, and zero depths add nothing to the sum
 #pragma unroll 4
-        for (int r = 0; r < SEG / 128; ++r) {
-            const int b = r * 128 + lane * 4;
-            const uint4 v = scan_row(b);
-            __stcs(reinterpret_cast<uint4 *>(out + b), v);
-            uint32_t x;                                              // if (depth >= minDep) { Cover++; Depth += depth; }  :319-323
-            x = v.x & mk; if (x >= md) { pc++; ps += x; }
-            x = v.y & mk; if (x >= md) { pc++; ps += x; }
-            x = v.z & mk; if (x >= md) { pc++; ps += x; }
-            x = v.w & mk; if (x >= md) { pc++; ps += x; }
+            for (int r = 0; r < SEG / 128; ++r) {
+                const int b = r * 128 + lane * 4;
+                const uint4 v = scan_row(b);
+                __stcs(reinterpret_cast<uint4 *>(out + b), v);
+                pc += (v.x != 0u) + (v.y != 0u) + (v.z != 0u) + (v.w != 0u);
+                ps += (unsigned long long)v.x + v.y + v.z + v.w;
+            }
+        } else {
+#pragma unroll 4
+            for (int r = 0; r < SEG / 128; ++r) {
+                const int b = r * 128 + lane * 4;
+                const uint4 v = scan_row(b);
+                __stcs(reinterpret_cast<uint4 *>(out + b), v);
+                uint32_t x;                                          // if (depth >= minDep) { Cover++; Depth += depth; }  :319-323
+                x = v.x & mk; if (x >= md) { pc++; ps += x; }
+                x = v.y & mk; if (x >= md) { pc++; ps += x; }
+                x = v.z & mk; if (x >= md) { pc++; ps += x; }
+                x = v.w & mk; if (x >= md) { pc++; ps += x; }
+            }
         }
 #pragma unroll
         for (int o = 16; o; o >>= 1) { pc += __shfl_xor_sync(FULL, pc, o); ps += __shfl_xor_sync(FULL, ps, o); }
