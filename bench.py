@@ -208,7 +208,10 @@ def ours(args):
     reads_per_contig = {t: int(lens[t] * args.coverage / READLEN) for t in mine}
     R_local = sum(reads_per_contig.values())
 
-    stream = torch.cuda.current_stream()
+    # a dedicated (non-default) torch stream is handed to the engine, so the CUDA events below are recorded on the very
+    # stream every kernel and copy is launched on
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     eng = pd.Engine(tlen, device=local_rank, owned=owned_mask(owner, rank))
     eng.set_stream(stream.cuda_stream)
     eng.set_reduce_hint(1, 0xFFFFFFFF)          # -d 1, uint32 path: known before the reads arrive, as in the CLI

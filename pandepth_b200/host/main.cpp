@@ -19,6 +19,7 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
 #include <future>
 #include <cstdio>
 #include <cstdlib>
@@ -117,6 +118,33 @@ struct Batch {
     }
 };
 
+// A few pinned staging slots shared by all workers.  A worker copies its finished batch into a slot in parallel with the
+// others (outside the engine lock); the locked section is then only a 55 GB/s H2D copy plus two kernel launches.
+// (Pushing pageable memory directly measured 2.4 GB/s under the lock and serialised the whole feeder.)
+struct PinnedPool {
+    struct Slot { int32_t *pos = nullptr; uint32_t *cigar = nullptr, *off = nullptr; size_t cap_r = 0, cap_c = 0; };
+    std::vector<Slot> slots; std::vector<int> free_ids;
+    std::mutex mu; std::condition_variable cv;
+    std::atomic<bool> ready{false};
+    void init(int n, size_t reads, size_t cig)
+    {
+        slots.resize((size_t)n);
+        for (int i = 0; i < n; i++) {
+            Slot &s = slots[(size_t)i];
+            s.pos = (int32_t *)pd_host_alloc(reads * 4); s.off = (uint32_t *)pd_host_alloc((reads + 1) * 4); s.cigar = (uint32_t *)pd_host_alloc(cig * 4);
+            if (!s.pos || !s.off || !s.cigar) { slots.resize((size_t)i); break; }
+            s.cap_r = reads; s.cap_c = cig;
+        }
+        std::lock_guard<std::mutex> g(mu);
+        for (size_t i = 0; i < slots.size(); i++) free_ids.push_back((int)i);
+        ready = !slots.empty();
+        cv.notify_all();
+    }
+    int acquire() { std::unique_lock<std::mutex> g(mu); cv.wait(g, [&] { return !free_ids.empty(); }); int id = free_ids.back(); free_ids.pop_back(); return id; }
+    void release(int id) { { std::lock_guard<std::mutex> g(mu); free_ids.push_back(id); } cv.notify_one(); }
+    ~PinnedPool() { for (auto &s : slots) { pd_host_free(s.pos); pd_host_free(s.off); pd_host_free(s.cigar); } }
+};
+
 struct WorkItem { int tid; int64_t beg, end, prev_end; int r0, r1; };   // 0-based [beg,end); merged regions [r0,r1) of the contig (modes 1-4)
 
 struct Feeder {
@@ -136,6 +164,7 @@ struct Feeder {
     // PANDEPTH_TIMING diagnostics (summed over workers, seconds); PANDEPTH_DRY=1 decodes without pushing
     std::atomic<uint64_t> ns_decode{0}, ns_wait{0}, ns_push{0}, n_push{0}, dry_digest{0};
     const BaiLinear *bai = nullptr;                      // non-null: scan raw BAM records directly (fastbam.hpp)
+    PinnedPool *pool = nullptr;                          // pinned staging (exists once the CUDA context does)
     bool dry = getenv("PANDEPTH_DRY") != nullptr;
     struct Pending { int tid; bool sorted; Batch b; };
     std::vector<Pending> pending;                        // batches decoded before the CUDA context was ready
@@ -149,6 +178,16 @@ struct Feeder {
     {
         if (b.n == 0) return true;
         if (dry) { reads_pushed += b.n; dry_digest += b.digest(tid); b.clear(); return true; }
+        // stage through a pinned slot when the pool is up and the batch fits (parallel memcpy, outside the engine lock)
+        int slot = -1;
+        if (pool && pool->ready && b.n <= pool->slots[0].cap_r && b.cigar.size() <= pool->slots[0].cap_c) {
+            slot = pool->acquire();
+            PinnedPool::Slot &s = pool->slots[(size_t)slot];
+            memcpy(s.pos, b.pos.data(), b.n * 4);
+            memcpy(s.cigar, b.cigar.data(), b.cigar.size() * 4);
+            if (!b.single_op) memcpy(s.off, b.off.data(), (b.n + 1) * 4);
+        }
+        struct Rel { PinnedPool *p; int id; ~Rel() { if (id >= 0) p->release(id); } } rel{pool, slot};
         const auto w0 = std::chrono::steady_clock::now();
         std::lock_guard<std::mutex> g(eng_mu);
         const auto w1 = std::chrono::steady_clock::now();
@@ -165,7 +204,12 @@ struct Feeder {
             if (!eng) { fail(std::string("Error: ") + pd_last_error(nullptr)); return false; }
         }
         if (!flush_pending_locked()) return false;
-        if (!push_locked(tid, b, sorted)) return false;
+        if (slot >= 0) {
+            PinnedPool::Slot &s = pool->slots[(size_t)slot];
+            int rc = pd_push_contig(eng, tid, (int64_t)b.n, s.pos, nullptr, nullptr, b.single_op ? nullptr : s.off, s.cigar, sorted ? PD_SORTED : 0u);
+            if (rc != PD_OK) { fail(std::string("pd_push_contig: ") + pd_last_error(eng)); return false; }
+            reads_pushed += b.n;
+        } else if (!push_locked(tid, b, sorted)) return false;
         b.clear();
         return true;
     }
@@ -389,6 +433,7 @@ int main(int argc, char **argv)
     std::vector<uint32_t> tlen(targets.size());
     std::vector<uint8_t> owned(targets.size(), 0);
     for (size_t t = 0; t < targets.size(); t++) { tlen[t] = targets[t].len; owned[t] = genes.count((int)t) ? 1 : 0; }
+    PinnedPool pool;
     const bool dry = getenv("PANDEPTH_DRY") != nullptr;      // decode only: no GPU is touched (diagnostics)
     // -d and the depth width are known before the first read: let the engine keep per-segment partials for pd_reduce
     const bool idx_early = (file_exists(o.input + ".bai") || file_exists(o.input + ".crai") || file_exists(o.input + ".csi")) && o.use_index;
@@ -398,6 +443,7 @@ int main(int argc, char **argv)
         if (dry) return nullptr;
         pd_engine *e = pd_create(device, (int)targets.size(), tlen.data(), owned.data(), o.xflags, o.min_mapq);
         if (e && hint_reduce) pd_set_reduce_hint(e, (uint32_t)o.min_dep, hint_mask);
+        if (e) pool.init(std::max(4, std::min(16, o.threads / 4)), (1u << 20) + 1024, 3u << 20);
         return e;
     }).share();
 
@@ -420,6 +466,7 @@ int main(int argc, char **argv)
     // ---- feed ---------------------------------------------------------------------------------------------------
     const bool region_modes = mode >= 1 && mode <= 4;
     Feeder feeder(o, eng_future, merged, indexed && region_modes);
+    feeder.pool = &pool;
     if (indexed) {
         int64_t total_len = 0;
         for (const auto &kv : merged) total_len += tlen[kv.first];

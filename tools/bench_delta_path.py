@@ -8,10 +8,11 @@ import pandepth_b200 as pd
 L = int(float(sys.argv[1])) if len(sys.argv) > 1 else 333_333_333
 R = int(L * 50 / 150)
 dev = torch.device("cuda", 0)
+_stream = torch.cuda.Stream(device=dev); torch.cuda.set_stream(_stream)   # non-default stream shared with the engine
 g = torch.Generator(device=dev); g.manual_seed(3)
 pos = torch.randint(0, L - 150, (R,), device=dev, dtype=torch.int32, generator=g)     # unsorted
 cig = torch.full((R,), 150 << 4, device=dev, dtype=torch.int32)
-eng = pd.Engine([L]); eng.set_stream(torch.cuda.current_stream().cuda_stream)
+eng = pd.Engine([L]); eng.set_stream(_stream.cuda_stream)
 iv = (np.zeros(1, np.int32), np.zeros(1, np.int32), np.array([L], np.int32))
 def step():
     eng.reset()

@@ -8,7 +8,8 @@ G = float(sys.argv[1]) if len(sys.argv) > 1 else 3.0e9
 W = int(sys.argv[2]) if len(sys.argv) > 2 else 100
 lens = [int(G) // 9] * 9
 dev = torch.device("cuda", 0)
-eng = pd.Engine(lens); eng.set_stream(torch.cuda.current_stream().cuda_stream)
+_stream = torch.cuda.Stream(device=dev); torch.cuda.set_stream(_stream)   # non-default stream shared with the engine
+eng = pd.Engine(lens); eng.set_stream(_stream.cuda_stream)
 g = torch.Generator(device=dev); g.manual_seed(7)
 tot_reads = 0
 for t, ln in enumerate(lens):

@@ -4,6 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import pandepth_b200 as pd
 dev = torch.device("cuda", 0)
+_stream = torch.cuda.Stream(device=dev); torch.cuda.set_stream(_stream)   # non-default stream shared with the engine
 n = 256 << 20
 h = torch.empty(n, dtype=torch.int32, pin_memory=True); h.fill_(3)
 d = torch.empty(n, dtype=torch.int32, device=dev)
