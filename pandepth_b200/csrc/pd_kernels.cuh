@@ -659,7 +659,22 @@ __global__ void __launch_bounds__(256) k_reduce_windows(WindowArgs a)
     const int lane = threadIdx.x & 31;
     const int64_t warp = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * 8;
-    if (a.win >= 32) {
+    if (a.win >= 32 && a.win <= 512 && (unsigned long long)a.win * a.mask < (1ull << 32)) {
+        // windows whose TotalDepth fits 32 bits (always true for mode 6: win < 150, 18-bit depth): lane-strided loads,
+        // one redux.sync each for CoveredSite and TotalDepth
+        for (int64_t k = warp; k < a.n_win; k += nwarps) {
+            const int64_t lo = a.start0 + k * a.win;
+            int64_t hi = lo + a.win; if (hi > a.len) hi = a.len;
+            uint32_t cov = 0, sum = 0;
+            for (int64_t q = lo + lane; q < hi; q += 32) {
+                const uint32_t x = __ldcs(a.depth + q) & a.mask;
+                if (x >= a.min_dep) { cov++; sum += x; }
+            }
+            cov = __reduce_add_sync(FULL, cov);
+            sum = __reduce_add_sync(FULL, sum);
+            if (lane == 0) { a.cov[k] = cov; a.sum[k] = sum; }
+        }
+    } else if (a.win >= 32) {
         for (int64_t k = warp; k < a.n_win; k += nwarps) {
             const int64_t lo = a.start0 + k * a.win;
             int64_t hi = lo + a.win; if (hi > a.len) hi = a.len;

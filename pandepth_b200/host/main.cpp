@@ -443,7 +443,7 @@ int main(int argc, char **argv)
         if (dry) return nullptr;
         pd_engine *e = pd_create(device, (int)targets.size(), tlen.data(), owned.data(), o.xflags, o.min_mapq);
         if (e && hint_reduce) pd_set_reduce_hint(e, (uint32_t)o.min_dep, hint_mask);
-        if (e) pool.init(std::max(4, std::min(16, o.threads / 4)), (1u << 20) + 1024, 3u << 20);
+        if (e) pool.init(8, (1u << 20) + 1024, (1u << 20) + (1u << 18));      // 8 x 13 MB pinned; bigger batches go pageable
         return e;
     }).share();
 
