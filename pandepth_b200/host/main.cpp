@@ -168,16 +168,36 @@ struct Feeder {
     bool dry = getenv("PANDEPTH_DRY") != nullptr;
     struct Pending { int tid; bool sorted; Batch b; };
     std::vector<Pending> pending;                        // batches decoded before the CUDA context was ready
+    std::mutex pend_mu;
+    std::atomic<bool> eng_ok{false};
 
     Feeder(const Options &oo, std::shared_future<pd_engine *> e, const std::map<int, std::vector<std::pair<int, int>>> &m, bool f)
         : o(oo), eng_future(e), merged(m), filter_by_region(f) {}
 
     void fail(const std::string &m) { std::lock_guard<std::mutex> g(err_mu); if (!failed.exchange(true)) err = m; }
 
+    bool engine_ready() { return eng_future.wait_for(std::chrono::seconds(0)) == std::future_status::ready; }
+
     bool push(int tid, Batch &b, bool sorted)
     {
         if (b.n == 0) return true;
         if (dry) { reads_pushed += b.n; dry_digest += b.digest(tid); b.clear(); return true; }
+        if (!eng_ok.load()) {
+            // the CUDA context is still coming up: park the batch and keep decoding (bounded: ~3 GB of parked reads)
+            if (!engine_ready()) {
+                std::unique_lock<std::mutex> g(pend_mu);
+                if (pending.size() < 256) {
+                    pending.push_back(Pending{tid, sorted, std::move(b)});
+                    b = Batch();
+                    return true;
+                }
+                g.unlock();
+                eng_future.wait();
+            }
+            std::lock_guard<std::mutex> g(eng_mu);
+            if (!eng) { eng = eng_future.get(); if (!eng) { fail(std::string("Error: ") + pd_last_error(nullptr)); return false; } }
+            eng_ok = true;
+        }
         // stage through a pinned slot when the pool is up and the batch fits (parallel memcpy, outside the engine lock)
         int slot = -1;
         if (pool && pool->ready && b.n <= pool->slots[0].cap_r && b.cigar.size() <= pool->slots[0].cap_c) {
@@ -193,17 +213,6 @@ struct Feeder {
         const auto w1 = std::chrono::steady_clock::now();
         ns_wait += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(w1 - w0).count();
         struct Done { Feeder *f; std::chrono::steady_clock::time_point t; ~Done() { f->ns_push += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t).count(); f->n_push++; } } done{this, w1};
-        if (!eng) {
-            // keep decoding while the CUDA context comes up: park the batch instead of blocking (never wait under the mutex)
-            if (eng_future.wait_for(std::chrono::seconds(0)) != std::future_status::ready) {
-                pending.push_back(Pending{tid, sorted, std::move(b)});
-                b = Batch();
-                return true;
-            }
-            eng = eng_future.get();
-            if (!eng) { fail(std::string("Error: ") + pd_last_error(nullptr)); return false; }
-        }
-        if (!flush_pending_locked()) return false;
         if (slot >= 0) {
             PinnedPool::Slot &s = pool->slots[(size_t)slot];
             int rc = pd_push_contig(eng, tid, (int64_t)b.n, s.pos, nullptr, nullptr, b.single_op ? nullptr : s.off, s.cigar, sorted ? PD_SORTED : 0u);
@@ -221,18 +230,22 @@ struct Feeder {
         reads_pushed += b.n;
         return true;
     }
-    bool flush_pending_locked()
-    {
-        for (auto &p : pending) if (!push_locked(p.tid, p.b, p.sorted)) return false;
-        pending.clear();
-        return true;
-    }
-    // after the workers are done: push whatever is still parked
+    // after the workers are done: the batches parked during CUDA start-up go through the normal (pinned, parallel) path
     bool finish()
     {
-        std::lock_guard<std::mutex> g(eng_mu);
-        if (!eng) { eng = eng_future.get(); if (!eng) { fail(std::string("Error: ") + pd_last_error(nullptr)); return false; } }
-        return flush_pending_locked();
+        pd_engine *e = eng_future.get();
+        if (!e) { fail(std::string("Error: ") + pd_last_error(nullptr)); return false; }
+        { std::lock_guard<std::mutex> g(eng_mu); eng = e; eng_ok = true; }
+        std::vector<Pending> todo;
+        { std::lock_guard<std::mutex> g(pend_mu); todo.swap(pending); }
+        std::atomic<size_t> nxt{0};
+        auto work = [&] { for (;;) { size_t k = nxt.fetch_add(1); if (k >= todo.size() || failed) break; push(todo[k].tid, todo[k].b, todo[k].sorted); } };
+        std::vector<std::thread> th;
+        const size_t nt = std::min<size_t>(std::max(1, o.threads), std::min<size_t>(16, todo.size()));
+        for (size_t i = 1; i < nt; i++) th.emplace_back(work);
+        work();
+        for (auto &t : th) t.join();
+        return !failed;
     }
 
     htsFile *open_input(sam_hdr_t **hdr, int nthreads)

@@ -9,4 +9,4 @@ THREADS="64 128" bash tools/bench_cli.sh 3000 A -g /tmp/pdcli_3000_A/genes.gff 2
 REPS=1 THREADS="64" bash tools/bench_cli.sh 3000 A -w 100 2>&1 | tee gpurun_out/cli_cfg3.log
 for t in 32 64 128; do PANDEPTH_TIMING=1 pandepth_b200/bin/pandepth -i /tmp/pdcli_3000_A/s.bam -o /tmp/pdcli_3000_A/x -t $t 2>&1 | grep timing | sed "s/^/t=$t /"; done | tee gpurun_out/cli_cfg2_timing.log
 PANDEPTH_TIMING=1 pandepth_b200/bin/pandepth -i /tmp/pdcli_3000_A/s.bam -o /tmp/pdcli_3000_A/x -t 64 -w 100 2>&1 | grep timing | tee -a gpurun_out/cli_cfg2_timing.log
-python tools/bench_windows.py 2>&1 | tail -1 | tee gpurun_out/windows_line.json
+python tools/bench_windows.py 3e9 100 2>&1 | tail -1 | tee gpurun_out/windows_line.json; python tools/bench_windows.py 3e9 1000 2>&1 | tail -1 | tee -a gpurun_out/windows_line.json
