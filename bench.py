@@ -110,6 +110,15 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the unmodified reference binary on a bounded BAM sample
 # ----------------------------------------------------------------------------------------------------------------
+def cpu_quota_cores():
+    """CPUs the container may actually use (cgroup v2 cpu.max), or None when unlimited/unknown."""
+    try:
+        a, p = open("/sys/fs/cgroup/cpu.max").read().split()
+        return None if a == "max" else float(a) / float(p)
+    except Exception:
+        return None
+
+
 def ref_paths():
     d = os.path.join(ROOT, "oracle", "_ref")
     return os.path.join(d, "pandepth_ref"), os.path.join(d, "bamgen")
@@ -172,7 +181,8 @@ def reference_arm(args):
         "gbases_per_s": value * READLEN / 1e3,
         "config": {"workload": "cfg2 shape (9 contigs, 50x, sorted 150M reads, per-chr mode), bounded sample: " + sample,
                    "cmd": f"pandepth_ref -i sample.bam -o out -t {threads}"},
-        "cpu_baseline": {"value": value, "unit": "Mreads/s", "cores": threads, "kind": "reference", "sample": sample,
+        "cpu_baseline": {"value": value, "unit": "Mreads/s", "cores": threads, "cpu_quota_cores": cpu_quota_cores(), "online_cpus": os.cpu_count(),
+                         "kind": "reference", "sample": sample,
                          "note": "reference runs min(t, #contigs)=9 workers + 2 BGZF threads each (PanDepth.cpp:4447-4452,:4511); includes its own BAM decode"},
         "e2e": {"value": value, "unit": "Mreads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -369,7 +379,8 @@ def ours(args):
             if bam:
                 times = time_reference(bam, reads, threads, 3, 1)
                 v = reads / min(times) / 1e6
-                line["cpu_baseline"] = {"value": v, "unit": "Mreads/s", "cores": threads, "kind": "reference",
+                line["cpu_baseline"] = {"value": v, "unit": "Mreads/s", "cores": threads, "cpu_quota_cores": cpu_quota_cores(),
+                                        "online_cpus": os.cpu_count(), "kind": "reference",
                                         "sample": f"{N_CONTIGS} contigs, {args.ref_sample_mb:.0f} Mb x {args.coverage:.0f}x = {reads} reads, "
                                                   f"BAM level 1 {'SEQ+QUAL' if args.ref_seq else 'SEQ=*'}, best of 3, pandepth_ref -t {threads}"}
             else:

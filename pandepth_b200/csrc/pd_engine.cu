@@ -529,7 +529,7 @@ int pd_reduce_windows(pd_engine *e, int32_t tid, int32_t start0, int32_t win, in
         d_cov = (uint32_t *)e->d_red; d_sum = (unsigned long long *)((char *)e->d_red + a_sum);
     }
     pdk::WindowArgs w{e->d_depth + e->off[tid], (int64_t)e->tlen[tid], start0, win, n_win, min_dep, depth_mask, d_cov, d_sum};
-    const int64_t warps_needed = win >= 32 ? n_win : (n_win + 31) / 32;
+    const int64_t warps_needed = (win >= 32 && win <= 160 && min_dep >= 1) ? (n_win + 3) / 4 : (win >= 32 ? n_win : (n_win + 31) / 32);
     const unsigned grid = (unsigned)std::min<int64_t>((warps_needed + 7) / 8, 148 * 64);
     rc = launch(e, K_WINDOWS, [&] { pdk::k_reduce_windows<<<grid, 256, 0, e->stream>>>(w); }); if (rc) return rc;
     if (!dev) {

@@ -659,9 +659,42 @@ __global__ void __launch_bounds__(256) k_reduce_windows(WindowArgs a)
     const int lane = threadIdx.x & 31;
     const int64_t warp = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * 8;
-    if (a.win >= 32 && a.win <= 512 && (unsigned long long)a.win * a.mask < (1ull << 32)) {
-        // windows whose TotalDepth fits 32 bits (always true for mode 6: win < 150, 18-bit depth): lane-strided loads,
-        // one redux.sync each for CoveredSite and TotalDepth
+    if (a.win >= 32 && a.win <= 160 && a.min_dep >= 1 && (unsigned long long)a.win * a.mask < (1ull << 32)) {
+        // mode-6 sized windows (-w < 150): a warp takes 4 consecutive windows per iteration and issues all of their loads
+        // (<= 5 per lane per window) before reducing any, then one redux.sync each for CoveredSite and TotalDepth
+        // (TotalDepth of such a window fits 32 bits: win * 18-bit depth)
+        constexpr int WB = 4, NL = 5;
+        const int64_t ngroups = (a.n_win + WB - 1) / WB;
+        for (int64_t g = warp; g < ngroups; g += nwarps) {
+            uint32_t x[WB][NL];
+#pragma unroll
+            for (int j = 0; j < WB; ++j) {
+                const int64_t k = g * WB + j;
+                const int64_t lo = a.start0 + k * a.win;
+                int64_t hi = lo + a.win; if (hi > a.len) hi = a.len;
+                if (k >= a.n_win) hi = lo;
+#pragma unroll
+                for (int i = 0; i < NL; ++i) {
+                    const int64_t q = lo + lane + 32 * i;
+                    x[j][i] = (q < hi) ? __ldcs(a.depth + q) : 0u;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < WB; ++j) {
+                const int64_t k = g * WB + j;
+                uint32_t cov = 0, sum = 0;
+#pragma unroll
+                for (int i = 0; i < NL; ++i) {
+                    const uint32_t v = x[j][i] & a.mask;          // lanes beyond the window loaded 0: never >= min_dep (>= 1)
+                    if (v >= a.min_dep) { cov++; sum += v; }
+                }
+                cov = __reduce_add_sync(FULL, cov);
+                sum = __reduce_add_sync(FULL, sum);
+                if (lane == 0 && k < a.n_win) { a.cov[k] = cov; a.sum[k] = sum; }
+            }
+        }
+    } else if (a.win >= 32 && a.win <= 512 && (unsigned long long)a.win * a.mask < (1ull << 32)) {
+        // windows whose TotalDepth fits 32 bits: lane-strided loads, one redux.sync each for CoveredSite and TotalDepth
         for (int64_t k = warp; k < a.n_win; k += nwarps) {
             const int64_t lo = a.start0 + k * a.win;
             int64_t hi = lo + a.win; if (hi > a.len) hi = a.len;

@@ -387,6 +387,27 @@ struct Feeder {
 
 bool file_exists(const std::string &p) { return access(p.c_str(), 0) == 0; }
 
+// CPUs this process may actually use: the cgroup v2 / v1 CPU quota if there is one, else the online CPU count.  Decode
+// workers beyond that only get throttled (possibly while holding the engine lock), so -t is clamped to it.
+int usable_cpus()
+{
+    long n = sysconf(_SC_NPROCESSORS_ONLN);
+    if (n < 1) n = 1;
+    double quota = 0;
+    if (FILE *f = fopen("/sys/fs/cgroup/cpu.max", "r")) {
+        char a[64]; long long period = 0;
+        if (fscanf(f, "%63s %lld", a, &period) == 2 && strcmp(a, "max") != 0 && period > 0) quota = atof(a) / (double)period;
+        fclose(f);
+    } else {
+        long long q = -1, p = 0;
+        if (FILE *fq = fopen("/sys/fs/cgroup/cpu/cpu.cfs_quota_us", "r")) { if (fscanf(fq, "%lld", &q) != 1) q = -1; fclose(fq); }
+        if (FILE *fp = fopen("/sys/fs/cgroup/cpu/cpu.cfs_period_us", "r")) { if (fscanf(fp, "%lld", &p) != 1) p = 0; fclose(fp); }
+        if (q > 0 && p > 0) quota = (double)q / (double)p;
+    }
+    if (quota >= 1.0 && quota < (double)n) n = (long)(quota + 0.5);
+    return (int)n;
+}
+
 // PANDEPTH_TIMING=1: phase wall times on stderr
 struct Timer {
     bool on = getenv("PANDEPTH_TIMING") != nullptr;
@@ -408,6 +429,10 @@ int main(int argc, char **argv)
     Options o;
     if (parse_args(argc, argv, o) != 0) return 0;
     Timer tm;
+    if (!getenv("PANDEPTH_NO_CLAMP")) {
+        const int cpus = usable_cpus();
+        if (o.threads > cpus) { if (tm.on) fprintf(stderr, "[timing] -t %d clamped to the %d usable CPUs (cgroup quota / online CPUs)\n", o.threads, cpus); o.threads = cpus; }
+    }
 
     std::string ext = o.input.substr(o.input.rfind('.') == std::string::npos ? o.input.size() : o.input.rfind('.') + 1);
     if (ext == "gz") {
