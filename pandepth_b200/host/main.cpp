@@ -694,6 +694,10 @@ int main(int argc, char **argv)
     }
     out.close();
     tm.mark("reduce+report");
+    // every output is flushed and closed: leave without the teardown of the CUDA context, 24 GB of device memory and the
+    // parked/pinned host buffers -- the OS reclaims all of it, and the orderly teardown only costs wall time
+    fflush(stdout); fflush(stderr);
+    if (!getenv("PANDEPTH_ORDERLY_EXIT")) _exit(0);
     pd_destroy(eng);
     sam_hdr_destroy(hdr);
     tm.mark("pd_destroy");
