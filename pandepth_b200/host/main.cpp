@@ -164,6 +164,8 @@ struct Feeder {
     // PANDEPTH_TIMING diagnostics (summed over workers, seconds); PANDEPTH_DRY=1 decodes without pushing
     std::atomic<uint64_t> ns_decode{0}, ns_wait{0}, ns_push{0}, n_push{0}, dry_digest{0};
     const BaiLinear *bai = nullptr;                      // non-null: scan raw BAM records directly (fastbam.hpp)
+    std::string input;                                   // the file being fed (multi-file mode feeds several in turn)
+    bool used_fast = false;
     PinnedPool *pool = nullptr;                          // pinned staging (exists once the CUDA context does)
     bool dry = getenv("PANDEPTH_DRY") != nullptr;
     struct Pending { int tid; bool sorted; Batch b; };
@@ -250,7 +252,7 @@ struct Feeder {
 
     htsFile *open_input(sam_hdr_t **hdr, int nthreads)
     {
-        htsFile *fp = hts_open(o.input.c_str(), "r");
+        htsFile *fp = hts_open(input.c_str(), "r");
         if (!fp) return nullptr;
         hts_set_log_level(HTS_LOG_OFF);
         if (fp->format.format == cram) {                                   // :637-643
@@ -270,7 +272,7 @@ struct Feeder {
         sam_hdr_t *hdr = nullptr;
         htsFile *fp = open_input(&hdr, 0);
         hts_idx_t *idx = shared_idx;
-        if (!fp || !idx) { fail("Error: Failed to open the index file or BAM/CRAM file: " + o.input); if (fp) hts_close(fp); return; }
+        if (!fp || !idx) { fail("Error: Failed to open the index file or BAM/CRAM file: " + input); if (fp) hts_close(fp); return; }
         bam1_t *b = bam_init1();
         Batch batch;
         const uint32_t xf = o.xflags;
@@ -316,8 +318,9 @@ struct Feeder {
     // indexed path for sorted BAM + .bai: raw record scan, no htslib in the loop
     void fast_worker()
     {
+        used_fast = true;
         BamRangeScanner sc;
-        if (!sc.open(o.input)) { fail("Error: Failed to open the BAM/CRAM file: " + o.input); return; }
+        if (!sc.open(input)) { fail("Error: Failed to open the BAM/CRAM file: " + input); return; }
         Batch batch;
         const uint32_t xf = o.xflags;
         const auto t_begin = std::chrono::steady_clock::now();
@@ -354,7 +357,7 @@ struct Feeder {
                 batch.add_raw(r);
                 if (batch.n >= (1u << 20)) ok_push = push(w.tid, batch, true);
             });
-            if (!ok) { fail("Error: malformed BAM while scanning " + o.input + ": " + sc.error()); break; }
+            if (!ok) { fail("Error: malformed BAM while scanning " + input + ": " + sc.error()); break; }
             if (!ok_push || !push(w.tid, batch, true)) break;
         }
     }
@@ -364,7 +367,7 @@ struct Feeder {
     {
         sam_hdr_t *hdr = nullptr;
         htsFile *fp = open_input(&hdr, o.threads);
-        if (!fp) { fail("Error: Failed to open the BAM/CRAM file: " + o.input); return false; }
+        if (!fp) { fail("Error: Failed to open the BAM/CRAM file: " + input); return false; }
         bam1_t *b = bam_init1();
         Batch batch;
         int cur = -1;
@@ -475,7 +478,9 @@ int main(int argc, char **argv)
     const bool dry = getenv("PANDEPTH_DRY") != nullptr;      // decode only: no GPU is touched (diagnostics)
     // -d and the depth width are known before the first read: let the engine keep per-segment partials for pd_reduce
     const bool idx_early = (file_exists(o.input + ".bai") || file_exists(o.input + ".crai") || file_exists(o.input + ".csi")) && o.use_index;
-    const uint32_t hint_mask = (!idx_early || o.site_output || mode == 6) ? 0x3FFFFu : 0xFFFFFFFFu;
+    const bool multi = o.inputs.size() > 1;                  // FileNum > 1 -> List_main / BamList_main (:3452-3458)
+    if (multi) std::cout << "INFO: Run multi-file data " << std::endl;
+    const uint32_t hint_mask = (multi || !idx_early || o.site_output || mode == 6) ? 0x3FFFFu : 0xFFFFFFFFu;
     const bool hint_reduce = mode != 6;
     std::shared_future<pd_engine *> eng_future = std::async(std::launch::async, [&]() -> pd_engine * {
         if (dry) return nullptr;
@@ -492,8 +497,9 @@ int main(int argc, char **argv)
 
     const bool have_index = file_exists(o.input + ".bai") || file_exists(o.input + ".crai") || file_exists(o.input + ".csi");   // :4121-4124
     const bool indexed = have_index && o.use_index;
-    // the reference's 18-bit SiteInfo paths: no index, -a, or mode 6 (:4127, :4553); everything else is the uint32 window path
-    const bool whole = !indexed || o.site_output || mode == 6;
+    // the reference's 18-bit SiteInfo paths: no index, -a, mode 6 (:4127, :4553) or several input files (BamList_main :2687);
+    // everything else is the uint32 window path
+    const bool whole = multi || !indexed || o.site_output || mode == 6;
     const uint32_t mask = whole ? 0x3FFFFu : 0xFFFFFFFFu;
 
     // merged regions per contig (RegionMerger, :3912-3972)
@@ -503,55 +509,83 @@ int main(int argc, char **argv)
 
     // ---- feed ---------------------------------------------------------------------------------------------------
     const bool region_modes = mode >= 1 && mode <= 4;
-    Feeder feeder(o, eng_future, merged, indexed && region_modes);
+    Feeder feeder(o, eng_future, merged, false);
     feeder.pool = &pool;
-    if (indexed) {
-        int64_t total_len = 0;
-        for (const auto &kv : merged) total_len += tlen[kv.first];
-        // bases per work item: ~6 items per thread, but never so small that BGZF blocks are decoded twice at every boundary
-        const int64_t RANGE = std::max<int64_t>(1 << 20, std::min<int64_t>(8 << 20, total_len / (6 * (int64_t)o.threads) + 1));
-        const int64_t GAP = 64 << 10;                        // merged regions closer than this share one index query
-        for (const auto &kv : merged) {
-            const int tid = kv.first;
-            const int64_t len = tlen[tid];
-            int64_t prev_end = 0;
-            if (!region_modes) {
-                for (int64_t b = 0; b < len; b += RANGE) { feeder.items.push_back({tid, b, std::min(len, b + RANGE), prev_end, 0, 0}); prev_end = std::min(len, b + RANGE); }
-            } else {
-                const auto &regs = kv.second;
-                size_t a = 0;
-                while (a < regs.size()) {
-                    size_t b = a + 1;
-                    int64_t beg = std::max<int64_t>((int64_t)regs[a].first - 1, 1) - 1;             // chr:first-1 .. second+1 (:700-706)
-                    int64_t end = std::min<int64_t>((int64_t)regs[a].second + 1, len);
-                    while (b < regs.size() && (int64_t)regs[b].first - 2 - end < GAP && end - beg < 2 * RANGE) { end = std::min<int64_t>((int64_t)regs[b].second + 1, len); b++; }
-                    if (end > beg) feeder.items.push_back({tid, beg, end, prev_end, (int)a, (int)b});
-                    prev_end = std::max(prev_end, end);
-                    a = b;
+    for (size_t fi = 0; fi < o.inputs.size() && !feeder.failed; fi++) {
+        const std::string &path = o.inputs[fi];
+        feeder.input = path;
+        bool f_bam = is_bam, f_sorted = sorted_hdr;
+        if (fi > 0) {                                        // later files: own format / sort order, the first file's targets (:2701-2862)
+            htsFile *fp = hts_open(path.c_str(), "r");
+            if (!fp) { std::cerr << "Error: Failed to open the BAM/CRAM file: " << path << std::endl; continue; }
+            if (fp->format.format == cram) hts_set_fai_filename(fp, o.reference.c_str());
+            f_bam = fp->format.format == bam;
+            sam_hdr_t *h2 = sam_hdr_read(fp);
+            f_sorted = false;
+            if (h2) {
+                const char *txt = sam_hdr_str(h2);
+                std::string text = txt ? txt : "";
+                size_t a = text.find("\tSO:");
+                if (a != std::string::npos) { a += 4; size_t b = text.find_first_of("\n\t", a); f_sorted = text.substr(a, b - a) == "coordinate"; }
+                sam_hdr_destroy(h2);
+            }
+            hts_close(fp);
+        }
+        const bool f_indexed = (file_exists(path + ".bai") || file_exists(path + ".crai") || file_exists(path + ".csi")) && o.use_index;
+        feeder.filter_by_region = f_indexed && region_modes;
+        if (f_indexed) {
+            if (feeder.items.empty()) {
+                int64_t total_len = 0;
+                for (const auto &kv : merged) total_len += tlen[kv.first];
+                // bases per work item: ~6 items per thread, but never so small that BGZF blocks are decoded twice at every boundary
+                const int64_t RANGE = std::max<int64_t>(1 << 20, std::min<int64_t>(8 << 20, total_len / (6 * (int64_t)o.threads) + 1));
+                const int64_t GAP = 64 << 10;                // merged regions closer than this share one index query
+                for (const auto &kv : merged) {
+                    const int tid = kv.first;
+                    const int64_t len = tlen[tid];
+                    int64_t prev_end = 0;
+                    if (!region_modes) {
+                        for (int64_t b = 0; b < len; b += RANGE) { feeder.items.push_back({tid, b, std::min(len, b + RANGE), prev_end, 0, 0}); prev_end = std::min(len, b + RANGE); }
+                    } else {
+                        const auto &regs = kv.second;
+                        size_t a = 0;
+                        while (a < regs.size()) {
+                            size_t b = a + 1;
+                            int64_t beg = std::max<int64_t>((int64_t)regs[a].first - 1, 1) - 1;     // chr:first-1 .. second+1 (:700-706)
+                            int64_t end = std::min<int64_t>((int64_t)regs[a].second + 1, len);
+                            while (b < regs.size() && (int64_t)regs[b].first - 2 - end < GAP && end - beg < 2 * RANGE) { end = std::min<int64_t>((int64_t)regs[b].second + 1, len); b++; }
+                            if (end > beg) feeder.items.push_back({tid, beg, end, prev_end, (int)a, (int)b});
+                            prev_end = std::max(prev_end, end);
+                            a = b;
+                        }
+                    }
                 }
             }
+            feeder.next = 0;
+            // sorted BAM + .bai: raw-record scanner; anything else (CRAM, .csi only, PANDEPTH_HTS_ITER=1): htslib iterators
+            BaiLinear bai;
+            feeder.bai = nullptr; feeder.shared_idx = nullptr;
+            if (f_bam && !getenv("PANDEPTH_HTS_ITER") && file_exists(path + ".bai") && bai.load(path + ".bai") && bai.refs.size() == targets.size())
+                feeder.bai = &bai;
+            if (!feeder.bai) {
+                htsFile *ifp = hts_open(path.c_str(), "r");
+                if (ifp) { feeder.shared_idx = sam_index_load(ifp, path.c_str()); hts_close(ifp); }
+            }
+            const int nthreads = (int)std::max<size_t>(1, std::min<size_t>((size_t)o.threads, feeder.items.size()));
+            std::vector<std::thread> th;
+            for (int i = 0; i < nthreads; i++) th.emplace_back([&] { if (feeder.bai) feeder.fast_worker(); else feeder.indexed_worker(); });
+            for (auto &t : th) t.join();
+            if (feeder.shared_idx) hts_idx_destroy(feeder.shared_idx);
+            feeder.bai = nullptr; feeder.shared_idx = nullptr;
+        } else {
+            if (f_sorted) std::cout << "Warning: PanDepth will run in No Index mode: " << path << std::endl;                       // :4606
+            else std::cout << "Warning: Can't find index file of input BAM/CRAM. PanDepth will run in No Index mode: " << path << std::endl;   // :4677
+            feeder.stream_all(f_sorted);
         }
-        // sorted BAM + .bai: raw-record scanner; anything else (CRAM, .csi only, PANDEPTH_HTS_ITER=1): htslib iterators
-        BaiLinear bai;
-        if (is_bam && !getenv("PANDEPTH_HTS_ITER") && file_exists(o.input + ".bai") && bai.load(o.input + ".bai") && bai.refs.size() == targets.size())
-            feeder.bai = &bai;
-        if (!feeder.bai) {
-            htsFile *ifp = hts_open(o.input.c_str(), "r");
-            if (ifp) { feeder.shared_idx = sam_index_load(ifp, o.input.c_str()); hts_close(ifp); }
-        }
-        const int nthreads = (int)std::max<size_t>(1, std::min<size_t>((size_t)o.threads, feeder.items.size()));
-        std::vector<std::thread> th;
-        for (int i = 0; i < nthreads; i++) th.emplace_back([&] { if (feeder.bai) feeder.fast_worker(); else feeder.indexed_worker(); });
-        for (auto &t : th) t.join();
-        if (feeder.shared_idx) hts_idx_destroy(feeder.shared_idx);
-    } else {
-        if (sorted_hdr) std::cout << "Warning: PanDepth will run in No Index mode: " << o.input << std::endl;                       // :4606
-        else std::cout << "Warning: Can't find index file of input BAM/CRAM. PanDepth will run in No Index mode: " << o.input << std::endl;   // :4677
-        feeder.stream_all(sorted_hdr);
     }
     if (dry) {
         tm.mark("decode (dry)");
-        std::cout << "dry: reads=" << feeder.reads_pushed.load() << " digest=" << feeder.dry_digest.load() << " path=" << (feeder.bai ? "fastbam" : "htslib") << std::endl;
+        std::cout << "dry: reads=" << feeder.reads_pushed.load() << " digest=" << feeder.dry_digest.load() << " path=" << (feeder.used_fast ? "fastbam" : "htslib") << std::endl;
         if (feeder.failed) { std::cerr << feeder.err << std::endl; return 1; }
         return 0;
     }

@@ -12,7 +12,8 @@ namespace pdh {
 
 // In3str1v (include/DataClass.h:22-59) with the defaults main() applies (:3444).
 struct Options {
-    std::string input;                 // -i
+    std::string input;                 // -i (first file)
+    std::vector<std::string> inputs;   // every -i / every line of a #.list file (:99-115); more than one = multi-file mode
     std::string out_arg;               // -o as given
     std::string gff;                   // -g
     std::string bed;                   // -b

@@ -91,7 +91,7 @@ void print_help()
 {
     std::cout << "Usage: pandepth -i in.bam [-g gene.gff | -b region.bed] -o outPrefix\n"
                  " Input/Output options:\n"
-                 "   -i    <str>     input of sam/bam/cram file\n"
+                 "   -i    <str>     input of sam/bam/cram or #.list file\n"
                  "   -o    <str>     prefix of output file\n"
                  " Target options:\n"
                  "   -g    <str>     input gff/gtf file for gene region\n"
@@ -132,11 +132,11 @@ int parse_args(int argc, char **argv, Options &o)
         if (flag == "i") {
             if (!need(v)) return 1;
             std::string ext = v.substr(v.rfind('.') == std::string::npos ? v.size() : v.rfind('.') + 1);
-            if (ext == "list" || ext == "List") {
-                std::cerr << "Error: multi-file #.list input is not supported by pandepth-b200 yet" << std::endl;
-                return 1;
-            }
-            o.input = v;
+            if (ext == "list" || ext == "List") {                  // ReadList, include/comm.h:31-50: one path per non-empty line
+                LineReader in(v);
+                if (!in.ok()) std::cerr << "open List error: " << v << std::endl;
+                else { std::string line; while (in.next(line)) if (!line.empty()) o.inputs.push_back(line); }
+            } else o.inputs.push_back(v);
         } else if (flag == "o") { if (!need(o.out_arg)) return 1; }
         else if (flag == "c") o.gc = true;
         else if (flag == "a") o.site_output = true;
@@ -171,6 +171,7 @@ int parse_args(int argc, char **argv, Options &o)
         else if (flag == "help" || flag == "h") { print_help(); return 1; }
         else { std::cerr << "Error UnKnow argument -" << flag << std::endl; return 1; }
     }
+    if (!o.inputs.empty()) o.input = o.inputs[0];
     if (o.input.empty() || o.out_arg.empty()) { std::cerr << "Error: lack argument -i or -o " << std::endl; return 1; }
     if (have_bed && o.gff.empty()) {                              // :262-289
         LineReader in(o.bed);

@@ -124,6 +124,18 @@ def main():
     add("big.default", "big.sam", [])
     add("big.w1000", "big.sam", ["-w", "1000"])
     add("big.bed", "big.sam", ["-b", "@big.bed"])
+    # multi-file mode (-i x.list, BamList_main PanDepth.cpp:2029-3410): depth of all files summed in one 18-bit array
+    add("list2k.default", "list:k.sam,k.sam", [])
+    add("list2k.w100", "list:k.sam,k.sam", ["-w", "100"])
+    add("list2k.bed4", "list:k.sam,k.sam", ["-b", "@k.bed4"])
+    add("list2k.gff", "list:k.sam,k.sam", ["-g", "@k.gff"])
+    add("list2k.a", "list:k.sam,k.sam", ["-a"])
+    # (the reference's multi-file arrays carry only +100 bases of slack (:2689) instead of +500, so fixtures whose reads overhang
+    # a contig end by more -- mix.sam, big.sam -- corrupt its heap: it segfaults, aborts or hangs.  Lists use k.sam only.)
+    add("list3k.default", "list:k.sam,k.sam,k.sam", ["-q", "5", "-d", "2"])
+    add("list3k.w7", "list:k.sam,k.sam,k.sam", ["-w", "7"])
+    add("list3k.w150", "list:k.sam,k.sam,k.sam", ["-w", "150"])
+    add("list2stack.default", "list:@stack,@stack", [])          # 2 x 262149 reads: the 18-bit sum wraps across files
     # 18-bit wrap vector (SURVEY App. C `w.sam`): 262149 stacked 10M reads at pos 100 of a 1 kb contig
     add("stack.default", "@stack", [])
     add("stack.w100", "@stack", ["-w", "100"])
@@ -137,7 +149,26 @@ def main():
             fh.write("@HD\tVN:1.6\tSO:coordinate\n@SQ\tSN:c\tLN:1000\n")
             fh.write("r\t0\tc\t100\t60\t10M\t*\t0\t0\t*\t*\n" * 262149)
         bams = {}
+        def to_bam(sam):
+            if sam not in bams:
+                b = os.path.join(tmp, os.path.basename(sam) + ".bam")
+                subprocess.run([BAMGEN, "-I", sam, "-o", b], check=True)
+                bams[sam] = b
+            return bams[sam]
         for c in cases:
+            if c["fixture"].startswith("list:"):
+                members = [stack if x == "@stack" else g(x) for x in c["fixture"][5:].split(",")]
+                if c["kind"] == "bam":
+                    members = [to_bam(m) for m in members]
+                inp = os.path.join(tmp, c["name"] + ".list")
+                with open(inp, "w") as fh:
+                    fh.write("\n".join(members) + "\n")
+                args = [g(a[1:]) if a.startswith("@") else a for a in c["args"]]
+                res = run_ref(inp, args, tmp, c["name"])
+                res = {k: compact(v) for k, v in res.items()}
+                out[c["name"]] = {"fixture": c["fixture"], "kind": c["kind"], "args": c["args"], "outputs": res}
+                print(c["name"], {k: (len(v) if isinstance(v, str) else v["n_bytes"]) for k, v in res.items()})
+                continue
             sam = stack if c["fixture"] == "@stack" else g(c["fixture"])
             if c["kind"] == "bam":
                 if sam not in bams:

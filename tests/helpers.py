@@ -14,6 +14,18 @@ STACK_TARGETS = [("c", 1000)]
 
 def load_fixture(name):
     """-> (targets, Records, sorted) for a golden fixture name ('k.sam', '@stack', ...)."""
+    if name.startswith("list:"):
+        parts = [load_fixture(x) for x in name[5:].split(",")]
+        targets = parts[0][0]
+        recs = [p[1] for p in parts]
+        off = [0]
+        for r in recs:
+            off.append(off[-1] + int(r.cigar.size))
+        cat = model.Records(np.concatenate([r.tid for r in recs]), np.concatenate([r.pos for r in recs]),
+                            np.concatenate([r.flag for r in recs]), np.concatenate([r.mapq for r in recs]),
+                            np.concatenate([[0]] + [r.cigar_off[1:].astype(np.int64) + o for r, o in zip(recs, off)]).astype(np.uint32),
+                            np.concatenate([r.cigar for r in recs]))
+        return targets, cat, False
     if name == "@stack":
         n = 262149
         rec = model.Records(np.zeros(n, np.int32), np.full(n, 99, np.int32), np.zeros(n, np.uint16),
@@ -23,10 +35,10 @@ def load_fixture(name):
     return model.parse_sam(os.path.join(GOLD, name))
 
 
-def options_from_args(args, kind):
+def options_from_args(args, kind, fixture=""):
     """Translate a golden case's CLI args into model.Options (what bamCov_help01 would set, PanDepth.cpp:84-293)."""
     o = model.Options()
-    o.indexed = (kind == "bam")
+    o.indexed = (kind == "bam") and not fixture.startswith("list:")     # multi-file mode is always the 18-bit path (:2687)
     it = iter(args)
     for a in it:
         if a == "-w":

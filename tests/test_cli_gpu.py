@@ -65,7 +65,13 @@ def _run(binary, inp, args, workdir, tag):
 def test_cli_matches_golden(case, inputs, workdir):
     c = _CASES[case]
     args = [os.path.join(GOLD, a[1:]) if a.startswith("@") else a for a in c["args"]]
-    outs, _ = _run(CLI, inputs[c["fixture"]][c["kind"]], args + ["-t", "4"], workdir, "our_" + case)
+    if c["fixture"].startswith("list:"):
+        inp = os.path.join(workdir, case + ".list")
+        with open(inp, "w") as fh:
+            fh.write("\n".join(inputs[m][c["kind"]] for m in c["fixture"][5:].split(",")) + "\n")
+    else:
+        inp = inputs[c["fixture"]][c["kind"]]
+    outs, _ = _run(CLI, inp, args + ["-t", "4"], workdir, "our_" + case)
     assert sorted(outs) == sorted(c["outputs"]), (sorted(outs), sorted(c["outputs"]))
     for k, want in c["outputs"].items():
         if k == ".SiteDepth.gz" and ("-b" in c["args"] or "-g" in c["args"]):

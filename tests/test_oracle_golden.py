@@ -20,7 +20,7 @@ with open(os.path.join(GOLD, "expected.json")) as _fh:
 def test_model_matches_reference(case):
     c = _CASES[case]
     targets, rec, _ = load_fixture(c["fixture"])
-    opts = options_from_args(c["args"], c["kind"])
+    opts = options_from_args(c["args"], c["kind"], c["fixture"])
     res = model.run_model(targets, rec, opts)
     outs = c["outputs"]
     assert res["suffix"] in outs, (res["suffix"], list(outs))
