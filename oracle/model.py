@@ -125,6 +125,64 @@ def parse_sam(path: str) -> Tuple[List[Tuple[str, int]], Records, bool]:
     return targets, records_from_tuples(rows, names), so
 
 
+def parse_paf(paths: List[str], xflags: int = 1796, min_mapq: int = -1) -> Tuple[List[Tuple[str, int]], Records, bool]:
+    """PAF text -> (targets, records, False), following paf_main (:852-2024).
+
+    Targets: column 6 / 7 of the FIRST file in first-seen order (:918-941).  Per line of every file (:1536-1623): dropped if
+    it contains "tp:A:S" and -x has bit 0x100, or if column 12 < -q; tid = Chr2IntMap[col 6] (unknown names default-insert
+    0); start/end = columns 8/9, swapped if start > end; a cg:Z: token at index > 1 is walked from the 0-based start (M = X
+    add depth, D N advance, anything else nothing), otherwise the line covers [start-1, end).  The filters are applied here,
+    so the records carry flag 0 / mapq 255."""
+    chr2int: Dict[str, int] = {}
+    targets: List[Tuple[str, int]] = []
+    opener = lambda p: gzip.open(p, "rt") if p.endswith(".gz") else open(p, "rt")
+    with opener(paths[0]) as fh:
+        for line in fh:
+            f = line.split()
+            if len(f) < 7:
+                continue
+            if f[5] not in chr2int:
+                chr2int[f[5]] = len(targets)
+                targets.append((f[5], _atoi(f[6])))
+    tid, pos, off, cig = [], [], [0], []
+    for path in paths:
+        with opener(path) as fh:
+            for line in fh:
+                line = line.rstrip("\n")
+                if not line:
+                    continue
+                if (xflags & 0x100) and "tp:A:S" in line:
+                    continue
+                f = _cpp_split(line, " \t")
+                if len(f) < 12:
+                    continue
+                t = chr2int.get(f[5], 0)
+                if _atoi(f[11]) < min_mapq:
+                    continue
+                a, z = _atoi(f[7]), _atoi(f[8])
+                if a > z:
+                    a, z = z, a
+                cg = next((i for i, x in enumerate(f) if x[:5] == "cg:Z:"), -1)
+                if cg > 1:
+                    ops = []
+                    for n, op in re.findall(r"(\d*)(\D|$)", f[cg][5:]):
+                        if not n and not op:
+                            continue
+                        code = {"M": 0, "=": 7, "X": 8, "D": 2, "N": 3}.get(op)
+                        if code is not None:
+                            ops.append((int(n or 0) << 4) | code)
+                    pos.append(a)
+                else:
+                    s0 = a - 1 if a > 0 else 0          # the reference's write at index -1 is dropped
+                    ops = [((z - s0) << 4) | 0] if z > s0 else []
+                    pos.append(s0)
+                tid.append(t); cig.extend(ops); off.append(len(cig))
+    n = len(tid)
+    rec = Records(np.array(tid, np.int32), np.array(pos, np.int32), np.zeros(n, np.uint16), np.full(n, 255, np.uint8),
+                  np.array(off, np.uint32), np.array(cig, np.uint32))
+    return targets, rec, False
+
+
 # --------------------------------------------------------------------------------------------------
 # L1 / L0 through the C restatement
 # --------------------------------------------------------------------------------------------------

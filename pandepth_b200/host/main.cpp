@@ -386,6 +386,77 @@ struct Feeder {
         hts_close(fp);
         return !failed;
     }
+
+    // PAF input (paf_main, :1536-1623): one text line per alignment.  Column 6 = target name, 8/9 = target start/end,
+    // 12 = mapping quality; a `cg:Z:` tag (token index > 1) is walked like a BAM CIGAR from the 0-based target start,
+    // otherwise the line covers [start-1, end).  Lines carrying "tp:A:S" are dropped when -x has bit 0x100 (:1552-1558),
+    // lines with mapq < -q are dropped (:1564-1568).  Unknown target names land on target 0 (`Chr2IntMap[inf[5]]`
+    // default-inserts 0, :1562).  Lines are not sorted: batches go through the unsorted (delta scatter) path.
+    bool paf_stream(std::map<std::string, int> &chr2int, size_t n_targets)
+    {
+        LineReader in(input);
+        if (!in.ok()) { fail("open PAF file error: " + input); return false; }
+        std::vector<Batch> batches(n_targets);
+        std::string line;
+        std::vector<std::pair<const char *, size_t>> tok;
+        const bool drop_secondary = (o.xflags & 0x100u) != 0;
+        auto to_int = [](const char *p, size_t n) { char b[32]; if (n > 31) n = 31; memcpy(b, p, n); b[n] = 0; return atoi(b); };
+        auto add_op = [](Batch &b, uint32_t op, int64_t len) {
+            while (len > 0) { const int64_t n = std::min<int64_t>(len, (1 << 28) - 1); b.cigar.push_back(((uint32_t)n << 4) | op); len -= n; }
+        };
+        while (!failed && in.next(line)) {
+            if (line.empty()) continue;
+            if (drop_secondary && line.find("tp:A:S") != std::string::npos) continue;
+            tok.clear();
+            const char *s = line.data(), *e = s + line.size();
+            while (s < e) {                                                    // split(line, inf, " \t")  (include/comm.h:98-109)
+                while (s < e && (*s == ' ' || *s == '\t')) s++;
+                const char *t = s;
+                while (s < e && *s != ' ' && *s != '\t') s++;
+                if (s > t) tok.emplace_back(t, (size_t)(s - t));
+            }
+            if (tok.size() < 12) continue;                                     // (the reference indexes inf[11] unchecked)
+            int tid = 0;
+            { auto it = chr2int.find(std::string(tok[5].first, tok[5].second)); if (it != chr2int.end()) tid = it->second; }
+            if (to_int(tok[11].first, tok[11].second) < o.min_mapq) continue;
+            int32_t a = to_int(tok[7].first, tok[7].second), z = to_int(tok[8].first, tok[8].second);
+            if (a > z) std::swap(a, z);
+            if ((size_t)tid >= n_targets) continue;
+            Batch &b = batches[(size_t)tid];
+            int cg = -1;
+            for (size_t k = 0; k < tok.size(); k++) if (tok[k].second >= 5 && memcmp(tok[k].first, "cg:Z:", 5) == 0) { cg = (int)k; break; }
+            const size_t c0 = b.cigar.size();
+            if (cg > 1) {                                                      // :1582-1613
+                if (a < 0) continue;
+                const char *q = tok[(size_t)cg].first + 5, *qe = tok[(size_t)cg].first + tok[(size_t)cg].second;
+                while (q < qe) {
+                    int64_t n = 0;
+                    while (q < qe && *q >= '0' && *q <= '9') { n = n * 10 + (*q - '0'); if (n > INT32_MAX) n = INT32_MAX; q++; }
+                    const char op = q < qe ? *q : 0;
+                    q++;
+                    switch (op) {
+                    case 'M': add_op(b, 0, n); break;
+                    case '=': add_op(b, 7, n); break;
+                    case 'X': add_op(b, 8, n); break;
+                    case 'D': add_op(b, 2, n); break;
+                    case 'N': add_op(b, 3, n); break;
+                    default: break;                                            // I S H P ...: no depth, no advance
+                    }
+                }
+                b.pos.push_back(a);
+            } else {                                                           // :1614-1620  for (i = StartRead-1; i < EndRead; ++i)
+                const int32_t s0 = a > 0 ? a - 1 : 0;                          // (the reference's write at index -1 is dropped)
+                if (z > s0) add_op(b, 0, (int64_t)z - s0);
+                b.pos.push_back(s0);
+            }
+            b.off.push_back((uint32_t)b.cigar.size());
+            b.n++;
+            if (b.cigar.size() - c0 != 1) b.single_op = false;
+            if (b.n >= (1u << 20) || b.cigar.size() >= (1u << 20)) { if (!push(tid, b, false)) break; }
+        }
+        for (size_t t = 0; t < n_targets && !failed; t++) push((int)t, batches[t], false);
+        return !failed;
+    }
 };
 
 bool file_exists(const std::string &p) { return access(p.c_str(), 0) == 0; }
@@ -442,26 +513,57 @@ int main(int argc, char **argv)
         std::string a = o.input.substr(0, o.input.rfind('.'));
         ext = a.substr(a.rfind('.') == std::string::npos ? a.size() : a.rfind('.') + 1);
     }
-    if (ext == "paf" || ext == "PAF") { std::cerr << "Error: PAF input is not supported by pandepth-b200 yet" << std::endl; return 1; }
+    const bool multi = o.inputs.size() > 1;                  // FileNum > 1 -> List_main / BamList_main (:3452-3458)
+    if (multi) std::cout << "INFO: Run multi-file data " << std::endl;
+    const bool is_paf = ext == "paf" || ext == "PAF";        // :3428 / :3474 (a trailing .gz is looked through)
+    if (is_paf) std::cout << (multi ? "INFO: Run PAF format data " : "INFO: Run paf Format data ") << std::endl;
 
-    // header (:3482-3507)
-    htsFile *in = hts_open(o.input.c_str(), "r");
-    hts_set_log_level(HTS_LOG_OFF);
-    if (!in) { std::cerr << "Error: Failed to open the BAM/CRAM file: " << o.input << std::endl; return 1; }
-    if (in->format.format == cram) hts_set_fai_filename(in, o.reference.c_str());
-    const bool is_bam = in->format.format == bam;
-    sam_hdr_t *hdr = sam_hdr_read(in);
-    if (!hdr) { std::cerr << "Error: Failed to read the header for the BAM/CRAM file: " << o.input << std::endl; return 1; }
-    std::vector<Target> targets((size_t)hdr->n_targets);
-    for (int i = 0; i < hdr->n_targets; i++) { targets[i].name = hdr->target_name[i]; targets[i].len = hdr->target_len[i]; }
-    bool sorted_hdr = false;
-    {
+    std::vector<Target> targets;
+    std::map<std::string, int> paf_chr2int;                  // Chr2IntMap of paf_main (:867)
+    sam_hdr_t *hdr = nullptr;
+    bool is_bam = false, sorted_hdr = false;
+    if (is_paf) {
+        // targets: column 6/7 of the first PAF in first-seen order (:918-941).  With -r the reference takes them from the
+        // FASTA and switches to its GC report (RefIn, :878-909 / :1488) -- GC content is outside the depth path.
+        if (!o.reference.empty()) { std::cerr << "Error: -r with PAF input selects the GC report, which pandepth-b200 does not provide" << std::endl; return 1; }
+        {
+            LineReader in0(o.input);
+            if (!in0.ok()) { std::cerr << "open PAF file error: " << o.input << std::endl; return 1; }
+            std::string line;
+            while (in0.next(line)) {
+                if (line.empty()) continue;
+                size_t k = 0, p = 0; std::string chr, len;
+                while (k < 7) {                                                  // isone>>tmp1..tmp5>>chr>>chrlength
+                    p = line.find_first_not_of(" \t\r\n\v\f", p);
+                    if (p == std::string::npos) break;
+                    const size_t q = line.find_first_of(" \t\r\n\v\f", p);
+                    if (k == 5) chr = line.substr(p, q == std::string::npos ? std::string::npos : q - p);
+                    if (k == 6) len = line.substr(p, q == std::string::npos ? std::string::npos : q - p);
+                    k++;
+                    if (q == std::string::npos) break;
+                    p = q;
+                }
+                if (k < 7) continue;
+                if (!paf_chr2int.count(chr)) { paf_chr2int[chr] = (int)targets.size(); targets.push_back(Target{chr, (uint32_t)atoi(len.c_str())}); }
+            }
+        }
+    } else {
+        // header (:3482-3507)
+        htsFile *in = hts_open(o.input.c_str(), "r");
+        hts_set_log_level(HTS_LOG_OFF);
+        if (!in) { std::cerr << "Error: Failed to open the BAM/CRAM file: " << o.input << std::endl; return 1; }
+        if (in->format.format == cram) hts_set_fai_filename(in, o.reference.c_str());
+        is_bam = in->format.format == bam;
+        hdr = sam_hdr_read(in);
+        if (!hdr) { std::cerr << "Error: Failed to read the header for the BAM/CRAM file: " << o.input << std::endl; return 1; }
+        targets.resize((size_t)hdr->n_targets);
+        for (int i = 0; i < hdr->n_targets; i++) { targets[i].name = hdr->target_name[i]; targets[i].len = hdr->target_len[i]; }
         const char *txt = sam_hdr_str(hdr);
         std::string text = txt ? txt : "";
         size_t a = text.find("\tSO:");                                       // :4537-4549
         if (a != std::string::npos) { a += 4; size_t b = text.find_first_of("\n\t", a); sorted_hdr = text.substr(a, b - a) == "coordinate"; }
+        hts_close(in);
     }
-    hts_close(in);
 
     GeneMap genes;
     std::string err;
@@ -478,9 +580,7 @@ int main(int argc, char **argv)
     const bool dry = getenv("PANDEPTH_DRY") != nullptr;      // decode only: no GPU is touched (diagnostics)
     // -d and the depth width are known before the first read: let the engine keep per-segment partials for pd_reduce
     const bool idx_early = (file_exists(o.input + ".bai") || file_exists(o.input + ".crai") || file_exists(o.input + ".csi")) && o.use_index;
-    const bool multi = o.inputs.size() > 1;                  // FileNum > 1 -> List_main / BamList_main (:3452-3458)
-    if (multi) std::cout << "INFO: Run multi-file data " << std::endl;
-    const uint32_t hint_mask = (multi || !idx_early || o.site_output || mode == 6) ? 0x3FFFFu : 0xFFFFFFFFu;
+    const uint32_t hint_mask = (is_paf || multi || !idx_early || o.site_output || mode == 6) ? 0x3FFFFu : 0xFFFFFFFFu;
     const bool hint_reduce = mode != 6;
     std::shared_future<pd_engine *> eng_future = std::async(std::launch::async, [&]() -> pd_engine * {
         if (dry) return nullptr;
@@ -499,7 +599,7 @@ int main(int argc, char **argv)
     const bool indexed = have_index && o.use_index;
     // the reference's 18-bit SiteInfo paths: no index, -a, mode 6 (:4127, :4553) or several input files (BamList_main :2687);
     // everything else is the uint32 window path
-    const bool whole = multi || !indexed || o.site_output || mode == 6;
+    const bool whole = is_paf || multi || !indexed || o.site_output || mode == 6;
     const uint32_t mask = whole ? 0x3FFFFu : 0xFFFFFFFFu;
 
     // merged regions per contig (RegionMerger, :3912-3972)
@@ -514,6 +614,7 @@ int main(int argc, char **argv)
     for (size_t fi = 0; fi < o.inputs.size() && !feeder.failed; fi++) {
         const std::string &path = o.inputs[fi];
         feeder.input = path;
+        if (is_paf) { feeder.paf_stream(paf_chr2int, targets.size()); continue; }
         bool f_bam = is_bam, f_sorted = sorted_hdr;
         if (fi > 0) {                                        // later files: own format / sort order, the first file's targets (:2701-2862)
             htsFile *fp = hts_open(path.c_str(), "r");
@@ -733,7 +834,7 @@ int main(int argc, char **argv)
     fflush(stdout); fflush(stderr);
     if (!getenv("PANDEPTH_ORDERLY_EXIT")) _exit(0);
     pd_destroy(eng);
-    sam_hdr_destroy(hdr);
+    if (hdr) sam_hdr_destroy(hdr);
     tm.mark("pd_destroy");
     return 0;
 }

@@ -2,7 +2,10 @@
 // reference), the region model, the htslib feeder and the report writer.  New code; behaviour follows
 // /root/reference/src/PanDepth.cpp (cited per function as :line).
 #pragma once
+#include <zlib.h>
+
 #include <cstdint>
+#include <cstring>
 #include <map>
 #include <string>
 #include <utility>
@@ -46,6 +49,28 @@ struct Gene {
 using GeneMap = std::map<int, std::map<std::string, Gene>>;     // tid -> GeneID -> Gene   (:3543)
 
 struct Target { std::string name; uint32_t len; };
+
+// plain or gzip text, line by line (the reference reads these through igzstream)
+struct LineReader {
+    gzFile fp = nullptr;
+    std::string buf;
+    explicit LineReader(const std::string &path) { fp = gzopen(path.c_str(), "rb"); }
+    ~LineReader() { if (fp) gzclose(fp); }
+    bool ok() const { return fp != nullptr; }
+    bool next(std::string &line)
+    {
+        line.clear();
+        char tmp[1 << 16];
+        bool got = false;
+        while (gzgets(fp, tmp, sizeof tmp)) {
+            got = true;
+            size_t n = strlen(tmp);
+            if (n && tmp[n - 1] == '\n') { line.append(tmp, n - 1); return true; }
+            line.append(tmp, n);
+        }
+        return got;
+    }
+};
 
 // :3547-3905 (GFF/GTF/BED parsers), :3975-4051 (pseudo-gene tiling).  Sets o.region_mode.
 bool build_regions(Options &o, const std::vector<Target> &targets, GeneMap &genes, std::string &err);

@@ -17,28 +17,6 @@ namespace pdh {
 // ---------------------------------------------------------------------------------------------------------------
 namespace {
 
-// plain or gzip text, line by line (the reference reads these through igzstream)
-struct LineReader {
-    gzFile fp = nullptr;
-    std::string buf;
-    explicit LineReader(const std::string &path) { fp = gzopen(path.c_str(), "rb"); }
-    ~LineReader() { if (fp) gzclose(fp); }
-    bool ok() const { return fp != nullptr; }
-    bool next(std::string &line)
-    {
-        line.clear();
-        char tmp[1 << 16];
-        bool got = false;
-        while (gzgets(fp, tmp, sizeof tmp)) {
-            got = true;
-            size_t n = strlen(tmp);
-            if (n && tmp[n - 1] == '\n') { line.append(tmp, n - 1); return true; }
-            line.append(tmp, n);
-        }
-        return got;
-    }
-};
-
 // include/comm.h:98-109 split(): tokens between any delimiter character, empties dropped
 std::vector<std::string> split_any(const std::string &s, const char *delims)
 {

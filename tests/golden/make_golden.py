@@ -55,6 +55,60 @@ K_GTF = (
     'k3\tsrc\tCDS\t80\t170\t.\t-\t0\tgene_id "g2"; transcript_id "t3";\n'
 )
 
+# PAF fixtures (paf_main, PanDepth.cpp:852-2024): cg:Z: walks, tag-less lines ([start-1, end)), tp:A:S lines, swapped
+# start/end, space-separated tags, a 1-bp target (vanishes from the report), an op the walk ignores (S, I)
+K_PAF = (
+    "r1\t500\t0\t100\t+\tp1\t400\t10\t110\t100\t100\t60\ttp:A:P\tcg:Z:100M\n"
+    "r2\t500\t0\t80\t-\tp1\t400\t50\t150\t70\t90\t30\ttp:A:P\tcg:Z:20M5I10M10D30=5X20N5M\n"
+    "r3\t500\t0\t50\t+\tp1\t400\t300\t350\t50\t50\t60\ttp:A:S\tcg:Z:50M\n"
+    "r4\t300\t0\t100\t+\tp2\t300\t21\t120\t99\t99\t5\ttp:A:P\n"
+    "r5\t300\t0\t50\t-\tp2\t300\t200\t150\t50\t50\t40\ttp:A:P\n"
+    "r6\t100\t0\t60\t+\tp4\t250\t99\t161\t60\t62\t0\ttp:A:P\tcg:Z:30M2D30M\n"
+    "r7\t100\t0\t10\t+\tp4\t250\t5\t15\t10\t10\t60 tp:A:P cg:Z:5S10M\n"
+    "r8\t10\t0\t1\t+\tp3\t1\t0\t1\t1\t1\t60\ttp:A:P\tcg:Z:1M\n"
+    "\n"
+    "r9\t500\t0\t100\t+\tp1\t400\t10\t110\t100\t100\t12\ttp:A:P\tcg:Z:100M\n"
+)
+K2_PAF = (
+    "s1\t500\t0\t100\t+\tp2\t300\t100\t220\t100\t120\t60\ttp:A:P\tcg:Z:60M20D40M\n"
+    "s2\t500\t0\t45\t+\tzz\t100\t5\t50\t45\t45\t60\ttp:A:P\tcg:Z:45M\n"
+    "s3\t500\t0\t100\t+\tp1\t400\t301\t400\t99\t99\t60\ttp:A:P\n"
+)
+K_PAF_BED = "p1\t1\t60\tx\np1\t40\t400\ty\np2\t90\t170\tx\np4\t100\t120\tz\n"
+
+
+
+def rand_paf(seed=5, n=600):
+    """Seeded PAF soup; every walk stays within len+400 (the reference's arrays carry +500 of slack, :1520)."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    names = [("t%d" % i, int(rng.integers(3000, 40000))) for i in range(5)] + [("tiny", 1)]
+    lines = []
+    for i in range(n):
+        nm, ln = names[int(rng.integers(0, len(names) - 1))] if i % 97 else names[-1]
+        s = int(rng.integers(1, ln)) if ln > 1 else 0
+        e = int(rng.integers(s, ln + 1))
+        tags = ["tp:A:" + "PSI"[int(rng.integers(0, 3))]]
+        if rng.random() < 0.7 or ln == 1:          # (a tag-less line at start 0 makes the reference write depth[-1])
+            budget, ops = ln + 400 - s, ""
+            for _ in range(int(rng.integers(1, 9))):
+                k = int(rng.integers(1, 400)); op = "M=XDNISH"[int(rng.integers(0, 8))]
+                if op in "M=XDN":
+                    if k > budget:
+                        continue
+                    budget -= k
+                ops += "%d%s" % (k, op)
+            tags.append("cg:Z:" + (ops or "1I"))
+        if rng.random() < 0.3:
+            tags.insert(0, "NM:i:3")
+        if rng.random() < 0.1:
+            s, e = e, s
+        sep = " " if rng.random() < 0.1 else "\t"
+        lines.append("\t".join(["q%d" % i, "1000", "0", "500", "+-"[i & 1], nm, str(ln), str(s), str(e), "10", "20",
+                                str(int(rng.integers(0, 61)))]) + sep + sep.join(tags))
+    return "\n".join(lines) + "\n"
+
+
 MIX_CONTIGS = "cA:100001,cB:1001,cC:1,cD:2,cE:300"
 BIG_CONTIGS = "cF:10000001,cG:150"
 MIX_BED = "cA\t1\t5000\ncA\t4000\t9000\ncA\t50000\t50100\ncA\t99000\t100001\ncB\t1001\t1001\ncB\t5\t900\ncE\t10\t290\ncD\t1\t2\n"
@@ -86,6 +140,7 @@ def main():
         sys.exit("build oracle/_ref first: make -C oracle")
     w = lambda name, text: open(os.path.join(HERE, name), "w").write(text)
     w("k.sam", K_SAM); w("k.bed3", K_BED3); w("k.bed4", K_BED4); w("k.bededge", K_BEDEDGE)
+    w("k.paf", K_PAF); w("k2.paf", K2_PAF); w("k.pafbed", K_PAF_BED); w("rand.paf", rand_paf())
     w("k.gff", K_GFF); w("k.gtf", K_GTF); w("mix.bed", MIX_BED); w("big.bed", BIG_BED)
     subprocess.run([BAMGEN, "-o", os.path.join(HERE, "mix.sam"), "-c", MIX_CONTIGS, "-n", "3000", "-m", "mixed",
                     "-s", "20260925", "-S"], check=True)
@@ -136,6 +191,20 @@ def main():
     add("list3k.w7", "list:k.sam,k.sam,k.sam", ["-w", "7"])
     add("list3k.w150", "list:k.sam,k.sam,k.sam", ["-w", "150"])
     add("list2stack.default", "list:@stack,@stack", [])          # 2 x 262149 reads: the 18-bit sum wraps across files
+    # PAF input (paf_main :852-2024): text lines, 18-bit arrays; .paf.gz is looked through (:3469-3473)
+    add("paf.default", "k.paf", [], kinds=("paf", "pafgz"))
+    add("paf.w100", "k.paf", ["-w", "100"], kinds=("paf",))
+    add("paf.w150", "k.paf", ["-w", "150"], kinds=("paf",))
+    add("paf.q10d2", "k.paf", ["-q", "10", "-d", "2"], kinds=("paf",))
+    add("paf.x0", "k.paf", ["-x", "0"], kinds=("paf",))
+    add("paf.bed4", "k.paf", ["-b", "@k.pafbed"], kinds=("paf",))
+    add("paf.a", "k.paf", ["-a"], kinds=("paf",))
+    add("pafrand.default", "rand.paf", [], kinds=("paf",))
+    add("pafrand.w100d2", "rand.paf", ["-w", "100", "-d", "2"], kinds=("paf",))
+    add("pafrand.x0q20", "rand.paf", ["-x", "0", "-q", "20"], kinds=("paf",))
+    add("pafrand.w1000", "rand.paf", ["-w", "1000", "-x", "0"], kinds=("paf",))
+    add("paflist.default", "list:k.paf,k2.paf", [], kinds=("paf",))
+    add("paflist.w7", "list:k.paf,k2.paf", ["-w", "7", "-x", "0"], kinds=("paf",))
     # 18-bit wrap vector (SURVEY App. C `w.sam`): 262149 stacked 10M reads at pos 100 of a 1 kb contig
     add("stack.default", "@stack", [])
     add("stack.w100", "@stack", ["-w", "100"])
@@ -170,7 +239,11 @@ def main():
                 print(c["name"], {k: (len(v) if isinstance(v, str) else v["n_bytes"]) for k, v in res.items()})
                 continue
             sam = stack if c["fixture"] == "@stack" else g(c["fixture"])
-            if c["kind"] == "bam":
+            if c["kind"] == "pafgz":
+                inp = os.path.join(tmp, os.path.basename(sam) + ".gz")
+                with open(sam, "rb") as fi, gzip.open(inp, "wb") as fo:
+                    fo.write(fi.read())
+            elif c["kind"] == "bam":
                 if sam not in bams:
                     b = os.path.join(tmp, os.path.basename(sam) + ".bam")
                     subprocess.run([BAMGEN, "-I", sam, "-o", b], check=True)

@@ -12,8 +12,22 @@ GOLD = os.path.join(ROOT, "tests", "golden")
 STACK_TARGETS = [("c", 1000)]
 
 
-def load_fixture(name):
-    """-> (targets, Records, sorted) for a golden fixture name ('k.sam', '@stack', ...)."""
+def _paf_filters(args):
+    """(-x, -q) of a golden case: paf_main applies both while parsing the text (PanDepth.cpp:1552-1568)."""
+    x, q = 1796, -1
+    for i, a in enumerate(args or []):
+        if a == "-x":
+            x = int(args[i + 1])
+        elif a == "-q":
+            q = int(args[i + 1])
+    return x, q
+
+
+def load_fixture(name, args=None):
+    """-> (targets, Records, sorted) for a golden fixture name ('k.sam', '@stack', 'k.paf', 'list:...')."""
+    members = name[5:].split(",") if name.startswith("list:") else [name]
+    if members[0].endswith(".paf"):
+        return model.parse_paf([os.path.join(GOLD, m) for m in members], *_paf_filters(args))
     if name.startswith("list:"):
         parts = [load_fixture(x) for x in name[5:].split(",")]
         targets = parts[0][0]
@@ -38,7 +52,7 @@ def load_fixture(name):
 def options_from_args(args, kind, fixture=""):
     """Translate a golden case's CLI args into model.Options (what bamCov_help01 would set, PanDepth.cpp:84-293)."""
     o = model.Options()
-    o.indexed = (kind == "bam") and not fixture.startswith("list:")     # multi-file mode is always the 18-bit path (:2687)
+    o.indexed = (kind == "bam") and not fixture.startswith("list:")     # multi-file mode (:2687) and PAF (:1520) are 18-bit paths
     it = iter(args)
     for a in it:
         if a == "-w":

@@ -78,7 +78,7 @@ def test_depth_matches_oracle_on_fixtures(fixture, path):
 def test_printed_output_matches_reference(case):
     """Engine depth + engine reduce -> the exact text the reference binary printed for this case."""
     c = _CASES[case]
-    targets, rec, _ = load_fixture(c["fixture"])
+    targets, rec, _ = load_fixture(c["fixture"], c["args"])
     opts = options_from_args(c["args"], c["kind"], c["fixture"])
     tlen = np.array([t[1] for t in targets], np.uint32)
     r = rec.select(_sorted_order(rec))

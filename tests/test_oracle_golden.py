@@ -19,7 +19,7 @@ with open(os.path.join(GOLD, "expected.json")) as _fh:
 @pytest.mark.parametrize("case", sorted(_CASES))
 def test_model_matches_reference(case):
     c = _CASES[case]
-    targets, rec, _ = load_fixture(c["fixture"])
+    targets, rec, _ = load_fixture(c["fixture"], c["args"])
     opts = options_from_args(c["args"], c["kind"], c["fixture"])
     res = model.run_model(targets, rec, opts)
     outs = c["outputs"]
