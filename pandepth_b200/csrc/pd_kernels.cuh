@@ -28,7 +28,8 @@ namespace pdk {
 constexpr int SEG = PD_SEG;   // bases owned by one warp of k_tile_accumulate (8 KB of depth at 2048)
 constexpr int HALO = 256;   // look-back window in bases; also the largest "common span" L the fast path models
 constexpr int WPC = 8;      // warps per CTA in k_tile_accumulate
-constexpr int TILE_SMEM_WORDS = SEG;   // per warp: E[SEG], +-count per base of the segment (4 KB)
+constexpr int ETAB = SEG + HALO;       // per warp: E[HALO + rel], +-count per base of the look-back window and the segment
+constexpr int TILE_SMEM_WORDS = ETAB + 32;   // + one sink word per lane for "nothing to apply" (9.1 KB per warp at SEG 2048)
 constexpr int TILE_MIN_CTAS = PD_TILE_MIN_CTAS;   // resident CTAs per SM k_tile_accumulate is compiled for (register cap)
 constexpr unsigned FULL = 0xffffffffu;
 
@@ -49,12 +50,20 @@ __device__ __forceinline__ void red_add_u32(uint32_t *addr, uint32_t v)
 // itself produces (2 instructions instead of shuffle + compare + select + add)
 __device__ __forceinline__ uint32_t scan_step_up(uint32_t t, int o)
 {
-    uint32_t r;
     asm volatile("{ .reg .u32 y; .reg .pred p;\n\t"
-                 "shfl.sync.up.b32 y|p, %1, %2, 0, 0xffffffff;\n\t"
-                 "@p add.u32 y, y, %1;\n\t"
-                 "@!p mov.u32 y, %1;\n\t"
-                 "mov.u32 %0, y; }" : "=r"(r) : "r"(t), "r"(o));
+                 "shfl.sync.up.b32 y|p, %0, %1, 0, 0xffffffff;\n\t"
+                 "@p add.u32 %0, %0, y; }" : "+r"(t) : "r"(o));
+    return t;
+}
+
+// (x != 0) + (y != 0) + (z != 0) + (w != 0) as four min.u32 and three-input adds (the compiler's own form is a serial
+// compare / add / conditional-move chain, three instructions per element)
+__device__ __forceinline__ uint32_t nonzero4(const uint4 v)
+{
+    uint32_t r;
+    asm("{ .reg .u32 a, b, c, d;\n\t"
+        "min.u32 a, %1, 1; min.u32 b, %2, 1; min.u32 c, %3, 1; min.u32 d, %4, 1;\n\t"
+        "add.u32 a, a, b; add.u32 c, c, d; add.u32 %0, a, c; }" : "=r"(r) : "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
     return r;
 }
 
@@ -189,7 +198,10 @@ __global__ void __launch_bounds__(WPC * 32, TILE_MIN_CTAS) k_tile_accumulate(Til
         return;
     }
 
-    uint32_t *E = smem + warp * TILE_SMEM_WORDS;     // (runs starting at b) - (runs ending at b) for b in [s0, s0+SEG)
+    // E[HALO + x] = (runs starting at s0+x) - (runs ending at s0+x) for x in [-HALO, SEG): the first HALO entries collect
+    // what lands left of the segment (their sum is the depth carried into it), the rest is the segment itself
+    uint32_t *E = smem + warp * TILE_SMEM_WORDS;
+    const uint32_t E_saddr = (uint32_t)__cvta_generic_to_shared(E);
     const int64_t clen = a.contig_len;
     {
         const uint4 z = make_uint4(0, 0, 0, 0);
@@ -199,15 +211,17 @@ __global__ void __launch_bounds__(WPC * 32, TILE_MIN_CTAS) k_tile_accumulate(Til
     }
     __syncwarp();
 
-    uint32_t carry_reg = 0;        // per-lane part of "depth just left of the segment": every +-1 that lands before s0
     int32_t carry_p = INT32_MIN;   // last position of the previous chunk (sortedness check)
-    // all coordinates below are relative to s0 (32-bit): a read seen by this warp has rel in [-HALO, SEG)
-    const int32_t s0i = (int32_t)s0;
-    const int32_t clen_rel = (int32_t)(clen - s0);
-    // delta v applies to every base >= x (x relative to s0)
+    uint32_t idx_max = 0;          // largest table index seen: anything >= ETAB means a read outside the window (inconsistent cut)
+    // all coordinates below are table indices (32-bit): idx = pos - (s0 - HALO); a read seen by this warp has idx in [0, ETAB)
+    const int32_t tab0 = (int32_t)hbase;                                  // position of table entry 0 (>= -HALO)
+    const int64_t clen_tab64 = clen - hbase;                              // contig end as a table index
+    const uint32_t clen_tab = (uint32_t)(clen_tab64 > 0x7fffffff ? 0x7fffffff : clen_tab64);
+    const uint32_t sink = (uint32_t)(ETAB + lane);
+    const int32_t pad_pos = (int32_t)(send - 1);                          // filler for lanes past the last read: in window, sorts last
+    // delta v applies to every base >= x (x = table index; anything at or beyond ETAB belongs to a later segment)
     auto emit = [&](int64_t x, uint32_t v) {
-        if (x < 0) carry_reg += v;
-        else if (x < SEG) atomicAdd(&E[(int)x], v);
+        if (x >= 0 && x < ETAB) atomicAdd(&E[(int)x], v);
     };
     for (uint32_t base = i_lo; base < i_hi; base += 32 * U) {
         // issue every load of TILE_UNROLL chunks before consuming any of them
@@ -219,8 +233,8 @@ __global__ void __launch_bounds__(WPC * 32, TILE_MIN_CTAS) k_tile_accumulate(Til
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const bool valid = (uint32_t)(u * 32 + lane) < left;
-            pv[u] = valid ? ldg_i32(ppos + u * 32) : INT32_MAX;
-            ov[u] = 0; nv[u] = 1; cv[u] = 0;
+            pv[u] = valid ? ldg_i32(ppos + u * 32) : pad_pos;
+            ov[u] = 0; nv[u] = 1; cv[u] = 0;                  // a filler lane carries a zero-length op: never applied
             if (HAS_OFF) {
                 ov[u] = valid ? ldg_u32(pcig + u * 32) : 0u;
                 nv[u] = valid ? ldg_u32(pcig + u * 32 + 1) : 0u;
@@ -243,7 +257,7 @@ __global__ void __launch_bounds__(WPC * 32, TILE_MIN_CTAS) k_tile_accumulate(Til
             }
         }
         // sortedness of everything just loaded: one rotate-shuffle per chunk (lane l gets lane l-1; lane 0 gets lane 31,
-        // which it compares with the NEXT chunk's first read).  Invalid lanes hold INT32_MAX and sort last.
+        // which it compares with the NEXT chunk's first read).  Filler lanes hold the window's last position and sort last.
         {
             int32_t prev_last = carry_p;
 #pragma unroll
@@ -257,47 +271,46 @@ __global__ void __launch_bounds__(WPC * 32, TILE_MIN_CTAS) k_tile_accumulate(Til
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             if ((uint32_t)(u * 32) >= left) break;            // warp-uniform
-            const bool valid = (uint32_t)(u * 32 + lane) < left;
             const int32_t p = pv[u];
             const uint32_t c = cv[u];
             const uint32_t nops = HAS_OFF ? nv[u] : 1u;
-            bool pass = valid && p >= 0;
+            const uint32_t idx = (uint32_t)p - (uint32_t)tab0;   // < ETAB for a consistent cut
+            const bool in_win = idx < (uint32_t)ETAB;
+            idx_max = max(idx_max, idx);                       // checked once after the loop
+            bool pass = in_win && p >= 0;
             if (HAS_FILTER && ((failm >> u) & 1u)) pass = false;
-            const int32_t rel = p - s0i;                       // in [-HALO, SEG) for a consistent cut
-            const bool in_win = (uint32_t)(rel + HALO) < (uint32_t)(SEG + HALO);
-            bad |= pass && !in_win;
-            pass = pass && in_win;
-            // first base (relative) that no segment seeing this read owns: segments see reads up to HALO to their left
-            const int32_t far_rel = (rel + HALO >= SEG) ? 2 * SEG : SEG;
             if (!HAS_OFF || nops == 1) {
                 // one CIGAR op (the common case): M/=/X is one run [p, p+len)                      :745-752
-                // written branch-free: predicated atomics, arithmetic carry
-                const int32_t e = min(rel + (int32_t)(c >> 4), clen_rel);         // len < 2^28: no overflow
-                const bool ok = pass && ((0x181u >> (c & 15u)) & 1u) && e > rel;
-                const bool s_in = ok && rel >= 0;
-                const bool e_in = ok && e >= 0 && e < SEG;
-                carry_reg += (uint32_t)(ok && rel < 0) - (uint32_t)(ok && e < 0);
-                if (s_in) atomicAdd(&E[rel], 1u);
-                if (e_in) atomicAdd(&E[e], 0xffffffffu);
-                if (s_in && e > far_rel) {                                          // rare: run longer than HALO
-                    red_add_u32(a.delta + s0 + far_rel, 1u);
-                    red_add_u32(a.delta + s0 + e, 0xffffffffu);
-                    *a.delta_used = 1;
+                // branch-free: both shared atomics are always issued; a lane with nothing to apply hits its own sink word
+                // (E[ETAB + lane]: 32 distinct banks), so there is no branch and no reconvergence barrier around them
+                const uint32_t e = min(idx + (c >> 4), clen_tab);                 // len < 2^28: no overflow
+                const bool ok = pass && ((0x181u >> (c & 15u)) & 1u) && e > idx;
+                atomicAdd(&E[ok ? idx : sink], 1u);
+                atomicAdd(&E[(ok && e < (uint32_t)ETAB) ? e : sink], 0xffffffffu);
+                if (ok && e > (uint32_t)ETAB) {                                           // the run leaves the segment (7% of 150M reads)
+                    // first base (table index) that no segment seeing this read owns: segments see reads up to HALO to their left
+                    const uint32_t far_tab = (idx >= (uint32_t)SEG) ? 2 * SEG + HALO : SEG + HALO;
+                    if (idx >= (uint32_t)HALO && e > far_tab) {                     // rare: run longer than HALO, applied by its owner
+                        red_add_u32(a.delta + hbase + far_tab, 1u);
+                        red_add_u32(a.delta + hbase + e, 0xffffffffu);
+                        *a.delta_used = 1;
+                    }
                 }
             } else if (pass) {
                 const uint32_t c0 = ov[u];
-                const bool owner = rel >= 0;
-                int64_t q = rel, rs = INT64_MIN, re = INT64_MIN;
+                const bool owner = idx >= (uint32_t)HALO;
+                const int64_t far_tab = (idx >= (uint32_t)SEG) ? 2 * SEG + HALO : SEG + HALO;
+                int64_t q = idx, rs = INT64_MIN, re = INT64_MIN;
                 auto flush = [&]() {
                     if (rs == INT64_MIN) return;
-                    const int64_t s = rs, e = re > (int64_t)clen_rel ? (int64_t)clen_rel : re;
+                    const int64_t s = rs, e = re > clen_tab64 ? clen_tab64 : re;
                     if (s >= e) return;
                     emit(s, 1u);
                     emit(e, 0xffffffffu);
-                    if (owner && e > far_rel) {
-                        const int64_t gs = s > far_rel ? s : far_rel;
-                        red_add_u32(a.delta + s0 + gs, 1u);
-                        red_add_u32(a.delta + s0 + e, 0xffffffffu);
+                    if (owner && e > far_tab) {
+                        const int64_t gs = s > far_tab ? s : far_tab;
+                        red_add_u32(a.delta + hbase + gs, 1u);
+                        red_add_u32(a.delta + hbase + e, 0xffffffffu);
                         *a.delta_used = 1;
                     }
                 };
@@ -316,8 +329,10 @@ __global__ void __launch_bounds__(WPC * 32, TILE_MIN_CTAS) k_tile_accumulate(Til
     }
     __syncwarp();
 
-    // depth just left of the segment
-    uint32_t carry = carry_reg;
+    // depth just left of the segment = everything that landed in the look-back part of the table
+    uint32_t carry = 0;
+#pragma unroll
+    for (int k = lane; k < HALO / 4; k += 32) { const uint4 h = reinterpret_cast<const uint4 *>(E)[k]; carry += h.x + h.y + h.z + h.w; }
 #pragma unroll
     for (int o = 16; o; o >>= 1) carry += __shfl_xor_sync(FULL, carry, o);
 
@@ -325,7 +340,7 @@ __global__ void __launch_bounds__(WPC * 32, TILE_MIN_CTAS) k_tile_accumulate(Til
     const bool fresh = (*st_ptr == 0);
     uint32_t *out = a.depth + s0;
     auto scan_row = [&](int b) -> uint4 {
-        const uint4 d = *reinterpret_cast<const uint4 *>(E + b);
+        const uint4 d = *reinterpret_cast<const uint4 *>(E + HALO + b);
         const uint32_t x0 = d.x, x1 = d.y + x0, x2 = d.z + x1, x3 = d.w + x2;
         uint32_t t = x3;
 #pragma unroll
@@ -346,7 +361,7 @@ __global__ void __launch_bounds__(WPC * 32, TILE_MIN_CTAS) k_tile_accumulate(Til
                 const int b = r * 128 + lane * 4;
                 const uint4 v = scan_row(b);
                 __stcs(reinterpret_cast<uint4 *>(out + b), v);
-                pc += (v.x != 0u) + (v.y != 0u) + (v.z != 0u) + (v.w != 0u);
+                pc += nonzero4(v);
                 ps += (unsigned long long)v.x + v.y + v.z + v.w;
             }
         } else {
@@ -384,7 +399,7 @@ __global__ void __launch_bounds__(WPC * 32, TILE_MIN_CTAS) k_tile_accumulate(Til
         }
         if (lane == 0) *st_ptr = 2;
     }
-    bad = __any_sync(FULL, bad);
+    bad = __any_sync(FULL, bad || idx_max >= (uint32_t)ETAB);
     if (lane == 0 && (bad || (int64_t)chk_l >= hbase || (int64_t)chk_r < send || chk_n > i_hi)) atomicOr(a.err, ERR_UNSORTED);
 }
 
@@ -663,34 +678,42 @@ __global__ void __launch_bounds__(256) k_reduce_windows(WindowArgs a)
         // mode-6 sized windows (-w < 150): a warp takes 4 consecutive windows per iteration and issues all of their loads
         // (<= 5 per lane per window) before reducing any, then one redux.sync each for CoveredSite and TotalDepth
         // (TotalDepth of such a window fits 32 bits: win * 18-bit depth)
+        // All per-window math is 32-bit and relative to the group's first base; only the group base pointer is 64-bit.
         constexpr int WB = 4, NL = 5;
         const int64_t ngroups = (a.n_win + WB - 1) / WB;
+        const uint32_t win = (uint32_t)a.win, md = a.min_dep, mk = a.mask;
         for (int64_t g = warp; g < ngroups; g += nwarps) {
+            const int64_t k0 = g * WB;
+            const int64_t lo0 = a.start0 + k0 * a.win;
+            const uint32_t *__restrict__ d0 = a.depth + lo0 + lane;
+            const int64_t rem64 = a.len - lo0;                                   // bases left in the contig from this group on
+            const uint32_t rem = rem64 <= 0 ? 0u : (rem64 > (int64_t)(WB * 160) ? (uint32_t)(WB * 160) : (uint32_t)rem64);
+            const uint32_t nw = (uint32_t)(a.n_win - k0 < WB ? a.n_win - k0 : WB);   // windows in this group
             uint32_t x[WB][NL];
 #pragma unroll
             for (int j = 0; j < WB; ++j) {
-                const int64_t k = g * WB + j;
-                const int64_t lo = a.start0 + k * a.win;
-                int64_t hi = lo + a.win; if (hi > a.len) hi = a.len;
-                if (k >= a.n_win) hi = lo;
+                const uint32_t off = (uint32_t)j * win;                          // window j starts `off` bases into the group
+                uint32_t wl = rem > off ? rem - off : 0u;                        // its length: min(win, bases left), 0 past n_win
+                if (wl > win) wl = win;
+                if ((uint32_t)j >= nw) wl = 0;
 #pragma unroll
                 for (int i = 0; i < NL; ++i) {
-                    const int64_t q = lo + lane + 32 * i;
-                    x[j][i] = (q < hi) ? __ldcs(a.depth + q) : 0u;
+                    const uint32_t t = (uint32_t)lane + 32u * i;
+                    x[j][i] = (t < wl) ? __ldcs(d0 + off + 32u * i) : 0u;
                 }
             }
 #pragma unroll
             for (int j = 0; j < WB; ++j) {
-                const int64_t k = g * WB + j;
                 uint32_t cov = 0, sum = 0;
 #pragma unroll
                 for (int i = 0; i < NL; ++i) {
-                    const uint32_t v = x[j][i] & a.mask;          // lanes beyond the window loaded 0: never >= min_dep (>= 1)
-                    if (v >= a.min_dep) { cov++; sum += v; }
+                    const uint32_t v = x[j][i] & mk;              // lanes beyond the window loaded 0: never >= min_dep (>= 1)
+                    const bool c = v >= md;
+                    cov += c ? 1u : 0u; sum += c ? v : 0u;
                 }
                 cov = __reduce_add_sync(FULL, cov);
                 sum = __reduce_add_sync(FULL, sum);
-                if (lane == 0 && k < a.n_win) { a.cov[k] = cov; a.sum[k] = sum; }
+                if (lane == 0 && (uint32_t)j < nw) { a.cov[k0 + j] = cov; a.sum[k0 + j] = sum; }
             }
         }
     } else if (a.win >= 32 && a.win <= 512 && (unsigned long long)a.win * a.mask < (1ull << 32)) {
