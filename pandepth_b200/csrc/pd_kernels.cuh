@@ -201,7 +201,6 @@ __global__ void __launch_bounds__(WPC * 32, TILE_MIN_CTAS) k_tile_accumulate(Til
     // E[HALO + x] = (runs starting at s0+x) - (runs ending at s0+x) for x in [-HALO, SEG): the first HALO entries collect
     // what lands left of the segment (their sum is the depth carried into it), the rest is the segment itself
     uint32_t *E = smem + warp * TILE_SMEM_WORDS;
-    const uint32_t E_saddr = (uint32_t)__cvta_generic_to_shared(E);
     const int64_t clen = a.contig_len;
     {
         const uint4 z = make_uint4(0, 0, 0, 0);
