@@ -28,8 +28,16 @@ namespace pdk {
 constexpr int SEG = PD_SEG;   // bases owned by one warp of k_tile_accumulate (8 KB of depth at 2048)
 constexpr int HALO = 256;   // look-back window in bases; also the largest "common span" L the fast path models
 constexpr int WPC = 8;      // warps per CTA in k_tile_accumulate
-constexpr int ETAB = SEG + HALO;       // per warp: E[HALO + rel], +-count per base of the look-back window and the segment
-constexpr int TILE_SMEM_WORDS = ETAB + 32;   // + one sink word per lane for "nothing to apply" (9.1 KB per warp at SEG 2048)
+#ifndef PD_HALO_TAB
+#define PD_HALO_TAB 0      // 1: the look-back window has its own table entries; 0: what lands left of the segment goes to a register
+#endif
+#ifndef PD_SINK
+#define PD_SINK 0          // 1: shared atomics always issued (idle lanes hit a per-lane sink word); 0: predicated by a branch
+#endif
+constexpr int WIN = SEG + HALO;              // bases a warp sees reads from: [s0 - HALO, s0 + SEG); "window index" = pos - (s0 - HALO)
+constexpr int TOFF = PD_HALO_TAB ? 0 : HALO; // window index of table entry 0
+constexpr int TLEN = WIN - TOFF;             // table entries that hold deltas
+constexpr int TILE_SMEM_WORDS = TLEN + (PD_SINK ? 32 : 0);   // per warp (8 KB at SEG 2048 without the extras)
 constexpr int TILE_MIN_CTAS = PD_TILE_MIN_CTAS;   // resident CTAs per SM k_tile_accumulate is compiled for (register cap)
 constexpr unsigned FULL = 0xffffffffu;
 
@@ -198,8 +206,9 @@ __global__ void __launch_bounds__(WPC * 32, TILE_MIN_CTAS) k_tile_accumulate(Til
         return;
     }
 
-    // E[HALO + x] = (runs starting at s0+x) - (runs ending at s0+x) for x in [-HALO, SEG): the first HALO entries collect
-    // what lands left of the segment (their sum is the depth carried into it), the rest is the segment itself
+    // E[w - TOFF] = (runs starting at window index w) - (runs ending there); window index w = pos - (s0 - HALO) in [0, WIN).
+    // Deltas left of the table (w < TOFF: the look-back part, unless PD_HALO_TAB keeps it in the table) go to a per-lane
+    // register; their sum is the depth carried into the segment.
     uint32_t *E = smem + warp * TILE_SMEM_WORDS;
     const int64_t clen = a.contig_len;
     {
@@ -210,17 +219,20 @@ __global__ void __launch_bounds__(WPC * 32, TILE_MIN_CTAS) k_tile_accumulate(Til
     }
     __syncwarp();
 
+    uint32_t carry_reg = 0;        // per-lane part of "depth just left of the segment"
     int32_t carry_p = INT32_MIN;   // last position of the previous chunk (sortedness check)
-    uint32_t idx_max = 0;          // largest table index seen: anything >= ETAB means a read outside the window (inconsistent cut)
-    // all coordinates below are table indices (32-bit): idx = pos - (s0 - HALO); a read seen by this warp has idx in [0, ETAB)
-    const int32_t tab0 = (int32_t)hbase;                                  // position of table entry 0 (>= -HALO)
-    const int64_t clen_tab64 = clen - hbase;                              // contig end as a table index
-    const uint32_t clen_tab = (uint32_t)(clen_tab64 > 0x7fffffff ? 0x7fffffff : clen_tab64);
-    const uint32_t sink = (uint32_t)(ETAB + lane);
+    uint32_t idx_max = 0;          // largest window index seen: anything >= WIN means a read outside the window (inconsistent cut)
+    const int32_t win0 = (int32_t)hbase;                                  // position of window index 0 (>= -HALO)
+    const int64_t clen_w64 = clen - hbase;                                // contig end as a window index
+    const uint32_t clen_w = (uint32_t)(clen_w64 > 0x7fffffff ? 0x7fffffff : clen_w64);
+#if PD_SINK
+    const uint32_t sink = (uint32_t)(TLEN + lane);
+#endif
     const int32_t pad_pos = (int32_t)(send - 1);                          // filler for lanes past the last read: in window, sorts last
-    // delta v applies to every base >= x (x = table index; anything at or beyond ETAB belongs to a later segment)
+    // delta v applies to every base >= window index x (anything at or beyond WIN belongs to a later segment)
     auto emit = [&](int64_t x, uint32_t v) {
-        if (x >= 0 && x < ETAB) atomicAdd(&E[(int)x], v);
+        if (x < TOFF) carry_reg += v;
+        else if (x < WIN) atomicAdd(&E[(int)x - TOFF], v);
     };
     for (uint32_t base = i_lo; base < i_hi; base += 32 * U) {
         // issue every load of TILE_UNROLL chunks before consuming any of them
@@ -273,50 +285,57 @@ __global__ void __launch_bounds__(WPC * 32, TILE_MIN_CTAS) k_tile_accumulate(Til
             const int32_t p = pv[u];
             const uint32_t c = cv[u];
             const uint32_t nops = HAS_OFF ? nv[u] : 1u;
-            const uint32_t idx = (uint32_t)p - (uint32_t)tab0;   // < ETAB for a consistent cut
-            const bool in_win = idx < (uint32_t)ETAB;
-            idx_max = max(idx_max, idx);                       // checked once after the loop
+            const uint32_t w = (uint32_t)p - (uint32_t)win0;   // window index: < WIN for a consistent cut
+            const bool in_win = w < (uint32_t)WIN;
+            idx_max = max(idx_max, w);                         // checked once after the loop
             bool pass = in_win && p >= 0;
             if (HAS_FILTER && ((failm >> u) & 1u)) pass = false;
             if (!HAS_OFF || nops == 1) {
                 // one CIGAR op (the common case): M/=/X is one run [p, p+len)                      :745-752
-                // branch-free: both shared atomics are always issued; a lane with nothing to apply hits its own sink word
-                // (E[ETAB + lane]: 32 distinct banks), so there is no branch and no reconvergence barrier around them
-                const uint32_t e = min(idx + (c >> 4), clen_tab);                 // len < 2^28: no overflow
-                const bool ok = pass && ((0x181u >> (c & 15u)) & 1u) && e > idx;
-                atomicAdd(&E[ok ? idx : sink], 1u);
-                atomicAdd(&E[(ok && e < (uint32_t)ETAB) ? e : sink], 0xffffffffu);
-                if (ok && e > (uint32_t)ETAB) {                                           // the run leaves the segment (7% of 150M reads)
-                    // first base (table index) that no segment seeing this read owns: segments see reads up to HALO to their left
-                    const uint32_t far_tab = (idx >= (uint32_t)SEG) ? 2 * SEG + HALO : SEG + HALO;
-                    if (idx >= (uint32_t)HALO && e > far_tab) {                     // rare: run longer than HALO, applied by its owner
-                        red_add_u32(a.delta + hbase + far_tab, 1u);
+                const uint32_t e = min(w + (c >> 4), clen_w);                      // len < 2^28: no overflow
+                const bool ok = pass && ((0x181u >> (c & 15u)) & 1u) && e > w;
+                const bool s_tab = ok && w >= (uint32_t)TOFF;                      // start / end land in the table
+                const bool e_tab = ok && (e - (uint32_t)TOFF) < (uint32_t)TLEN;
+                if (TOFF) carry_reg += (uint32_t)(ok && w < (uint32_t)TOFF) - (uint32_t)(ok && e < (uint32_t)TOFF);
+#if PD_SINK
+                // both shared atomics are always issued; a lane with nothing to apply hits its own sink word (32 distinct banks)
+                atomicAdd(&E[s_tab ? w - TOFF : sink], 1u);
+                atomicAdd(&E[e_tab ? e - TOFF : sink], 0xffffffffu);
+#else
+                if (s_tab) atomicAdd(&E[w - TOFF], 1u);
+                if (e_tab) atomicAdd(&E[e - TOFF], 0xffffffffu);
+#endif
+                if (ok && e > (uint32_t)WIN) {                                      // the run leaves the segment (7% of 150M reads)
+                    // first base (window index) that no segment seeing this read owns: segments see reads up to HALO to their left
+                    const uint32_t far_w = (w >= (uint32_t)SEG) ? 2 * SEG + HALO : SEG + HALO;
+                    if (w >= (uint32_t)HALO && e > far_w) {                         // rare: run longer than HALO, applied by its owner
+                        red_add_u32(a.delta + hbase + far_w, 1u);
                         red_add_u32(a.delta + hbase + e, 0xffffffffu);
                         *a.delta_used = 1;
                     }
                 }
             } else if (pass) {
                 const uint32_t c0 = ov[u];
-                const bool owner = idx >= (uint32_t)HALO;
-                const int64_t far_tab = (idx >= (uint32_t)SEG) ? 2 * SEG + HALO : SEG + HALO;
-                int64_t q = idx, rs = INT64_MIN, re = INT64_MIN;
+                const bool owner = w >= (uint32_t)HALO;
+                const int64_t far_w = (w >= (uint32_t)SEG) ? 2 * SEG + HALO : SEG + HALO;
+                int64_t q = w, rs = INT64_MIN, re = INT64_MIN;
                 auto flush = [&]() {
                     if (rs == INT64_MIN) return;
-                    const int64_t s = rs, e = re > clen_tab64 ? clen_tab64 : re;
+                    const int64_t s = rs, e = re > clen_w64 ? clen_w64 : re;
                     if (s >= e) return;
                     emit(s, 1u);
                     emit(e, 0xffffffffu);
-                    if (owner && e > far_tab) {
-                        const int64_t gs = s > far_tab ? s : far_tab;
+                    if (owner && e > far_w) {
+                        const int64_t gs = s > far_w ? s : far_w;
                         red_add_u32(a.delta + hbase + gs, 1u);
                         red_add_u32(a.delta + hbase + e, 0xffffffffu);
                         *a.delta_used = 1;
                     }
                 };
                 for (uint32_t k = 0; k < nops; ++k) {
-                    const uint32_t w = (k == 0) ? c : ldg_u32(a.cigar + c0 + k);
-                    const uint32_t op = w & 15u;
-                    const int64_t n = w >> 4;
+                    const uint32_t cw = (k == 0) ? c : ldg_u32(a.cigar + c0 + k);
+                    const uint32_t op = cw & 15u;
+                    const int64_t n = cw >> 4;
                     if (is_match_op(op)) {                                     // :745-752  adjacent M/=/X merge into one run
                         if (re == q && rs != INT64_MIN) re = q + n; else { flush(); rs = q; re = q + n; }
                         q += n;
@@ -328,10 +347,12 @@ __global__ void __launch_bounds__(WPC * 32, TILE_MIN_CTAS) k_tile_accumulate(Til
     }
     __syncwarp();
 
-    // depth just left of the segment = everything that landed in the look-back part of the table
-    uint32_t carry = 0;
+    // depth just left of the segment: the register part plus, with PD_HALO_TAB, the look-back entries of the table
+    uint32_t carry = carry_reg;
+#if PD_HALO_TAB
 #pragma unroll
     for (int k = lane; k < HALO / 4; k += 32) { const uint4 h = reinterpret_cast<const uint4 *>(E)[k]; carry += h.x + h.y + h.z + h.w; }
+#endif
 #pragma unroll
     for (int o = 16; o; o >>= 1) carry += __shfl_xor_sync(FULL, carry, o);
 
@@ -339,7 +360,7 @@ __global__ void __launch_bounds__(WPC * 32, TILE_MIN_CTAS) k_tile_accumulate(Til
     const bool fresh = (*st_ptr == 0);
     uint32_t *out = a.depth + s0;
     auto scan_row = [&](int b) -> uint4 {
-        const uint4 d = *reinterpret_cast<const uint4 *>(E + HALO + b);
+        const uint4 d = *reinterpret_cast<const uint4 *>(E + (HALO - TOFF) + b);
         const uint32_t x0 = d.x, x1 = d.y + x0, x2 = d.z + x1, x3 = d.w + x2;
         uint32_t t = x3;
 #pragma unroll
@@ -398,7 +419,7 @@ __global__ void __launch_bounds__(WPC * 32, TILE_MIN_CTAS) k_tile_accumulate(Til
         }
         if (lane == 0) *st_ptr = 2;
     }
-    bad = __any_sync(FULL, bad || idx_max >= (uint32_t)ETAB);
+    bad = __any_sync(FULL, bad || idx_max >= (uint32_t)WIN);
     if (lane == 0 && (bad || (int64_t)chk_l >= hbase || (int64_t)chk_r < send || chk_n > i_hi)) atomicOr(a.err, ERR_UNSORTED);
 }
 

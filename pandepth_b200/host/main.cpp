@@ -76,34 +76,43 @@ struct GzWriter {
     void close() { if (!fp) return; if (!wrote) { std::string z = gz_member(std::string()); fwrite(z.data(), 1, z.size(), fp); } fclose(fp); fp = nullptr; }
 };
 
-// SoA batch of one contig's records in plain (pageable) host memory: workers can fill it before the CUDA context exists
+// SoA batch of one contig's records in plain (pageable) host memory: workers can fill it before the CUDA context exists.
+// The arrays are sized once to their capacity and filled through raw pointers (n reads, nc CIGAR words): the per-record
+// cost of the decode loop is a handful of stores, not three vector::push_back calls.
 struct Batch {
-    std::vector<int32_t> pos; std::vector<uint32_t> cigar, off;
-    size_t n = 0;
+    size_t cap;                                              // reads (and, for single-op reads, CIGAR words) per batch
+    std::vector<int32_t> pos; std::vector<uint32_t> cigar, off;   // allocated by the first add
+    size_t n = 0, nc = 0;
     bool single_op = true;
-    Batch() { pos.reserve(1u << 20); cigar.reserve(1u << 20); off.reserve((1u << 20) + 1); off.push_back(0); }
-    void clear() { pos.clear(); cigar.clear(); off.clear(); off.push_back(0); n = 0; single_op = true; }
-    bool add(const bam1_t *b)
+    explicit Batch(size_t capacity = 1u << 20) : cap(capacity) {}
+    void clear() { n = 0; nc = 0; single_op = true; }
+    bool full() const { return n >= cap || nc >= cap; }      // callers flush a full batch before the next add
+    void alloc() { pos.resize(cap); off.resize(cap + 1); off[0] = 0; cigar.resize(cap + (1u << 12)); }
+    uint32_t *room(size_t k)
+    {
+        if (pos.empty()) alloc();
+        if (nc + k > cigar.size()) cigar.resize(std::max(cigar.size() * 2, nc + k));
+        return cigar.data() + nc;
+    }
+    void commit(int32_t p, size_t k) { if (pos.empty()) alloc(); pos[n] = p; nc += k; off[++n] = (uint32_t)nc; if (k != 1) single_op = false; }
+    void add(const bam1_t *b)
     {
         const uint32_t k = b->core.n_cigar;
-        pos.push_back((int32_t)b->core.pos);                  // hts_pos_t truncated to int32 like :736
-        const uint32_t *c = bam_get_cigar(b);
-        cigar.insert(cigar.end(), c, c + k);
-        off.push_back((uint32_t)cigar.size());
-        n++;
-        if (k != 1) single_op = false;
-        return true;
+        if (k) memcpy(room(k), bam_get_cigar(b), (size_t)k * 4);
+        commit((int32_t)b->core.pos, k);                      // hts_pos_t truncated to int32 like :736
     }
     void add_raw(const RawRead &r)
     {
-        pos.push_back(r.pos);
-        const size_t at = cigar.size();
-        cigar.resize(at + r.n_cigar);
-        if (r.n_cigar) memcpy(&cigar[at], r.cigar, (size_t)r.n_cigar * 4);
-        off.push_back((uint32_t)cigar.size());
-        n++;
-        if (r.n_cigar != 1) single_op = false;
+        uint32_t *c = room(r.n_cigar);
+        if (r.n_cigar == 1) memcpy(c, r.cigar, 4);
+        else if (r.n_cigar) memcpy(c, r.cigar, (size_t)r.n_cigar * 4);
+        commit(r.pos, r.n_cigar);
     }
+    void add_op(uint32_t op, int64_t len)                     // one more op of the read being built (PAF); split above 2^28-1
+    {
+        while (len > 0) { const int64_t m = std::min<int64_t>(len, (1 << 28) - 1); *room(1) = ((uint32_t)m << 4) | op; nc++; len -= m; }
+    }
+    void commit_built(int32_t p, size_t nc_before) { if (pos.empty()) alloc(); pos[n] = p; off[++n] = (uint32_t)nc; if (nc - nc_before != 1) single_op = false; }
     // order-independent digest of the batch (PANDEPTH_DRY diagnostics: compare decode paths without a GPU)
     uint64_t digest(int tid) const
     {
@@ -202,11 +211,11 @@ struct Feeder {
         }
         // stage through a pinned slot when the pool is up and the batch fits (parallel memcpy, outside the engine lock)
         int slot = -1;
-        if (pool && pool->ready && b.n <= pool->slots[0].cap_r && b.cigar.size() <= pool->slots[0].cap_c) {
+        if (pool && pool->ready && b.n <= pool->slots[0].cap_r && b.nc <= pool->slots[0].cap_c) {
             slot = pool->acquire();
             PinnedPool::Slot &s = pool->slots[(size_t)slot];
             memcpy(s.pos, b.pos.data(), b.n * 4);
-            memcpy(s.cigar, b.cigar.data(), b.cigar.size() * 4);
+            memcpy(s.cigar, b.cigar.data(), b.nc * 4);
             if (!b.single_op) memcpy(s.off, b.off.data(), (b.n + 1) * 4);
         }
         struct Rel { PinnedPool *p; int id; ~Rel() { if (id >= 0) p->release(id); } } rel{pool, slot};
@@ -305,7 +314,7 @@ struct Feeder {
                     if (!hit) continue;
                 }
                 batch.add(b);
-                if (batch.n >= (1u << 20)) { if (!push(w.tid, batch, true)) break; }
+                if (batch.full()) { if (!push(w.tid, batch, true)) break; }
             }
             hts_itr_destroy(it);
             if (!push(w.tid, batch, true)) break;
@@ -355,7 +364,7 @@ struct Feeder {
                     if (!hit) return;
                 }
                 batch.add_raw(r);
-                if (batch.n >= (1u << 20)) ok_push = push(w.tid, batch, true);
+                if (batch.full()) ok_push = push(w.tid, batch, true);
             });
             if (!ok) { fail("Error: malformed BAM while scanning " + input + ": " + sc.error()); break; }
             if (!ok_push || !push(w.tid, batch, true)) break;
@@ -378,7 +387,7 @@ struct Feeder {
             if (t < 0) continue;
             if (t != cur) { if (!push(cur, batch, sorted)) break; cur = t; }
             batch.add(b);
-            if (batch.n >= (1u << 20)) { if (!push(cur, batch, sorted)) break; }
+            if (batch.full()) { if (!push(cur, batch, sorted)) break; }
         }
         if (!failed) push(cur, batch, sorted);
         bam_destroy1(b);
@@ -396,14 +405,12 @@ struct Feeder {
     {
         LineReader in(input);
         if (!in.ok()) { fail("open PAF file error: " + input); return false; }
-        std::vector<Batch> batches(n_targets);
+        // per-target batches: bounded in total (many-contig assemblies), flushed through the unsorted path
+        std::vector<Batch> batches(n_targets, Batch(std::min<size_t>(1u << 20, std::max<size_t>(4096, (64u << 20) / std::max<size_t>(1, n_targets)))));
         std::string line;
         std::vector<std::pair<const char *, size_t>> tok;
         const bool drop_secondary = (o.xflags & 0x100u) != 0;
         auto to_int = [](const char *p, size_t n) { char b[32]; if (n > 31) n = 31; memcpy(b, p, n); b[n] = 0; return atoi(b); };
-        auto add_op = [](Batch &b, uint32_t op, int64_t len) {
-            while (len > 0) { const int64_t n = std::min<int64_t>(len, (1 << 28) - 1); b.cigar.push_back(((uint32_t)n << 4) | op); len -= n; }
-        };
         while (!failed && in.next(line)) {
             if (line.empty()) continue;
             if (drop_secondary && line.find("tp:A:S") != std::string::npos) continue;
@@ -425,7 +432,7 @@ struct Feeder {
             Batch &b = batches[(size_t)tid];
             int cg = -1;
             for (size_t k = 0; k < tok.size(); k++) if (tok[k].second >= 5 && memcmp(tok[k].first, "cg:Z:", 5) == 0) { cg = (int)k; break; }
-            const size_t c0 = b.cigar.size();
+            const size_t c0 = b.nc;
             if (cg > 1) {                                                      // :1582-1613
                 if (a < 0) continue;
                 const char *q = tok[(size_t)cg].first + 5, *qe = tok[(size_t)cg].first + tok[(size_t)cg].second;
@@ -435,24 +442,21 @@ struct Feeder {
                     const char op = q < qe ? *q : 0;
                     q++;
                     switch (op) {
-                    case 'M': add_op(b, 0, n); break;
-                    case '=': add_op(b, 7, n); break;
-                    case 'X': add_op(b, 8, n); break;
-                    case 'D': add_op(b, 2, n); break;
-                    case 'N': add_op(b, 3, n); break;
+                    case 'M': b.add_op(0, n); break;
+                    case '=': b.add_op(7, n); break;
+                    case 'X': b.add_op(8, n); break;
+                    case 'D': b.add_op(2, n); break;
+                    case 'N': b.add_op(3, n); break;
                     default: break;                                            // I S H P ...: no depth, no advance
                     }
                 }
-                b.pos.push_back(a);
+                b.commit_built(a, c0);
             } else {                                                           // :1614-1620  for (i = StartRead-1; i < EndRead; ++i)
                 const int32_t s0 = a > 0 ? a - 1 : 0;                          // (the reference's write at index -1 is dropped)
-                if (z > s0) add_op(b, 0, (int64_t)z - s0);
-                b.pos.push_back(s0);
+                if (z > s0) b.add_op(0, (int64_t)z - s0);
+                b.commit_built(s0, c0);
             }
-            b.off.push_back((uint32_t)b.cigar.size());
-            b.n++;
-            if (b.cigar.size() - c0 != 1) b.single_op = false;
-            if (b.n >= (1u << 20) || b.cigar.size() >= (1u << 20)) { if (!push(tid, b, false)) break; }
+            if (b.full()) { if (!push(tid, b, false)) break; }
         }
         for (size_t t = 0; t < n_targets && !failed; t++) push((int)t, batches[t], false);
         return !failed;
