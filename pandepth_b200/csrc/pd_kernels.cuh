@@ -34,6 +34,12 @@ constexpr int WPC = 8;      // warps per CTA in k_tile_accumulate
 #ifndef PD_SINK
 #define PD_SINK 0          // 1: shared atomics always issued (idle lanes hit a per-lane sink word); 0: predicated by a branch
 #endif
+#ifndef PD_SCAN_PACK
+#define PD_SCAN_PACK 0     // 1: the prefix scan moves two rows per shuffle (16-bit fields) when the lane sums allow it
+#endif
+#ifndef PD_ZERO_BULK
+#define PD_ZERO_BULK 0     // 1: the table is cleared by one st.bulk instead of 128-bit stores
+#endif
 constexpr int WIN = SEG + HALO;              // bases a warp sees reads from: [s0 - HALO, s0 + SEG); "window index" = pos - (s0 - HALO)
 constexpr int TOFF = PD_HALO_TAB ? 0 : HALO; // window index of table entry 0
 constexpr int TLEN = WIN - TOFF;             // table entries that hold deltas
@@ -211,12 +217,16 @@ __global__ void __launch_bounds__(WPC * 32, TILE_MIN_CTAS) k_tile_accumulate(Til
     // register; their sum is the depth carried into the segment.
     uint32_t *E = smem + warp * TILE_SMEM_WORDS;
     const int64_t clen = a.contig_len;
+#if PD_ZERO_BULK
+    if (lane == 0) asm volatile("st.bulk.weak.shared::cta [%0], %1, 0;" :: "r"((uint32_t)__cvta_generic_to_shared(E)), "n"(TILE_SMEM_WORDS * 4) : "memory");
+#else
     {
         const uint4 z = make_uint4(0, 0, 0, 0);
         uint4 *E4 = reinterpret_cast<uint4 *>(E);
 #pragma unroll
         for (int k = lane; k < TILE_SMEM_WORDS / 4; k += 32) E4[k] = z;
     }
+#endif
     __syncwarp();
 
     uint32_t carry_reg = 0;        // per-lane part of "depth just left of the segment"
@@ -353,21 +363,46 @@ __global__ void __launch_bounds__(WPC * 32, TILE_MIN_CTAS) k_tile_accumulate(Til
 #pragma unroll
     for (int k = lane; k < HALO / 4; k += 32) { const uint4 h = reinterpret_cast<const uint4 *>(E)[k]; carry += h.x + h.y + h.z + h.w; }
 #endif
-#pragma unroll
-    for (int o = 16; o; o >>= 1) carry += __shfl_xor_sync(FULL, carry, o);
+    carry = __reduce_add_sync(FULL, carry);
 
     uint8_t *st_ptr = a.seg_state + (a.seg0 + j);
     const bool fresh = (*st_ptr == 0);
     uint32_t *out = a.depth + s0;
-    auto scan_row = [&](int b) -> uint4 {
-        const uint4 d = *reinterpret_cast<const uint4 *>(E + (HALO - TOFF) + b);
-        const uint32_t x0 = d.x, x1 = d.y + x0, x2 = d.z + x1, x3 = d.w + x2;
-        uint32_t t = x3;
+    // two rows (128 bases each, a lane holds 4 consecutive bases of either) per call: inclusive prefix of the table plus the
+    // running carry.  Row totals come from redux.sync (no shuffle); with PD_SCAN_PACK the cross-lane scan of both rows
+    // shares its five shuffles: the lane sums, biased by 1024, travel as two 16-bit fields (32 x 2047 < 2^16: no field
+    // overflows into the other); rows whose lane sums do not fit [-1024, 1023] (deep pile-ups) take the 32-bit scan.
+    auto scan_pair = [&](int b, uint4 &vA, uint4 &vB) {
+        const uint4 dA = *reinterpret_cast<const uint4 *>(E + (HALO - TOFF) + b);
+        const uint4 dB = *reinterpret_cast<const uint4 *>(E + (HALO - TOFF) + b + 128);
+        const uint32_t a0 = dA.x, a1 = dA.y + a0, a2 = dA.z + a1, a3 = dA.w + a2;
+        const uint32_t b0 = dB.x, b1 = dB.y + b0, b2 = dB.z + b1, b3 = dB.w + b2;
+        uint32_t exA, exB;
+#if PD_SCAN_PACK
+        const uint32_t fa = a3 + 1024u, fb = b3 + 1024u;
+        if (__all_sync(FULL, (fa | fb) < 2048u)) {
+            uint32_t t = fa | (fb << 16);
+            const uint32_t red = __reduce_add_sync(FULL, t);
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) t = scan_step_up(t, o);
-        const uint32_t ex = t - x3 + carry;
-        carry += __shfl_sync(FULL, t, 31);
-        return make_uint4(x0 + ex, x1 + ex, x2 + ex, x3 + ex);
+            for (int o = 1; o < 32; o <<= 1) t = scan_step_up(t, o);
+            const uint32_t bias = 1024u * (uint32_t)(lane + 1);
+            exA = (t & 0xffffu) - bias - a3 + carry;
+            carry += (red & 0xffffu) - 32768u;
+            exB = (t >> 16) - bias - b3 + carry;
+            carry += (red >> 16) - 32768u;
+        } else
+#endif
+        {
+            uint32_t t = a3, u = b3;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { t = scan_step_up(t, o); u = scan_step_up(u, o); }
+            exA = t - a3 + carry;
+            carry += __reduce_add_sync(FULL, a3);
+            exB = u - b3 + carry;
+            carry += __reduce_add_sync(FULL, b3);
+        }
+        vA = make_uint4(a0 + exA, a1 + exA, a2 + exA, a3 + exA);
+        vB = make_uint4(b0 + exB, b1 + exB, b2 + exB, b3 + exB);
     };
     // partials only for a first write of a segment that lies completely inside the contig
     const bool do_part = fresh && a.hint_on && send <= clen;
@@ -376,46 +411,59 @@ __global__ void __launch_bounds__(WPC * 32, TILE_MIN_CTAS) k_tile_accumulate(Til
         uint32_t pc = 0; unsigned long long ps = 0;
         if (md == 1u && mk == 0xffffffffu) {
             // default -d 1 on the uint32 path: covered == non-zero, and zero depths add nothing to the sum
-#pragma unroll 4
-            for (int r = 0; r < SEG / 128; ++r) {
+#pragma unroll 2
+            for (int r = 0; r < SEG / 128; r += 2) {
                 const int b = r * 128 + lane * 4;
-                const uint4 v = scan_row(b);
+                uint4 v, w;
+                scan_pair(b, v, w);
                 __stcs(reinterpret_cast<uint4 *>(out + b), v);
-                pc += nonzero4(v);
-                ps += (unsigned long long)v.x + v.y + v.z + v.w;
+                __stcs(reinterpret_cast<uint4 *>(out + b + 128), w);
+                pc += nonzero4(v) + nonzero4(w);
+                ps += ((unsigned long long)v.x + v.y + v.z + v.w) + ((unsigned long long)w.x + w.y + w.z + w.w);
             }
         } else {
-#pragma unroll 4
-            for (int r = 0; r < SEG / 128; ++r) {
-                const int b = r * 128 + lane * 4;
-                const uint4 v = scan_row(b);
-                __stcs(reinterpret_cast<uint4 *>(out + b), v);
-                uint32_t x;                                          // if (depth >= minDep) { Cover++; Depth += depth; }  :319-323
+            auto acc = [&](const uint4 v) {                          // if (depth >= minDep) { Cover++; Depth += depth; }  :319-323
+                uint32_t x;
                 x = v.x & mk; if (x >= md) { pc++; ps += x; }
                 x = v.y & mk; if (x >= md) { pc++; ps += x; }
                 x = v.z & mk; if (x >= md) { pc++; ps += x; }
                 x = v.w & mk; if (x >= md) { pc++; ps += x; }
+            };
+#pragma unroll 2
+            for (int r = 0; r < SEG / 128; r += 2) {
+                const int b = r * 128 + lane * 4;
+                uint4 v, w;
+                scan_pair(b, v, w);
+                __stcs(reinterpret_cast<uint4 *>(out + b), v);
+                __stcs(reinterpret_cast<uint4 *>(out + b + 128), w);
+                acc(v); acc(w);
             }
         }
+        pc = __reduce_add_sync(FULL, pc);
 #pragma unroll
-        for (int o = 16; o; o >>= 1) { pc += __shfl_xor_sync(FULL, pc, o); ps += __shfl_xor_sync(FULL, ps, o); }
+        for (int o = 16; o; o >>= 1) ps += __shfl_xor_sync(FULL, ps, o);
         if (lane == 0) { a.part_cov[a.seg0 + j] = pc; a.part_sum[a.seg0 + j] = ps; *st_ptr = 1; }
     } else if (fresh) {
-#pragma unroll 4
-        for (int r = 0; r < SEG / 128; ++r) {
+#pragma unroll 2
+        for (int r = 0; r < SEG / 128; r += 2) {
             const int b = r * 128 + lane * 4;
-            __stcs(reinterpret_cast<uint4 *>(out + b), scan_row(b));
+            uint4 v, w;
+            scan_pair(b, v, w);
+            __stcs(reinterpret_cast<uint4 *>(out + b), v);
+            __stcs(reinterpret_cast<uint4 *>(out + b + 128), w);
         }
         if (lane == 0) *st_ptr = 2;
     } else {
-#pragma unroll 2
-        for (int r = 0; r < SEG / 128; ++r) {
+#pragma unroll 1
+        for (int r = 0; r < SEG / 128; r += 2) {
             const int b = r * 128 + lane * 4;
             uint4 *dst = reinterpret_cast<uint4 *>(out + b);
-            const uint4 old = *dst;
-            uint4 v = scan_row(b);
-            v.x += old.x; v.y += old.y; v.z += old.z; v.w += old.w;
-            *dst = v;
+            const uint4 oA = dst[0], oB = dst[32];                   // +128 bases
+            uint4 v, w;
+            scan_pair(b, v, w);
+            v.x += oA.x; v.y += oA.y; v.z += oA.z; v.w += oA.w;
+            w.x += oB.x; w.y += oB.y; w.z += oB.z; w.w += oB.w;
+            dst[0] = v; dst[32] = w;
         }
         if (lane == 0) *st_ptr = 2;
     }
@@ -702,6 +750,8 @@ __global__ void __launch_bounds__(256) k_reduce_windows(WindowArgs a)
         constexpr int WB = 4, NL = 5;
         const int64_t ngroups = (a.n_win + WB - 1) / WB;
         const uint32_t win = (uint32_t)a.win, md = a.min_dep, mk = a.mask;
+        // window starts are multiples of 4 elements from a 16-byte aligned base (contig offsets are multiples of 4096)
+        const bool vec_ok = md == 1u && (win & 3u) == 0u && win <= 128u && (a.start0 & 3) == 0 && ((uintptr_t)a.depth & 15u) == 0;
         for (int64_t g = warp; g < ngroups; g += nwarps) {
             const int64_t k0 = g * WB;
             const int64_t lo0 = a.start0 + k0 * a.win;
@@ -709,6 +759,24 @@ __global__ void __launch_bounds__(256) k_reduce_windows(WindowArgs a)
             const int64_t rem64 = a.len - lo0;                                   // bases left in the contig from this group on
             const uint32_t rem = rem64 <= 0 ? 0u : (rem64 > (int64_t)(WB * 160) ? (uint32_t)(WB * 160) : (uint32_t)rem64);
             const uint32_t nw = (uint32_t)(a.n_win - k0 < WB ? a.n_win - k0 : WB);   // windows in this group
+            if (vec_ok && nw == WB && rem >= WB * win) {
+                // four full windows whose first bases are 16-byte aligned: one 128-bit load per lane per window
+                // (lanes 0 .. win/4-1), -d 1: covered == non-zero and zeros add nothing
+                const uint4 *__restrict__ d4 = reinterpret_cast<const uint4 *>(a.depth + lo0);
+                const uint32_t q = win >> 2;                                      // uint4 per window (<= 32)
+                uint4 v[WB];
+#pragma unroll
+                for (int j = 0; j < WB; ++j) v[j] = ((uint32_t)lane < q) ? __ldcs(d4 + (uint32_t)j * q + lane) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+                for (int j = 0; j < WB; ++j) {
+                    const uint4 m = make_uint4(v[j].x & mk, v[j].y & mk, v[j].z & mk, v[j].w & mk);
+                    uint32_t cov = nonzero4(m), sum = (m.x + m.y) + (m.z + m.w);
+                    cov = __reduce_add_sync(FULL, cov);
+                    sum = __reduce_add_sync(FULL, sum);
+                    if (lane == 0) { a.cov[k0 + j] = cov; a.sum[k0 + j] = sum; }
+                }
+                continue;
+            }
             uint32_t x[WB][NL];
 #pragma unroll
             for (int j = 0; j < WB; ++j) {
