@@ -56,6 +56,7 @@ struct pd_engine {
     uint32_t *d_part_cov = nullptr; unsigned long long *d_part_sum = nullptr;   // per-segment reduce partials (hint)
     bool hint_on = false; uint32_t hint_min_dep = 1, hint_mask = 0xFFFFFFFFu;
     bool pushed_since_reset = false;
+    int32_t tile_resident_warps = 148 * 3 * pdk::WPC;   // warps of k_tile_accumulate resident on the device (prefetch distance)
     unsigned long long *d_desc = nullptr; unsigned int *d_counter = nullptr;
 
     cudaStream_t own_stream = nullptr, copy_stream = nullptr, stream = nullptr;
@@ -145,12 +146,16 @@ int run_batch(pd_engine *e, int32_t tid, uint32_t n, const int32_t *pos, const u
         pdk::TileArgs t{pos, cigar, cigar_off, flag, mapq, e->d_lo, e->d_hi, n, (int32_t)seg_a, nseg, (int32_t)e->tlen[tid],
                         e->d_depth + off, e->d_delta + off, e->d_seg_state + off / pdk::SEG, e->xflags, e->min_mapq,
                         e->d_flags, e->d_flags + 1,
-                        e->hint_on ? 1u : 0u, e->hint_min_dep, e->hint_mask, e->d_part_cov + off / pdk::SEG, e->d_part_sum + off / pdk::SEG};
+                        e->hint_on ? 1u : 0u, e->hint_min_dep, e->hint_mask, e->d_part_cov + off / pdk::SEG, e->d_part_sum + off / pdk::SEG,
+                        e->tile_resident_warps};
         const size_t smem = (size_t)pdk::WPC * pdk::TILE_SMEM_WORDS * 4;
         const unsigned grid = (nseg + pdk::WPC - 1) / pdk::WPC, blk = pdk::WPC * 32;
         const bool has_off = cigar_off != nullptr, has_filter = flag != nullptr || mapq != nullptr;
+        // 128-bit read loads need 16-byte aligned pos / cigar arrays (cudaMalloc and the staging slots give 256)
+        const bool vec = PD_VEC_LOAD && !has_off && ((((uintptr_t)pos) | ((uintptr_t)cigar)) & 15u) == 0;
         rc = launch(e, K_TILE, [&] {
-            if (has_off) { if (has_filter) pdk::k_tile_accumulate<true, true><<<grid, blk, smem, e->stream>>>(t); else pdk::k_tile_accumulate<true, false><<<grid, blk, smem, e->stream>>>(t); }
+            if (vec) { if (has_filter) pdk::k_tile_accumulate<false, true, true><<<grid, blk, smem, e->stream>>>(t); else pdk::k_tile_accumulate<false, false, true><<<grid, blk, smem, e->stream>>>(t); }
+            else if (has_off) { if (has_filter) pdk::k_tile_accumulate<true, true><<<grid, blk, smem, e->stream>>>(t); else pdk::k_tile_accumulate<true, false><<<grid, blk, smem, e->stream>>>(t); }
             else { if (has_filter) pdk::k_tile_accumulate<false, true><<<grid, blk, smem, e->stream>>>(t); else pdk::k_tile_accumulate<false, false><<<grid, blk, smem, e->stream>>>(t); }
         });
         if (rc) return rc;
@@ -286,6 +291,14 @@ pd_engine *pd_create(int device, int n_targets, const uint32_t *target_len, cons
         if ((ce = cudaFuncSetAttribute(pdk::k_tile_accumulate<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return bail("cudaFuncSetAttribute", ce);
         if ((ce = cudaFuncSetAttribute(pdk::k_tile_accumulate<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return bail("cudaFuncSetAttribute", ce);
         if ((ce = cudaFuncSetAttribute(pdk::k_tile_accumulate<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return bail("cudaFuncSetAttribute", ce);
+        if ((ce = cudaFuncSetAttribute(pdk::k_tile_accumulate<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return bail("cudaFuncSetAttribute", ce);
+        if ((ce = cudaFuncSetAttribute(pdk::k_tile_accumulate<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return bail("cudaFuncSetAttribute", ce);
+    }
+    {
+        int n_sm = 0, per_sm = 0;
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pdk::k_tile_accumulate<false, false>, pdk::WPC * 32, pdk::WPC * pdk::TILE_SMEM_WORDS * 4) == cudaSuccess && n_sm > 0 && per_sm > 0)
+            e->tile_resident_warps = n_sm * per_sm * pdk::WPC;
     }
     if ((ce = cudaStreamSynchronize(e->stream)) != cudaSuccess) return bail("sync", ce);
     return e;

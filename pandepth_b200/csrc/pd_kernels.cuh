@@ -37,6 +37,12 @@ constexpr int WPC = 8;      // warps per CTA in k_tile_accumulate
 #ifndef PD_SCAN_PACK
 #define PD_SCAN_PACK 0     // 1: the prefix scan moves two rows per shuffle (16-bit fields) when the lane sums allow it
 #endif
+#ifndef PD_VEC_LOAD
+#define PD_VEC_LOAD 0      // 1: single-op batches with 16-byte aligned arrays load 4 consecutive reads per lane (128-bit loads)
+#endif
+#ifndef PD_PREFETCH
+#define PD_PREFETCH 0      // 1: every warp prefetches (to L2) the reads of the segment one wave of resident warps ahead
+#endif
 #ifndef PD_ZERO_BULK
 #define PD_ZERO_BULK 0     // 1: the table is cleared by one st.bulk instead of 128-bit stores
 #endif
@@ -181,19 +187,37 @@ struct TileArgs {
     // reduce hint (pd_set_reduce_hint): per-segment CoveredSite/TotalDepth partials for segments written exactly once
     uint32_t hint_on, hint_min_dep, hint_mask;
     uint32_t *part_cov; unsigned long long *part_sum;     // contig base, one entry per segment
+    int32_t pf_dist;      // PD_PREFETCH: segments between a warp's own segment and the one whose reads it prefetches
 };
 
 constexpr int TILE_UNROLL = PD_TILE_UNROLL;   // 32-read chunks whose loads are issued together (memory-level parallelism)
 
-template <bool HAS_OFF, bool HAS_FILTER>
+template <bool HAS_OFF, bool HAS_FILTER, bool VEC = false>
 __global__ void __launch_bounds__(WPC * 32, TILE_MIN_CTAS) k_tile_accumulate(TileArgs a)
 {
+    static_assert(!(VEC && HAS_OFF), "128-bit loads are for single-op batches");
     constexpr int U = HAS_OFF ? (TILE_UNROLL > 8 ? 8 : TILE_UNROLL) : TILE_UNROLL;   // offsets cost two more registers per chunk
     extern __shared__ __align__(16) uint32_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int j = blockIdx.x * WPC + warp;
     if (j >= a.nseg) return;
     const uint32_t i_lo = a.lo[j], i_hi = a.hi[j + 1];        // hi[] holds lower_bound(s0_j): nseg+1 entries
+#if PD_PREFETCH
+    // the reads of segment j + pf_dist (the segment that takes this warp's place when it retires) are pulled into L2 now,
+    // so that warp finds them there instead of in DRAM: one 128-byte line (32 reads) per lane and instruction
+    {
+        const int jp = j + a.pf_dist;
+        if (jp < a.nseg) {
+            const uint32_t plo = a.lo[jp], phi = a.hi[jp + 1];
+            if (plo < phi && phi <= a.n && phi - plo <= 32u * 32u * 8u) {
+                for (uint32_t q = (plo & ~31u) + lane * 32; q < phi; q += 32 * 32) {
+                    asm volatile("prefetch.global.L2 [%0];" :: "l"(a.pos + q));
+                    asm volatile("prefetch.global.L2 [%0];" :: "l"((HAS_OFF ? a.cigar_off : a.cigar) + q));
+                }
+            }
+        }
+    }
+#endif
     const int64_t s0 = (int64_t)(a.seg0 + j) * SEG;
     const int64_t hbase = s0 - HALO;
     const int64_t send = s0 + SEG;
@@ -244,11 +268,53 @@ __global__ void __launch_bounds__(WPC * 32, TILE_MIN_CTAS) k_tile_accumulate(Til
         if (x < TOFF) carry_reg += v;
         else if (x < WIN) atomicAdd(&E[(int)x - TOFF], v);
     };
-    for (uint32_t base = i_lo; base < i_hi; base += 32 * U) {
+    // VEC: a lane owns 4 consecutive reads per 128-bit load, so "chunk" u = 4v+k holds every lane's k-th read of vector v;
+    // the group starts at a multiple of 4 reads (reads before i_lo are replaced by a filler at the window start)
+    const int32_t lead_pos = (int32_t)hbase;
+    for (uint32_t base = VEC ? (i_lo & ~3u) : i_lo; base < i_hi; base += 32 * U) {
         // issue every load of TILE_UNROLL chunks before consuming any of them
         int32_t pv[U]; uint32_t cv[U]; uint32_t ov[U]; uint32_t nv[U];
         uint32_t failm = 0;        // bit u: fails the record filter
         const uint32_t left = i_hi - base;                    // reads left in this and later chunks (>= 1)
+        if (VEC) {
+#pragma unroll
+            for (int v = 0; v < U / 4; ++v) {
+                const uint32_t first = base + v * 128 + lane * 4;
+                int32_t P[4] = {pad_pos, pad_pos, pad_pos, pad_pos}; uint32_t C[4] = {0u, 0u, 0u, 0u};
+                if (first + 3 < a.n) {
+                    if (first < i_hi) {
+                        const int4 p4 = __ldg(reinterpret_cast<const int4 *>(a.pos + first));
+                        const uint4 c4 = __ldg(reinterpret_cast<const uint4 *>(a.cigar + first));
+                        P[0] = p4.x; P[1] = p4.y; P[2] = p4.z; P[3] = p4.w; C[0] = c4.x; C[1] = c4.y; C[2] = c4.z; C[3] = c4.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) if (first + k < i_hi) { P[k] = ldg_i32(a.pos + first + k); C[k] = ldg_u32(a.cigar + first + k); }
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t i = first + k;
+                    const bool valid = i >= i_lo && i < i_hi;
+                    pv[4 * v + k] = valid ? P[k] : (i < i_lo ? lead_pos : pad_pos);
+                    cv[4 * v + k] = valid ? C[k] : 0u;
+                    ov[4 * v + k] = 0; nv[4 * v + k] = 1;
+                    if (HAS_FILTER && valid) {
+                        if (a.flag && (__ldg(a.flag + i) & a.xflags)) failm |= 1u << (4 * v + k);       // :732
+                        if (a.mapq && (int)__ldg(a.mapq + i) < a.min_mapq) failm |= 1u << (4 * v + k);  // :733
+                    }
+                }
+            }
+            // sortedness: in-lane order of the 4 reads, and one rotate-shuffle per vector against the previous lane's last read
+            int32_t prev_last = carry_p;
+#pragma unroll
+            for (int v = 0; v < U / 4; ++v) {
+                const int32_t r = __shfl_sync(FULL, pv[4 * v + 3], (lane + 31) & 31);
+                bad |= pv[4 * v] < (lane == 0 ? prev_last : r);
+                bad |= pv[4 * v + 1] < pv[4 * v] || pv[4 * v + 2] < pv[4 * v + 1] || pv[4 * v + 3] < pv[4 * v + 2];
+                prev_last = r;                                 // meaningful in lane 0 only
+            }
+            carry_p = prev_last;
+        } else {
         const int32_t *ppos = a.pos + base + lane;
         const uint32_t *pcig = HAS_OFF ? a.cigar_off + base + lane : a.cigar + base + lane;
 #pragma unroll
@@ -289,9 +355,10 @@ __global__ void __launch_bounds__(WPC * 32, TILE_MIN_CTAS) k_tile_accumulate(Til
             }
             carry_p = prev_last;
         }
+        }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            if ((uint32_t)(u * 32) >= left) break;            // warp-uniform
+            if ((uint32_t)(VEC ? (u >> 2) * 128 + (u & 3) : u * 32) >= left) break;            // warp-uniform: no lane has a read in this chunk
             const int32_t p = pv[u];
             const uint32_t c = cv[u];
             const uint32_t nops = HAS_OFF ? nv[u] : 1u;
