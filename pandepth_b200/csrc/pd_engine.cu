@@ -151,11 +151,8 @@ int run_batch(pd_engine *e, int32_t tid, uint32_t n, const int32_t *pos, const u
         const size_t smem = (size_t)pdk::WPC * pdk::TILE_SMEM_WORDS * 4;
         const unsigned grid = (nseg + pdk::WPC - 1) / pdk::WPC, blk = pdk::WPC * 32;
         const bool has_off = cigar_off != nullptr, has_filter = flag != nullptr || mapq != nullptr;
-        // 128-bit read loads need 16-byte aligned pos / cigar arrays (cudaMalloc and the staging slots give 256)
-        const bool vec = PD_VEC_LOAD && !has_off && ((((uintptr_t)pos) | ((uintptr_t)cigar)) & 15u) == 0;
         rc = launch(e, K_TILE, [&] {
-            if (vec) { if (has_filter) pdk::k_tile_accumulate<false, true, true><<<grid, blk, smem, e->stream>>>(t); else pdk::k_tile_accumulate<false, false, true><<<grid, blk, smem, e->stream>>>(t); }
-            else if (has_off) { if (has_filter) pdk::k_tile_accumulate<true, true><<<grid, blk, smem, e->stream>>>(t); else pdk::k_tile_accumulate<true, false><<<grid, blk, smem, e->stream>>>(t); }
+            if (has_off) { if (has_filter) pdk::k_tile_accumulate<true, true><<<grid, blk, smem, e->stream>>>(t); else pdk::k_tile_accumulate<true, false><<<grid, blk, smem, e->stream>>>(t); }
             else { if (has_filter) pdk::k_tile_accumulate<false, true><<<grid, blk, smem, e->stream>>>(t); else pdk::k_tile_accumulate<false, false><<<grid, blk, smem, e->stream>>>(t); }
         });
         if (rc) return rc;
@@ -291,8 +288,6 @@ pd_engine *pd_create(int device, int n_targets, const uint32_t *target_len, cons
         if ((ce = cudaFuncSetAttribute(pdk::k_tile_accumulate<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return bail("cudaFuncSetAttribute", ce);
         if ((ce = cudaFuncSetAttribute(pdk::k_tile_accumulate<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return bail("cudaFuncSetAttribute", ce);
         if ((ce = cudaFuncSetAttribute(pdk::k_tile_accumulate<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return bail("cudaFuncSetAttribute", ce);
-        if ((ce = cudaFuncSetAttribute(pdk::k_tile_accumulate<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return bail("cudaFuncSetAttribute", ce);
-        if ((ce = cudaFuncSetAttribute(pdk::k_tile_accumulate<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return bail("cudaFuncSetAttribute", ce);
     }
     {
         int n_sm = 0, per_sm = 0;

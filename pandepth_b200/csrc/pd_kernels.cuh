@@ -28,28 +28,13 @@ namespace pdk {
 constexpr int SEG = PD_SEG;   // bases owned by one warp of k_tile_accumulate (8 KB of depth at 2048)
 constexpr int HALO = 256;   // look-back window in bases; also the largest "common span" L the fast path models
 constexpr int WPC = 8;      // warps per CTA in k_tile_accumulate
-#ifndef PD_HALO_TAB
-#define PD_HALO_TAB 0      // 1: the look-back window has its own table entries; 0: what lands left of the segment goes to a register
-#endif
-#ifndef PD_SINK
-#define PD_SINK 0          // 1: shared atomics always issued (idle lanes hit a per-lane sink word); 0: predicated by a branch
-#endif
-#ifndef PD_SCAN_PACK
-#define PD_SCAN_PACK 0     // 1: the prefix scan moves two rows per shuffle (16-bit fields) when the lane sums allow it
-#endif
-#ifndef PD_VEC_LOAD
-#define PD_VEC_LOAD 0      // 1: single-op batches with 16-byte aligned arrays load 4 consecutive reads per lane (128-bit loads)
-#endif
 #ifndef PD_PREFETCH
-#define PD_PREFETCH 0      // 1: every warp prefetches (to L2) the reads of the segment one wave of resident warps ahead
-#endif
-#ifndef PD_ZERO_BULK
-#define PD_ZERO_BULK 0     // 1: the table is cleared by one st.bulk instead of 128-bit stores
+#define PD_PREFETCH 1      // every warp prefetches (to L2) the reads of the segment one wave of resident warps ahead
 #endif
 constexpr int WIN = SEG + HALO;              // bases a warp sees reads from: [s0 - HALO, s0 + SEG); "window index" = pos - (s0 - HALO)
-constexpr int TOFF = PD_HALO_TAB ? 0 : HALO; // window index of table entry 0
-constexpr int TLEN = WIN - TOFF;             // table entries that hold deltas
-constexpr int TILE_SMEM_WORDS = TLEN + (PD_SINK ? 32 : 0);   // per warp (8 KB at SEG 2048 without the extras)
+constexpr int TOFF = HALO;                   // window index of table entry 0: the table covers the segment itself
+constexpr int TLEN = WIN - TOFF;             // table entries (= SEG)
+constexpr int TILE_SMEM_WORDS = TLEN;        // per warp: 8 KB at SEG 2048
 constexpr int TILE_MIN_CTAS = PD_TILE_MIN_CTAS;   // resident CTAs per SM k_tile_accumulate is compiled for (register cap)
 constexpr unsigned FULL = 0xffffffffu;
 
@@ -192,10 +177,9 @@ struct TileArgs {
 
 constexpr int TILE_UNROLL = PD_TILE_UNROLL;   // 32-read chunks whose loads are issued together (memory-level parallelism)
 
-template <bool HAS_OFF, bool HAS_FILTER, bool VEC = false>
+template <bool HAS_OFF, bool HAS_FILTER>
 __global__ void __launch_bounds__(WPC * 32, TILE_MIN_CTAS) k_tile_accumulate(TileArgs a)
 {
-    static_assert(!(VEC && HAS_OFF), "128-bit loads are for single-op batches");
     constexpr int U = HAS_OFF ? (TILE_UNROLL > 8 ? 8 : TILE_UNROLL) : TILE_UNROLL;   // offsets cost two more registers per chunk
     extern __shared__ __align__(16) uint32_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -237,20 +221,17 @@ __global__ void __launch_bounds__(WPC * 32, TILE_MIN_CTAS) k_tile_accumulate(Til
     }
 
     // E[w - TOFF] = (runs starting at window index w) - (runs ending there); window index w = pos - (s0 - HALO) in [0, WIN).
-    // Deltas left of the table (w < TOFF: the look-back part, unless PD_HALO_TAB keeps it in the table) go to a per-lane
-    // register; their sum is the depth carried into the segment.
+    // Deltas left of the table (w < TOFF: the look-back part) go to a per-lane register; their sum is the depth carried
+    // into the segment.  (Keeping them in the table instead, and issuing the atomics unconditionally with per-lane sink
+    // words, both measured slower: the LSU data pipe is this kernel's busiest unit -- profiles/r01b_tile_pipe_breakdown.txt.)
     uint32_t *E = smem + warp * TILE_SMEM_WORDS;
     const int64_t clen = a.contig_len;
-#if PD_ZERO_BULK
-    if (lane == 0) asm volatile("st.bulk.weak.shared::cta [%0], %1, 0;" :: "r"((uint32_t)__cvta_generic_to_shared(E)), "n"(TILE_SMEM_WORDS * 4) : "memory");
-#else
     {
         const uint4 z = make_uint4(0, 0, 0, 0);
         uint4 *E4 = reinterpret_cast<uint4 *>(E);
 #pragma unroll
         for (int k = lane; k < TILE_SMEM_WORDS / 4; k += 32) E4[k] = z;
     }
-#endif
     __syncwarp();
 
     uint32_t carry_reg = 0;        // per-lane part of "depth just left of the segment"
@@ -259,62 +240,17 @@ __global__ void __launch_bounds__(WPC * 32, TILE_MIN_CTAS) k_tile_accumulate(Til
     const int32_t win0 = (int32_t)hbase;                                  // position of window index 0 (>= -HALO)
     const int64_t clen_w64 = clen - hbase;                                // contig end as a window index
     const uint32_t clen_w = (uint32_t)(clen_w64 > 0x7fffffff ? 0x7fffffff : clen_w64);
-#if PD_SINK
-    const uint32_t sink = (uint32_t)(TLEN + lane);
-#endif
     const int32_t pad_pos = (int32_t)(send - 1);                          // filler for lanes past the last read: in window, sorts last
     // delta v applies to every base >= window index x (anything at or beyond WIN belongs to a later segment)
     auto emit = [&](int64_t x, uint32_t v) {
         if (x < TOFF) carry_reg += v;
         else if (x < WIN) atomicAdd(&E[(int)x - TOFF], v);
     };
-    // VEC: a lane owns 4 consecutive reads per 128-bit load, so "chunk" u = 4v+k holds every lane's k-th read of vector v;
-    // the group starts at a multiple of 4 reads (reads before i_lo are replaced by a filler at the window start)
-    const int32_t lead_pos = (int32_t)hbase;
-    for (uint32_t base = VEC ? (i_lo & ~3u) : i_lo; base < i_hi; base += 32 * U) {
+    for (uint32_t base = i_lo; base < i_hi; base += 32 * U) {
         // issue every load of TILE_UNROLL chunks before consuming any of them
         int32_t pv[U]; uint32_t cv[U]; uint32_t ov[U]; uint32_t nv[U];
         uint32_t failm = 0;        // bit u: fails the record filter
         const uint32_t left = i_hi - base;                    // reads left in this and later chunks (>= 1)
-        if (VEC) {
-#pragma unroll
-            for (int v = 0; v < U / 4; ++v) {
-                const uint32_t first = base + v * 128 + lane * 4;
-                int32_t P[4] = {pad_pos, pad_pos, pad_pos, pad_pos}; uint32_t C[4] = {0u, 0u, 0u, 0u};
-                if (first + 3 < a.n) {
-                    if (first < i_hi) {
-                        const int4 p4 = __ldg(reinterpret_cast<const int4 *>(a.pos + first));
-                        const uint4 c4 = __ldg(reinterpret_cast<const uint4 *>(a.cigar + first));
-                        P[0] = p4.x; P[1] = p4.y; P[2] = p4.z; P[3] = p4.w; C[0] = c4.x; C[1] = c4.y; C[2] = c4.z; C[3] = c4.w;
-                    }
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) if (first + k < i_hi) { P[k] = ldg_i32(a.pos + first + k); C[k] = ldg_u32(a.cigar + first + k); }
-                }
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const uint32_t i = first + k;
-                    const bool valid = i >= i_lo && i < i_hi;
-                    pv[4 * v + k] = valid ? P[k] : (i < i_lo ? lead_pos : pad_pos);
-                    cv[4 * v + k] = valid ? C[k] : 0u;
-                    ov[4 * v + k] = 0; nv[4 * v + k] = 1;
-                    if (HAS_FILTER && valid) {
-                        if (a.flag && (__ldg(a.flag + i) & a.xflags)) failm |= 1u << (4 * v + k);       // :732
-                        if (a.mapq && (int)__ldg(a.mapq + i) < a.min_mapq) failm |= 1u << (4 * v + k);  // :733
-                    }
-                }
-            }
-            // sortedness: in-lane order of the 4 reads, and one rotate-shuffle per vector against the previous lane's last read
-            int32_t prev_last = carry_p;
-#pragma unroll
-            for (int v = 0; v < U / 4; ++v) {
-                const int32_t r = __shfl_sync(FULL, pv[4 * v + 3], (lane + 31) & 31);
-                bad |= pv[4 * v] < (lane == 0 ? prev_last : r);
-                bad |= pv[4 * v + 1] < pv[4 * v] || pv[4 * v + 2] < pv[4 * v + 1] || pv[4 * v + 3] < pv[4 * v + 2];
-                prev_last = r;                                 // meaningful in lane 0 only
-            }
-            carry_p = prev_last;
-        } else {
         const int32_t *ppos = a.pos + base + lane;
         const uint32_t *pcig = HAS_OFF ? a.cigar_off + base + lane : a.cigar + base + lane;
 #pragma unroll
@@ -355,10 +291,9 @@ __global__ void __launch_bounds__(WPC * 32, TILE_MIN_CTAS) k_tile_accumulate(Til
             }
             carry_p = prev_last;
         }
-        }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            if ((uint32_t)(VEC ? (u >> 2) * 128 + (u & 3) : u * 32) >= left) break;            // warp-uniform: no lane has a read in this chunk
+            if ((uint32_t)(u * 32) >= left) break;            // warp-uniform
             const int32_t p = pv[u];
             const uint32_t c = cv[u];
             const uint32_t nops = HAS_OFF ? nv[u] : 1u;
@@ -373,15 +308,9 @@ __global__ void __launch_bounds__(WPC * 32, TILE_MIN_CTAS) k_tile_accumulate(Til
                 const bool ok = pass && ((0x181u >> (c & 15u)) & 1u) && e > w;
                 const bool s_tab = ok && w >= (uint32_t)TOFF;                      // start / end land in the table
                 const bool e_tab = ok && (e - (uint32_t)TOFF) < (uint32_t)TLEN;
-                if (TOFF) carry_reg += (uint32_t)(ok && w < (uint32_t)TOFF) - (uint32_t)(ok && e < (uint32_t)TOFF);
-#if PD_SINK
-                // both shared atomics are always issued; a lane with nothing to apply hits its own sink word (32 distinct banks)
-                atomicAdd(&E[s_tab ? w - TOFF : sink], 1u);
-                atomicAdd(&E[e_tab ? e - TOFF : sink], 0xffffffffu);
-#else
+                carry_reg += (uint32_t)(ok && w < (uint32_t)TOFF) - (uint32_t)(ok && e < (uint32_t)TOFF);
                 if (s_tab) atomicAdd(&E[w - TOFF], 1u);
                 if (e_tab) atomicAdd(&E[e - TOFF], 0xffffffffu);
-#endif
                 if (ok && e > (uint32_t)WIN) {                                      // the run leaves the segment (7% of 150M reads)
                     // first base (window index) that no segment seeing this read owns: segments see reads up to HALO to their left
                     const uint32_t far_w = (w >= (uint32_t)SEG) ? 2 * SEG + HALO : SEG + HALO;
@@ -424,41 +353,20 @@ __global__ void __launch_bounds__(WPC * 32, TILE_MIN_CTAS) k_tile_accumulate(Til
     }
     __syncwarp();
 
-    // depth just left of the segment: the register part plus, with PD_HALO_TAB, the look-back entries of the table
-    uint32_t carry = carry_reg;
-#if PD_HALO_TAB
-#pragma unroll
-    for (int k = lane; k < HALO / 4; k += 32) { const uint4 h = reinterpret_cast<const uint4 *>(E)[k]; carry += h.x + h.y + h.z + h.w; }
-#endif
-    carry = __reduce_add_sync(FULL, carry);
+    // depth just left of the segment
+    uint32_t carry = __reduce_add_sync(FULL, carry_reg);
 
     uint8_t *st_ptr = a.seg_state + (a.seg0 + j);
     const bool fresh = (*st_ptr == 0);
     uint32_t *out = a.depth + s0;
     // two rows (128 bases each, a lane holds 4 consecutive bases of either) per call: inclusive prefix of the table plus the
-    // running carry.  Row totals come from redux.sync (no shuffle); with PD_SCAN_PACK the cross-lane scan of both rows
-    // shares its five shuffles: the lane sums, biased by 1024, travel as two 16-bit fields (32 x 2047 < 2^16: no field
-    // overflows into the other); rows whose lane sums do not fit [-1024, 1023] (deep pile-ups) take the 32-bit scan.
+    // running carry; the two shuffle chains interleave, row totals come from redux.sync (no shuffle)
     auto scan_pair = [&](int b, uint4 &vA, uint4 &vB) {
-        const uint4 dA = *reinterpret_cast<const uint4 *>(E + (HALO - TOFF) + b);
-        const uint4 dB = *reinterpret_cast<const uint4 *>(E + (HALO - TOFF) + b + 128);
+        const uint4 dA = *reinterpret_cast<const uint4 *>(E + b);
+        const uint4 dB = *reinterpret_cast<const uint4 *>(E + b + 128);
         const uint32_t a0 = dA.x, a1 = dA.y + a0, a2 = dA.z + a1, a3 = dA.w + a2;
         const uint32_t b0 = dB.x, b1 = dB.y + b0, b2 = dB.z + b1, b3 = dB.w + b2;
         uint32_t exA, exB;
-#if PD_SCAN_PACK
-        const uint32_t fa = a3 + 1024u, fb = b3 + 1024u;
-        if (__all_sync(FULL, (fa | fb) < 2048u)) {
-            uint32_t t = fa | (fb << 16);
-            const uint32_t red = __reduce_add_sync(FULL, t);
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) t = scan_step_up(t, o);
-            const uint32_t bias = 1024u * (uint32_t)(lane + 1);
-            exA = (t & 0xffffu) - bias - a3 + carry;
-            carry += (red & 0xffffu) - 32768u;
-            exB = (t >> 16) - bias - b3 + carry;
-            carry += (red >> 16) - 32768u;
-        } else
-#endif
         {
             uint32_t t = a3, u = b3;
 #pragma unroll
