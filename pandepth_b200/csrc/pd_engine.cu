@@ -4,8 +4,10 @@
 //   depth   uint32[total]   all owned contigs back to back; contig t starts at off[t] (a multiple of 4096 elements) and is
 //                           followed by >= 1 element of padding, so a run's closing -1 at `len` never lands in a neighbour
 //   delta   uint32[total]   same geometry; +-1 run endpoints of the unsorted / far path; all-zero outside a pending scan
-//   seg_state uint8[total/1024]  0 = no batch has written this 1024-base segment yet (first write is a plain store)
-// 3 Gb genome: 12 GB + 12 GB + 3 MB of the 180 GB.
+//   seg_state uint8[total/SEG]   per 2048-base segment: 0 = never written (first write is a plain store), 1 = written once and
+//                           its CoveredSite/TotalDepth partial is valid (reduce hint), 2 = written
+//   part_cov/part_sum       per-segment partials of the reduce hint (12 B per segment)
+// 3 Gb genome: 12 GB + 12 GB + 19 MB of the 180 GB.
 #include "../../include/pandepth_b200.h"
 #include "pd_kernels.cuh"
 

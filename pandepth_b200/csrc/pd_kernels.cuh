@@ -2,7 +2,7 @@
 //
 // Roles (reference = /root/reference/src/PanDepth.cpp):
 //   k_cut              index a sorted batch by genomic segment (no CPU counterpart; replaces the BAI window queries :726)
-//   k_tile_accumulate  filter + CIGAR walk -> per-base depth, one warp per 1024-base segment   (:732-760)
+//   k_tile_accumulate  filter + CIGAR walk -> per-base depth, one warp per 2048-base segment   (:732-760)
 //   k_delta_scatter    same walk for unsorted / long-span batches: +-1 deltas with global reductions (:732-760)
 //   k_scan_add         prefix-sum of the delta array folded into depth (the CPU increments every base instead)
 //   k_fill_untouched   zero-fill segments no batch touched (the `depth[ccv]=0` loop :718-721, only where needed)
@@ -147,14 +147,16 @@ __global__ void __launch_bounds__(256) k_cut(CutArgs a, const uint32_t *coarse, 
 // ---------------------------------------------------------------------------------------------------------------
 // k_tile_accumulate: one warp per SEG-base segment of one contig.
 //
-// The warp sees every read whose pos lies in [s0-HALO, s0+SEG) (lo/hi from k_cut) and builds, in its private 4 KB of
+// The warp sees every read whose pos lies in [s0-HALO, s0+SEG) (lo/hi from k_cut) and builds, in its private 8 KB of
 // shared memory, E[b] = (runs starting at b) - (runs ending at b) for the bases of its segment with shared-memory atomics
 // (warp-private table, so the only contention is equal positions inside one 32-read chunk); every +-1 that lands left of
 // s0 goes to a per-lane register carry instead.  Loads of TILE_UNROLL chunks are issued together before any is consumed.
 // Runs that reach past the segments that see the read (pos + HALO) are "far": the owner segment scatters them as +-1
 // deltas into the global delta array, folded in by k_scan_add at finalize.
-// The segment is then prefix-summed (warp shuffles) and written with coalesced 16-byte stores: a plain streaming store if
-// no earlier batch touched the segment (zero-initialisation is fused away), else load+add+store.
+// The segment is then prefix-summed (warp shuffles, two rows of 128 bases interleaved, row totals by redux.sync) and written
+// with coalesced 16-byte stores: a plain streaming store if no earlier batch touched the segment (zero-initialisation is
+// fused away), else load+add+store.  Each warp also prefetches, into L2, the reads of the segment one wave of resident
+// warps ahead (exact range from the cut arrays).
 // (Measured alternative, dropped: modelling reads as one common span and applying group counts with plain two-phase
 // read-modify-writes was 15% slower than the atomics on B200 -- see DESIGN.md.)
 // ---------------------------------------------------------------------------------------------------------------

@@ -151,7 +151,7 @@ bool BamRangeScanner::inflate_next_block()
     }
 }
 
-bool BamRangeScanner::fill(size_t need)
+bool BamRangeScanner::fill_slow(size_t need)
 {
     while (blen_ - bpos_ < need) if (!inflate_next_block()) return false;
     return true;

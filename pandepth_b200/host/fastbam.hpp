@@ -42,7 +42,9 @@ public:
     const std::string &error() const { return err_; }
 
 private:
-    bool fill(size_t need);            // make at least `need` bytes available at buf_[bpos_]; false at EOF/error
+    // make at least `need` bytes available at buf_[bpos_]; false at EOF/error (the common case -- already there -- is inline)
+    bool fill(size_t need) { return blen_ - bpos_ >= need ? true : fill_slow(need); }
+    bool fill_slow(size_t need);
     bool inflate_next_block();
     int fd_ = -1;
     void *dec_ = nullptr;
