@@ -9,6 +9,7 @@
  *   bamgen -o out.bam -c name:len[,name:len...] -n reads [-s seed] [-l readlen] [-m uniform|mixed]
  *   bamgen -I in.sam -o out.bam      (convert a SAM fixture to BAM + .bai)
  *          [-q] (emit random SEQ+QUAL, flavour B; default SEQ='*', flavour A) [-t threads] [-S] (write SAM text)
+ *   an output name ending in .cram is written as CRAM 3.x without a reference (no_ref) + .crai
  *
  * mode uniform : every read flag 0, mapq 60, CIGAR <readlen>M.
  * mode mixed   : random CIGARs over MIDNSHP=X, random flags (incl. UNMAP/SECONDARY/QCFAIL/DUP/SUPP bits),
@@ -28,6 +29,16 @@
 struct Contig { std::string name; int64_t len; };
 
 static void die(const char *m) { fprintf(stderr, "bamgen: %s\n", m); exit(2); }
+
+static bool is_cram_name(const std::string &p) { return p.size() > 5 && p.compare(p.size() - 5, 5, ".cram") == 0; }
+
+static htsFile *open_out(const std::string &path, bool samtext)
+{
+    const bool cram = is_cram_name(path);
+    htsFile *fp = hts_open(path.c_str(), samtext ? "w" : (cram ? "wc" : "wb1"));
+    if (fp && cram && hts_set_opt(fp, CRAM_OPT_NO_REF, 1) != 0) die("cannot set no_ref");
+    return fp;
+}
 
 static void make_mixed_cigar(std::mt19937_64 &rng, int readlen, std::vector<uint32_t> &cig, int &qlen, int &rlen)
 {
@@ -78,7 +89,7 @@ int main(int argc, char **argv)
         if (!in) die("cannot open input SAM");
         sam_hdr_t *h = sam_hdr_read(in);
         if (!h) die("cannot read SAM header");
-        htsFile *o = hts_open(out.c_str(), "wb1");
+        htsFile *o = open_out(out, false);
         if (!o || sam_hdr_write(o, h) < 0) die("cannot write BAM");
         bam1_t *r = bam_init1();
         while (sam_read1(in, h, r) >= 0) if (sam_write1(o, h, r) < 0) die("write failed");
@@ -106,7 +117,7 @@ int main(int argc, char **argv)
     sam_hdr_t *hdr = sam_hdr_parse(text.size(), text.c_str());
     if (!hdr) die("header parse failed");
 
-    htsFile *fp = hts_open(out.c_str(), samtext ? "w" : "wb1");
+    htsFile *fp = open_out(out, samtext);
     if (!fp) die("cannot open output");
     if (threads > 1 && !samtext) hts_set_threads(fp, threads);
     if (sam_hdr_write(fp, hdr) < 0) die("header write failed");

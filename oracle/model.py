@@ -449,13 +449,9 @@ def _wrap_i32(v: int) -> int:
     return v - (1 << 32) if v & 0x80000000 else v
 
 
-def run_model(targets: List[Tuple[str, int]], rec: Records, opts: Options,
-              depth_override: Optional[List[np.ndarray]] = None) -> Dict[str, str]:
-    """Produce {'stat': text, 'suffix': str, 'site': text-or-None} exactly as the reference would print them.
-
-    depth_override lets tests substitute per-base depth produced by the CUDA engine for the oracle's own."""
+def build_region_model(targets: List[Tuple[str, int]], opts: Options) -> Tuple[int, Dict[int, Dict[str, Gene]]]:
+    """(mode, genes) as main() builds them: -g/-b regions (:3547-3905), else pseudo-gene tiles (:3975-4051)."""
     names = [t[0] for t in targets]
-    tlen = np.array([t[1] for t in targets], dtype=np.uint32)
     mode, genes = parse_regions(opts, names)
     if not genes:                                                   # :3975-4051
         if opts.win == 0:
@@ -468,6 +464,17 @@ def run_model(targets: List[Tuple[str, int]], rec: Records, opts: Options,
             a, b = tile_contig(ln, W)
             for s, e in zip(a.tolist(), b.tolist()):
                 _add_gene(genes, t, f"{nm}{s}", s, e)
+    return mode, genes
+
+
+def run_model(targets: List[Tuple[str, int]], rec: Records, opts: Options,
+              depth_override: Optional[List[np.ndarray]] = None) -> Dict[str, str]:
+    """Produce {'stat': text, 'suffix': str, 'site': text-or-None} exactly as the reference would print them.
+
+    depth_override lets tests substitute per-base depth produced by the CUDA engine for the oracle's own."""
+    names = [t[0] for t in targets]
+    tlen = np.array([t[1] for t in targets], dtype=np.uint32)
+    mode, genes = build_region_model(targets, opts)
     whole_contig = (not opts.indexed) or opts.site_output or mode == 6   # :4124-4127 -> SiteInfo 18-bit paths
     mask = 0x3FFFF if whole_contig else 0xFFFFFFFF
 

@@ -3,7 +3,8 @@
 // HBM layout (one engine = one GPU):
 //   depth   uint32[total]   all owned contigs back to back; contig t starts at off[t] (a multiple of 4096 elements) and is
 //                           followed by >= 1 element of padding, so a run's closing -1 at `len` never lands in a neighbour
-//   delta   uint32[total]   same geometry; +-1 run endpoints of the unsorted / far path; all-zero outside a pending scan
+//   delta   uint32[total]   same geometry; +-1 run endpoints of the unsorted / far path; all-zero before the first batch;
+//                           stale (consumed, not yet cleared) after a scan until the next batch or reset clears it
 //   seg_state uint8[total/SEG]   per 2048-base segment: 0 = never written (first write is a plain store), 1 = written once and
 //                           its CoveredSite/TotalDepth partial is valid (reduce hint), 2 = written
 //   part_cov/part_sum       per-segment partials of the reduce hint (12 B per segment)
@@ -22,7 +23,8 @@ namespace {
 
 std::string g_create_error;
 
-constexpr uint64_t PAD_ELEMS = pdk::SCAN_TILE;           // contig offsets / total are multiples of this
+constexpr uint64_t PAD_ELEMS = pdk::SCAN_TILE > 4096 ? pdk::SCAN_TILE : 4096;   // contig offsets / total are multiples of this (and of SCAN_TILE)
+static_assert(PAD_ELEMS % pdk::SCAN_TILE == 0 && PAD_ELEMS % 4096 == 0, "padding must hold whole scan tiles");
 constexpr int64_t HOST_CHUNK_READS = 8 << 20;            // staging chunk for host-resident pushes
 constexpr int N_SLOTS = 2;
 
@@ -69,6 +71,7 @@ struct pd_engine {
 
     bool finalized = false;
     bool host_delta_used = false;    // a scatter-path batch was queued since the last scan
+    bool delta_stale = false;        // the last scan consumed the deltas but left them in place: clear before the next writer
     pd_stats stats{};
     bool profiling = false;
     struct Ev { int k; cudaEvent_t a, b; };
@@ -134,6 +137,10 @@ int run_batch(pd_engine *e, int32_t tid, uint32_t n, const int32_t *pos, const u
               const uint32_t *cigar_off, const uint32_t *cigar, bool sorted, int64_t seg_a, int64_t seg_b)
 {
     const uint64_t off = e->off[tid];
+    if (e->delta_stale) {            // a batch after a scan (rare): both paths may write deltas, so the consumed ones go first
+        CK(cudaMemsetAsync(e->d_delta, 0, e->total * 4, e->stream));
+        e->delta_stale = false;
+    }
     if (sorted) {
         const int32_t nseg = (int32_t)(seg_b - seg_a + 1);
         int rc = ensure_cut(e, (size_t)nseg + 1); if (rc) return rc;
@@ -330,8 +337,9 @@ int pd_reset(pd_engine *e)
     e->err.clear();
     CK(cudaMemsetAsync(e->d_seg_state, 0, e->n_seg, e->stream));
     CK(cudaMemsetAsync(e->d_flags, 0, 8, e->stream));
-    if (e->host_delta_used) CK(cudaMemsetAsync(e->d_delta, 0, e->total * 4, e->stream));
+    if (e->host_delta_used || e->delta_stale) CK(cudaMemsetAsync(e->d_delta, 0, e->total * 4, e->stream));
     e->host_delta_used = false;
+    e->delta_stale = false;
     e->finalized = false;
     e->pushed_since_reset = false;
     uint64_t keep = e->stats.hbm_bytes_allocated;
@@ -448,6 +456,7 @@ int pd_finalize(pd_engine *e)
         CK(cudaMemsetAsync(e->d_seg_state, 2, e->n_seg, e->stream));     // written, partials (if any) no longer valid
         CK(cudaMemsetAsync(e->d_flags + 1, 0, 4, e->stream));
         e->host_delta_used = false;
+        e->delta_stale = true;
         e->stats.scan_passes++;
     } else {
         rc = launch(e, K_FILL, [&] { pdk::k_fill_untouched<<<(unsigned)((e->n_seg + 7) / 8), 256, 0, e->stream>>>(e->d_depth, e->d_seg_state, e->n_seg, e->hint_on ? 1u : 0u, e->d_part_cov, e->d_part_sum); });

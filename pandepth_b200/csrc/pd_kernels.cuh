@@ -492,16 +492,33 @@ __global__ void __launch_bounds__(256) k_delta_scatter(ScatterArgs a)
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// k_scan_add: depth[i] (+)= inclusive_prefix_sum(delta)[i]; delta[i] = 0.  Single pass, decoupled look-back
+// k_scan_add: depth[i] (+)= inclusive_prefix_sum(delta)[i].  Single pass, decoupled look-back
 // (tile aggregates published through 64-bit {status,value} descriptors), dynamic tile ids for forward progress.
 // Every contig's deltas sum to zero before its padding ends, so one scan over the whole array needs no resets.
+// The consumed deltas are NOT zeroed here (that would be a third 4 B/base stream in a bandwidth-bound kernel): the engine
+// marks the delta array stale and clears it only if another batch arrives after the scan (pd_engine.cu, delta_stale).
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int SCAN_THREADS = 256;
-constexpr int SCAN_ITEMS = 16;                           // uint32 per thread (4 x uint4)
+#ifndef PD_SCAN_THREADS
+#define PD_SCAN_THREADS 256
+#endif
+#ifndef PD_SCAN_ITEMS
+#define PD_SCAN_ITEMS 16
+#endif
+#ifndef PD_SCAN_POLL_LD
+#define PD_SCAN_POLL_LD 1      // 1: look-back polls with ld.relaxed.gpu instead of an atomic read-modify-write
+#endif
+#ifndef PD_SCAN_MIN_CTAS
+#define PD_SCAN_MIN_CTAS 8     // 8 resident CTAs/SM (32 registers, 64 warps): measured best of {1 (40 regs, 6 CTAs), 8} x
+#endif                         // {items 16, 32} x {threads 128, 256, 512} -- tools/gpu_r01d.sh, profiles/r01c_scan_ab.txt
+constexpr int SCAN_THREADS = PD_SCAN_THREADS;
+constexpr int SCAN_ITEMS = PD_SCAN_ITEMS;                // uint32 per thread (SCAN_ROWS x uint4)
+constexpr int SCAN_ROWS = SCAN_ITEMS / 4;                // rows of 128 elements a warp owns
+constexpr int SCAN_WARP_ELEMS = 32 * SCAN_ITEMS;         // consecutive elements of one warp (512 at 16 items)
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;     // 4096 elements = one 16 KB tile
-static_assert(SEG % 512 == 0 && SCAN_TILE % SEG == 0 || SEG % SCAN_TILE == 0, "a scan warp (512 elements) must lie inside one segment");
+static_assert(SCAN_ITEMS % 4 == 0 && SEG % SCAN_WARP_ELEMS == 0, "a scan warp's elements must lie inside one segment");
+static_assert(SCAN_TILE % SEG == 0 || SEG % SCAN_TILE == 0, "scan tiles and segments must nest");
 
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_add(uint32_t *__restrict__ depth, uint32_t *__restrict__ delta,
+__global__ void __launch_bounds__(SCAN_THREADS, PD_SCAN_MIN_CTAS) k_scan_add(uint32_t *__restrict__ depth, const uint32_t *__restrict__ delta,
                                                            uint64_t n_elems, unsigned long long *desc, unsigned int *counter,
                                                            const uint8_t *__restrict__ seg_state)
 {
@@ -515,15 +532,14 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_add(uint32_t *__restrict_
     const uint64_t tbase = (uint64_t)tile * SCAN_TILE;
     if (tbase >= n_elems) return;
 
-    // warp w owns 512 consecutive elements: 4 rows of 128 (lane holds 4)
-    uint4 v[4];
-    uint32_t row_tot[4];
-    const uint64_t wbase = tbase + (uint64_t)warp * 512;
+    // warp w owns SCAN_WARP_ELEMS consecutive elements: SCAN_ROWS rows of 128 (lane holds 4)
+    uint4 v[SCAN_ROWS];
+    const uint64_t wbase = tbase + (uint64_t)warp * SCAN_WARP_ELEMS;
     uint32_t wcarry = 0;
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
+    for (int r = 0; r < SCAN_ROWS; ++r) {
         const uint64_t e = wbase + r * 128 + lane * 4;      // n_elems is a multiple of SCAN_TILE (engine pads)
-        uint4 x = *reinterpret_cast<const uint4 *>(delta + e);
+        uint4 x = __ldcs(reinterpret_cast<const uint4 *>(delta + e));
         x.y += x.x; x.z += x.y; x.w += x.z;
         uint32_t t = x.w;
 #pragma unroll
@@ -534,8 +550,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_add(uint32_t *__restrict_
         const uint32_t ex = t - x.w + wcarry;
         x.x += ex; x.y += ex; x.z += ex; x.w += ex;
         v[r] = x;
-        row_tot[r] = __shfl_sync(FULL, t, 31);
-        wcarry += row_tot[r];
+        wcarry += __shfl_sync(FULL, t, 31);
     }
     if (lane == 0) s_warp_tot[warp] = wcarry;
     __syncthreads();
@@ -560,7 +575,11 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_add(uint32_t *__restrict_
                 unsigned long long d = 0;
                 uint32_t status = 2, val = 0;
                 if (idx >= 0) {
+#if PD_SCAN_POLL_LD
+                    do { asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(d) : "l"(desc + idx) : "memory"); status = (uint32_t)(d >> 32); } while (status == 0);
+#else
                     do { d = atomicAdd(desc + idx, 0ull); status = (uint32_t)(d >> 32); } while (status == 0);
+#endif
                     val = (uint32_t)d;
                 }
                 // lanes up to and including the first inclusive descriptor contribute
@@ -578,19 +597,17 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_add(uint32_t *__restrict_
     }
     __syncthreads();
     const uint32_t add = s_prefix + woff;
-    const uint4 z = make_uint4(0, 0, 0, 0);
-    // a warp's 512 elements lie inside one segment (SEG is a multiple of 512): segments no tile batch has written yet
+    // a warp's elements lie inside one segment (SEG is a multiple of SCAN_WARP_ELEMS): segments no tile batch has written yet
     // take a plain store (the engine marks every segment written after this kernel)
     const bool fresh = seg_state[wbase / SEG] == 0;
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
+    for (int r = 0; r < SCAN_ROWS; ++r) {
         const uint64_t e = wbase + r * 128 + lane * 4;
         uint4 *dp = reinterpret_cast<uint4 *>(depth + e);
         uint4 o = make_uint4(0, 0, 0, 0);
         if (!fresh) o = *dp;
         o.x += v[r].x + add; o.y += v[r].y + add; o.z += v[r].z + add; o.w += v[r].w + add;
         __stcs(dp, o);
-        __stcs(reinterpret_cast<uint4 *>(delta + e), z);
     }
 }
 

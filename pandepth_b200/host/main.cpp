@@ -281,6 +281,10 @@ struct Feeder {
         sam_hdr_t *hdr = nullptr;
         htsFile *fp = open_input(&hdr, 0);
         hts_idx_t *idx = shared_idx;
+        // a .crai lives inside the cram_fd it was loaded through (the hts_idx_t is only a handle to it), so every
+        // worker loads its own; BAM indexes are plain read-only tables and are shared
+        const bool own_idx = fp && fp->format.format == cram;
+        if (own_idx) idx = sam_index_load(fp, input.c_str());
         if (!fp || !idx) { fail("Error: Failed to open the index file or BAM/CRAM file: " + input); if (fp) hts_close(fp); return; }
         bam1_t *b = bam_init1();
         Batch batch;
@@ -320,6 +324,7 @@ struct Feeder {
             if (!push(w.tid, batch, true)) break;
         }
         bam_destroy1(b);
+        if (own_idx) hts_idx_destroy(idx);
         sam_hdr_destroy(hdr);
         hts_close(fp);
     }
@@ -525,7 +530,7 @@ int main(int argc, char **argv)
     std::vector<Target> targets;
     std::map<std::string, int> paf_chr2int;                  // Chr2IntMap of paf_main (:867)
     sam_hdr_t *hdr = nullptr;
-    bool is_bam = false, sorted_hdr = false;
+    bool is_bam = false, is_cram = false, sorted_hdr = false;
     if (is_paf) {
         // targets: column 6/7 of the first PAF in first-seen order (:918-941).  With -r the reference takes them from the
         // FASTA and switches to its GC report (RefIn, :878-909 / :1488) -- GC content is outside the depth path.
@@ -557,7 +562,7 @@ int main(int argc, char **argv)
         hts_set_log_level(HTS_LOG_OFF);
         if (!in) { std::cerr << "Error: Failed to open the BAM/CRAM file: " << o.input << std::endl; return 1; }
         if (in->format.format == cram) hts_set_fai_filename(in, o.reference.c_str());
-        is_bam = in->format.format == bam;
+        is_bam = in->format.format == bam; is_cram = in->format.format == cram;
         hdr = sam_hdr_read(in);
         if (!hdr) { std::cerr << "Error: Failed to read the header for the BAM/CRAM file: " << o.input << std::endl; return 1; }
         targets.resize((size_t)hdr->n_targets);
@@ -610,6 +615,25 @@ int main(int argc, char **argv)
     std::map<int, std::vector<std::pair<int, int>>> merged;
     for (const auto &kv : genes) merged[kv.first] = merge_regions(kv.second);
     tm.mark("header+regions");
+    // PANDEPTH_DRY=1 PANDEPTH_DUMP_REGIONS=<file>: the region model as text (host-logic tests; no GPU is touched)
+    if (const char *dump = getenv("PANDEPTH_DUMP_REGIONS")) {
+        if (FILE *f = fopen(dump, "w")) {
+            fprintf(f, "mode %d mask %x\n", mode, (unsigned)mask);
+            for (const auto &kv : genes) {
+                for (const auto &gk : kv.second) {
+                    const Gene &g = gk.second;
+                    fprintf(f, "G\t%d\t%s\t%d\t%d\t%llu", kv.first, gk.first.c_str(), g.start, g.end, (unsigned long long)g.length);
+                    for (const auto &c : g.cds) fprintf(f, "\t%d,%d", c.first, c.second);
+                    fputc('\n', f);
+                }
+                fprintf(f, "M\t%d", kv.first);
+                for (const auto &r : merged[kv.first]) fprintf(f, "\t%d,%d", r.first, r.second);
+                fputc('\n', f);
+                for (const auto &wk : indexed_window_counts(merged[kv.first], kv.second, (int)tlen[kv.first])) fprintf(f, "W\t%d\t%s\t%d\n", kv.first, wk.first.c_str(), wk.second);
+            }
+            fclose(f);
+        }
+    }
 
     // ---- feed ---------------------------------------------------------------------------------------------------
     const bool region_modes = mode >= 1 && mode <= 4;
@@ -619,12 +643,12 @@ int main(int argc, char **argv)
         const std::string &path = o.inputs[fi];
         feeder.input = path;
         if (is_paf) { feeder.paf_stream(paf_chr2int, targets.size()); continue; }
-        bool f_bam = is_bam, f_sorted = sorted_hdr;
+        bool f_bam = is_bam, f_cram = is_cram, f_sorted = sorted_hdr;
         if (fi > 0) {                                        // later files: own format / sort order, the first file's targets (:2701-2862)
             htsFile *fp = hts_open(path.c_str(), "r");
             if (!fp) { std::cerr << "Error: Failed to open the BAM/CRAM file: " << path << std::endl; continue; }
             if (fp->format.format == cram) hts_set_fai_filename(fp, o.reference.c_str());
-            f_bam = fp->format.format == bam;
+            f_bam = fp->format.format == bam; f_cram = fp->format.format == cram;
             sam_hdr_t *h2 = sam_hdr_read(fp);
             f_sorted = false;
             if (h2) {
@@ -672,7 +696,7 @@ int main(int argc, char **argv)
             feeder.bai = nullptr; feeder.shared_idx = nullptr;
             if (f_bam && !getenv("PANDEPTH_HTS_ITER") && file_exists(path + ".bai") && bai.load(path + ".bai") && bai.refs.size() == targets.size())
                 feeder.bai = &bai;
-            if (!feeder.bai) {
+            if (!feeder.bai && !f_cram) {
                 htsFile *ifp = hts_open(path.c_str(), "r");
                 if (ifp) { feeder.shared_idx = sam_index_load(ifp, path.c_str()); hts_close(ifp); }
             }

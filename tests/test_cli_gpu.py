@@ -132,6 +132,32 @@ def test_cli_matches_reference_binary_on_random_bams(seed, contigs, reads, workd
             assert ref[name] == our[name], f"seed {seed} opts {opts}: {name} differs from the reference binary"
 
 
+def test_cli_matches_reference_binary_on_cram(workdir):
+    """CRAM + .crai input (htslib iterators, `hts_set_fai_filename` / required-fields options of PanDepth.cpp:637-643):
+    same bytes as the reference binary, indexed and -s, per-chr / window / BED modes."""
+    contigs = "a:300001,b:1,c:5000,d:70000,e:2,f:1001"
+    cram = os.path.join(workdir, "rand21.cram")
+    subprocess.run([BAMGEN, "-o", cram, "-c", contigs, "-n", "60000", "-m", "mixed", "-s", "21"], check=True)
+    assert os.path.exists(cram + ".crai")
+    bed = os.path.join(workdir, "rand21.bed")
+    with open(bed, "w") as fb:
+        for c in contigs.split(","):
+            nm, ln = c.split(":")[0], int(c.split(":")[1])
+            if ln < 200:
+                fb.write(f"{nm}\t1\t{ln}\n")
+                continue
+            step = max(ln // 40, 150)
+            for s in range(1, ln - 100, step):
+                fb.write(f"{nm}\t{s}\t{min(ln, s + step // 3)}\n")
+    for k, opts in enumerate([[], ["-w", "100"], ["-w", "1000"], ["-s"], ["-q", "20", "-d", "2"], ["-b", bed], ["-t", "1"], ["-t", "9", "-x", "0"]]):
+        extra = [] if "-t" in opts else ["-t", "4"]
+        ref, _ = _run(REF, cram, opts + extra, workdir, f"refcram_{k}")
+        our, _ = _run(CLI, cram, opts + extra, workdir, f"ourcram_{k}")
+        assert sorted(ref) == sorted(our), (opts, sorted(ref), sorted(our))
+        for name in ref:
+            assert ref[name] == our[name], f"cram opts {opts}: {name} differs from the reference binary"
+
+
 def test_cli_usage_errors_exit_zero_like_the_reference(workdir):
     r = subprocess.run([CLI], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
     assert r.returncode == 0 and "Usage: pandepth" in r.stdout

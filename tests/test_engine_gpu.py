@@ -345,3 +345,49 @@ def test_reduce_hint_partials_give_identical_results(style):
                 eng.set_reduce_hint(1, 0xFFFFFFFF)
             eng.reset()
             eng.set_reduce_hint(1, 0xFFFFFFFF)
+
+
+@pytest.mark.parametrize("second", ["unsorted", "sorted_far", "sorted_near", "reset"])
+def test_batches_after_a_scan_see_a_clean_delta_array(second):
+    """k_scan_add leaves the consumed deltas in place; the engine must clear them before anything writes deltas again:
+    a later scatter batch, a later tile batch with far runs, a tile batch followed by a second finalize, and pd_reset."""
+    import pandepth_b200 as pd
+    rng = np.random.default_rng(33)
+    lens = [250_000, 9_000]
+    tlen = np.array(lens, np.uint32)
+
+    def make(n_frac, far):
+        rows = []
+        for t, ln in enumerate(lens):
+            for p in np.sort(rng.integers(0, ln - 150, int(ln * n_frac))).tolist():
+                cs = f"{rng.integers(10, 70)}M{rng.integers(400, 9000)}N{rng.integers(10, 70)}M" if far and rng.integers(0, 3) == 0 else "150M"
+                rows.append((0, t, p + 1, 60, cs))
+        return model.records_from_tuples(rows, ["a", "b"])
+
+    first = make(0.2, True)
+    with _engine(tlen) as eng:
+        _push_all(eng, first.select(rng.permutation(first.n)), False, 2)        # scatter path -> finalize runs the scan
+        eng.finalize()
+        assert eng.stats()["scan_passes"] == 1
+        _check_depth(eng, tlen, model.accumulate(tlen, first))
+        if second == "reset":
+            eng.reset()
+            nxt = make(0.1, True)
+            _push_all(eng, nxt.select(rng.permutation(nxt.n)), False, 1)
+            eng.finalize()
+            _check_depth(eng, tlen, model.accumulate(tlen, nxt))
+            return
+        nxt = make(0.15, second != "sorted_near")
+        if second == "unsorted":
+            _push_all(eng, nxt.select(rng.permutation(nxt.n)), False, 1)
+        else:
+            _push_all(eng, nxt, True, 3)
+        eng.finalize()
+        both = model.accumulate(tlen, first)
+        add = model.accumulate(tlen, nxt)
+        _check_depth(eng, tlen, [a + b for a, b in zip(both, add)])
+        # and once more on top: a third generation after the second scan / fill
+        third = make(0.05, True)
+        _push_all(eng, third, True, 1)
+        eng.finalize()
+        _check_depth(eng, tlen, [a + b + c for a, b, c in zip(both, add, model.accumulate(tlen, third))])

@@ -56,3 +56,17 @@ def test_scanner_feeds_the_same_reads_as_htslib(name, bams):
         slow = _digest(bams[name], opts, hts=True)
         assert fast[2] == "fastbam" and slow[2] == "htslib"
         assert fast[:2] == slow[:2], (name, opts, fast, slow)
+
+
+def test_cram_indexed_ranges_feed_the_same_reads_as_one_sequential_pass(tmp_path):
+    """CRAM + .crai goes through htslib iterators, one cram_fd and one index per worker (a .crai lives inside the cram_fd
+    it was loaded through).  The range-parallel feed must hand over exactly the reads of a single sequential pass (-s)."""
+    cram = str(tmp_path / "r.cram")
+    subprocess.run([BAMGEN, "-o", cram, "-c", "a:300001,b:1,c:5000,d:70000,e:2,f:1001", "-n", "60000", "-m", "mixed", "-s", "21"], check=True)
+    assert os.path.exists(cram + ".crai")
+    seq = _digest(cram, ["-s"], hts=False)
+    assert seq[2] == "htslib" and seq[0] > 10000
+    for opts in ([], ["-t", "1"], ["-t", "7", "-w", "100"]):
+        assert _digest(cram, opts, hts=False)[:2] == seq[:2], opts
+    for opts in (["-q", "20"], ["-x", "0"]):
+        assert _digest(cram, opts, hts=False)[:2] == _digest(cram, opts + ["-s"], hts=False)[:2], opts
