@@ -83,18 +83,29 @@ struct Batch {
     size_t cap;                                              // reads (and, for single-op reads, CIGAR words) per batch
     std::vector<int32_t> pos; std::vector<uint32_t> cigar, off;   // allocated by the first add
     size_t n = 0, nc = 0;
-    bool single_op = true;
+    bool single_op = true;                                   // every read so far has exactly one op: off[] is the identity and
+    size_t off_valid = 0;                                    //   is only written up to off_valid (filled in when it is needed)
+    int32_t *pos_p = nullptr; uint32_t *cig_p = nullptr; size_t cig_cap = 0;   // raw views of pos / cigar for the hot path
     explicit Batch(size_t capacity = 1u << 20) : cap(capacity) {}
-    void clear() { n = 0; nc = 0; single_op = true; }
+    void clear() { n = 0; nc = 0; single_op = true; off_valid = 0; }
     bool full() const { return n >= cap || nc >= cap; }      // callers flush a full batch before the next add
-    void alloc() { pos.resize(cap); off.resize(cap + 1); off[0] = 0; cigar.resize(cap + (1u << 12)); }
+    void alloc() { pos.resize(cap); off.resize(cap + 1); off[0] = 0; cigar.resize(cap + (1u << 12)); views(); }
+    void views() { pos_p = pos.data(); cig_p = cigar.data(); cig_cap = cigar.size(); }
     uint32_t *room(size_t k)
     {
         if (pos.empty()) alloc();
-        if (nc + k > cigar.size()) cigar.resize(std::max(cigar.size() * 2, nc + k));
+        if (nc + k > cigar.size()) { cigar.resize(std::max(cigar.size() * 2, nc + k)); views(); }
         return cigar.data() + nc;
     }
-    void commit(int32_t p, size_t k) { if (pos.empty()) alloc(); pos[n] = p; nc += k; off[++n] = (uint32_t)nc; if (k != 1) single_op = false; }
+    // off[0..n] made explicit (single-op batches keep it implicit: off[i] == i)
+    void materialize_off() { if (pos.empty()) alloc(); for (size_t i = off_valid; i <= n; i++) off[i] = (uint32_t)i; off_valid = n + 1; }
+    void commit(int32_t p, size_t k)
+    {
+        if (pos.empty()) alloc();
+        if (k != 1 && single_op) { materialize_off(); single_op = false; }
+        pos[n] = p; nc += k; ++n;
+        if (!single_op) { off[n] = (uint32_t)nc; off_valid = n + 1; }
+    }
     void add(const bam1_t *b)
     {
         const uint32_t k = b->core.n_cigar;
@@ -103,16 +114,25 @@ struct Batch {
     }
     void add_raw(const RawRead &r)
     {
+        if (__builtin_expect(r.n_cigar == 1 && single_op && nc < cig_cap, 1)) {     // the common read: two 4-byte stores
+            memcpy(cig_p + nc, r.cigar, 4); pos_p[n] = r.pos; ++nc; ++n;
+            return;
+        }
         uint32_t *c = room(r.n_cigar);
-        if (r.n_cigar == 1) memcpy(c, r.cigar, 4);
-        else if (r.n_cigar) memcpy(c, r.cigar, (size_t)r.n_cigar * 4);
+        if (r.n_cigar) memcpy(c, r.cigar, (size_t)r.n_cigar * 4);
         commit(r.pos, r.n_cigar);
     }
     void add_op(uint32_t op, int64_t len)                     // one more op of the read being built (PAF); split above 2^28-1
     {
         while (len > 0) { const int64_t m = std::min<int64_t>(len, (1 << 28) - 1); *room(1) = ((uint32_t)m << 4) | op; nc++; len -= m; }
     }
-    void commit_built(int32_t p, size_t nc_before) { if (pos.empty()) alloc(); pos[n] = p; off[++n] = (uint32_t)nc; if (nc - nc_before != 1) single_op = false; }
+    void commit_built(int32_t p, size_t nc_before)
+    {
+        if (pos.empty()) alloc();
+        if (nc - nc_before != 1 && single_op) { materialize_off(); single_op = false; }
+        pos[n] = p; ++n;
+        if (!single_op) { off[n] = (uint32_t)nc; off_valid = n + 1; }
+    }
     // order-independent digest of the batch (PANDEPTH_DRY diagnostics: compare decode paths without a GPU)
     uint64_t digest(int tid) const
     {
@@ -120,7 +140,8 @@ struct Batch {
         uint64_t sum = 0;
         for (size_t i = 0; i < n; i++) {
             uint64_t h = mix(((uint64_t)(uint32_t)tid << 32) | (uint32_t)pos[i]);
-            for (uint32_t k = off[i]; k < off[i + 1]; k++) h = mix(h ^ cigar[k]);
+            const uint32_t k0 = single_op ? (uint32_t)i : off[i], k1 = single_op ? (uint32_t)i + 1 : off[i + 1];
+            for (uint32_t k = k0; k < k1; k++) h = mix(h ^ cigar[k]);
             sum += h;
         }
         return sum;
@@ -177,6 +198,7 @@ struct Feeder {
     bool used_fast = false;
     PinnedPool *pool = nullptr;                          // pinned staging (exists once the CUDA context does)
     bool dry = getenv("PANDEPTH_DRY") != nullptr;
+    bool dry_nodigest = dry && getenv("PANDEPTH_DRY")[0] == '2';     // PANDEPTH_DRY=2: decode timing without the digest
     struct Pending { int tid; bool sorted; Batch b; };
     std::vector<Pending> pending;                        // batches decoded before the CUDA context was ready
     std::mutex pend_mu;
@@ -192,7 +214,7 @@ struct Feeder {
     bool push(int tid, Batch &b, bool sorted)
     {
         if (b.n == 0) return true;
-        if (dry) { reads_pushed += b.n; dry_digest += b.digest(tid); b.clear(); return true; }
+        if (dry) { reads_pushed += b.n; if (!dry_nodigest) dry_digest += b.digest(tid); b.clear(); return true; }
         if (!eng_ok.load()) {
             // the CUDA context is still coming up: park the batch and keep decoding (bounded: ~3 GB of parked reads)
             if (!engine_ready()) {

@@ -70,3 +70,22 @@ def test_cram_indexed_ranges_feed_the_same_reads_as_one_sequential_pass(tmp_path
         assert _digest(cram, opts, hts=False)[:2] == seq[:2], opts
     for opts in (["-q", "20"], ["-x", "0"]):
         assert _digest(cram, opts, hts=False)[:2] == _digest(cram, opts + ["-s"], hts=False)[:2], opts
+
+
+def test_feeders_hand_over_exactly_the_oracle_parsers_records(bams):
+    """An independent pin of the batch layout (pos / cigar / cigar offsets, implicit offsets of single-op batches): the digest
+    of everything the CLI would push equals the digest of the records the oracle's SAM parser (oracle/model.py parse_sam)
+    keeps after the record filter (PanDepth.cpp:732-733), for the SAM stream, the raw BAM scanner and the htslib iterators."""
+    from oracle import model
+    from tests.test_paf_host_cpu import _digest_of
+    import numpy as np
+    for fx in ("k", "mix", "big"):
+        sam = os.path.join(GOLD, fx + ".sam")
+        _, rec, _ = model.parse_sam(sam)
+        for opts, x, q in (([], 1796, -1), (["-x", "0"], 0, -1), (["-x", "3844", "-q", "3"], 3844, 3)):
+            keep = np.flatnonzero(((rec.flag & x) == 0) & (rec.mapq.astype(np.int64) >= q) & (rec.tid >= 0))
+            want = rec.select(keep)
+            want = (want.n, _digest_of(want))
+            assert _digest(sam, opts, hts=False)[:2] == want, (fx, opts, "sam stream")
+            assert _digest(bams[fx], opts, hts=False)[:2] == want, (fx, opts, "fastbam")
+            assert _digest(bams[fx], opts + ["-t", "5"], hts=True)[:2] == want, (fx, opts, "htslib iterators")
