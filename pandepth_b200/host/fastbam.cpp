@@ -1,5 +1,6 @@
 // fastbam.cpp -- see fastbam.hpp.  BAM / BGZF / BAI layouts follow the SAM/BAM specification (SAMv1.pdf sections 4.1, 4.2, 5.2).
 #include "fastbam.hpp"
+#include <algorithm>
 
 #include <fcntl.h>
 #include <unistd.h>
@@ -99,13 +100,17 @@ bool BamRangeScanner::inflate_next_block()
         // need the fixed 18-byte BGZF header (12 gzip + 6 extra) before anything else
         if (raw_len_ - raw_pos_ < (1u << 16) + 64 && !eof_) {
             if (raw_pos_) { memmove(raw_.data(), raw_.data() + raw_pos_, raw_len_ - raw_pos_); raw_len_ -= raw_pos_; raw_pos_ = 0; }
+            // read-ahead grows with the scan (128 KB, 256 KB, ... up to the 2 MB buffer): a range that ends after a few
+            // records (tens of thousands of small contigs) must not pay for 2 MB of page-cache copies
             while (raw_len_ < raw_.size()) {
-                ssize_t k = pread(fd_, raw_.data() + raw_len_, raw_.size() - raw_len_, (off_t)file_pos_);
+                const size_t want = std::min(raw_.size() - raw_len_, read_ahead_);
+                ssize_t k = pread(fd_, raw_.data() + raw_len_, want, (off_t)file_pos_);
                 if (k < 0) { err_ = "read error"; return false; }
                 if (k == 0) { eof_ = true; break; }
                 raw_len_ += (size_t)k; file_pos_ += (uint64_t)k;
                 if (raw_len_ - raw_pos_ >= (1u << 16) + 64) break;
             }
+            if (read_ahead_ < raw_.size()) read_ahead_ *= 2;
         }
         const size_t avail = raw_len_ - raw_pos_;
         if (avail == 0) return false;                                         // clean EOF

@@ -49,6 +49,7 @@ private:
     int fd_ = -1;
     void *dec_ = nullptr;
     std::vector<uint8_t> raw_; size_t raw_len_ = 0, raw_pos_ = 0; uint64_t file_pos_ = 0; bool eof_ = false;
+    size_t read_ahead_ = 128u << 10;   // bytes per pread; reset by scan(), doubled as the scan goes on
     std::vector<uint8_t> buf_; size_t blen_ = 0, bpos_ = 0;
     std::vector<uint32_t> cg_;         // long CIGAR recovered from the CG tag
     std::string err_;
@@ -62,7 +63,7 @@ template <typename F>
 bool BamRangeScanner::scan(uint64_t voff, int tid, int64_t end_pos, F &&fn)
 {
     // position the compressed stream at the block, the inflated stream at the in-block offset
-    file_pos_ = voff >> 16; raw_len_ = raw_pos_ = 0; eof_ = false;
+    file_pos_ = voff >> 16; raw_len_ = raw_pos_ = 0; eof_ = false; read_ahead_ = 128u << 10;
     blen_ = bpos_ = 0;
     if (!inflate_next_block()) return err_.empty();
     bpos_ = (size_t)(voff & 0xffff);
