@@ -84,8 +84,11 @@ struct GzWriter {
     FILE *fp = nullptr;
     int threads = 1;
     bool wrote = false;
-    bool open(const std::string &path, int nthreads) { fp = fopen(path.c_str(), "wb"); threads = std::max(1, nthreads); return fp != nullptr; }
-    void put(const std::string &text) { if (text.empty()) return; std::string z = gz_member(text); fwrite(z.data(), 1, z.size(), fp); wrote = true; }
+    bool failed = false;                                     // a short write (disk full, quota): reported by close()
+    std::string path;
+    bool open(const std::string &p, int nthreads) { path = p; fp = fopen(p.c_str(), "wb"); threads = std::max(1, nthreads); return fp != nullptr; }
+    void emit(const std::string &z) { if (z.empty()) return; if (fwrite(z.data(), 1, z.size(), fp) != z.size()) failed = true; wrote = true; }
+    void put(const std::string &text) { if (text.empty()) return; emit(gz_member(text)); }
     // chunks 0..n-1, text of chunk k = produce(k); chunks must be < 2 GiB each
     template <typename F> void put_chunks(size_t n, F &&produce)
     {
@@ -100,10 +103,19 @@ struct GzWriter {
             for (size_t i = 1; i < nt; i++) th.emplace_back(work);
             work();
             for (auto &t : th) t.join();
-            for (size_t k = 0; k < m; k++) if (!z[k].empty()) { fwrite(z[k].data(), 1, z[k].size(), fp); wrote = true; }
+            for (size_t k = 0; k < m; k++) emit(z[k]);
         }
     }
-    void close() { if (!fp) return; if (!wrote) { std::string z = gz_member(std::string()); fwrite(z.data(), 1, z.size(), fp); } fclose(fp); fp = nullptr; }
+    // false if anything could not be written; the caller reports it and exits non-zero
+    bool close()
+    {
+        if (!fp) return !failed;
+        if (!wrote) emit(gz_member(std::string()));
+        if (fclose(fp) != 0) failed = true;
+        fp = nullptr;
+        if (failed) std::cerr << "Error: write failed (disk full?): " << path << std::endl;
+        return !failed;
+    }
 };
 
 // SoA batch of one contig's records in plain (pageable) host memory: workers can fill it before the CUDA context exists.
@@ -827,7 +839,7 @@ int main(int argc, char **argv)
                     });
                 }
             }
-            site.close();
+            if (!site.close()) return 1;
         }
     }
     tm.mark("finalize(+site dump)");
@@ -918,7 +930,7 @@ int main(int argc, char **argv)
                          (unsigned long long)SS_Len, (unsigned long long)SS_Cov, Coverage, MeanDepth);
         out.put(std::string(row, (size_t)m));
     }
-    out.close();
+    if (!out.close()) return 1;
     tm.mark("reduce+report");
     // every output is flushed and closed: leave without the teardown of the CUDA context, 24 GB of device memory and the
     // parked/pinned host buffers -- the OS reclaims all of it, and the orderly teardown only costs wall time
