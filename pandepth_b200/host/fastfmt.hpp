@@ -3,6 +3,7 @@
 // formatter itself a hot loop, so integers are written by hand and the two ratios by an exact integer shortcut.
 #pragma once
 #include <cstdint>
+#include <climits>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -73,6 +74,35 @@ inline std::string format_window_rows(const char *chr, int64_t W, int64_t CC, co
         *p++ = '\t'; p = put_i64(p, GeneDepth);
         *p++ = '\t'; p = put_ratio2(p, (int64_t)GeneCover * 100, GeneLength);
         *p++ = '\t'; p = put_ratio2(p, (int64_t)GeneDepth, GeneLength);
+        *p++ = '\n';
+    }
+    text.resize((size_t)(p - &text[0]));
+    return text;
+}
+
+// Rows k in [a, b) of the mode-5 report of one contig (-w >= 150 pseudo-genes, :5080-5118): tile k is 1-based closed
+// [1 + k*W, min(k*W + W, len)]; GeneCover is an int, Length and TotalDepth are 64-bit, Coverage = GeneCover*100.0/Length,
+// MeanDepth = GeneDepth*1.0/Length.  cov[k] / sum[k] belong to tile k of this contig.
+inline std::string format_tile_rows(const std::string &chr, int64_t W, int64_t len, const uint64_t *cov, const uint64_t *sum, int64_t a, int64_t b)
+{
+    std::string text;
+    text.resize((size_t)(b - a) * (chr.size() + 176));
+    char *p = &text[0];
+    for (int64_t k = a; k < b; k++) {
+        const int64_t Start = 1 + k * W;
+        const int64_t End = Start + W - 1 < len ? Start + W - 1 : len;
+        const int64_t Length = End - Start + 1;
+        const int GeneCover = (int)(int64_t)cov[(size_t)k];
+        memcpy(p, chr.data(), chr.size()); p += chr.size();
+        *p++ = '\t'; p = put_i64(p, Start);
+        *p++ = '\t'; p = put_i64(p, End);
+        *p++ = '\t'; p = put_u64(p, (uint64_t)Length);
+        *p++ = '\t'; p = put_i64(p, GeneCover);
+        *p++ = '\t'; p = put_u64(p, sum[(size_t)k]);
+        *p++ = '\t'; p = put_ratio2(p, (int64_t)GeneCover * 100, Length);
+        *p++ = '\t';
+        if (sum[(size_t)k] <= (uint64_t)INT64_MAX) p = put_ratio2(p, (int64_t)sum[(size_t)k], Length);
+        else p += snprintf(p, 48, "%.2f", sum[(size_t)k] * 1.0 / (uint64_t)Length);
         *p++ = '\n';
     }
     text.resize((size_t)(p - &text[0]));

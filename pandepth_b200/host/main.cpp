@@ -683,6 +683,24 @@ int main(int argc, char **argv)
     if (const char *dump = getenv("PANDEPTH_DUMP_REGIONS")) {
         if (FILE *f = fopen(dump, "w")) {
             fprintf(f, "mode %d mask %x\n", mode, (unsigned)mask);
+            if (mode == 5) {
+                // implicit -w tiles (pd_host.hpp n_tiles), in the std::map<string> order of their ids; every tile is its own
+                // merged region (adjacent tiles do not merge, :3919-3972) and is handed over exactly once
+                for (const auto &kv : genes) {
+                    const long long W = o.tile_win, len = tlen[kv.first], nt = n_tiles(len, W);
+                    std::vector<std::pair<std::string, long long>> ids;
+                    for (long long k = 0; k < nt; k++) ids.emplace_back(targets[(size_t)kv.first].name + std::to_string(1 + k * W), k);
+                    std::sort(ids.begin(), ids.end());
+                    for (const auto &id : ids) {
+                        const long long S = 1 + id.second * W, E = std::min(S + W - 1, len);
+                        fprintf(f, "G\t%d\t%s\t%lld\t%lld\t%lld\t%lld,%lld\n", kv.first, id.first.c_str(), S, E, E - S + 1, S, E);
+                    }
+                    fprintf(f, "M\t%d", kv.first);
+                    for (long long k = 0; k < nt; k++) fprintf(f, "\t%lld,%lld", 1 + k * W, std::min(k * W + W, len));
+                    fputc('\n', f);
+                    for (const auto &id : ids) fprintf(f, "W\t%d\t%s\t1\n", kv.first, id.first.c_str());
+                }
+            } else
             for (const auto &kv : genes) {
                 for (const auto &gk : kv.second) {
                     const Gene &g = gk.second;
@@ -868,6 +886,43 @@ int main(int argc, char **argv)
                 const int64_t j = 1 + k * W;
                 const int64_t End = std::min(j - 1 + W, CC);
                 SS_Cov += (uint64_t)(int64_t)(int)cov[(size_t)k]; SS_Len += (uint64_t)(int64_t)(int)(End - j + 1); SS_TotalD += (uint64_t)(int64_t)(int)sum[(size_t)k];
+            }
+        }
+    } else if (mode == 5) {
+        // -w >= 150: the pseudo-gene tiles are enumerated arithmetically (pd_host.hpp n_tiles) -- one pd_reduce over all of them,
+        // rows formatted and compressed in parallel.  Same rows, same order (GeneStart) and same totals as the generic
+        // branch below produces from materialised genes (:5080-5118); every tile counts exactly once (pd_host.hpp).
+        const long long W = o.tile_win;
+        std::vector<int> tids;
+        std::vector<size_t> base;                                                            // first interval of each contig
+        size_t n_iv = 0;
+        for (auto &kv : genes) { tids.push_back(kv.first); base.push_back(n_iv); n_iv += (size_t)n_tiles(tlen[kv.first], W); }
+        std::vector<int32_t> iv_t(n_iv), iv_s(n_iv), iv_e(n_iv);
+        for (size_t ci = 0; ci < tids.size(); ci++) {
+            const long long len = tlen[tids[ci]], nt = n_tiles(len, W);
+            for (long long k = 0; k < nt; k++) {
+                iv_t[base[ci] + (size_t)k] = tids[ci];
+                iv_s[base[ci] + (size_t)k] = (int32_t)(k * W);
+                iv_e[base[ci] + (size_t)k] = (int32_t)std::min(k * W + W, len);
+            }
+        }
+        std::vector<uint64_t> cov(n_iv), sum(n_iv);
+        if (pd_reduce(eng, (int64_t)n_iv, iv_t.data(), iv_s.data(), iv_e.data(), (uint32_t)o.min_dep, mask, cov.data(), sum.data(), 0) != PD_OK) {
+            std::cerr << "Error: " << pd_last_error(eng) << std::endl; return 1;
+        }
+        for (size_t ci = 0; ci < tids.size(); ci++) {
+            const long long len = tlen[tids[ci]], nt = n_tiles(len, W);
+            const std::string &chr = targets[(size_t)tids[ci]].name;
+            const uint64_t *c = cov.data() + base[ci], *d = sum.data() + base[ci];
+            const long long SUB = 1 << 16;
+            out.put_chunks((size_t)((nt + SUB - 1) / SUB), [&](size_t ch) {
+                const long long a = (long long)ch * SUB, b = std::min(nt, a + SUB);
+                return format_tile_rows(chr, W, len, c, d, a, b);
+            });
+            for (long long k = 0; k < nt; k++) {
+                SS_Cov += (uint64_t)(int64_t)(int)(int64_t)c[k];
+                SS_Len += (uint64_t)(std::min(k * W + W, len) - k * W);
+                SS_TotalD += d[k];
             }
         }
     } else {

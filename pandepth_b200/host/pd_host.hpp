@@ -30,6 +30,7 @@ struct Options {
     int win = 0;                       // -w  (clamped >= 1 when given, :211-215)
     int threads = 3;                   // -t
     int region_mode = 0;               // InInt2: 0 chr, 1 gff, 2 gtf, 3 bed3, 4 bed4, 5 window>=150, 6 window<150
+    long long tile_win = 0;            // mode 5: width of the -w pseudo-gene tiles, which stay implicit (see n_tiles)
     bool gc = false;                   // -c (not supported by this build; reported)
     bool help = false;
 };
@@ -72,7 +73,17 @@ struct LineReader {
     }
 };
 
+// Pseudo-gene tiles of a contig (:3997-4044): tile k is 1-based closed [1 + k*W, min(k*W + W, len)] and exists while
+// k*W + 2 <= len (`End` is pre-set to 2 and bumped by 2 after each tile) -- contigs shorter than 2 bp have none and a
+// final 1-bp remainder (len % W == 1) is dropped.
+inline long long n_tiles(long long len, long long W) { return len >= 2 ? (len - 2) / W + 1 : 0; }
+
 // :3547-3905 (GFF/GTF/BED parsers), :3975-4051 (pseudo-gene tiling).  Sets o.region_mode.
+// Mode 5 (-w >= 150 without -g/-b) can mean 2x10^7 tiles on a 3 Gb genome: they are NOT materialised as map entries (the
+// reference's std::map costs it tens of seconds there); `genes` then holds 10 Mb tiles, only to say which contigs exist, and
+// o.tile_win carries W.  The report enumerates tile k arithmetically; every tile is handed to StatChrDepthWin exactly once
+// (windows of ProDealChrBambai start and end on tile boundaries, :695-784), which tests/test_regions_host_cpu.py checks
+// against the oracle's generic hand-over count.
 bool build_regions(Options &o, const std::vector<Target> &targets, GeneMap &genes, std::string &err);
 // :3919-3972
 std::vector<std::pair<int, int>> merge_regions(const std::map<std::string, Gene> &genes);

@@ -233,7 +233,7 @@ bool build_regions(Options &o, const std::vector<Target> &targets, GeneMap &gene
         long long W = 10000000;
         if (o.win == 0) o.region_mode = 0;
         else if (o.win < 150) o.region_mode = 6;
-        else { o.region_mode = 5; W = o.win; }
+        else { o.region_mode = 5; o.tile_win = o.win; }       // W-wide tiles stay implicit (pd_host.hpp); 10 Mb tiles mark the contigs
         for (size_t t = 0; t < targets.size(); t++) {
             const long long len = targets[t].len;
             long long Start = 1, End = 2;                      // End pre-set to 2, bumped by 2 after each tile (:3997-4044)

@@ -122,6 +122,7 @@ def _region_files(workdir, tag, contigs):
     (31, "a:300001,b:1,c:5000,d:70000,e:2,f:1001", 30000, "bam"),
     (32, "chrA:1000001,chrB:151,chrC:299999", 40000, "bam"),
     (33, "a:300001,b:1,c:5000,d:70000,e:2,f:1001", 30000, "cram"),
+    (34, "big:20000123,s:149,t:10000001", 30000, "bam"),      # contigs longer than the reference's 10 Mb windows (:695-784)
 ])
 def test_host_program_matches_reference_binary_on_random_inputs(seed, contigs, reads, ext, workdir, standin_env):
     inp = os.path.join(workdir, f"rand{seed}.{ext}")
