@@ -83,7 +83,7 @@ inline long long n_tiles(long long len, long long W) { return len >= 2 ? (len - 
 // reference's std::map costs it tens of seconds there); `genes` then holds 10 Mb tiles, only to say which contigs exist, and
 // o.tile_win carries W.  The report enumerates tile k arithmetically; every tile is handed to StatChrDepthWin exactly once
 // (windows of ProDealChrBambai start and end on tile boundaries, :695-784), which tests/test_regions_host_cpu.py checks
-// against the oracle's generic hand-over count.
+// against the generic hand-over count of the CPU model.
 bool build_regions(Options &o, const std::vector<Target> &targets, GeneMap &genes, std::string &err);
 // :3919-3972
 std::vector<std::pair<int, int>> merge_regions(const std::map<std::string, Gene> &genes);
