@@ -6,8 +6,12 @@
 #include <unistd.h>
 #include <zlib.h>
 
+#include <condition_variable>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <thread>
 
 #ifdef PD_HAVE_LIBDEFLATE
 // libdeflate's public C API (the reference vendors lib/libdeflate.a without its header)
@@ -164,7 +168,8 @@ bool BamRangeScanner::fill_slow(size_t need)
 
 // CIGARs with more than 65535 ops are stored in the CG:B,I tag behind a placeholder `<l_seq>S<ref_len>N` (SAMv1 4.2.2);
 // htslib's reader swaps the real one in, and so must we.
-bool BamRangeScanner::resolve_long_cigar(const uint8_t *rec, uint32_t block_size, uint32_t l_read_name, uint32_t n_cigar, int32_t l_seq, RawRead &r)
+bool resolve_long_cigar_tag(const uint8_t *rec, uint32_t block_size, uint32_t l_read_name, uint32_t n_cigar, int32_t l_seq,
+                            std::vector<uint32_t> &cg_, RawRead &r)
 {
     const uint8_t *cg = rec + 32 + l_read_name;
     const uint32_t c0 = le32(cg), c1 = le32(cg + 4);
@@ -199,6 +204,224 @@ bool BamRangeScanner::resolve_long_cigar(const uint8_t *rec, uint32_t block_size
         p += sz;
     }
     return false;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// whole-file stream: ordered parallel inflate
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+
+// one deflate payload -> out (isize bytes); thread-safe (own decompressor per call site)
+struct Inflater {
+#ifdef PD_HAVE_LIBDEFLATE
+    libdeflate_decompressor *d = libdeflate_alloc_decompressor();
+    ~Inflater() { if (d) libdeflate_free_decompressor(d); }
+    bool run(const uint8_t *in, size_t n, uint8_t *out, size_t isize)
+    {
+        size_t got = 0;
+        return d && libdeflate_deflate_decompress(d, in, n, out, isize, &got) == 0 && got == isize;
+    }
+#else
+    bool run(const uint8_t *in, size_t n, uint8_t *out, size_t isize)
+    {
+        z_stream zs; memset(&zs, 0, sizeof zs);
+        if (inflateInit2(&zs, -15) != Z_OK) return false;
+        zs.next_in = (Bytef *)in; zs.avail_in = (uInt)n; zs.next_out = out; zs.avail_out = (uInt)isize;
+        const int rc = inflate(&zs, Z_FINISH);
+        inflateEnd(&zs);
+        return rc == Z_STREAM_END && zs.avail_out == 0;
+    }
+#endif
+};
+
+// BGZF block at h (avail bytes): > 0 total size (payload in cdata/clen, inflated size in isize); 0 = more bytes needed
+// (header or block not complete within avail); -1 = not a BGZF block
+int64_t bgzf_block(const uint8_t *h, size_t avail, const uint8_t **cdata, size_t *clen, uint32_t *isize)
+{
+    if (avail < 18) return 0;
+    if (h[0] != 31 || h[1] != 139 || h[2] != 8 || !(h[3] & 4)) return -1;
+    const uint32_t xlen = le16(h + 10);
+    if (avail < 12 + (size_t)xlen) return 0;
+    uint32_t bsize = 0;
+    for (uint32_t x = 0; x + 4 <= xlen;) {
+        const uint8_t *f = h + 12 + x;
+        const uint32_t slen = le16(f + 2);
+        if (f[0] == 'B' && f[1] == 'C' && slen == 2) { bsize = (uint32_t)le16(f + 4) + 1; break; }
+        x += 4 + slen;
+    }
+    if (bsize < 12 + xlen + 8) return -1;
+    if (bsize > avail) return 0;
+    *cdata = h + 12 + xlen; *clen = bsize - xlen - 12 - 8; *isize = le32(h + bsize - 4);
+    return bsize;
+}
+
+}  // namespace
+
+// Groups of consecutive BGZF blocks (up to ~4 MB inflated / 2 MB compressed) are cut by whoever asks for work next: the cut
+// needs the block headers, a sequential walk, so it happens under the lock on a shared read-ahead buffer and copies only the
+// group's compressed bytes out.  The worker inflates outside the lock and hands the group to the consumer strictly in
+// sequence through a small ring of slots.
+struct BamStreamScanner::Impl {
+    // group size: measured on 8 cores, 100 M SEQ-less reads / 10 M reads with SEQ+QUAL: 0.5 MB groups 1.9 / 1.6 s, 4 MB groups
+    // 1.2 / 1.2 s, 16 MB groups 1.2 / 1.1 s (every hand-over is a lock + a wake-up of the consumer)
+    static constexpr size_t GROUP_IN = 2u << 20, GROUP_OUT = 4u << 20, AHEAD = 8u << 20;
+    struct Slot { std::vector<uint8_t> out; size_t len = 0; uint64_t seq = ~0ull; bool ready = false, bad = false, last = false; };
+    struct Blk { size_t off, clen; uint32_t isize; size_t out_off; };
+    int fd = -1;
+    std::vector<std::thread> workers;
+    std::vector<Slot> ring;
+    std::mutex mu;
+    std::condition_variable cv_ready, cv_free;
+    std::vector<uint8_t> ahead; size_t a_len = 0, a_pos = 0; uint64_t file_pos = 0; bool file_end = false;   // shared read-ahead
+    uint64_t next_seq = 0, consumed = 0;                 // groups [consumed, consumed + ring.size()) may be in flight
+    bool eof = false, stop = false;
+    uint64_t held = ~0ull;                               // the group the consumer is reading (its slot is not reused yet)
+
+    // under the lock: make at least `need` bytes available at ahead[a_pos] if the file has them
+    void fill(size_t need)
+    {
+        if (a_len - a_pos >= need || file_end) return;
+        if (a_pos) { memmove(ahead.data(), ahead.data() + a_pos, a_len - a_pos); a_len -= a_pos; a_pos = 0; }
+        while (a_len < ahead.size()) {
+            const ssize_t k = pread(fd, ahead.data() + a_len, ahead.size() - a_len, (off_t)file_pos);
+            if (k <= 0) { file_end = true; break; }
+            a_len += (size_t)k; file_pos += (uint64_t)k;
+        }
+    }
+
+    // under the lock: cut the next group into raw/blks; returns false when nothing is left (bad = not BGZF)
+    bool cut(std::vector<uint8_t> &raw, std::vector<Blk> &blks, size_t &out_len, bool &bad)
+    {
+        blks.clear(); out_len = 0; bad = false;
+        size_t in_len = 0;
+        while (in_len < GROUP_IN && out_len < GROUP_OUT) {
+            fill((1u << 16) + 64);
+            const uint8_t *cd; size_t cl; uint32_t is;
+            const int64_t b = bgzf_block(ahead.data() + a_pos, a_len - a_pos, &cd, &cl, &is);
+            if (b < 0) { bad = true; break; }
+            if (b == 0) break;                                                 // end of file (a truncated last block ends the stream quietly)
+            if (raw.size() < in_len + (size_t)b) raw.resize(in_len + (size_t)b + (1u << 16));
+            memcpy(raw.data() + in_len, ahead.data() + a_pos, (size_t)b);
+            blks.push_back(Blk{in_len + (size_t)(cd - (ahead.data() + a_pos)), cl, is, out_len});
+            out_len += is; in_len += (size_t)b; a_pos += (size_t)b;
+        }
+        return !blks.empty();
+    }
+
+    void worker()
+    {
+        Inflater inf;
+        std::vector<uint8_t> raw(GROUP_IN + (1u << 17));
+        std::vector<Blk> blks;
+        for (;;) {
+            uint64_t seq; size_t out_len = 0; bool last = false, bad = false;
+            {
+                std::unique_lock<std::mutex> g(mu);
+                cv_free.wait(g, [&] { return stop || eof || next_seq < consumed + ring.size(); });
+                if (stop || eof) return;
+                seq = next_seq++;
+                if (!cut(raw, blks, out_len, bad)) { last = true; eof = true; }
+            }
+            // the slot is free: seq < consumed + ring.size() means its previous tenant (seq - ring.size()) was released
+            Slot &s = ring[seq % ring.size()];
+            if (s.out.size() < out_len) s.out.resize(out_len);
+            if (!bad) for (const Blk &b : blks) if (b.isize && !inf.run(raw.data() + b.off, b.clen, s.out.data() + b.out_off, b.isize)) { bad = true; break; }
+            {
+                std::lock_guard<std::mutex> g(mu);
+                s.len = bad ? 0 : out_len; s.seq = seq; s.bad = bad; s.last = last; s.ready = true;
+            }
+            cv_ready.notify_all();
+            if (last) { cv_free.notify_all(); return; }
+        }
+    }
+};
+
+BamStreamScanner::BamStreamScanner() : im_(new Impl) {}
+
+BamStreamScanner::~BamStreamScanner()
+{
+    { std::lock_guard<std::mutex> g(im_->mu); im_->stop = true; }
+    im_->cv_free.notify_all();
+    for (auto &t : im_->workers) t.join();
+    if (im_->fd >= 0) close(im_->fd);
+    delete im_;
+}
+
+bool BamStreamScanner::open(const std::string &path, int n_threads)
+{
+    im_->fd = ::open(path.c_str(), O_RDONLY);
+    if (im_->fd < 0) { err_ = "cannot open " + path; return false; }
+    // must start with a BGZF block whose payload starts with "BAM\1"
+    uint8_t head[1u << 16];
+    const ssize_t k = pread(im_->fd, head, sizeof head, 0);
+    const uint8_t *cd; size_t cl; uint32_t is;
+    if (k < 28 || bgzf_block(head, (size_t)k, &cd, &cl, &is) <= 0 || is < 4) return false;
+    std::vector<uint8_t> first(is);
+    Inflater inf;
+    if (!inf.run(cd, cl, first.data(), is) || memcmp(first.data(), "BAM\1", 4) != 0) return false;
+    const int nt = std::max(1, n_threads);
+    im_->ring.resize((size_t)nt * 2 + 2);
+    im_->ahead.resize(Impl::AHEAD);
+    for (int i = 0; i < nt; i++) im_->workers.emplace_back([this] { im_->worker(); });
+    return true;
+}
+
+bool BamStreamScanner::next_group()
+{
+    Impl &m = *im_;
+    std::unique_lock<std::mutex> g(m.mu);
+    if (m.held != ~0ull) { m.held = ~0ull; m.consumed++; m.cv_free.notify_one(); }      // release the group just finished: one slot, one worker
+    const uint64_t want = m.consumed;
+    Impl::Slot &s = m.ring[want % m.ring.size()];
+    m.cv_ready.wait(g, [&] { return s.ready && s.seq == want; });
+    s.ready = false;
+    if (s.bad) { err_ = "BGZF stream is corrupt"; return false; }
+    m.held = want;
+    cur_ = s.out.data(); cur_len_ = s.len; cur_pos_ = 0;
+    if (s.last && s.len == 0) return false;
+    return true;
+}
+
+const uint8_t *BamStreamScanner::take(size_t n)
+{
+    if (cur_len_ - cur_pos_ >= n) { const uint8_t *p = cur_ + cur_pos_; cur_pos_ += n; return p; }
+    // straddles groups: assemble in carry_
+    carry_.clear();
+    while (carry_.size() < n) {
+        const size_t have = cur_len_ - cur_pos_, need = n - carry_.size(), k = have < need ? have : need;
+        carry_.insert(carry_.end(), cur_ + cur_pos_, cur_ + cur_pos_ + k);
+        cur_pos_ += k;
+        if (carry_.size() < n && !next_group()) return nullptr;
+    }
+    return carry_.data();
+}
+
+bool BamStreamScanner::skip(size_t n)
+{
+    while (n) {
+        const size_t have = cur_len_ - cur_pos_, k = have < n ? have : n;
+        cur_pos_ += k; n -= k;
+        if (n && !next_group()) return false;
+    }
+    return true;
+}
+
+bool BamStreamScanner::read_header()
+{
+    const uint8_t *p = take(8);
+    if (!p || memcmp(p, "BAM\1", 4) != 0) { if (err_.empty()) err_ = "not a BAM stream"; return false; }
+    const uint32_t l_text = le32(p + 4);
+    if (!skip(l_text)) return false;
+    p = take(4);
+    if (!p) return false;
+    const uint32_t n_ref = le32(p);
+    for (uint32_t i = 0; i < n_ref; i++) {
+        p = take(4);
+        if (!p) return false;
+        const uint32_t l_name = le32(p);
+        if (!skip((size_t)l_name + 4)) return false;
+    }
+    return true;
 }
 
 }  // namespace pdh

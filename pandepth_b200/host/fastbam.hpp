@@ -53,8 +53,41 @@ private:
     std::vector<uint8_t> buf_; size_t blen_ = 0, bpos_ = 0;
     std::vector<uint32_t> cg_;         // long CIGAR recovered from the CG tag
     std::string err_;
-    bool resolve_long_cigar(const uint8_t *rec, uint32_t block_size, uint32_t l_read_name, uint32_t n_cigar, int32_t l_seq, RawRead &r);
 };
+
+// The whole-file counterpart for BAMs without an index (the reference's "No Index mode", PanDepth.cpp:4604-4713, reads them
+// through `sam_read1` on one thread): BGZF blocks are independent deflate streams, so a pool of workers inflates groups of
+// consecutive blocks in parallel, and ONE consumer walks the records of the re-assembled stream in file order -- the order
+// matters (batches are cut at contig changes and sorted input keeps the tile path).  The walk costs ~7 ns per record, the
+// inflate 23-860 ns, so the consumer is not the bottleneck until ~8 inflating cores on SEQ-less files.
+class BamStreamScanner {
+public:
+    struct Read : RawRead { int32_t tid; };
+    BamStreamScanner();
+    ~BamStreamScanner();
+    // false if the file cannot be opened or does not start with a BGZF block holding the BAM magic (caller falls back to htslib)
+    bool open(const std::string &bam_path, int n_threads);
+    // Calls fn(const Read&) for every record of the file in order.  Returns false on a malformed stream (see error());
+    // a truncated final record ends the scan quietly, as `while (sam_read1(...) >= 0)` does.
+    template <typename F> bool scan_all(F &&fn);
+    const std::string &error() const { return err_; }
+
+private:
+    struct Impl;
+    Impl *im_;
+    std::string err_;
+    std::vector<uint8_t> carry_;        // bytes of a record (or header field) that straddles two groups
+    const uint8_t *cur_ = nullptr; size_t cur_len_ = 0, cur_pos_ = 0;
+    std::vector<uint32_t> cg_;
+    bool next_group();                                   // advance cur_ to the next inflated group; false at EOF / error
+    const uint8_t *take(size_t n);                       // n contiguous bytes of the stream (stitched through carry_), or nullptr at EOF
+    bool skip(size_t n);
+    bool read_header();
+};
+
+// long CIGAR (> 65535 ops) kept in the CG:B,I tag behind a `<l_seq>S<ref_len>N` placeholder (SAMv1 4.2.2): fills r from it
+bool resolve_long_cigar_tag(const uint8_t *rec, uint32_t block_size, uint32_t l_read_name, uint32_t n_cigar, int32_t l_seq,
+                            std::vector<uint32_t> &store, RawRead &r);
 
 inline uint32_t le32(const uint8_t *p) { return (uint32_t)p[0] | (uint32_t)p[1] << 8 | (uint32_t)p[2] << 16 | (uint32_t)p[3] << 24; }
 inline uint16_t le16(const uint8_t *p) { return (uint16_t)((uint16_t)p[0] | (uint16_t)p[1] << 8); }
@@ -84,9 +117,33 @@ bool BamRangeScanner::scan(uint64_t voff, int tid, int64_t end_pos, F &&fn)
         r.n_cigar = n_cigar;
         if (32 + l_read_name + 4 * (size_t)n_cigar > block_size) { err_ = "BAM record shorter than its CIGAR"; return false; }
         r.cigar = rec + 32 + l_read_name;
-        if (n_cigar == 2) resolve_long_cigar(rec, block_size, l_read_name, n_cigar, r.l_seq, r);
+        if (n_cigar == 2) resolve_long_cigar_tag(rec, block_size, l_read_name, n_cigar, r.l_seq, cg_, r);
         fn(r);
         bpos_ += 4 + (size_t)block_size;
+    }
+}
+
+template <typename F>
+bool BamStreamScanner::scan_all(F &&fn)
+{
+    if (!read_header()) return err_.empty();
+    for (;;) {
+        const uint8_t *h = take(4);
+        if (!h) return err_.empty();
+        const uint32_t block_size = le32(h);
+        if (block_size < 32 || block_size > (1u << 30)) { err_ = "implausible BAM record size"; return false; }
+        const uint8_t *rec = take(block_size);
+        if (!rec) return err_.empty();                                        // truncated final record: stop quietly
+        const uint32_t l_read_name = rec[8];
+        const uint32_t n_cigar = le16(rec + 12);
+        Read r;
+        r.tid = (int32_t)le32(rec); r.pos = (int32_t)le32(rec + 4);
+        r.mapq = rec[9]; r.flag = le16(rec + 14); r.l_seq = (int32_t)le32(rec + 16);
+        r.n_cigar = n_cigar;
+        if (32 + l_read_name + 4 * (size_t)n_cigar > block_size) { err_ = "BAM record shorter than its CIGAR"; return false; }
+        r.cigar = rec + 32 + l_read_name;
+        if (n_cigar == 2) resolve_long_cigar_tag(rec, block_size, l_read_name, n_cigar, r.l_seq, cg_, r);
+        fn(r);
     }
 }
 

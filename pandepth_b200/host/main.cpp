@@ -440,6 +440,32 @@ struct Feeder {
         }
     }
 
+    // no-index path for BAM input: ordered parallel BGZF inflate + one record walker (fastbam.hpp BamStreamScanner).
+    // Returns false without having pushed anything if the file is not a BAM this scanner handles (caller uses htslib).
+    bool stream_all_fast(bool sorted, size_t n_targets)
+    {
+        BamStreamScanner sc;
+        if (!sc.open(input, std::max(1, o.threads))) return false;
+        used_fast = true;
+        Batch batch;
+        int cur = -1;
+        bool ok_push = true;
+        const uint32_t xf = o.xflags; const int mq = o.min_mapq;
+        const bool ok = sc.scan_all([&](const BamStreamScanner::Read &r) {
+            if (!ok_push) return;
+            if ((int)r.mapq < mq) return;
+            if (r.flag & xf) return;
+            const int t = r.tid;
+            if (t < 0 || (size_t)t >= n_targets) return;
+            if (t != cur) { ok_push = push(cur, batch, sorted); cur = t; if (!ok_push) return; }
+            batch.add_raw(r);
+            if (batch.full()) ok_push = push(cur, batch, sorted);
+        });
+        if (!ok) { fail("Error: malformed BAM while reading " + input + ": " + sc.error()); return true; }
+        if (ok_push && !failed) push(cur, batch, sorted);
+        return true;
+    }
+
     // no-index path (:4604-4713): one pass over the file, batches split at contig changes
     bool stream_all(bool sorted)
     {
@@ -820,7 +846,8 @@ int main(int argc, char **argv)
         } else {
             if (f_sorted) std::cout << "Warning: PanDepth will run in No Index mode: " << path << std::endl;                       // :4606
             else std::cout << "Warning: Can't find index file of input BAM/CRAM. PanDepth will run in No Index mode: " << path << std::endl;   // :4677
-            feeder.stream_all(f_sorted);
+            // BAM: own parallel stream reader; SAM / CRAM / PANDEPTH_HTS_ITER=1: htslib's sam_read1
+            if (!(f_bam && !getenv("PANDEPTH_HTS_ITER") && feeder.stream_all_fast(f_sorted, targets.size()))) feeder.stream_all(f_sorted);
         }
     }
     if (dry) {

@@ -89,3 +89,35 @@ def test_feeders_hand_over_exactly_the_oracle_parsers_records(bams):
             assert _digest(sam, opts, hts=False)[:2] == want, (fx, opts, "sam stream")
             assert _digest(bams[fx], opts, hts=False)[:2] == want, (fx, opts, "fastbam")
             assert _digest(bams[fx], opts + ["-t", "5"], hts=True)[:2] == want, (fx, opts, "htslib iterators")
+
+
+@pytest.mark.parametrize("name", ["k", "mix", "big", "r1", "r2"])
+def test_stream_scanner_feeds_the_same_reads_as_sam_read1(name, bams):
+    """No-index mode (-s): the ordered parallel BGZF reader + single record walker against htslib's sam_read1 loop."""
+    for opts in (["-s"], ["-s", "-t", "1"], ["-s", "-x", "0", "-t", "7"], ["-s", "-q", "20", "-w", "100"]):
+        fast = _digest(bams[name], opts, hts=False)
+        slow = _digest(bams[name], opts, hts=True)
+        assert fast[2] == "fastbam" and slow[2] == "htslib"
+        assert fast[:2] == slow[:2], (name, opts, fast, slow)
+
+
+def test_stream_scanner_on_large_and_damaged_files(tmp_path):
+    """Records and the header straddling many blocks and groups; a file cut in the middle of a block or of a record ends
+    quietly with a prefix of the reads (the reference's `while (sam_read1(...) >= 0)` does the same); garbage is an error."""
+    big = str(tmp_path / "s.bam")        # SEQ+QUAL: ~100 MB inflated, groups of 4 MB -> records straddle every group boundary
+    subprocess.run([BAMGEN, "-o", big, "-c", "a:3000001,b:999,c:2000000", "-n", "400000", "-s", "5", "-q"], check=True)
+    want = _digest(big, [], hts=False)
+    assert _digest(big, ["-s"], hts=False)[:2] == want[:2] == _digest(big, ["-s"], hts=True)[:2]
+    data = open(big, "rb").read()
+    for cut in (len(data) // 2, len(data) - 40, 70000):
+        t = str(tmp_path / f"cut{cut}.bam")
+        with open(t, "wb") as fh:
+            fh.write(data[:cut])
+        n, _, path = _digest(t, ["-s"], hts=False)
+        assert path == "fastbam" and 0 <= n < want[0]
+    g = str(tmp_path / "garbage.bam")
+    with open(g, "wb") as fh:
+        fh.write(data[:300000] + bytes(range(256)) * 400 + data[300000:])
+    env = dict(os.environ, PANDEPTH_DRY="1")
+    r = subprocess.run([CLI, "-i", g, "-o", g + ".out", "-s"], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+    assert r.returncode == 1 and "malformed BAM" in r.stderr
