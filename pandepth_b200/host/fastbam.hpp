@@ -67,7 +67,7 @@ public:
     ~BamStreamScanner();
     // false if the file cannot be opened or does not start with a BGZF block holding the BAM magic (caller falls back to htslib)
     bool open(const std::string &bam_path, int n_threads);
-    // Calls fn(const Read&) for every record of the file in order.  Returns false on a malformed stream (see error());
+    // Calls fn(const Read&) -> bool for every record of the file in order until it returns false.  Returns false on a malformed stream (see error());
     // a truncated final record ends the scan quietly, as `while (sam_read1(...) >= 0)` does.
     template <typename F> bool scan_all(F &&fn);
     const std::string &error() const { return err_; }
@@ -143,7 +143,7 @@ bool BamStreamScanner::scan_all(F &&fn)
         if (32 + l_read_name + 4 * (size_t)n_cigar > block_size) { err_ = "BAM record shorter than its CIGAR"; return false; }
         r.cigar = rec + 32 + l_read_name;
         if (n_cigar == 2) resolve_long_cigar_tag(rec, block_size, l_read_name, n_cigar, r.l_seq, cg_, r);
-        fn(r);
+        if (!fn(r)) return true;
     }
 }
 

@@ -345,6 +345,36 @@ struct Feeder {
         }
     }
 
+    // The reference's no-index pass over a coordinate-sorted file (:4604-4675, list mode :2859-2945) does not accumulate every
+    // read: per contig it keeps a cursor into the merged regions, skips reads that end before the cursor's region
+    // (`bam_endpos`, which is pos+1 for a read flagged unmapped, whatever its CIGAR says), moves the cursor past regions the
+    // read starts beyond, gives up on a contig after its last region and stops reading once every contig is finished.
+    // Which reads reach the depth array therefore depends on that cursor; it is restated here so that the same reads do.
+    struct RegionCursor {
+        const std::map<int, std::vector<std::pair<int, int>>> &merged;
+        std::vector<const std::vector<std::pair<int, int>> *> regs;   // per tid; nullptr = no regions (EndChr starts true)
+        std::vector<size_t> at;
+        std::vector<char> done;
+        size_t open_contigs = 0;
+        RegionCursor(const std::map<int, std::vector<std::pair<int, int>>> &m, size_t n_targets) : merged(m), regs(n_targets, nullptr), at(n_targets, 0), done(n_targets, 1)
+        {
+            for (const auto &kv : merged) if (kv.first >= 0 && (size_t)kv.first < n_targets && !kv.second.empty()) { regs[(size_t)kv.first] = &kv.second; done[(size_t)kv.first] = 0; open_contigs++; }
+        }
+        bool contig_done(int t) const { return done[(size_t)t] != 0; }
+        // 0 = skip the read, 1 = accumulate it, 2 = every contig is finished: stop reading (this read is not accumulated)
+        int step(int t, int64_t pos, int64_t endpos)
+        {
+            const auto &r = *regs[(size_t)t];
+            size_t &k = at[(size_t)t];
+            if (endpos < r[k].first) return 0;
+            if (pos > r[k].second) {
+                for (++k; k < r.size(); ++k) if (pos <= r[k].second) break;
+                if (k == r.size()) { done[(size_t)t] = 1; if (--open_contigs == 0) return 2; }
+            }
+            return 1;
+        }
+    };
+
     // no-index path for BAM input: ordered parallel BGZF inflate + one record walker (fastbam.hpp BamStreamScanner).
     // Returns false without having pushed anything if the file is not a BAM this scanner handles (caller uses htslib).
     bool stream_all_fast(bool sorted, size_t n_targets)
@@ -356,15 +386,25 @@ struct Feeder {
         int cur = -1;
         bool ok_push = true;
         const uint32_t xf = o.xflags; const int mq = o.min_mapq;
-        const bool ok = sc.scan_all([&](const BamStreamScanner::Read &r) {
-            if (!ok_push) return;
-            if ((int)r.mapq < mq) return;
-            if (r.flag & xf) return;
+        RegionCursor cursor(merged, n_targets);
+        const bool ok = sc.scan_all([&](const BamStreamScanner::Read &r) -> bool {
+            if (!ok_push) return false;
             const int t = r.tid;
-            if (t < 0 || (size_t)t >= n_targets) return;
-            if (t != cur) { ok_push = push(cur, batch, sorted); cur = t; if (!ok_push) return; }
+            if (t < 0 || (size_t)t >= n_targets) return true;
+            if (sorted && cursor.contig_done(t)) return true;              // :4610
+            if ((int)r.mapq < mq) return true;
+            if (r.flag & xf) return true;
+            if (sorted) {
+                int64_t rlen = 0;                                         // bam_endpos(): unmapped or no reference-consuming op -> pos + 1
+                if (!(r.flag & 4)) for (uint32_t c = 0; c < r.n_cigar; c++) { const uint32_t wd = r.word(c); if ((0x18du >> (wd & 15u)) & 1u) rlen += wd >> 4; }
+                const int act = cursor.step(t, r.pos, (int64_t)r.pos + (rlen ? rlen : 1));
+                if (act == 0) return true;
+                if (act == 2) return false;
+            }
+            if (t != cur) { ok_push = push(cur, batch, sorted); cur = t; if (!ok_push) return false; }
             batch.add_raw(r);
             if (batch.full()) ok_push = push(cur, batch, sorted);
+            return ok_push;
         });
         if (!ok) { fail("Error: malformed BAM while reading " + input + ": " + sc.error()); return true; }
         if (ok_push && !failed) push(cur, batch, sorted);
@@ -372,7 +412,7 @@ struct Feeder {
     }
 
     // no-index path (:4604-4713): one pass over the file, batches split at contig changes
-    bool stream_all(bool sorted)
+    bool stream_all(bool sorted, size_t n_targets)
     {
         sam_hdr_t *hdr = nullptr;
         htsFile *fp = open_input(&hdr, o.threads);
@@ -380,11 +420,18 @@ struct Feeder {
         bam1_t *b = bam_init1();
         Batch batch;
         int cur = -1;
+        RegionCursor cursor(merged, n_targets);
         while (sam_read1(fp, hdr, b) >= 0) {
+            const int t = b->core.tid;
+            if (t < 0 || (size_t)t >= n_targets) continue;
+            if (sorted && cursor.contig_done(t)) continue;                 // :4610
             if ((int)b->core.qual < o.min_mapq) continue;
             if (b->core.flag & o.xflags) continue;
-            const int t = b->core.tid;
-            if (t < 0) continue;
+            if (sorted) {
+                const int act = cursor.step(t, b->core.pos, bam_endpos(b));
+                if (act == 0) continue;
+                if (act == 2) break;
+            }
             if (t != cur) { if (!push(cur, batch, sorted)) break; cur = t; }
             batch.add(b);
             if (batch.full()) { if (!push(cur, batch, sorted)) break; }

@@ -258,7 +258,7 @@ void feed_hts_file(Feeder &feeder, const Options &o, const std::string &path, bo
         if (f_sorted) std::cout << "Warning: PanDepth will run in No Index mode: " << path << std::endl;                       // :4606
         else std::cout << "Warning: Can't find index file of input BAM/CRAM. PanDepth will run in No Index mode: " << path << std::endl;   // :4677
         // BAM: own parallel stream reader; SAM / CRAM / PANDEPTH_HTS_ITER=1: htslib's sam_read1
-        if (!(f_bam && !getenv("PANDEPTH_HTS_ITER") && feeder.stream_all_fast(f_sorted, n_targets))) feeder.stream_all(f_sorted);
+        if (!(f_bam && !getenv("PANDEPTH_HTS_ITER") && feeder.stream_all_fast(f_sorted, n_targets))) feeder.stream_all(f_sorted, n_targets);
         return;
     }
     if (feeder.items.empty()) plan_items(feeder, merged, tlen, region_modes, o.threads);

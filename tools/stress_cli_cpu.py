@@ -1,0 +1,120 @@
+#!/usr/bin/env python
+"""Randomised differential campaign for the HOST program (no GPU): pandepth_b200/bin/pandepth, with the CUDA library replaced by
+the test stand-in (tests/stand_in/pd_standin.cpp, built into a temp dir), against the reference binary oracle/_ref/pandepth_ref
+on random inputs (BAM / CRAM / SAM, single file or list), random region files and random option sets.  Any difference in the
+decompressed outputs is printed with the command line that reproduces it.
+usage: python tools/stress_cli_cpu.py [seconds] [first_seed]"""
+import gzip, os, random, subprocess, sys, tempfile, time, shutil
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLI = os.path.join(ROOT, "pandepth_b200", "bin", "pandepth")
+REF = os.path.join(ROOT, "oracle", "_ref", "pandepth_ref")
+GEN = os.path.join(ROOT, "oracle", "_ref", "bamgen")
+ORA = os.path.join(ROOT, "oracle", "_ref")
+budget = float(sys.argv[1]) if len(sys.argv) > 1 else 300.0
+seed0 = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
+
+work = tempfile.mkdtemp(prefix="pdstress")
+so_dir = os.path.join(work, "standin"); os.makedirs(so_dir)
+subprocess.run(["g++", "-O2", "-std=c++14", "-fPIC", "-shared", os.path.join(ROOT, "tests", "stand_in", "pd_standin.cpp"), "-L" + ORA, "-lpd_oracle",
+                "-Wl,-rpath," + ORA, "-Wl,-soname,libpandepth_b200.so", "-o", os.path.join(so_dir, "libpandepth_b200.so")], check=True)
+ENV = dict(os.environ, LD_LIBRARY_PATH=so_dir + os.pathsep + os.environ.get("LD_LIBRARY_PATH", ""))
+
+
+def run(binary, inp, args, tag, env=None):
+    pre = os.path.join(work, tag)
+    try:
+        r = subprocess.run([binary, "-i", inp, "-o", pre] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120, env=env)
+        rc = r.returncode
+    except subprocess.TimeoutExpired:
+        rc = -999
+    outs = {}
+    for fn in sorted(os.listdir(work)):
+        if fn.startswith(tag + ".") and fn.endswith(".gz"):
+            try:
+                with gzip.open(os.path.join(work, fn), "rt") as fh:
+                    outs[fn[len(tag):]] = fh.read()
+            except (EOFError, OSError):
+                outs[fn[len(tag):]] = "<truncated>"
+            if not os.environ.get("PDSTRESS_KEEP"): os.unlink(os.path.join(work, fn))
+    return rc, outs
+
+
+t_end = time.time() + budget
+seed, n_cmp, n_bad = seed0, 0, 0
+while time.time() < t_end:
+    rng = random.Random(seed)
+    n_ctg = rng.choice([1, 2, 3, 6, 12])
+    lens = []
+    for _ in range(n_ctg):
+        k = rng.random()
+        lens.append(rng.choice([1, 2, 3, 149, 150, 151, 2048, 4095, 4096, 4097]) if k < 0.25 else
+                    rng.randint(200, 400000) if k < 0.9 else rng.randint(10_000_000, 10_400_000))
+    names = [f"c{i}" for i in range(n_ctg)]
+    spec = ",".join(f"{n}:{l}" for n, l in zip(names, lens))
+    reads = rng.choice([1, 50, 5000, 60000])
+    kind = rng.choice(["bam", "bam", "bam", "cram", "sam", "list"])
+    seq = ["-q"] if rng.random() < 0.3 else []
+    inputs = []
+    for part in range(2 if kind == "list" else 1):
+        ext = {"bam": "bam", "cram": "cram", "sam": "sam", "list": rng.choice(["bam", "sam"])}[kind]
+        path = os.path.join(work, f"in{seed}_{part}.{ext}")
+        cmd = [GEN, "-o", path, "-c", spec, "-n", str(reads), "-m", rng.choice(["mixed", "mixed", "uniform"]), "-s", str(seed * 7 + part)] + seq
+        if ext == "sam":
+            cmd.append("-S")
+        subprocess.run(cmd, check=True)
+        inputs.append(path)
+    if kind == "list":
+        inp = os.path.join(work, f"in{seed}.list")
+        with open(inp, "w") as fh:
+            fh.write("\n".join(inputs) + "\n")
+    else:
+        inp = inputs[0]
+    bed = os.path.join(work, f"r{seed}.bed"); gff = os.path.join(work, f"r{seed}.gff")
+    bed4 = rng.random() < 0.5
+    with open(bed, "w") as fb, open(gff, "w") as fg:
+        fg.write("##gff-version 3\n")
+        for k in range(rng.choice([1, 5, 60])):
+            t = rng.randrange(n_ctg + 1)
+            nm = names[t] if t < n_ctg else "nowhere"
+            ln = lens[t] if t < n_ctg else 1000
+            s = rng.randint(1, max(1, ln)); e = min(ln, s + rng.randint(0, 3000))     # inside the contig: past its end the reference reads its slack (undefined)
+            fb.write(f"{nm}\t{s}\t{e}" + (f"\tg{k // 2}" if bed4 else "") + "\n")
+            fg.write(f"{nm}\tsrc\tCDS\t{s}\t{e}\t.\t+\t0\tID=x{k};Parent=t{k // 3}\n")
+    big = sum(lens) > 2_000_000
+    for trial in range(6):
+        opts = []
+        r = rng.random()
+        if r < 0.3: opts += ["-w", str(rng.choice([1, 2, 7, 33, 100, 128, 129, 149, 150, 151, 160, 161, 500, 1000, 2000]))]
+        elif r < 0.45: opts += ["-b", bed]
+        elif r < 0.6: opts += ["-g", gff]
+        if rng.random() < 0.3: opts += ["-d", str(rng.choice([1, 2, 5]))]
+        if rng.random() < 0.3: opts += ["-q", str(rng.choice([0, 1, 20, 60]))]
+        if rng.random() < 0.3: opts += ["-x", str(rng.choice([0, 4, 1796, 3844, 256]))]
+        if rng.random() < 0.25: opts += ["-s"]
+        # -a with regions: the reference's indexed path and its no-index path disagree with each other; the no-index
+        # path (region cursor) is restated exactly, so there the per-site dump is compared too
+        noindex = "-s" in opts or kind == "sam"
+        if rng.random() < 0.2 and not big and (noindex or not ("-b" in opts or "-g" in opts)): opts += ["-a"]
+        if "-w" in opts and int(opts[opts.index("-w") + 1]) < 7 and sum(lens) > 300_000: continue
+        opts += ["-t", str(rng.choice([1, 3, 8]))]
+        rc_r, ref = run(REF, inp, opts, f"ref{seed}_{trial}")
+        rc_o, our = run(CLI, inp, opts, f"our{seed}_{trial}", ENV)
+        if rc_r < 0:
+            print(f"note: the reference crashed or hung (rc {rc_r}) seed={seed} kind={kind} opts={opts}; ours rc {rc_o}", flush=True)
+            continue
+        n_cmp += 1
+        if ref != our or (rc_r == 0) != (rc_o == 0):
+            n_bad += 1
+            diff = [k for k in set(ref) | set(our) if ref.get(k) != our.get(k)]
+            print(f"DIFF seed={seed} kind={kind} spec={spec} reads={reads} seq={seq} opts={opts} rc={rc_r}/{rc_o} files={diff}", flush=True)
+    if not os.environ.get("PDSTRESS_KEEP"):
+        for p in inputs:
+            for q in (p, p + ".bai", p + ".crai"):
+                if os.path.exists(q): os.unlink(q)
+    seed += 1
+    if os.environ.get("PDSTRESS_ONE"): break
+print(f"seeds {seed0}..{seed - 1}: {n_cmp} comparisons, {n_bad} differences")
+if os.environ.get("PDSTRESS_KEEP"): print("kept", work)
+else: shutil.rmtree(work, ignore_errors=True)
+sys.exit(1 if n_bad else 0)
