@@ -128,7 +128,8 @@ def test_host_program_matches_reference_binary_on_random_inputs(seed, contigs, r
     inp = os.path.join(workdir, f"rand{seed}.{ext}")
     subprocess.run([BAMGEN, "-o", inp, "-c", contigs, "-n", str(reads), "-m", "mixed", "-s", str(seed)], check=True)
     bed, gff, lens = _region_files(workdir, f"rand{seed}", contigs)
-    sets = OPTION_SETS + [["-w", "150"], ["-w", "151", "-d", "2"], ["-b", bed], ["-b", bed, "-d", "3"], ["-g", gff], ["-g", gff, "-s"], ["-b", bed, "-s"]]
+    sets = OPTION_SETS + [["-w", "150"], ["-w", "151", "-d", "2"], ["-b", bed], ["-b", bed, "-d", "3"], ["-g", gff], ["-g", gff, "-s"], ["-b", bed, "-s"],
+                          ["-a", "-b", bed], ["-a", "-g", gff, "-s"], ["-a", "-b", bed, "-s", "-x", "0"]]
     for k, opts in enumerate(sets):
         if "-a" in opts and sum(lens) > 500_000:
             continue                     # the per-site dump is one line per base
@@ -137,6 +138,4 @@ def test_host_program_matches_reference_binary_on_random_inputs(seed, contigs, r
         our, _ = _run(CLI, inp, opts + extra, workdir, f"our{seed}_{k}", standin_env)
         assert sorted(ref) == sorted(our), (opts, sorted(ref), sorted(our))
         for name in ref:
-            if name == ".SiteDepth.gz" and ("-b" in opts or "-g" in opts):
-                continue
             assert ref[name] == our[name], f"seed {seed} {ext} opts {opts}: {name} differs from the reference binary"

@@ -94,7 +94,7 @@ while time.time() < t_end:
         if rng.random() < 0.25: opts += ["-s"]
         # -a with regions: the reference's indexed path and its no-index path disagree with each other; the no-index
         # path (region cursor) is restated exactly, so there the per-site dump is compared too
-        noindex = "-s" in opts or kind == "sam"
+        noindex = "-s" in opts or kind == "sam" or bool(os.environ.get("PDSTRESS_A_ALL"))
         if rng.random() < 0.2 and not big and (noindex or not ("-b" in opts or "-g" in opts)): opts += ["-a"]
         if "-w" in opts and int(opts[opts.index("-w") + 1]) < 7 and sum(lens) > 300_000: continue
         opts += ["-t", str(rng.choice([1, 3, 8]))]
