@@ -3,7 +3,7 @@
 the test stand-in (tests/stand_in/pd_standin.cpp, built into a temp dir), against the reference binary oracle/_ref/pandepth_ref
 on random inputs (BAM / CRAM / SAM, single file or list), random region files and random option sets.  Any difference in the
 decompressed outputs is printed with the command line that reproduces it.
-usage: python tools/stress_cli_cpu.py [seconds] [first_seed]"""
+usage: python tools/stress_cli_cpu.py [seconds | n=<seeds>] [first_seed]"""
 import gzip, os, random, subprocess, sys, tempfile, time, shutil
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -11,7 +11,8 @@ CLI = os.path.join(ROOT, "pandepth_b200", "bin", "pandepth")
 REF = os.path.join(ROOT, "oracle", "_ref", "pandepth_ref")
 GEN = os.path.join(ROOT, "oracle", "_ref", "bamgen")
 ORA = os.path.join(ROOT, "oracle", "_ref")
-budget = float(sys.argv[1]) if len(sys.argv) > 1 else 300.0
+n_seeds = int(sys.argv[1][2:]) if len(sys.argv) > 1 and sys.argv[1].startswith("n=") else None
+budget = 1e9 if n_seeds else (float(sys.argv[1]) if len(sys.argv) > 1 else 300.0)
 seed0 = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
 
 work = tempfile.mkdtemp(prefix="pdstress")
@@ -42,7 +43,8 @@ def run(binary, inp, args, tag, env=None):
 
 t_end = time.time() + budget
 seed, n_cmp, n_bad = seed0, 0, 0
-while time.time() < t_end:
+n_empty, by_kind = 0, {}
+while time.time() < t_end and (n_seeds is None or seed < seed0 + n_seeds):
     rng = random.Random(seed)
     n_ctg = rng.choice([1, 2, 3, 6, 12])
     lens = []
@@ -53,10 +55,36 @@ while time.time() < t_end:
     names = [f"c{i}" for i in range(n_ctg)]
     spec = ",".join(f"{n}:{l}" for n, l in zip(names, lens))
     reads = rng.choice([1, 50, 5000, 60000])
-    kind = rng.choice(["bam", "bam", "bam", "cram", "sam", "list"])
+    kind = rng.choice(["bam", "bam", "bam", "cram", "sam", "list", "paf"])
     seq = ["-q"] if rng.random() < 0.3 else []
     inputs = []
-    for part in range(2 if kind == "list" else 1):
+    if kind == "paf":
+        # PAF lines (paf_main, :1536-1623): target columns 6-9, mapq column 12, optional cg:Z: walk.  Kept inside the contig: the
+        # reference walks past the end of its arrays otherwise (undefined there, clipped here).
+        lens = [max(l, 200) for l in lens]
+        path = os.path.join(work, f"in{seed}.paf" + (".gz" if rng.random() < 0.3 else ""))
+        lines = []
+        for i in range(min(reads, 5000)):
+            t = rng.randrange(n_ctg); ln = lens[t]
+            a = rng.randint(1, ln - 1); z = rng.randint(a, ln)
+            tags = ["tp:A:" + rng.choice("PSI")]
+            if rng.random() < 0.7:
+                ops, room = [], z - a
+                for _ in range(rng.randint(1, 8)):
+                    op = rng.choice("M=XDNISH"); n = rng.randint(1, 300)
+                    if op in "M=XDN":
+                        if n > room: continue
+                        room -= n
+                    ops.append(f"{n}{op}")
+                if ops: tags.append("cg:Z:" + "".join(ops))
+            if rng.random() < 0.3: tags.insert(0, "NM:i:3")
+            lines.append("\t".join([f"q{i}", "1000", "0", "500", "+-"[i & 1], names[t], str(ln), str(a), str(z), "10", "20", str(rng.randint(0, 60))] + tags))
+        # every target appears (the reference takes the target list from the file itself, :918-941)
+        text = "\n".join(lines) + "\n"
+        with (gzip.open(path, "wt") if path.endswith(".gz") else open(path, "w")) as fh:
+            fh.write(text)
+        inputs.append(path)
+    for part in range(0 if kind == "paf" else (2 if kind == "list" else 1)):
         ext = {"bam": "bam", "cram": "cram", "sam": "sam", "list": rng.choice(["bam", "sam"])}[kind]
         path = os.path.join(work, f"in{seed}_{part}.{ext}")
         cmd = [GEN, "-o", path, "-c", spec, "-n", str(reads), "-m", rng.choice(["mixed", "mixed", "uniform"]), "-s", str(seed * 7 + part)] + seq
@@ -104,6 +132,8 @@ while time.time() < t_end:
             print(f"note: the reference crashed or hung (rc {rc_r}) seed={seed} kind={kind} opts={opts}; ours rc {rc_o}", flush=True)
             continue
         n_cmp += 1
+        by_kind[kind] = by_kind.get(kind, 0) + 1
+        if not ref: n_empty += 1
         if ref != our or (rc_r == 0) != (rc_o == 0):
             n_bad += 1
             diff = [k for k in set(ref) | set(our) if ref.get(k) != our.get(k)]
@@ -114,7 +144,7 @@ while time.time() < t_end:
                 if os.path.exists(q): os.unlink(q)
     seed += 1
     if os.environ.get("PDSTRESS_ONE"): break
-print(f"seeds {seed0}..{seed - 1}: {n_cmp} comparisons, {n_bad} differences")
+print(f"seeds {seed0}..{seed - 1}: {n_cmp} comparisons, {n_bad} differences; by input kind {by_kind}; runs without any output file {n_empty}")
 if os.environ.get("PDSTRESS_KEEP"): print("kept", work)
 else: shutil.rmtree(work, ignore_errors=True)
 sys.exit(1 if n_bad else 0)
