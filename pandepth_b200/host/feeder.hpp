@@ -33,8 +33,9 @@ struct Batch {
     bool single_op = true;                                   // every read so far has exactly one op: off[] is the identity and
     size_t off_valid = 0;                                    //   is only written up to off_valid (filled in when it is needed)
     int32_t *pos_p = nullptr; uint32_t *cig_p = nullptr; size_t cig_cap = 0;   // raw views of pos / cigar for the hot path
+    int32_t last_pos = INT32_MIN; bool in_order = true;      // positions seen so far are non-decreasing (PD_SORTED is only claimed then)
     explicit Batch(size_t capacity = 1u << 20) : cap(capacity) {}
-    void clear() { n = 0; nc = 0; single_op = true; off_valid = 0; }
+    void clear() { n = 0; nc = 0; single_op = true; off_valid = 0; last_pos = INT32_MIN; in_order = true; }
     bool full() const { return n >= cap || nc >= cap; }      // callers flush a full batch before the next add
     void alloc() { pos.resize(cap); off.resize(cap + 1); off[0] = 0; cigar.resize(cap + (1u << 12)); views(); }
     void views() { pos_p = pos.data(); cig_p = cigar.data(); cig_cap = cigar.size(); }
@@ -50,6 +51,8 @@ struct Batch {
     {
         if (pos.empty()) alloc();
         if (k != 1 && single_op) { materialize_off(); single_op = false; }
+        if (p < last_pos) in_order = false;
+        last_pos = p;
         pos[n] = p; nc += k; ++n;
         if (!single_op) { off[n] = (uint32_t)nc; off_valid = n + 1; }
     }
@@ -63,6 +66,8 @@ struct Batch {
     {
         if (__builtin_expect(r.n_cigar == 1 && single_op && nc < cig_cap, 1)) {     // the common read: two 4-byte stores
             memcpy(cig_p + nc, r.cigar, 4); pos_p[n] = r.pos; ++nc; ++n;
+            if (r.pos < last_pos) in_order = false;
+            last_pos = r.pos;
             return;
         }
         uint32_t *c = room(r.n_cigar);
@@ -77,6 +82,8 @@ struct Batch {
     {
         if (pos.empty()) alloc();
         if (nc - nc_before != 1 && single_op) { materialize_off(); single_op = false; }
+        if (p < last_pos) in_order = false;
+        last_pos = p;
         pos[n] = p; ++n;
         if (!single_op) { off[n] = (uint32_t)nc; off_valid = n + 1; }
     }
@@ -161,6 +168,9 @@ struct Feeder {
     bool push(int tid, Batch &b, bool sorted)
     {
         if (b.n == 0) return true;
+        // a file whose header says SO:coordinate but whose records are not in order (the reference does not care) must not
+        // reach the tile kernel as PD_SORTED: the claim is made per batch, from what the batch actually holds
+        sorted = sorted && b.in_order;
         if (dry) { reads_pushed += b.n; if (!dry_nodigest) dry_digest += b.digest(tid); b.clear(); return true; }
         if (!eng_ok.load()) {
             // the CUDA context is still coming up: park the batch and keep decoding (bounded: ~3 GB of parked reads)

@@ -139,3 +139,23 @@ def test_host_program_matches_reference_binary_on_random_inputs(seed, contigs, r
         assert sorted(ref) == sorted(our), (opts, sorted(ref), sorted(our))
         for name in ref:
             assert ref[name] == our[name], f"seed {seed} {ext} opts {opts}: {name} differs from the reference binary"
+
+
+def test_header_says_sorted_but_records_are_not(workdir, standin_env):
+    """`@HD SO:coordinate` over shuffled records: the reference does not care (its no-index loop just walks them); the host
+    must not claim PD_SORTED for batches that are not in order (the stand-in, like the engine, rejects such a claim)."""
+    import random
+    sam = os.path.join(workdir, "claims_sorted.sam")
+    subprocess.run([BAMGEN, "-o", sam, "-c", "a:200000,b:3000", "-n", "20000", "-m", "mixed", "-s", "77", "-S"], check=True)
+    lines = open(sam).read().splitlines(keepends=True)
+    head = [x for x in lines if x.startswith("@")]
+    body = [x for x in lines if not x.startswith("@")]
+    random.Random(5).shuffle(body)
+    body.sort(key=lambda x: x.split("\t")[2])            # keep contigs together, positions shuffled inside
+    with open(sam, "w") as fh:
+        fh.writelines(head + body)
+    assert "SO:coordinate" in head[0]
+    for k, opts in enumerate([[], ["-w", "100"], ["-q", "20"]]):
+        ref, _ = _run(REF, sam, opts + ["-t", "2"], workdir, f"refclaim_{k}")
+        our, _ = _run(CLI, sam, opts + ["-t", "2"], workdir, f"ourclaim_{k}", standin_env)
+        assert ref == our, opts
