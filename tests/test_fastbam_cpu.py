@@ -38,6 +38,8 @@ def bams(tmp_path_factory):
     subprocess.run([BAMGEN, "-o", out["r1"], "-c", "a:300001,b:1,c:5000,d:70000,e:2,f:1001", "-n", "60000", "-m", "mixed", "-s", "11"], check=True)
     out["r2"] = str(d / "r2.bam")     # with SEQ/QUAL: records span BGZF blocks
     subprocess.run([BAMGEN, "-o", out["r2"], "-c", "chrA:2000001,chrB:999999", "-n", "150000", "-m", "mixed", "-s", "12", "-q"], check=True)
+    out["long"] = str(d / "long.bam")    # 100 kb reads with SEQ/QUAL: every record is larger than a BGZF block
+    subprocess.run([BAMGEN, "-o", out["long"], "-c", "a:5000000,b:300000", "-n", "300", "-l", "100000", "-m", "mixed", "-s", "9", "-q"], check=True)
     bed = str(d / "r.bed")
     with open(bed, "w") as fh:
         for nm, ln in (("a", 300001), ("c", 5000), ("d", 70000), ("f", 1001), ("chrA", 2000001), ("chrB", 999999), ("cA", 100001), ("cB", 1001), ("k1", 301)):
@@ -49,7 +51,7 @@ def bams(tmp_path_factory):
     return out
 
 
-@pytest.mark.parametrize("name", ["k", "mix", "big", "r1", "r2"])
+@pytest.mark.parametrize("name", ["k", "mix", "big", "r1", "r2", "long"])
 def test_scanner_feeds_the_same_reads_as_htslib(name, bams):
     for opts in ([], ["-w", "100"], ["-b", bams["bed"]], ["-x", "0"], ["-q", "20"], ["-x", "3844", "-q", "3", "-t", "7"], ["-t", "1"]):
         fast = _digest(bams[name], opts, hts=False)
@@ -91,7 +93,7 @@ def test_feeders_hand_over_exactly_the_oracle_parsers_records(bams):
             assert _digest(bams[fx], opts + ["-t", "5"], hts=True)[:2] == want, (fx, opts, "htslib iterators")
 
 
-@pytest.mark.parametrize("name", ["k", "mix", "big", "r1", "r2"])
+@pytest.mark.parametrize("name", ["k", "mix", "big", "r1", "r2", "long"])
 def test_stream_scanner_feeds_the_same_reads_as_sam_read1(name, bams):
     """No-index mode (-s): the ordered parallel BGZF reader + single record walker against htslib's sam_read1 loop."""
     for opts in (["-s"], ["-s", "-t", "1"], ["-s", "-x", "0", "-t", "7"], ["-s", "-q", "20", "-w", "100"]):
