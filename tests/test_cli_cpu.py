@@ -159,3 +159,22 @@ def test_header_says_sorted_but_records_are_not(workdir, standin_env):
         ref, _ = _run(REF, sam, opts + ["-t", "2"], workdir, f"refclaim_{k}")
         our, _ = _run(CLI, sam, opts + ["-t", "2"], workdir, f"ourclaim_{k}", standin_env)
         assert ref == our, opts
+
+
+def test_cigar_longer_than_65535_ops_in_the_cg_tag(workdir, standin_env):
+    """BAM keeps CIGARs with more than 65535 operations in a CG:B,I tag behind a `<l_seq>S<ref_len>N` placeholder
+    (SAMv1 4.2.2); htslib's reader swaps the real one in, and so do the raw scanners (fastbam.hpp)."""
+    sam = os.path.join(workdir, "cg.sam")
+    ops = "1M1D" * 35000 + "10M"
+    with open(sam, "w") as fh:
+        fh.write("@HD\tVN:1.6\tSO:coordinate\n@SQ\tSN:a\tLN:200000\n")
+        fh.write("r0\t0\ta\t100\t60\t50M\t*\t0\t0\t*\t*\n")
+        fh.write(f"r1\t0\ta\t1000\t60\t{ops}\t*\t0\t0\t*\t*\n")
+        fh.write("r2\t0\ta\t1500\t60\t5S20M\t*\t0\t0\t*\t*\n")
+    bam = os.path.join(workdir, "cg.bam")
+    subprocess.run([BAMGEN, "-I", sam, "-o", bam], check=True)
+    for k, opts in enumerate([[], ["-s"], ["-w", "100"]]):
+        ref, _ = _run(REF, bam, opts + ["-t", "2"], workdir, f"refcg_{k}")
+        our, _ = _run(CLI, bam, opts + ["-t", "2"], workdir, f"ourcg_{k}", standin_env)
+        assert ref == our, opts
+        assert "35070" in ref[".chr.stat.gz" if "-w" not in opts else ".win.stat.gz"] or "-w" in opts
