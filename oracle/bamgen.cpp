@@ -10,6 +10,7 @@
  *   bamgen -I in.sam -o out.bam      (convert a SAM fixture to BAM + .bai)
  *          [-q] (emit random SEQ+QUAL, flavour B; default SEQ='*', flavour A) [-t threads] [-S] (write SAM text)
  *   an output name ending in .cram is written as CRAM 3.x without a reference (no_ref) + .crai
+ *          [-X] build a .csi index (min_shift 14) instead of the .bai
  *
  * mode uniform : every read flag 0, mapq 60, CIGAR <readlen>M.
  * mode mixed   : random CIGARs over MIDNSHP=X, random flags (incl. UNMAP/SECONDARY/QCFAIL/DUP/SUPP bits),
@@ -67,7 +68,7 @@ static void make_mixed_cigar(std::mt19937_64 &rng, int readlen, std::vector<uint
 int main(int argc, char **argv)
 {
     std::string out, cspec, mode = "uniform", insam;
-    int64_t nreads = 0; uint64_t seed = 12345; int readlen = 150; bool withseq = false; int threads = 4; bool samtext = false;
+    int64_t nreads = 0; uint64_t seed = 12345; int readlen = 150; bool withseq = false; int threads = 4; bool samtext = false; int min_shift = 0;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
         auto need = [&]() -> const char * { if (i + 1 >= argc) die("missing argument"); return argv[++i]; };
@@ -81,6 +82,7 @@ int main(int argc, char **argv)
         else if (a == "-t") threads = atoi(need());
         else if (a == "-S") samtext = true;
         else if (a == "-I") insam = need();
+        else if (a == "-X") min_shift = 14;
         else die("unknown option");
     }
     if (!insam.empty()) {                                   // SAM text -> BAM (+ .bai): fixture conversion
@@ -96,7 +98,7 @@ int main(int argc, char **argv)
         bam_destroy1(r); hts_close(in);
         if (hts_close(o) < 0) die("close failed");
         sam_hdr_destroy(h);
-        if (sam_index_build3(out.c_str(), NULL, 0, 1) < 0) die("index build failed");
+        if (sam_index_build3(out.c_str(), NULL, min_shift, 1) < 0) die("index build failed");
         return 0;
     }
     if (out.empty() || cspec.empty() || nreads <= 0) die("usage: bamgen -o out.bam -c name:len,... -n reads [-s seed] [-l len] [-m uniform|mixed] [-q] [-t thr] [-S]");
@@ -172,6 +174,6 @@ int main(int argc, char **argv)
     bam_destroy1(b);
     if (hts_close(fp) < 0) die("close failed");
     sam_hdr_destroy(hdr);
-    if (!samtext) { if (sam_index_build3(out.c_str(), NULL, 0, threads) < 0) die("index build failed"); }
+    if (!samtext) { if (sam_index_build3(out.c_str(), NULL, min_shift, threads) < 0) die("index build failed"); }
     return 0;
 }

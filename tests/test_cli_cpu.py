@@ -123,10 +123,12 @@ def _region_files(workdir, tag, contigs):
     (32, "chrA:1000001,chrB:151,chrC:299999", 40000, "bam"),
     (33, "a:300001,b:1,c:5000,d:70000,e:2,f:1001", 30000, "cram"),
     (34, "big:20000123,s:149,t:10000001", 30000, "bam"),      # contigs longer than the reference's 10 Mb windows (:695-784)
+    (35, "a:300001,b:1,c:5000,d:70000,e:2,f:1001", 30000, "csi"),  # BAM with a .csi index only: htslib iterators
 ])
 def test_host_program_matches_reference_binary_on_random_inputs(seed, contigs, reads, ext, workdir, standin_env):
-    inp = os.path.join(workdir, f"rand{seed}.{ext}")
-    subprocess.run([BAMGEN, "-o", inp, "-c", contigs, "-n", str(reads), "-m", "mixed", "-s", str(seed)], check=True)
+    inp = os.path.join(workdir, f"rand{seed}.{'bam' if ext == 'csi' else ext}")
+    subprocess.run([BAMGEN, "-o", inp, "-c", contigs, "-n", str(reads), "-m", "mixed", "-s", str(seed)] + (["-X"] if ext == "csi" else []), check=True)
+    assert os.path.exists(inp + {"bam": ".bai", "cram": ".crai", "csi": ".csi"}[ext])
     bed, gff, lens = _region_files(workdir, f"rand{seed}", contigs)
     sets = OPTION_SETS + [["-w", "150"], ["-w", "151", "-d", "2"], ["-b", bed], ["-b", bed, "-d", "3"], ["-g", gff], ["-g", gff, "-s"], ["-b", bed, "-s"],
                           ["-a", "-b", bed], ["-a", "-g", gff, "-s"], ["-a", "-b", bed, "-s", "-x", "0"]]
