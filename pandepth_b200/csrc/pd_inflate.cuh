@@ -38,7 +38,14 @@ struct BitReader {
     const uint8_t *in; uint32_t len, pos; uint64_t buf; int cnt;
     PD_HD void init(const uint8_t *p, uint32_t n) { in = p; len = n; pos = 0; buf = 0; cnt = 0; }
     // at least 32 valid bits in buf while input lasts (bytes past the end read as zero; over-consumption is detected at the end)
-    PD_HD void refill() { while (cnt <= 56) { buf |= (uint64_t)(pos < len ? in[pos] : 0) << cnt; pos++; cnt += 8; } }
+    PD_HD void refill()
+    {
+        if (cnt > 32) return;
+        if (pos + 4 <= len) {                                // four bytes at once (byte loads: the stream is not aligned)
+            const uint32_t w = (uint32_t)in[pos] | (uint32_t)in[pos + 1] << 8 | (uint32_t)in[pos + 2] << 16 | (uint32_t)in[pos + 3] << 24;
+            buf |= (uint64_t)w << cnt; pos += 4; cnt += 32;
+        } else while (cnt <= 56) { buf |= (uint64_t)(pos < len ? in[pos] : 0) << cnt; pos++; cnt += 8; }
+    }
     PD_HD uint32_t peek(int n) const { return (uint32_t)(buf & ((1ull << n) - 1)); }
     PD_HD void drop(int n) { buf >>= n; cnt -= n; }
     PD_HD uint32_t bits(int n) { refill(); const uint32_t v = peek(n); drop(n); return v; }
@@ -92,10 +99,6 @@ PD_HD int inf_symbol(BitReader &br, const uint16_t *count, const uint16_t *sym, 
 // ISIZE, so a well-formed block fills it exactly.
 PD_HD int inflate_raw(const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_t out_cap, InflateTables &T)
 {
-    const uint16_t LBASE[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
-    const uint8_t LEXT[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
-    const uint16_t DBASE[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
-    const uint8_t DEXT[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
     const uint8_t ORDER[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
     BitReader br; br.init(in, in_len);
     uint32_t o = 0;
@@ -147,16 +150,41 @@ PD_HD int inflate_raw(const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_t
                 if (r < 0 || (r > 0 && ndist - T.dist_count[0] != 1)) return INF_ERR_CODE;
             }
             for (;;) {
+                // literal fast path: one refill leaves >= 33 bits, enough for two table hits (<= 10 bits each) in a row
+                br.refill();
+                uint16_t e = T.lit_fast[br.peek(INF_LIT_BITS)];
+                if (e && e < (256u << 4)) {
+                    if (o >= out_cap) return INF_ERR_OUTPUT;
+                    br.drop(e & 15); out[o++] = (uint8_t)(e >> 4);
+                    e = T.lit_fast[br.peek(INF_LIT_BITS)];
+                    if (e && e < (256u << 4)) {
+                        if (o >= out_cap) return INF_ERR_OUTPUT;
+                        br.drop(e & 15); out[o++] = (uint8_t)(e >> 4);
+                        e = T.lit_fast[br.peek(INF_LIT_BITS)];
+                        if (e && e < (256u << 4)) {
+                            if (o >= out_cap) return INF_ERR_OUTPUT;
+                            br.drop(e & 15); out[o++] = (uint8_t)(e >> 4);
+                        }
+                    }
+                    continue;
+                }
                 int s = inf_symbol(br, T.lit_count, T.lit_sym, T.lit_fast, INF_LIT_BITS);
                 if (s < 0) return INF_ERR_CODE;
                 if (s < 256) { if (o >= out_cap) return INF_ERR_OUTPUT; out[o++] = (uint8_t)s; continue; }
                 if (s == 256) break;
                 s -= 257;
                 if (s >= 29) return INF_ERR_CODE;
-                const uint32_t mlen = LBASE[s] + br.bits(LEXT[s]);
+                // length and distance codes (RFC 1951 3.2.5) are arithmetic: code s has e = (s-4)>>2 extra bits and base
+                // 3 + ((4 + (s&3)) << e) (258 for the last one); distance code d has e = (d-2)>>1 and base 1 + ((2 + (d&1)) << e)
+                uint32_t mlen;
+                if (s < 8) mlen = 3u + (uint32_t)s;
+                else if (s == 28) mlen = 258u;
+                else { const int e = (s - 4) >> 2; mlen = 3u + ((4u + ((uint32_t)s & 3u)) << e) + br.bits(e); }
                 const int d = inf_symbol(br, T.dist_count, T.dist_sym, T.dist_fast, INF_DIST_BITS);
                 if (d < 0 || d >= 30) return INF_ERR_CODE;
-                const uint32_t dist = DBASE[d] + br.bits(DEXT[d]);
+                uint32_t dist;
+                if (d < 4) dist = 1u + (uint32_t)d;
+                else { const int e = (d - 2) >> 1; dist = 1u + ((2u + ((uint32_t)d & 1u)) << e) + br.bits(e); }
                 if (dist > o) return INF_ERR_DIST;
                 if (o + mlen > out_cap) return INF_ERR_OUTPUT;
                 for (uint32_t k = 0; k < mlen; k++) out[o + k] = out[o + k - dist];   // byte order matters when the match overlaps itself
