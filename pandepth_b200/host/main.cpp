@@ -468,6 +468,25 @@ int main(int argc, char **argv)
     const bool whole = in.is_paf || multi || !indexed || o.site_output || mode == 6;
     const uint32_t mask = whole ? 0x3FFFFu : 0xFFFFFFFFu;
 
+    if (targets.empty()) {
+        // a header without @SQ lines: nothing to accumulate.  The reference still writes its files (header line, the summary
+        // row with 0/0 ratios, an empty -a dump); no engine is needed for that.
+        const std::string prefix0 = output_prefix(o.out_arg);
+        GzWriter out0;
+        const std::string stat0 = prefix0 + stat_suffix(mode);
+        if (!out0.open(stat0, 1)) { std::cerr << "open OUT File error: " << stat0 << std::endl; return 0; }
+        if (!in.is_paf && !(has_index(o.input) && o.use_index))
+            std::cout << (in.sorted_hdr ? "Warning: PanDepth will run in No Index mode: " : "Warning: Can't find index file of input BAM/CRAM. PanDepth will run in No Index mode: ") << o.input << std::endl;
+        std::cout << "INFO: Input data read done" << std::endl;
+        if (o.site_output) { GzWriter s0; if (s0.open(prefix0 + ".SiteDepth.gz", 1)) s0.close(); }
+        out0.put(stat_header(mode));
+        char row0[256];
+        volatile uint64_t z = 0;                              // 0 * 100.0 / 0 at run time, like the reference (prints -nan)
+        int m0 = snprintf(row0, sizeof row0, "##RegionLength: %llu\tCoveredSite: %llu\tCoverage(%%): %.2f\tMeanDepth: %.2f\n", 0ull, 0ull, z * 100.0 / z, z * 1.0 / z);
+        out0.put(std::string(row0, (size_t)m0));
+        return out0.close() ? 0 : 1;
+    }
+
     // the CUDA context (~0.5 s) is created in the background while the host threads already decode
     int device = 0;
     if (const char *d = getenv("PANDEPTH_DEVICE")) device = atoi(d);

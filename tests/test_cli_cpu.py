@@ -180,3 +180,22 @@ def test_cigar_longer_than_65535_ops_in_the_cg_tag(workdir, standin_env):
         our, _ = _run(CLI, bam, opts + ["-t", "2"], workdir, f"ourcg_{k}", standin_env)
         assert ref == our, opts
         assert "35070" in ref[".chr.stat.gz" if "-w" not in opts else ".win.stat.gz"] or "-w" in opts
+
+
+def test_degenerate_inputs_match_the_reference(workdir, standin_env):
+    """A header without @SQ lines (no engine is created), a header-only file, a zero-length contig."""
+    nosq = os.path.join(workdir, "nosq.sam")
+    with open(nosq, "w") as fh:
+        fh.write("@HD\tVN:1.6\n")
+    empty = os.path.join(workdir, "empty.sam")
+    with open(empty, "w") as fh:
+        fh.write("@HD\tVN:1.6\tSO:coordinate\n@SQ\tSN:a\tLN:5000\n@SQ\tSN:b\tLN:0\n")
+    empty_bam = os.path.join(workdir, "empty.bam")
+    subprocess.run([BAMGEN, "-I", empty, "-o", empty_bam], check=True)
+    k = 0
+    for inp in (nosq, empty, empty_bam):
+        for opts in ([], ["-a"], ["-w", "100"], ["-w", "1000"], ["-s"]):
+            ref, _ = _run(REF, inp, opts, workdir, f"refdeg_{k}")
+            our, _ = _run(CLI, inp, opts, workdir, f"ourdeg_{k}", standin_env)
+            assert ref == our, (inp, opts)
+            k += 1
