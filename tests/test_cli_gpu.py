@@ -122,6 +122,10 @@ def test_cli_matches_reference_binary_on_random_bams(seed, contigs, reads, workd
                 g += 1
             fb.write(f"{nm}\t{ln}\t{ln}\n")          # region on the last base: the MeMEnd clip quirk (PanDepth.cpp:299-308)
     sets = OPTION_SETS + [["-b", bed], ["-b", bed, "-d", "3"], ["-g", gff], ["-g", gff, "-s"], ["-b", bed, "-s"]]
+    if seed != 11:
+        # every option set runs against the reference on the CPU as well (tests/test_cli_cpu.py, host program + stand-in); on
+        # the GPU the larger genomes keep the sets that differ in what they ask of the engine (each run pays a CUDA start-up)
+        sets = [[], ["-w", "100"], ["-w", "1000"], ["-q", "20", "-d", "2"], ["-s"], ["-t", "16", "-d", "5"], ["-b", bed], ["-g", gff, "-s"]]
     for k, opts in enumerate(sets):
         if "-a" in opts and sum(lens) > 5_000_000:
             continue                     # keep the suite quick: the per-site dump is one line per base
