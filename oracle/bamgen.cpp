@@ -11,6 +11,8 @@
  *          [-q] (emit random SEQ+QUAL, flavour B; default SEQ='*', flavour A) [-t threads] [-S] (write SAM text)
  *   an output name ending in .cram is written as CRAM 3.x without a reference (no_ref) + .crai
  *          [-X] build a .csi index (min_shift 14) instead of the .bai
+ *          [-O] mixed mode: no read may run past its contig's end (the reference's multi-file path has no slack behind its
+ *               arrays: overhanging reads corrupt its heap)
  *
  * mode uniform : every read flag 0, mapq 60, CIGAR <readlen>M.
  * mode mixed   : random CIGARs over MIDNSHP=X, random flags (incl. UNMAP/SECONDARY/QCFAIL/DUP/SUPP bits),
@@ -68,7 +70,7 @@ static void make_mixed_cigar(std::mt19937_64 &rng, int readlen, std::vector<uint
 int main(int argc, char **argv)
 {
     std::string out, cspec, mode = "uniform", insam;
-    int64_t nreads = 0; uint64_t seed = 12345; int readlen = 150; bool withseq = false; int threads = 4; bool samtext = false; int min_shift = 0;
+    int64_t nreads = 0; uint64_t seed = 12345; int readlen = 150; bool withseq = false; int threads = 4; bool samtext = false; int min_shift = 0; bool no_overhang = false;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
         auto need = [&]() -> const char * { if (i + 1 >= argc) die("missing argument"); return argv[++i]; };
@@ -83,6 +85,7 @@ int main(int argc, char **argv)
         else if (a == "-S") samtext = true;
         else if (a == "-I") insam = need();
         else if (a == "-X") min_shift = 14;
+        else if (a == "-O") no_overhang = true;
         else die("unknown option");
     }
     if (!insam.empty()) {                                   // SAM text -> BAM (+ .bai): fixture conversion
@@ -142,7 +145,7 @@ int main(int argc, char **argv)
             int qlen = readlen, rlen = readlen; uint16_t flag = 0; uint8_t mapq = 60;
             if (mixed) {
                 make_mixed_cigar(rng, readlen, cig, qlen, rlen);
-                if ((int64_t)starts[i] + rlen > len + 400) {            // keep overhang inside the reference's +500 slack (:4132)
+                if ((int64_t)starts[i] + rlen > len + (no_overhang ? 0 : 400)) {            // keep overhang inside the reference's +500 slack (:4132)
                     int m = (int)std::min<int64_t>(readlen, std::max<int64_t>(1, len - starts[i]));
                     cig.assign(1, (uint32_t)m << 4 | BAM_CMATCH); qlen = rlen = m;
                 }

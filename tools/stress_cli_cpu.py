@@ -90,6 +90,8 @@ while time.time() < t_end and (n_seeds is None or seed < seed0 + n_seeds):
         cmd = [GEN, "-o", path, "-c", spec, "-n", str(reads), "-m", rng.choice(["mixed", "mixed", "uniform"]), "-s", str(seed * 7 + part)] + seq
         if ext == "sam":
             cmd.append("-S")
+        if kind == "list":
+            cmd.append("-O")      # BamList_main has no slack behind its arrays: an overhanging read lands in another contig's depth
         subprocess.run(cmd, check=True)
         inputs.append(path)
     if kind == "list":
