@@ -55,7 +55,7 @@ while time.time() < t_end and (n_seeds is None or seed < seed0 + n_seeds):
     names = [f"c{i}" for i in range(n_ctg)]
     spec = ",".join(f"{n}:{l}" for n, l in zip(names, lens))
     reads = rng.choice([1, 50, 5000, 60000])
-    kind = rng.choice(["bam", "bam", "bam", "cram", "sam", "list", "paf"])
+    kind = rng.choice(["bam", "bam", "csi", "cram", "sam", "list", "paf"])
     seq = ["-q"] if rng.random() < 0.3 else []
     inputs = []
     if kind == "paf":
@@ -85,11 +85,13 @@ while time.time() < t_end and (n_seeds is None or seed < seed0 + n_seeds):
             fh.write(text)
         inputs.append(path)
     for part in range(0 if kind == "paf" else (2 if kind == "list" else 1)):
-        ext = {"bam": "bam", "cram": "cram", "sam": "sam", "list": rng.choice(["bam", "sam"])}[kind]
+        ext = {"bam": "bam", "csi": "bam", "cram": "cram", "sam": "sam", "list": rng.choice(["bam", "sam"])}[kind]
         path = os.path.join(work, f"in{seed}_{part}.{ext}")
         cmd = [GEN, "-o", path, "-c", spec, "-n", str(reads), "-m", rng.choice(["mixed", "mixed", "uniform"]), "-s", str(seed * 7 + part)] + seq
         if ext == "sam":
             cmd.append("-S")
+        if kind == "csi":
+            cmd.append("-X")      # .csi index only: htslib iterators instead of the raw scanner
         if kind == "list":
             cmd.append("-O")      # BamList_main has no slack behind its arrays: an overhanging read lands in another contig's depth
         subprocess.run(cmd, check=True)
@@ -102,7 +104,8 @@ while time.time() < t_end and (n_seeds is None or seed < seed0 + n_seeds):
         inp = inputs[0]
     bed = os.path.join(work, f"r{seed}.bed"); gff = os.path.join(work, f"r{seed}.gff")
     bed4 = rng.random() < 0.5
-    with open(bed, "w") as fb, open(gff, "w") as fg:
+    gtf = os.path.join(work, f"r{seed}.gtf")
+    with open(bed, "w") as fb, open(gff, "w") as fg, open(gtf, "w") as ft:
         fg.write("##gff-version 3\n")
         for k in range(rng.choice([1, 5, 60])):
             t = rng.randrange(n_ctg + 1)
@@ -110,14 +113,20 @@ while time.time() < t_end and (n_seeds is None or seed < seed0 + n_seeds):
             ln = lens[t] if t < n_ctg else 1000
             s = rng.randint(1, max(1, ln)); e = min(ln, s + rng.randint(0, 3000))     # inside the contig: past its end the reference reads its slack (undefined)
             fb.write(f"{nm}\t{s}\t{e}" + (f"\tg{k // 2}" if bed4 else "") + "\n")
-            fg.write(f"{nm}\tsrc\tCDS\t{s}\t{e}\t.\t+\t0\tID=x{k};Parent=t{k // 3}\n")
+            feat = "CDS" if k % 4 else "exon"
+            fg.write(f"{nm}\tsrc\t{feat}\t{s}\t{e}\t.\t+\t0\tID=x{k};Parent=t{k // 3}\n")
+            ft.write(f'{nm}\tsrc\t{feat}\t{s}\t{e}\t.\t+\t0\tgene_id "g{k // 3}"; transcript_id "t{k // 3}";\n')
+    if rng.random() < 0.3:                                   # region files may be gzip-compressed (igzstream in the reference)
+        with open(bed, "rb") as fi, gzip.open(bed + ".gz", "wb") as fo: fo.write(fi.read())
+        bed = bed + ".gz"
+    if rng.random() < 0.3: gff = gtf
     big = sum(lens) > 2_000_000
     for trial in range(6):
         opts = []
         r = rng.random()
         if r < 0.3: opts += ["-w", str(rng.choice([1, 2, 7, 33, 100, 128, 129, 149, 150, 151, 160, 161, 500, 1000, 2000]))]
         elif r < 0.45: opts += ["-b", bed]
-        elif r < 0.6: opts += ["-g", gff]
+        elif r < 0.6: opts += ["-g", gff] + (["-f", "exon"] if rng.random() < 0.3 else [])
         if rng.random() < 0.3: opts += ["-d", str(rng.choice([1, 2, 5]))]
         if rng.random() < 0.3: opts += ["-q", str(rng.choice([0, 1, 20, 60]))]
         if rng.random() < 0.3: opts += ["-x", str(rng.choice([0, 4, 1796, 3844, 256]))]
