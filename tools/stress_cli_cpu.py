@@ -3,6 +3,7 @@
 the test stand-in (tests/stand_in/pd_standin.cpp, built into a temp dir), against the reference binary oracle/_ref/pandepth_ref
 on random inputs (BAM / CRAM / SAM, single file or list), random region files and random option sets.  Any difference in the
 decompressed outputs is printed with the command line that reproduces it.
+PDSTRESS_REAL_ENGINE=1 (on a GPU box) runs the same campaign against the real CUDA library instead of the stand-in.
 usage: python tools/stress_cli_cpu.py [seconds | n=<seeds>] [first_seed]"""
 import gzip, os, random, subprocess, sys, tempfile, time, shutil
 
@@ -19,7 +20,7 @@ work = tempfile.mkdtemp(prefix="pdstress")
 so_dir = os.path.join(work, "standin"); os.makedirs(so_dir)
 subprocess.run(["g++", "-O2", "-std=c++14", "-fPIC", "-shared", os.path.join(ROOT, "tests", "stand_in", "pd_standin.cpp"), "-L" + ORA, "-lpd_oracle",
                 "-Wl,-rpath," + ORA, "-Wl,-soname,libpandepth_b200.so", "-o", os.path.join(so_dir, "libpandepth_b200.so")], check=True)
-ENV = dict(os.environ, LD_LIBRARY_PATH=so_dir + os.pathsep + os.environ.get("LD_LIBRARY_PATH", ""))
+ENV = dict(os.environ) if os.environ.get("PDSTRESS_REAL_ENGINE") else dict(os.environ, LD_LIBRARY_PATH=so_dir + os.pathsep + os.environ.get("LD_LIBRARY_PATH", ""))
 
 
 def run(binary, inp, args, tag, env=None):
