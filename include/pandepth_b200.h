@@ -33,7 +33,8 @@ enum {
     PD_ERR_CUDA = 2,      /* CUDA runtime failure (text in pd_last_error) */
     PD_ERR_STATE = 3,     /* call not valid in the engine's current state */
     PD_ERR_UNSORTED = 4,  /* a batch pushed with PD_SORTED was not sorted by pos */
-    PD_ERR_NOMEM = 5
+    PD_ERR_NOMEM = 5,
+    PD_ERR_FALLBACK = 6   /* pd_push_bgzf only: this input is not handled on the device; nothing was accumulated */
 };
 
 /* flags for pd_push* / pd_reduce* */
@@ -76,6 +77,19 @@ int pd_push_contig(pd_engine *e, int32_t tid, int64_t n_reads, const int32_t *po
 int pd_push(pd_engine *e, int64_t n_reads, const int32_t *tid, const int32_t *pos,
             const uint16_t *flag, const uint8_t *mapq,
             const uint32_t *cigar_off, const uint32_t *cigar, uint32_t flags);
+
+/* Decode AND accumulate a chunk of a BAM file on the device: `blocks` are consecutive BGZF blocks (payload offset / length
+ * inside `bytes`, inflated size) whose first record starts `first_skip` bytes into the first block's inflated data.  The
+ * engine inflates the blocks, walks the BAM records (role of the sam_read1 / sam_itr_next loops, PanDepth.cpp:4608 / :730,
+ * and of the filter :732-733 with the xflags / min_mapq given to pd_create) and accumulates them like pd_push_contig.
+ * Returns PD_ERR_FALLBACK -- with nothing accumulated -- when the chunk holds something the device path does not handle
+ * (a record larger than a BGZF block, a CIGAR kept in the CG tag) or when the build has no device decoder; the caller then
+ * feeds the same records through pd_push_contig.  Status of this entry point: the block-parallel decoder behind it
+ * (pandepth_b200/csrc/pd_inflate.cuh, pd_decode.hpp) is verified on the CPU; in this build the engine always answers
+ * PD_ERR_FALLBACK. */
+typedef struct pd_bgzf_block { uint64_t in_off; uint32_t in_len; uint32_t out_len; } pd_bgzf_block;
+int pd_push_bgzf(pd_engine *e, const uint8_t *bytes, size_t n_bytes, const pd_bgzf_block *blocks, int64_t n_blocks,
+                 uint32_t first_skip, uint32_t flags);
 
 /* Wait until every queued push has been consumed (host buffers may be reused). */
 int pd_sync(pd_engine *e);

@@ -431,6 +431,13 @@ int pd_push(pd_engine *e, int64_t n_reads, const int32_t *tid, const int32_t *po
     return PD_OK;
 }
 
+int pd_push_bgzf(pd_engine *e, const uint8_t *, size_t, const pd_bgzf_block *, int64_t, uint32_t, uint32_t)
+{
+    // the device decoder (pd_inflate.cuh / pd_decode.hpp) is not wired in yet: callers take their host decode path
+    if (!e) return PD_ERR_ARG;
+    return fail(e, PD_ERR_FALLBACK, "pd_push_bgzf: device-side BGZF decode is not enabled in this build");
+}
+
 int pd_sync(pd_engine *e)
 {
     if (!e) return PD_ERR_ARG;

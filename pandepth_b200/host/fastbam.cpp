@@ -336,6 +336,67 @@ struct BamStreamScanner::Impl {
     }
 };
 
+// ---------------------------------------------------------------------------------------------------------------
+// BgzfChunker
+// ---------------------------------------------------------------------------------------------------------------
+BgzfChunker::~BgzfChunker() { if (fd_ >= 0) close(fd_); }
+
+bool BgzfChunker::open(const std::string &path, uint32_t &first_skip)
+{
+    fd_ = ::open(path.c_str(), O_RDONLY);
+    if (fd_ < 0) { err_ = "cannot open " + path; return false; }
+    // inflate leading blocks until the BAM header (magic, text, reference table) is complete; the first record starts at
+    // inflated offset q, inside the block that covers it
+    Inflater inf;
+    std::vector<uint8_t> head, raw((1u << 16) + 64), out(1u << 16);
+    std::vector<std::pair<uint64_t, uint64_t>> starts;       // (file offset of the block, inflated offset of its first byte)
+    uint64_t fpos = 0;
+    for (;;) {
+        const ssize_t k = pread(fd_, raw.data(), raw.size(), (off_t)fpos);
+        const uint8_t *cd; size_t cl; uint32_t is;
+        const int64_t b = k > 0 ? bgzf_block(raw.data(), (size_t)k, &cd, &cl, &is) : 0;
+        if (b <= 0) return false;
+        if (is) {
+            if (!inf.run(cd, cl, out.data(), is)) return false;
+            starts.emplace_back(fpos, (uint64_t)head.size());
+            head.insert(head.end(), out.begin(), out.begin() + is);
+        }
+        fpos += (uint64_t)b;
+        if (head.size() < 12) continue;
+        if (memcmp(head.data(), "BAM\1", 4) != 0) return false;
+        size_t q = 8 + (size_t)le32(head.data() + 4);
+        if (head.size() < q + 4) continue;
+        const uint32_t n_ref = le32(head.data() + q); q += 4;
+        bool complete = true;
+        for (uint32_t r = 0; r < n_ref; r++) { if (head.size() < q + 4) { complete = false; break; } q += 8 + (size_t)le32(head.data() + q); }
+        if (!complete || head.size() < q) continue;
+        // the block holding inflated offset q (q == head.size() means: the next block, at fpos)
+        pos_ = fpos; first_skip = 0;
+        for (size_t i = starts.size(); i-- > 0;) if (starts[i].second <= q && q < head.size()) { pos_ = starts[i].first; first_skip = (uint32_t)(q - starts[i].second); break; }
+        return true;
+    }
+}
+
+bool BgzfChunker::next(size_t max_bytes, std::vector<uint8_t> &bytes, std::vector<Block> &blocks)
+{
+    blocks.clear();
+    if (bytes.size() < max_bytes + (1u << 16) + 64) bytes.resize(max_bytes + (1u << 16) + 64);
+    const ssize_t k = pread(fd_, bytes.data(), bytes.size(), (off_t)pos_);
+    if (k <= 0) return false;
+    size_t p = 0;
+    while (p < (size_t)k && p < max_bytes) {
+        const uint8_t *cd; size_t cl; uint32_t is;
+        const int64_t b = bgzf_block(bytes.data() + p, (size_t)k - p, &cd, &cl, &is);
+        if (b < 0) { err_ = "not a BGZF block"; return false; }
+        if (b == 0) break;                                   // truncated last block: the stream ends here
+        if (is) blocks.push_back(Block{(uint64_t)(cd - bytes.data()), (uint32_t)cl, is});
+        p += (size_t)b;
+    }
+    if (p == 0) return false;
+    pos_ += p;
+    return true;                                             // (a chunk of empty blocks only -- the EOF marker -- has no blocks)
+}
+
 BamStreamScanner::BamStreamScanner() : im_(new Impl) {}
 
 BamStreamScanner::~BamStreamScanner()

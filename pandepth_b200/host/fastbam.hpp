@@ -85,6 +85,21 @@ private:
     bool read_header();
 };
 
+// Sequential reader of whole BGZF blocks for callers that hand the compressed bytes on (pd_push_bgzf): finds the first BAM
+// record (the header may span blocks) and then returns runs of consecutive blocks with their payload offsets.
+class BgzfChunker {
+public:
+    struct Block { uint64_t in_off; uint32_t in_len; uint32_t out_len; };        // payload offset inside the chunk's bytes
+    ~BgzfChunker();
+    // false if the file is not a BAM in BGZF blocks; first_skip = offset of the first record inside the first block returned
+    bool open(const std::string &bam_path, uint32_t &first_skip);
+    // next chunk of up to max_bytes compressed bytes (whole blocks, at least one); false at the end of the file
+    bool next(size_t max_bytes, std::vector<uint8_t> &bytes, std::vector<Block> &blocks);
+    const std::string &error() const { return err_; }
+private:
+    int fd_ = -1; uint64_t pos_ = 0; std::string err_;
+};
+
 // long CIGAR (> 65535 ops) kept in the CG:B,I tag behind a `<l_seq>S<ref_len>N` placeholder (SAMv1 4.2.2): fills r from it
 bool resolve_long_cigar_tag(const uint8_t *rec, uint32_t block_size, uint32_t l_read_name, uint32_t n_cigar, int32_t l_seq,
                             std::vector<uint32_t> &store, RawRead &r);

@@ -151,6 +151,7 @@ struct Feeder {
     std::string input;                                   // the file being fed (multi-file mode feeds several in turn)
     bool used_fast = false;
     PinnedPool *pool = nullptr;                          // pinned staging (exists once the CUDA context does)
+    const std::vector<Target> *targets = nullptr;        // contig table (names, lengths)
     bool dry = getenv("PANDEPTH_DRY") != nullptr;
     bool dry_nodigest = dry && getenv("PANDEPTH_DRY")[0] == '2';     // PANDEPTH_DRY=2: decode timing without the digest
     struct Pending { int tid; bool sorted; Batch b; };
@@ -366,24 +367,71 @@ struct Feeder {
         std::vector<size_t> at;
         std::vector<char> done;
         size_t open_contigs = 0;
-        RegionCursor(const std::map<int, std::vector<std::pair<int, int>>> &m, size_t n_targets) : merged(m), regs(n_targets, nullptr), at(n_targets, 0), done(n_targets, 1)
+        // mode 5: the reference's merged regions are the -w tiles themselves (adjacent tiles do not merge); they stay implicit
+        // here (pd_host.hpp n_tiles): region k of contig t is [1 + k*W, min(k*W + W, len)]
+        long long tile_win = 0; std::vector<long long> tlen;
+        RegionCursor(const std::map<int, std::vector<std::pair<int, int>>> &m, size_t n_targets, long long tile_w, const std::vector<Target> *targets)
+            : merged(m), regs(n_targets, nullptr), at(n_targets, 0), done(n_targets, 1), tile_win(tile_w)
         {
             for (const auto &kv : merged) if (kv.first >= 0 && (size_t)kv.first < n_targets && !kv.second.empty()) { regs[(size_t)kv.first] = &kv.second; done[(size_t)kv.first] = 0; open_contigs++; }
+            if (tile_win && targets) for (const auto &t : *targets) tlen.push_back((long long)t.len);
         }
         bool contig_done(int t) const { return done[(size_t)t] != 0; }
+        size_t n_regions(int t) const { return tile_win ? (size_t)n_tiles(tlen[(size_t)t], tile_win) : regs[(size_t)t]->size(); }
+        long long first(int t, size_t k) const { return tile_win ? 1 + (long long)k * tile_win : (*regs[(size_t)t])[k].first; }
+        long long second(int t, size_t k) const { return tile_win ? std::min<long long>((long long)k * tile_win + tile_win, tlen[(size_t)t]) : (*regs[(size_t)t])[k].second; }
         // 0 = skip the read, 1 = accumulate it, 2 = every contig is finished: stop reading (this read is not accumulated)
         int step(int t, int64_t pos, int64_t endpos)
         {
-            const auto &r = *regs[(size_t)t];
             size_t &k = at[(size_t)t];
-            if (endpos < r[k].first) return 0;
-            if (pos > r[k].second) {
-                for (++k; k < r.size(); ++k) if (pos <= r[k].second) break;
-                if (k == r.size()) { done[(size_t)t] = 1; if (--open_contigs == 0) return 2; }
+            const size_t n = n_regions(t);
+            if (endpos < first(t, k)) return 0;
+            if (pos > second(t, k)) {
+                for (++k; k < n; ++k) if (pos <= second(t, k)) break;
+                if (k == n) { done[(size_t)t] = 1; if (--open_contigs == 0) return 2; }
             }
             return 1;
         }
     };
+
+    // PANDEPTH_GPU_DECODE=1, whole-genome modes, BAM input: the compressed file goes to the engine chunk by chunk
+    // (pd_push_bgzf: inflate + record walk + accumulate on the device).  Returns 1 = the whole file was accumulated this way,
+    // 0 = not applicable or the engine asked for the host path (nothing of this file is accumulated: the engine was reset if
+    // needed), -1 = failed.
+    int stream_bgzf()
+    {
+        if (dry) return 0;
+        uint32_t first_skip = 0;
+        BgzfChunker ch;
+        if (!ch.open(input, first_skip)) return 0;
+        eng_future.wait();
+        {
+            std::lock_guard<std::mutex> g(eng_mu);
+            if (!eng) { eng = eng_future.get(); if (!eng) { fail(std::string("Error: ") + pd_last_error(nullptr)); return -1; } }
+            eng_ok = true;
+        }
+        std::vector<uint8_t> bytes; std::vector<BgzfChunker::Block> blocks; std::vector<pd_bgzf_block> pb;
+        size_t n_chunks = 0;
+        while (ch.next(16u << 20, bytes, blocks)) {
+            if (blocks.empty()) continue;
+            pb.resize(blocks.size());
+            for (size_t i = 0; i < blocks.size(); i++) pb[i] = pd_bgzf_block{blocks[i].in_off, blocks[i].in_len, blocks[i].out_len};
+            std::lock_guard<std::mutex> g(eng_mu);
+            const int rc = pd_push_bgzf(eng, bytes.data(), bytes.size(), pb.data(), (int64_t)pb.size(), n_chunks == 0 ? first_skip : 0u, 0u);
+            if (rc == PD_ERR_FALLBACK) {
+                // (typically the very first chunk: reads larger than a block.)  Depth is additive but the chunks already
+                // accumulated cannot be taken back one by one, so this file starts over on the host path from a clean engine;
+                // only valid while this is the first input file
+                if (n_chunks && pd_reset(eng) != PD_OK) { fail(std::string("pd_reset: ") + pd_last_error(eng)); return -1; }
+                return 0;
+            }
+            if (rc != PD_OK) { fail(std::string("pd_push_bgzf: ") + pd_last_error(eng)); return -1; }
+            n_chunks++;
+        }
+        if (!ch.error().empty()) { fail("Error: malformed BAM while reading " + input + ": " + ch.error()); return -1; }
+        used_fast = true;
+        return 1;
+    }
 
     // no-index path for BAM input: ordered parallel BGZF inflate + one record walker (fastbam.hpp BamStreamScanner).
     // Returns false without having pushed anything if the file is not a BAM this scanner handles (caller uses htslib).
@@ -396,7 +444,7 @@ struct Feeder {
         int cur = -1;
         bool ok_push = true;
         const uint32_t xf = o.xflags; const int mq = o.min_mapq;
-        RegionCursor cursor(merged, n_targets);
+        RegionCursor cursor(merged, n_targets, o.tile_win, targets);
         const bool ok = sc.scan_all([&](const BamStreamScanner::Read &r) -> bool {
             if (!ok_push) return false;
             const int t = r.tid;
@@ -430,7 +478,7 @@ struct Feeder {
         bam1_t *b = bam_init1();
         Batch batch;
         int cur = -1;
-        RegionCursor cursor(merged, n_targets);
+        RegionCursor cursor(merged, n_targets, o.tile_win, targets);
         while (sam_read1(fp, hdr, b) >= 0) {
             const int t = b->core.tid;
             if (t < 0 || (size_t)t >= n_targets) continue;

@@ -250,9 +250,15 @@ void plan_items(Feeder &feeder, const RegionsByContig &merged, const std::vector
 
 // One SAM / BAM / CRAM file into the engine: range-parallel through the index when there is one, else one pass.
 void feed_hts_file(Feeder &feeder, const Options &o, const std::string &path, bool f_bam, bool f_cram, bool f_sorted, bool region_modes,
-                   const RegionsByContig &merged, const std::vector<uint32_t> &tlen, size_t n_targets)
+                   const RegionsByContig &merged, const std::vector<uint32_t> &tlen, size_t n_targets, bool first_file)
 {
     const bool f_indexed = has_index(path) && o.use_index;
+    // experimental (off by default): device-side decode of the whole file -- whole-genome modes, first input file only, and
+    // not where the reference's no-index region cursor decides which reads count (sorted header without an index)
+    if (getenv("PANDEPTH_GPU_DECODE") && f_bam && !region_modes && first_file && (f_indexed || !f_sorted)) {
+        const int r = feeder.stream_bgzf();
+        if (r != 0) return;
+    }
     feeder.filter_by_region = f_indexed && region_modes;
     if (!f_indexed) {
         if (f_sorted) std::cout << "Warning: PanDepth will run in No Index mode: " << path << std::endl;                       // :4606
@@ -516,6 +522,7 @@ int main(int argc, char **argv)
     // ---- feed ---------------------------------------------------------------------------------------------------
     Feeder feeder(o, eng_future, merged, false);
     feeder.pool = &pool;
+    feeder.targets = &targets;
     for (size_t fi = 0; fi < o.inputs.size() && !feeder.failed; fi++) {
         const std::string &path = o.inputs[fi];
         feeder.input = path;
@@ -531,7 +538,7 @@ int main(int argc, char **argv)
             if (h2) sam_hdr_destroy(h2);
             hts_close(fp);
         }
-        feed_hts_file(feeder, o, path, f_bam, f_cram, f_sorted, region_modes, merged, tlen, targets.size());
+        feed_hts_file(feeder, o, path, f_bam, f_cram, f_sorted, region_modes, merged, tlen, targets.size(), fi == 0);
     }
     if (dry) {
         tm.mark("decode (dry)");

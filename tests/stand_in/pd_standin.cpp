@@ -13,7 +13,9 @@
  */
 #include "../../include/pandepth_b200.h"
 #include "../../oracle/pd_oracle.h"
+#include "../../pandepth_b200/csrc/pd_decode.hpp"      // the block-parallel decoder, here on a host backend
 
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -30,6 +32,12 @@ struct pd_engine {
 };
 
 static std::string g_err;
+// PD_STANDIN_TRACE=<file>: one line per pd_push_bgzf call, so a test can tell the decoder ran from the fallback having run
+static void trace(const char *what, long long a, long long b)
+{
+    if (const char *p = getenv("PD_STANDIN_TRACE")) if (FILE *f = fopen(p, "a")) { fprintf(f, "%s %lld %lld\n", what, a, b); fclose(f); }
+}
+
 static int fail(pd_engine *e, int code, const char *m) { if (e) e->err = m; else g_err = m; return code; }
 
 extern "C" {
@@ -101,6 +109,55 @@ int pd_push(pd_engine *e, int64_t n, const int32_t *tid, const int32_t *pos, con
         }
         b = end;
     }
+    return PD_OK;
+}
+
+namespace {
+// pd_decode.hpp's backend interface with plain loops (what the CUDA backend does with one block per warp / thread)
+struct HostBackend {
+    std::vector<uint8_t> inflated_v; std::vector<pdk::BlockCount> counts_v;
+    std::vector<int32_t> tid, pos; std::vector<uint32_t> cigar_off, cigar;
+    uint8_t *inflated = nullptr; pdk::BlockCount *counts_host = nullptr;
+    int inflate(const uint8_t *in, size_t, const pdk::ChunkBlock *blk, const uint64_t *out_off, uint32_t n, uint64_t out_total)
+    {
+        inflated_v.assign(out_total + 8, 0); inflated = inflated_v.data();
+        static pdk::InflateTables T;
+        for (uint32_t b = 0; b < n; b++)
+            if (blk[b].out_len && pdk::inflate_raw(in + blk[b].in_off, blk[b].in_len, inflated + out_off[b], blk[b].out_len, T) != (int)blk[b].out_len) return -1;
+        return 0;
+    }
+    void count(const pdk::ChunkBlock *blk, const uint64_t *out_off, uint32_t n, uint32_t first_skip, int32_t n_targets, uint32_t xflags, int32_t min_mapq)
+    {
+        counts_v.resize(n); counts_host = counts_v.data();
+        for (uint32_t b = 0; b < n; b++) { const uint32_t sk = b == 0 ? first_skip : 0; counts_v[b] = pdk::count_block(inflated + out_off[b] + sk, blk[b].out_len - sk, n_targets, xflags, min_mapq); }
+    }
+    void emit(const pdk::ChunkBlock *blk, const uint64_t *out_off, uint32_t n, uint32_t first_skip, const uint32_t *r0, const uint32_t *c0, uint32_t n_reads, uint32_t n_cigar,
+              int32_t n_targets, uint32_t xflags, int32_t min_mapq)
+    {
+        tid.assign(n_reads, -7); pos.assign(n_reads, -7); cigar_off.assign((size_t)n_reads + 1, 0); cigar.assign(n_cigar, 0);
+        for (uint32_t b = 0; b < n; b++) { const uint32_t sk = b == 0 ? first_skip : 0; pdk::emit_block(inflated + out_off[b] + sk, blk[b].out_len - sk, n_targets, xflags, min_mapq, r0[b], c0[b], tid.data(), pos.data(), cigar_off.data(), cigar.data()); }
+        cigar_off[n_reads] = n_cigar;
+    }
+    int32_t tid_at(uint32_t r) { return tid[r]; }
+};
+}  // namespace
+
+int pd_push_bgzf(pd_engine *e, const uint8_t *bytes, size_t n_bytes, const pd_bgzf_block *blocks, int64_t n_blocks, uint32_t first_skip, uint32_t)
+{
+    if (!e) return PD_ERR_ARG;
+    if (n_blocks <= 0) return PD_OK;
+    std::vector<pdk::ChunkBlock> blk((size_t)n_blocks);
+    for (int64_t b = 0; b < n_blocks; b++) blk[(size_t)b] = pdk::ChunkBlock{blocks[b].in_off, blocks[b].in_len, blocks[b].out_len};
+    HostBackend be; std::vector<pdk::ContigRun> runs; uint32_t n_reads = 0, n_cigar = 0;
+    const int rc = pdk::decode_chunk(be, bytes, n_bytes, blk, first_skip, (int32_t)e->tlen.size(), e->xflags, e->min_mapq, runs, n_reads, n_cigar);
+    if (rc == pdk::DEC_STRADDLE || rc == pdk::DEC_CG_TAG) { trace("bgzf_fallback", n_blocks, rc); return fail(e, PD_ERR_FALLBACK, "pd_push_bgzf: chunk not handled by the block-parallel decoder"); }
+    if (rc != pdk::DEC_OK) return fail(e, PD_ERR_ARG, "pd_push_bgzf: malformed BGZF / BAM data");
+    for (const pdk::ContigRun &r : runs) {
+        // the filter was applied by the decoder: no flag / mapq arrays; cigar_off is absolute into cigar[]
+        const int prc = pd_push_contig(e, r.tid, (int64_t)(r.r1 - r.r0), be.pos.data() + r.r0, nullptr, nullptr, be.cigar_off.data() + r.r0, be.cigar.data(), r.sorted ? PD_SORTED : 0u);
+        if (prc) return prc;
+    }
+    trace("bgzf_ok", n_blocks, n_reads);
     return PD_OK;
 }
 

@@ -16,7 +16,7 @@ def _declared():
 
 def test_header_declares_the_boundary():
     names = _declared()
-    for must in ("pd_create", "pd_push", "pd_push_contig", "pd_finalize", "pd_reduce", "pd_reduce_windows",
+    for must in ("pd_create", "pd_push", "pd_push_contig", "pd_push_bgzf", "pd_finalize", "pd_reduce", "pd_reduce_windows",
                  "pd_depth_read", "pd_destroy", "pd_last_error"):
         assert must in names
 

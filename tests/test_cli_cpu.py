@@ -157,7 +157,7 @@ def test_header_says_sorted_but_records_are_not(workdir, standin_env):
     with open(sam, "w") as fh:
         fh.writelines(head + body)
     assert "SO:coordinate" in head[0]
-    for k, opts in enumerate([[], ["-w", "100"], ["-q", "20"]]):
+    for k, opts in enumerate([[], ["-w", "100"], ["-q", "20"], ["-w", "1000"], ["-w", "151", "-d", "2"]]):
         ref, _ = _run(REF, sam, opts + ["-t", "2"], workdir, f"refclaim_{k}")
         our, _ = _run(CLI, sam, opts + ["-t", "2"], workdir, f"ourclaim_{k}", standin_env)
         assert ref == our, opts
@@ -199,3 +199,26 @@ def test_degenerate_inputs_match_the_reference(workdir, standin_env):
             our, _ = _run(CLI, inp, opts, workdir, f"ourdeg_{k}", standin_env)
             assert ref == our, (inp, opts)
             k += 1
+
+
+def test_device_decode_entry_point_through_the_host_program(workdir, standin_env):
+    """PANDEPTH_GPU_DECODE=1 (experimental, off by default): the host hands BGZF chunks to pd_push_bgzf.  The stand-in answers
+    with the block-parallel decoder of pandepth_b200/csrc/pd_decode.hpp on a host backend, so this runs the chunker, the header
+    skip, the contig runs and the fallback (reads larger than a block -> PD_ERR_FALLBACK -> host feeders) end to end; the
+    real engine of this build always answers PD_ERR_FALLBACK, which the same fallback handles."""
+    trace = os.path.join(workdir, "standin_trace.txt")
+    env = dict(standin_env, PANDEPTH_GPU_DECODE="1", PD_STANDIN_TRACE=trace)
+    cases = [("gd_mixed.bam", ["-c", "a:300001,b:1,c:5000,d:70000,e:2,f:1001", "-n", "60000", "-m", "mixed", "-s", "41", "-q"]),
+             ("gd_long.bam", ["-c", "a:3000000,b:300000", "-n", "120", "-l", "100000", "-m", "mixed", "-s", "42", "-q"]),
+             ("gd_small.bam", ["-c", "a:2000", "-n", "3", "-s", "43"])]
+    for name, gen in cases:
+        bam = os.path.join(workdir, name)
+        subprocess.run([BAMGEN, "-o", bam] + gen, check=True)
+        for k, opts in enumerate([[], ["-w", "100"], ["-w", "1000"], ["-q", "20", "-x", "0"], ["-a"] if "small" in name or "mixed" in name else ["-d", "3"]]):
+            ref, _ = _run(REF, bam, opts + ["-t", "3"], workdir, f"refgd_{name}_{k}")
+            if os.path.exists(trace):
+                os.unlink(trace)
+            our, _ = _run(CLI, bam, opts + ["-t", "3"], workdir, f"ourgd_{name}_{k}", env)
+            assert ref == our, (name, opts)
+            calls = open(trace).read().split()[0::3] if os.path.exists(trace) else []
+            assert calls == (["bgzf_fallback"] if "long" in name else ["bgzf_ok"]), (name, opts, calls)     # the decoder ran / the fallback ran
