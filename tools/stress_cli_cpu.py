@@ -96,6 +96,15 @@ while time.time() < t_end and (n_seeds is None or seed < seed0 + n_seeds):
         if kind == "list":
             cmd.append("-O")      # BamList_main has no slack behind its arrays: an overhanging read lands in another contig's depth
         subprocess.run(cmd, check=True)
+        if ext == "sam" and kind == "sam" and rng.random() < 0.25:
+            # a header that says SO:coordinate over records that are not in order: the reference's no-index cursor then decides
+            # which reads count; the host restates it (Feeder::RegionCursor)
+            lines = open(path).read().splitlines(keepends=True)
+            body = [x for x in lines if not x.startswith("@")]
+            rng.shuffle(body)
+            if rng.random() < 0.5: body.sort(key=lambda x: x.split("\t")[2])
+            with open(path, "w") as fh:
+                fh.writelines([x for x in lines if x.startswith("@")] + body)
         inputs.append(path)
     if kind == "list":
         inp = os.path.join(work, f"in{seed}.list")
