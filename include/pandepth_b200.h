@@ -34,7 +34,7 @@ enum {
     PD_ERR_STATE = 3,     /* call not valid in the engine's current state */
     PD_ERR_UNSORTED = 4,  /* a batch pushed with PD_SORTED was not sorted by pos */
     PD_ERR_NOMEM = 5,
-    PD_ERR_FALLBACK = 6   /* pd_push_bgzf only: this input is not handled on the device; nothing was accumulated */
+    PD_ERR_FALLBACK = 6   /* pd_push_bgzf only: this input needs the host decode path (pd_reset, then pd_push_contig) */
 };
 
 /* flags for pd_push* / pd_reduce* */
@@ -79,15 +79,23 @@ int pd_push(pd_engine *e, int64_t n_reads, const int32_t *tid, const int32_t *po
             const uint32_t *cigar_off, const uint32_t *cigar, uint32_t flags);
 
 /* Decode AND accumulate a chunk of a BAM file on the device: `blocks` are consecutive BGZF blocks (payload offset / length
- * inside `bytes`, inflated size) whose first record starts `first_skip` bytes into the first block's inflated data.  The
- * engine inflates the blocks, walks the BAM records (role of the sam_read1 / sam_itr_next loops, PanDepth.cpp:4608 / :730,
- * and of the filter :732-733 with the xflags / min_mapq given to pd_create) and accumulates them like pd_push_contig.
- * Returns PD_ERR_FALLBACK -- with nothing accumulated -- when the chunk holds something the device path does not handle
- * (a record larger than a BGZF block, a CIGAR kept in the CG tag) or when the build has no device decoder; the caller then
- * feeds the same records through pd_push_contig.  Status of this entry point: the block-parallel decoder behind it
- * (pandepth_b200/csrc/pd_inflate.cuh, pd_decode.hpp) is verified on the CPU; in this build the engine always answers
- * PD_ERR_FALLBACK. */
+ * inside `bytes`, inflated size <= 65536) whose first record starts `first_skip` bytes into the first block's inflated data
+ * (the BAM header in front of it; 0 for every later chunk).  The engine inflates the blocks (one warp per block), walks the
+ * BAM records (role of the sam_read1 / sam_itr_next loops, PanDepth.cpp:4608 / :730, and of the filter :732-733 with the
+ * xflags / min_mapq given to pd_create) and accumulates them: runs of blocks that hold one contig in coordinate order take
+ * the tile path, blocks with a contig change or records out of order take the delta-scatter path -- so any BAM gives the
+ * same depth as pd_push_contig on the same records, chunks may arrive in any order, and a file of many small contigs costs
+ * one launch per chunk, not per contig.
+ *   PD_ASYNC   return once the chunk is queued (up to PD_BGZF_DEPTH chunks decode concurrently); its accumulate kernels are
+ *              queued, and an error of this chunk is reported, by a later pd_push_bgzf / pd_sync / pd_finalize call.
+ *              `bytes` must stay valid until PD_BGZF_DEPTH later pd_push_bgzf calls, or pd_sync, have returned.
+ *   PD_DEVICE  `bytes` is a device pointer (>= 8 readable bytes behind the last payload); `blocks` stays a host pointer.
+ * Returns PD_ERR_FALLBACK when the chunk holds something the device path does not handle -- a record that does not start
+ * on a BGZF block boundary (writers other than htslib, reads larger than a block) or a CIGAR kept in the CG tag.  Depth
+ * accumulated by earlier chunks stays in the engine: the caller resets it and feeds the file through pd_push_contig.
+ * A block that does not inflate to its ISIZE is PD_ERR_ARG. */
 typedef struct pd_bgzf_block { uint64_t in_off; uint32_t in_len; uint32_t out_len; } pd_bgzf_block;
+#define PD_BGZF_DEPTH 2   /* PD_ASYNC: `bytes` of a call is no longer read once this many later pd_push_bgzf calls have returned */
 int pd_push_bgzf(pd_engine *e, const uint8_t *bytes, size_t n_bytes, const pd_bgzf_block *blocks, int64_t n_blocks,
                  uint32_t first_skip, uint32_t flags);
 

@@ -467,8 +467,81 @@ def build_region_model(targets: List[Tuple[str, int]], opts: Options) -> Tuple[i
     return mode, genes
 
 
+def _endpos(rec: Records, i: int) -> int:
+    """bam_endpos(): pos + reference length of the CIGAR; pos + 1 for a read flagged unmapped or without a reference-consuming op."""
+    p = int(rec.pos[i])
+    if int(rec.flag[i]) & 4:
+        return p + 1
+    n = 0
+    for c in rec.cigar[rec.cigar_off[i]:rec.cigar_off[i + 1]]:
+        if (0x18d >> (int(c) & 15)) & 1:                 # M D N = X
+            n += int(c) >> 4
+    return p + (n if n else 1)
+
+
+def reads_reaching_depth(targets: List[Tuple[str, int]], rec: Records, opts: Options, sorted_hdr: bool = True) -> np.ndarray:
+    """Indices of the records the reference hands to its depth loop in region modes (-g / -b), in file order.
+
+    Only the per-site dump (-a) can tell: region statistics never look between regions.
+      indexed    : reads returned by the `chr:first-1..second+1` queries of the merged regions (:700-706, :726)
+      no index   : every read, unless the header says SO:coordinate -- then the per-contig region cursor of :4610-4646 skips
+                   reads ending before the cursor's region, walks the cursor forward, closes a contig after its last region
+                   and stops the file once every contig is closed.
+    The record filter (:732-733) is NOT applied here."""
+    mode, genes = build_region_model(targets, opts)
+    if mode not in (1, 2, 3, 4):
+        return np.arange(rec.n)
+    merged = {t: merge_regions(g) for t, g in genes.items() if g}
+    keep = []
+    if opts.indexed:
+        for i in range(rec.n):
+            t = int(rec.tid[i])
+            if t not in merged:
+                continue
+            p, e = int(rec.pos[i]), _endpos(rec, i)
+            for first, second in merged[t]:
+                wb = max(first - 1, 1) - 1
+                if wb >= e:
+                    break
+                if second + 1 > p:
+                    keep.append(i)
+                    break
+        return np.array(keep, np.int64)
+    if not sorted_hdr:
+        return np.arange(rec.n)
+    at = {t: 0 for t in merged}
+    done = {t: False for t in merged}
+    open_contigs = len(merged)
+    for i in range(rec.n):
+        t = int(rec.tid[i])
+        if t < 0 or t >= len(targets) or t not in merged or done[t]:
+            continue
+        if int(rec.mapq[i]) < opts.min_mapq or (int(rec.flag[i]) & opts.xflags):
+            continue
+        p, e = int(rec.pos[i]), _endpos(rec, i)
+        regs = merged[t]
+        k = at[t]
+        if e < regs[k][0]:
+            continue
+        stop = False
+        if p > regs[k][1]:
+            k += 1
+            while k < len(regs) and p > regs[k][1]:
+                k += 1
+            if k == len(regs):
+                done[t] = True
+                open_contigs -= 1
+                if open_contigs == 0:
+                    stop = True
+            at[t] = min(k, len(regs) - 1)
+        if stop:
+            break
+        keep.append(i)
+    return np.array(keep, np.int64)
+
+
 def run_model(targets: List[Tuple[str, int]], rec: Records, opts: Options,
-              depth_override: Optional[List[np.ndarray]] = None) -> Dict[str, str]:
+              depth_override: Optional[List[np.ndarray]] = None, sorted_hdr: bool = True) -> Dict[str, str]:
     """Produce {'stat': text, 'suffix': str, 'site': text-or-None} exactly as the reference would print them.
 
     depth_override lets tests substitute per-base depth produced by the CUDA engine for the oracle's own."""
@@ -478,7 +551,12 @@ def run_model(targets: List[Tuple[str, int]], rec: Records, opts: Options,
     whole_contig = (not opts.indexed) or opts.site_output or mode == 6   # :4124-4127 -> SiteInfo 18-bit paths
     mask = 0x3FFFF if whole_contig else 0xFFFFFFFF
 
-    depth = depth_override if depth_override is not None else accumulate(tlen, rec, opts.xflags, opts.min_mapq)
+    if depth_override is not None:
+        depth = depth_override
+    elif opts.site_output and mode in (1, 2, 3, 4):
+        depth = accumulate(tlen, rec.select(reads_reaching_depth(targets, rec, opts, sorted_hdr)), opts.xflags, opts.min_mapq)
+    else:
+        depth = accumulate(tlen, rec, opts.xflags, opts.min_mapq)
 
     # L0: per-gene reduce
     for t in sorted(genes):

@@ -1,0 +1,537 @@
+// pd_bgzf.cuh -- device-side BGZF decode: DEFLATE inflate + BAM record walk, one warp per BGZF block (sm_100a).
+//
+// Role in the reference: the decode side of the `sam_read1` / `sam_itr_next` loops (PanDepth.cpp:4608, :730, inside
+// lib/libhts.a: bgzf_read_block + bam_read1) and the record filter :732-733.  A BGZF file is a sequence of independent
+// <= 64 KB deflate streams and htslib's writer starts every block on a record boundary (bam_write1 flushes first) unless a
+// single record is larger than a block, so blocks inflate AND parse independently: tens of thousands of decoders in flight.
+//
+//   k_bgzf_decode   warp per block (dynamic tickets).  Lane 0 runs the Huffman symbol loop (RFC 1951; same arithmetic as the
+//                   CPU-verified pd_inflate.cuh); the 32 lanes build the decoding tables together, copy matches / stored
+//                   blocks together (coalesced), and then walk the block's records together: lane 0 follows the
+//                   block_size chain 32 records at a time, every lane parses one record, applies the filter and writes
+//                   (tid, pos, cigar offset, CIGAR words) of the records that pass into the block's own staging region,
+//                   plus a 32-byte summary per block.
+//   k_bgzf_offsets  exclusive prefix sums of the per-block (reads, CIGAR words) counts -> final positions (one CTA).
+//   k_bgzf_compact  staging regions -> dense pos[] / tid[] / cigar_off[] / cigar[] arrays (warp per block, coalesced),
+//                   i.e. exactly what k_cut / k_tile_accumulate / k_delta_scatter take.
+//
+// Bounds: this kernel is latency / issue bound (a serial bit stream per block), not HBM bound.  Measured numbers live in
+// DESIGN.md; algorithmic bytes per block = compressed bytes in + inflated bytes out.
+#pragma once
+#ifndef PD_WARP_EMU              // tests/cpp/warp_emu.h runs these kernels on the CPU (one host thread per lane)
+#include <cuda_runtime.h>
+#endif
+#include <stdint.h>
+
+namespace pdk {
+
+struct BgzfBlockDesc { uint64_t in_off; uint32_t in_len; uint32_t out_len; uint64_t out_off; };   // payload inside the chunk; out_off = prefix of out_len
+
+enum { BZ_MALFORMED = 1, BZ_CG_TAG = 2, BZ_UNSORTED = 4, BZ_MULTI_OP = 8, BZ_INFLATE = 16, BZ_STRADDLE = 32 };
+
+struct BgzfSummary {                 // per block, 32 bytes
+    uint32_t n_reads;                // records passing the filter
+    uint32_t n_cigar;                // their CIGAR words
+    uint32_t used;                   // inflated bytes consumed by whole records (incl. the first block's skip)
+    uint32_t flags;                  // BZ_*
+    int32_t first_tid, last_tid;     // refID of the first / last passing record (INT32_MIN when none)
+    int32_t first_pos, last_pos;
+};
+
+// staging geometry: a block with L inflated bytes holds at most L/36 records and fewer than L/4 CIGAR words
+__host__ __device__ __forceinline__ uint64_t bz_rec_base(uint64_t out_off, uint32_t b) { return out_off / 32 + 2ull * b; }
+__host__ __device__ __forceinline__ uint64_t bz_cig_base(uint64_t out_off, uint32_t b) { return out_off / 4 + b; }
+
+constexpr int BZ_LIT_BITS = 10, BZ_DIST_BITS = 8;
+constexpr int BZ_WPC = 8;            // warps (decoders) per CTA
+
+struct BzTables {                    // per warp, shared memory
+    uint16_t lit_fast[1 << BZ_LIT_BITS];     // (symbol << 4) | code length, 0 = longer than the table
+    uint16_t dist_fast[1 << BZ_DIST_BITS];
+    uint16_t lit_sym[288];                   // symbols in canonical code order
+    uint16_t dist_sym[32];
+    uint32_t lit_cnt[16], dist_cnt[16];      // codes per length
+    uint32_t aux[48];                        // table build: running offsets / first code / first index per length
+    uint32_t rec_off[32];                    // record walk: offsets of the 32 records being parsed
+    uint8_t lens[320 + 24];                  // code-length code (19, padded to 24) then literal/length + distance lengths
+};
+
+struct BzArgs {
+    const uint8_t *in;               // compressed bytes of the chunk (padded by >= 8 readable bytes)
+    uint8_t *out;                    // inflated bytes (padded by >= 8 bytes)
+    const BgzfBlockDesc *blk; uint32_t n_blocks; uint32_t first_skip;
+    int32_t n_targets; uint32_t xflags; int32_t min_mapq;
+    int32_t *st_pos; int32_t *st_tid; uint32_t *st_coff; uint32_t *st_cig;   // staging, indexed by bz_rec_base / bz_cig_base
+    BgzfSummary *sum;
+    uint32_t *ticket;                // dynamic block ids
+};
+
+// ---- bit reader over aligned 32-bit words (lane 0 only) -----------------------------------------------------------
+struct BzBits {
+    const uint32_t *w; uint32_t wi, wlimit; uint64_t buf; int cnt; int mis;
+    __device__ __forceinline__ void init(const uint8_t *p, uint32_t n)
+    {
+        mis = (int)((uintptr_t)p & 3);
+        w = reinterpret_cast<const uint32_t *>(p - mis);
+        wlimit = (uint32_t)((mis + n + 3) >> 2);                 // words holding stream bytes; beyond them zeros are fed
+        buf = (uint64_t)(wlimit ? w[0] : 0u) >> (8 * mis);
+        cnt = 32 - 8 * mis; wi = 1;
+    }
+    __device__ __forceinline__ void refill()                      // >= 33 valid bits afterwards
+    {
+        if (cnt <= 32) { const uint32_t x = wi < wlimit ? w[wi] : 0u; buf |= (uint64_t)x << cnt; wi++; cnt += 32; }
+    }
+    __device__ __forceinline__ uint32_t peek(int n) const { return (uint32_t)buf & ((1u << n) - 1u); }
+    __device__ __forceinline__ void drop(int n) { buf >>= n; cnt -= n; }
+    __device__ __forceinline__ uint32_t bits(int n) { refill(); const uint32_t v = peek(n); drop(n); return v; }
+    // bytes of the stream consumed so far (rounded up to whole bytes)
+    __device__ __forceinline__ int64_t consumed_bits() const { return (int64_t)wi * 32 - 8 * mis - cnt; }
+    __device__ __forceinline__ void seek_bytes(uint32_t byte_pos)  // continue at stream byte `byte_pos`
+    {
+        const uint32_t a = (uint32_t)mis + byte_pos;
+        wi = a >> 2;
+        const int sh = (int)(a & 3) * 8;
+        buf = (uint64_t)(wi < wlimit ? w[wi] : 0u) >> sh; cnt = 32 - sh; wi++;
+    }
+};
+
+// canonical Huffman tables from code lengths, built by the whole warp.  Returns (to every lane) `left` as in
+// inf_build(): < 0 over-subscribed, 0 complete, > 0 incomplete.
+__device__ __forceinline__ int bz_build(const uint8_t *lens, int n, uint32_t *cnt, uint16_t *sym, uint16_t *fast, int fast_bits,
+                                        uint32_t *aux, int lane)
+{
+    if (lane < 16) cnt[lane] = 0;
+    for (int i = lane; i < (1 << fast_bits); i += 32) fast[i] = 0;
+    __syncwarp();
+    for (int s = lane; s < n; s += 32) atomicAdd(&cnt[lens[s]], 1u);
+    __syncwarp();
+    if (cnt[0] == (uint32_t)n) return 0;                          // no codes at all
+    int left = 1;
+    for (int l = 1; l < 16; l++) { left <<= 1; left -= (int)cnt[l]; if (left < 0) return left; }
+    // aux[l] = running index (symbols of length l placed so far), aux[16+l] = first code of length l, aux[32+l] = first index
+    if (lane < 16) {
+        uint32_t off = 0, code = 0;
+        for (int l = 1; l < lane; l++) { off += cnt[l]; code = (code + cnt[l]) << 1; }
+        if (lane >= 1) { aux[lane] = off; aux[16 + lane] = code; aux[32 + lane] = off; }
+    }
+    __syncwarp();
+    // symbols in canonical order: by length, then by symbol value.  32 symbols at a time; equal lengths inside a group are
+    // ranked with match_any.
+    for (int g = 0; g < n; g += 32) {
+        const int s = g + lane;
+        const uint32_t l = s < n ? lens[s] : 0u;
+        const unsigned same = __match_any_sync(0xffffffffu, l);
+        if (l) {
+            const uint32_t rank = __popc(same & ((1u << lane) - 1u));
+            sym[aux[l] + rank] = (uint16_t)s;
+        }
+        __syncwarp();
+        if (l && (same >> lane) == 1u) aux[l] += __popc(same);   // the highest lane of each length group advances its cursor
+        __syncwarp();
+    }
+    // first-level table: symbol at canonical index i with length l <= fast_bits has code first[l] + (i - first_index[l]);
+    // every fast_bits-bit pattern whose low l bits are the reversed code decodes to it
+    const int coded = n - (int)cnt[0];
+    for (int i = lane; i < coded; i += 32) {
+        const uint32_t s = sym[i], l = lens[s];
+        if (l <= (uint32_t)fast_bits) {
+            const uint32_t code = aux[16 + l] + ((uint32_t)i - aux[32 + l]);
+            const uint32_t rev = __brev(code) >> (32 - l);
+            const uint16_t e = (uint16_t)((s << 4) | l);
+            for (uint32_t p = rev; p < (1u << fast_bits); p += 1u << l) fast[p] = e;
+        }
+    }
+    __syncwarp();
+    return left;
+}
+
+// one symbol (lane 0): first-level hit, else canonical bit-by-bit decode (RFC 1951 3.2.2)
+__device__ __forceinline__ int bz_symbol(BzBits &br, const uint32_t *cnt, const uint16_t *sym, const uint16_t *fast, int fast_bits)
+{
+    br.refill();
+    const uint16_t e = fast[br.peek(fast_bits)];
+    if (e) { br.drop(e & 15); return e >> 4; }
+    int code = 0, first = 0, index = 0;
+    uint64_t b = br.buf;
+    for (int l = 1; l < 16; l++) {
+        code |= (int)(b & 1); b >>= 1;
+        const int c = (int)cnt[l];
+        if (code - c < first) { br.drop(l); return sym[index + (code - first)]; }
+        index += c; first += c; first <<= 1; code <<= 1;
+    }
+    return -1;
+}
+
+__device__ __forceinline__ uint32_t bz_ld32(const uint8_t *p)     // little-endian u32 at any alignment (reads <= 7 bytes ahead)
+{
+    const uint32_t *a = reinterpret_cast<const uint32_t *>((uintptr_t)p & ~(uintptr_t)3);
+    const uint32_t sh = (uint32_t)((uintptr_t)p & 3) * 8;
+    const uint32_t w0 = a[0], w1 = a[1];
+    return __funnelshift_r(w0, w1, sh);
+}
+
+// Inflate one raw deflate stream with the whole warp.  Returns (to every lane) bytes written, or < 0 on a malformed stream.
+__device__ __forceinline__ int bz_inflate(const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_t out_cap, BzTables &T, int lane)
+{
+    constexpr unsigned FULLM = 0xffffffffu;
+    BzBits br; br.init(in, in_len);
+    uint32_t o = 0;
+    const int64_t in_bits = (int64_t)in_len * 8;
+    for (;;) {
+        // ---- block header (lane 0), broadcast ----
+        uint32_t hdr = 0;
+        if (lane == 0) { hdr = br.bits(3); if (br.consumed_bits() > in_bits + 64) hdr |= 8u; }
+        hdr = __shfl_sync(FULLM, hdr, 0);
+        if (hdr & 8u) return -1;
+        const uint32_t last = hdr & 1u, type = (hdr >> 1) & 3u;
+        if (type == 0) {                                         // stored block: copied by all lanes
+            uint32_t n = 0, p = 0; int bad = 0;
+            if (lane == 0) {
+                br.drop(br.cnt & 7);
+                n = br.bits(16); const uint32_t nn = br.bits(16);
+                if ((n ^ nn) != 0xffffu) bad = 1;
+                p = (uint32_t)(br.consumed_bits() >> 3);         // byte position of the payload in the stream
+                if ((uint64_t)p + n > in_len || o + n > out_cap) bad = 1;
+            }
+            bad = __shfl_sync(FULLM, bad, 0);
+            if (bad) return -1;
+            n = __shfl_sync(FULLM, n, 0); p = __shfl_sync(FULLM, p, 0); o = __shfl_sync(FULLM, o, 0);
+            for (uint32_t k = lane; k < n; k += 32) out[o + k] = in[p + k];
+            o += n;
+            if (lane == 0) br.seek_bytes(p + n);
+            __syncwarp();
+        } else if (type == 1 || type == 2) {
+            int nlen = 288, ndist = 30;
+            if (type == 1) {                                     // fixed code (RFC 1951 3.2.6)
+                for (int i = lane; i < 288; i += 32) T.lens[24 + i] = i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : 8;
+                if (lane < 30) T.lens[24 + 288 + lane] = 5;
+                __syncwarp();
+            } else {                                             // dynamic code (3.2.7)
+                uint32_t h = 0;
+                if (lane == 0) h = br.bits(14);
+                h = __shfl_sync(FULLM, h, 0);
+                nlen = (int)(h & 31u) + 257; ndist = (int)((h >> 5) & 31u) + 1;
+                const int ncode = (int)(h >> 10) + 4;
+                if (nlen > 286 || ndist > 30) return -1;
+                if (lane < 24) T.lens[lane] = 0;
+                __syncwarp();
+                if (lane == 0) {
+                    const uint8_t ORDER[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+                    for (int i = 0; i < ncode; i++) T.lens[ORDER[i]] = (uint8_t)br.bits(3);
+                }
+                __syncwarp();
+                // the code-length code is decoded through the distance tables' storage
+                if (bz_build(T.lens, 19, T.dist_cnt, T.dist_sym, T.dist_fast, BZ_DIST_BITS, T.aux, lane) != 0) return -1;
+                int bad = 0;
+                if (lane == 0) {
+                    int idx = 0;
+                    while (idx < nlen + ndist) {
+                        const int s = bz_symbol(br, T.dist_cnt, T.dist_sym, T.dist_fast, BZ_DIST_BITS);
+                        if (s < 0) { bad = 1; break; }
+                        if (s < 16) { T.lens[24 + idx++] = (uint8_t)s; continue; }
+                        int rep, val = 0;
+                        if (s == 16) { if (idx == 0) { bad = 1; break; } val = T.lens[24 + idx - 1]; rep = 3 + (int)br.bits(2); }
+                        else if (s == 17) rep = 3 + (int)br.bits(3);
+                        else rep = 11 + (int)br.bits(7);
+                        if (idx + rep > nlen + ndist) { bad = 1; break; }
+                        while (rep--) T.lens[24 + idx++] = (uint8_t)val;
+                    }
+                    if (!bad && T.lens[24 + 256] == 0) bad = 1;   // no end-of-block code
+                    if (br.consumed_bits() > in_bits + 64) bad = 1;
+                }
+                bad = __shfl_sync(FULLM, bad, 0);
+                if (bad) return -1;
+                __syncwarp();
+            }
+            int r = bz_build(T.lens + 24, nlen, T.lit_cnt, T.lit_sym, T.lit_fast, BZ_LIT_BITS, T.aux, lane);
+            if (r < 0 || (r > 0 && (type == 1 ? false : nlen - (int)T.lit_cnt[0] != 1))) return -1;
+            r = bz_build(T.lens + 24 + nlen, ndist, T.dist_cnt, T.dist_sym, T.dist_fast, BZ_DIST_BITS, T.aux, lane);
+            if (r < 0 || (r > 0 && (type == 1 ? false : ndist - (int)T.dist_cnt[0] != 1))) return -1;
+            // ---- symbols: lane 0 decodes and stores literals; a match is copied by all lanes ----
+            for (;;) {
+                int cmd = 0;                                     // 1 = match, 2 = end of block, 3 = error
+                uint32_t mlen = 0, dist = 0;
+                if (lane == 0) {
+                    for (;;) {
+                        // one refill leaves >= 33 bits: enough for three first-level literal hits (<= 10 bits each) in a row
+                        br.refill();
+                        uint16_t e = T.lit_fast[br.peek(BZ_LIT_BITS)];
+                        if (e && e < (256u << 4)) {
+                            if (o >= out_cap) { cmd = 3; break; }
+                            br.drop(e & 15); out[o++] = (uint8_t)(e >> 4);
+                            e = T.lit_fast[br.peek(BZ_LIT_BITS)];
+                            if (e && e < (256u << 4)) {
+                                if (o >= out_cap) { cmd = 3; break; }
+                                br.drop(e & 15); out[o++] = (uint8_t)(e >> 4);
+                                e = T.lit_fast[br.peek(BZ_LIT_BITS)];
+                                if (e && e < (256u << 4)) {
+                                    if (o >= out_cap) { cmd = 3; break; }
+                                    br.drop(e & 15); out[o++] = (uint8_t)(e >> 4);
+                                }
+                            }
+                            continue;
+                        }
+                        int s = bz_symbol(br, T.lit_cnt, T.lit_sym, T.lit_fast, BZ_LIT_BITS);
+                        if (s < 0) { cmd = 3; break; }
+                        if (s < 256) { if (o >= out_cap) { cmd = 3; break; } out[o++] = (uint8_t)s; continue; }
+                        if (s == 256) { cmd = 2; break; }
+                        s -= 257;
+                        if (s >= 29) { cmd = 3; break; }
+                        // length / distance codes (3.2.5) are arithmetic: code s has e = (s-4)>>2 extra bits and base
+                        // 3 + ((4 + (s&3)) << e) (258 for the last one); distance code d: e = (d-2)>>1, base 1 + ((2 + (d&1)) << e)
+                        if (s < 8) mlen = 3u + (uint32_t)s;
+                        else if (s == 28) mlen = 258u;
+                        else { const int x = (s - 4) >> 2; mlen = 3u + ((4u + ((uint32_t)s & 3u)) << x) + br.bits(x); }
+                        const int d = bz_symbol(br, T.dist_cnt, T.dist_sym, T.dist_fast, BZ_DIST_BITS);
+                        if (d < 0 || d >= 30) { cmd = 3; break; }
+                        if (d < 4) dist = 1u + (uint32_t)d;
+                        else { const int x = (d - 2) >> 1; dist = 1u + ((2u + ((uint32_t)d & 1u)) << x) + br.bits(x); }
+                        if (dist > o || o + mlen > out_cap) { cmd = 3; break; }
+                        cmd = 1;
+                        break;
+                    }
+                }
+                cmd = __shfl_sync(FULLM, cmd, 0);                // (also orders lane 0's literal stores before the copy below)
+                if (cmd == 3) return -1;
+                if (cmd == 2) break;
+                mlen = __shfl_sync(FULLM, mlen, 0); dist = __shfl_sync(FULLM, dist, 0); o = __shfl_sync(FULLM, o, 0);
+                __syncwarp();
+                // byte o+k of a match equals byte o-dist+(k mod dist): every source lies before o, so all lanes copy at once
+                const uint8_t *src = out + o - dist;
+                if (dist >= mlen) { for (uint32_t k = lane; k < mlen; k += 32) out[o + k] = src[k]; }
+                else { for (uint32_t k = lane; k < mlen; k += 32) out[o + k] = src[k % dist]; }
+                o += mlen;
+                __syncwarp();
+            }
+        } else return -1;
+        int over = 0;
+        if (lane == 0) over = br.consumed_bits() > in_bits + 7 ? 1 : 0;      // consumed more bytes than the stream has
+        over = __shfl_sync(FULLM, over, 0);
+        o = __shfl_sync(FULLM, o, 0);
+        if (over) return -1;
+        if (last) break;
+    }
+    __syncwarp();
+    return (int)o;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// k_bgzf_decode
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BZ_WPC * 32, 4) k_bgzf_decode(BzArgs a)
+{
+    constexpr unsigned FULLM = 0xffffffffu;
+    __shared__ BzTables tabs[BZ_WPC];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    BzTables &T = tabs[warp];
+    for (;;) {
+        uint32_t b = 0;
+        if (lane == 0) b = atomicAdd(a.ticket, 1u);
+        b = __shfl_sync(FULLM, b, 0);
+        if (b >= a.n_blocks) return;
+        const BgzfBlockDesc k = a.blk[b];
+        uint8_t *out = a.out + k.out_off;
+        uint32_t flags = 0;
+        const int got = k.out_len ? bz_inflate(a.in + k.in_off, k.in_len, out, k.out_len, T, lane) : 0;
+        if (got != (int)k.out_len) flags |= BZ_INFLATE;
+        __syncwarp();
+
+        // ---- BAM records of the block (SAMv1 4.2): block_size, refID, pos, l_read_name, mapq, bin, n_cigar_op, flag, ... ----
+        const uint64_t rb = bz_rec_base(k.out_off, b), cb = bz_cig_base(k.out_off, b);
+        const uint32_t len = k.out_len;
+        uint32_t p = b == 0 ? a.first_skip : 0u;                 // lane 0's chain position
+        uint32_t n_reads = 0, n_cig = 0;
+        int32_t first_tid = INT32_MIN, first_pos = 0, last_tid = INT32_MIN, last_pos = INT32_MIN;
+        bool chain_end = (flags != 0) || p > len;
+        if (p > len) flags |= BZ_MALFORMED;
+        while (!chain_end) {
+            // lane 0 follows the block_size chain for up to 32 records
+            uint32_t nrec = 0;
+            if (lane == 0) {
+                while (nrec < 32 && p + 4 <= len) {
+                    const uint32_t bs = bz_ld32(out + p);
+                    if (bs < 32 || bs > (1u << 30)) { nrec |= 0x100u; break; }       // malformed
+                    if ((uint64_t)p + 4 + bs > len) { nrec |= 0x200u; break; }       // continues in the next block
+                    T.rec_off[nrec++] = p;
+                    p += 4 + bs;
+                }
+                if (!(nrec & 0x300u) && p + 4 > len) nrec |= 0x400u;                 // end of the block reached
+            }
+            nrec = __shfl_sync(FULLM, nrec, 0);
+            if (nrec & 0x100u) flags |= BZ_MALFORMED;
+            if (nrec & 0x700u) chain_end = true;
+            nrec &= 0xffu;
+            __syncwarp();
+            // every lane parses one record
+            bool keep = false; int32_t tid = 0, pos = 0; uint32_t ncg = 0; const uint8_t *cig = nullptr;
+            if ((uint32_t)lane < nrec) {
+                const uint8_t *rec = out + T.rec_off[lane] + 4;
+                const uint32_t bs = bz_ld32(rec - 4);
+                tid = (int32_t)bz_ld32(rec); pos = (int32_t)bz_ld32(rec + 4);
+                const uint32_t w8 = bz_ld32(rec + 8), w12 = bz_ld32(rec + 12);
+                const uint32_t l_name = w8 & 0xffu, mapq = (w8 >> 8) & 0xffu;
+                ncg = w12 & 0xffffu;
+                const uint32_t flag = w12 >> 16;
+                if (32 + l_name + 4 * ncg > bs) flags |= BZ_MALFORMED;
+                else {
+                    cig = rec + 32 + l_name;
+                    keep = tid >= 0 && tid < a.n_targets && !(flag & a.xflags) && (int32_t)mapq >= a.min_mapq;   // :732-733
+                    if (keep && ncg == 2 && (bz_ld32(cig) & 15u) == 4u && (bz_ld32(cig + 4) & 15u) == 3u) flags |= BZ_CG_TAG;   // `<l_seq>S<ref_len>N`: CIGAR may be in the CG tag
+                    if (keep && ncg != 1) flags |= BZ_MULTI_OP;
+                }
+            }
+            const unsigned km = __ballot_sync(FULLM, keep);
+            if (km) {
+                // order among the records that pass: each compares with the previous passing one
+                const unsigned before = km & ((1u << lane) - 1u);
+                const int src = before ? 31 - __clz(before) : lane;
+                const int32_t ptid = __shfl_sync(FULLM, tid, src), ppos = __shfl_sync(FULLM, pos, src);
+                if (keep) {
+                    const int32_t qt = before ? ptid : last_tid, qp = before ? ppos : last_pos;
+                    if (tid < qt || (tid == qt && pos < qp)) flags |= BZ_UNSORTED;
+                }
+                // staging: record rank and CIGAR word offset by warp prefix sums
+                const uint32_t rank = n_reads + __popc(before);
+                uint32_t c = keep ? ncg : 0u, incl = c;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(FULLM, incl, o); if (lane >= o) incl += y; }
+                const uint32_t coff = n_cig + incl - c;
+                if (keep) {
+                    a.st_pos[rb + rank] = pos; a.st_tid[rb + rank] = tid; a.st_coff[rb + rank] = coff;
+                    for (uint32_t j = 0; j < ncg; j++) a.st_cig[cb + coff + j] = bz_ld32(cig + 4 * j);
+                }
+                const int lo_lane = __ffs(km) - 1, hi_lane = 31 - __clz(km);
+                if (first_tid == INT32_MIN) { first_tid = __shfl_sync(FULLM, tid, lo_lane); first_pos = __shfl_sync(FULLM, pos, lo_lane); }
+                last_tid = __shfl_sync(FULLM, tid, hi_lane); last_pos = __shfl_sync(FULLM, pos, hi_lane);
+                n_reads += __popc(km);
+                n_cig += __shfl_sync(FULLM, incl, 31);
+            }
+            __syncwarp();
+        }
+        p = __shfl_sync(FULLM, p, 0);
+        // flags raised by single lanes
+        flags = __reduce_or_sync(FULLM, flags);
+        if (!(flags & (BZ_INFLATE | BZ_MALFORMED)) && p != len) flags |= BZ_STRADDLE;
+        if (lane == 0) {
+            BgzfSummary s;
+            s.n_reads = n_reads; s.n_cigar = n_cig; s.used = p; s.flags = flags;
+            s.first_tid = first_tid; s.last_tid = last_tid; s.first_pos = first_pos; s.last_pos = last_tid == INT32_MIN ? 0 : last_pos;
+            a.sum[b] = s;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// k_bgzf_offsets: r0[b], c0[b] = exclusive prefix sums of n_reads / n_cigar; totals[0..2] = reads, CIGAR words, OR of flags.
+// One CTA of 1024 threads; a chunk has at most a few hundred thousand blocks.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_bgzf_offsets(const BgzfSummary *sum, uint32_t n_blocks, uint32_t *r0, uint32_t *c0, uint32_t *totals)
+{
+    __shared__ uint32_t w_r[32], w_c[32], w_f[32];
+    __shared__ uint32_t carry_r, carry_c;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) { carry_r = 0; carry_c = 0; }
+    uint32_t fl = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n_blocks; base += 1024) {
+        const uint32_t b = base + threadIdx.x;
+        uint32_t r = 0, c = 0;
+        if (b < n_blocks) { r = sum[b].n_reads; c = sum[b].n_cigar; fl |= sum[b].flags; }
+        uint32_t ir = r, ic = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t yr = __shfl_up_sync(0xffffffffu, ir, o), yc = __shfl_up_sync(0xffffffffu, ic, o);
+            if (lane >= o) { ir += yr; ic += yc; }
+        }
+        if (lane == 31) { w_r[warp] = ir; w_c[warp] = ic; }
+        __syncthreads();
+        uint32_t pr = carry_r, pc = carry_c;
+        for (int w = 0; w < warp; w++) { pr += w_r[w]; pc += w_c[w]; }
+        if (b < n_blocks) { r0[b] = pr + ir - r; c0[b] = pc + ic - c; }
+        __syncthreads();
+        if (threadIdx.x == 1023) { carry_r = pr + ir; carry_c = pc + ic; }
+        __syncthreads();
+    }
+    fl = __reduce_or_sync(0xffffffffu, fl);
+    if (lane == 0) w_f[warp] = fl;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t f = 0;
+        for (int w = 0; w < 32; w++) f |= w_f[w];
+        totals[0] = carry_r; totals[1] = carry_c; totals[2] = f; totals[3] = n_blocks;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// k_bgzf_compact: block-local staging -> dense arrays.  cigar_off[i] is absolute into cigar[]; cigar_off[n_total] is written
+// by the last block's warp.
+// ---------------------------------------------------------------------------------------------------------------
+struct BzCompactArgs {
+    const BgzfBlockDesc *blk; const BgzfSummary *sum; const uint32_t *r0; const uint32_t *c0; uint32_t n_blocks;
+    const int32_t *st_pos; const int32_t *st_tid; const uint32_t *st_coff; const uint32_t *st_cig;
+    int32_t *pos; int32_t *tid; uint32_t *cigar_off; uint32_t *cigar;
+};
+
+__global__ void __launch_bounds__(256) k_bgzf_compact(BzCompactArgs a)
+{
+    const uint32_t b = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (b >= a.n_blocks) return;
+    const int lane = threadIdx.x & 31;
+    const uint64_t rb = bz_rec_base(a.blk[b].out_off, b), cb = bz_cig_base(a.blk[b].out_off, b);
+    const uint32_t n = a.sum[b].n_reads, nc = a.sum[b].n_cigar, r0 = a.r0[b], c0 = a.c0[b];
+    for (uint32_t i = lane; i < n; i += 32) {
+        a.pos[r0 + i] = a.st_pos[rb + i];
+        a.tid[r0 + i] = a.st_tid[rb + i];
+        a.cigar_off[r0 + i] = c0 + a.st_coff[rb + i];
+    }
+    for (uint32_t j = lane; j < nc; j += 32) a.cigar[c0 + j] = a.st_cig[cb + j];
+    if (b == a.n_blocks - 1 && lane == 0) a.cigar_off[r0 + n] = c0 + nc;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// k_delta_scatter_multi: the delta-scatter walk (PanDepth.cpp:735-760) for records of ANY contig (per-record tid): blocks of
+// a decoded chunk that hold a contig change or records out of order.  The device decoder already applied the filter.
+// ---------------------------------------------------------------------------------------------------------------
+struct ScatterMultiArgs {
+    const int32_t *tid; const int32_t *pos; const uint32_t *cigar; const uint32_t *cigar_off;
+    uint32_t n;
+    const uint64_t *contig_off; const uint32_t *contig_len; const uint8_t *owned; int32_t n_targets;
+    uint32_t *delta;   // array base
+};
+
+__global__ void __launch_bounds__(256) k_delta_scatter_multi(ScatterMultiArgs a)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    const int32_t t = a.tid[i];
+    if (t < 0 || t >= a.n_targets || !a.owned[t]) return;
+    const int32_t p = a.pos[i];
+    if (p < 0) return;
+    const uint32_t c0 = a.cigar_off[i], nops = a.cigar_off[i + 1] - c0;
+    const int64_t clen = a.contig_len[t];
+    uint32_t *delta = a.delta + a.contig_off[t];
+    int64_t q = p, rs = -1, re = -1;
+    auto flush = [&]() {
+        if (rs < 0) return;
+        const int64_t s = rs, e = re > clen ? clen : re;
+        if (s >= e) return;
+#ifndef PD_WARP_EMU
+        asm volatile("red.global.add.u32 [%0], %1;" ::"l"(delta + s), "r"(1u) : "memory");
+        asm volatile("red.global.add.u32 [%0], %1;" ::"l"(delta + e), "r"(0xffffffffu) : "memory");
+#else
+        atomicAdd(delta + s, 1u); atomicAdd(delta + e, 0xffffffffu);
+#endif
+    };
+    for (uint32_t k = 0; k < nops; ++k) {
+        const uint32_t w = a.cigar[c0 + k];
+        const uint32_t op = w & 15u;
+        const int64_t n = w >> 4;
+        if ((0x181u >> op) & 1u) {                               // M = X
+            if (rs >= 0 && re == q) re = q + n; else { flush(); rs = q; re = q + n; }
+            q += n;
+        } else if ((0x00cu >> op) & 1u) q += n;                  // D N
+    }
+    flush();
+}
+
+}  // namespace pdk

@@ -11,6 +11,7 @@
 // 3 Gb genome: 12 GB + 12 GB + 19 MB of the 180 GB.
 #include "../../include/pandepth_b200.h"
 #include "pd_kernels.cuh"
+#include "pd_bgzf.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -28,9 +29,9 @@ static_assert(PAD_ELEMS % pdk::SCAN_TILE == 0 && PAD_ELEMS % 4096 == 0, "padding
 constexpr int64_t HOST_CHUNK_READS = 8 << 20;            // staging chunk for host-resident pushes
 constexpr int N_SLOTS = 2;
 
-enum KernelId { K_CUT = 0, K_TILE, K_SCATTER, K_SCAN, K_FILL, K_REDUCE, K_WINDOWS, K_COUNT };
+enum KernelId { K_CUT = 0, K_TILE, K_SCATTER, K_SCAN, K_FILL, K_REDUCE, K_WINDOWS, K_BGZF, K_BGZF_PACK, K_COUNT };
 const char *const kKernelNames[K_COUNT] = {"k_cut", "k_tile_accumulate", "k_delta_scatter", "k_scan_add",
-                                           "k_fill_untouched", "k_reduce_units", "k_reduce_windows"};
+                                           "k_fill_untouched", "k_reduce_units", "k_reduce_windows", "k_bgzf_decode", "k_bgzf_pack"};
 
 struct Slot {
     int32_t *pos = nullptr; uint32_t *cigar = nullptr; uint32_t *cigar_off = nullptr;
@@ -39,6 +40,24 @@ struct Slot {
     cudaEvent_t copied = nullptr, consumed = nullptr;
     bool used = false;
 };
+
+// One chunk of BGZF blocks in flight through the device decoder (pd_push_bgzf): compressed bytes in, dense record arrays out.
+struct BzSlot {
+    uint8_t *d_in = nullptr; size_t in_cap = 0;
+    uint8_t *d_out = nullptr; size_t out_cap = 0;                 // inflated bytes
+    pdk::BgzfBlockDesc *d_blk = nullptr; pdk::BgzfSummary *d_sum = nullptr; uint32_t *d_r0 = nullptr, *d_c0 = nullptr; size_t blk_cap = 0;
+    int32_t *st_pos = nullptr, *st_tid = nullptr; uint32_t *st_coff = nullptr; size_t st_rec_cap = 0;
+    uint32_t *st_cig = nullptr; size_t st_cig_cap = 0;
+    int32_t *pos = nullptr, *tid = nullptr; uint32_t *coff = nullptr; size_t rec_cap = 0;
+    uint32_t *cig = nullptr; size_t cig_cap = 0;
+    uint32_t *d_totals = nullptr; uint32_t *d_ticket = nullptr;
+    pdk::BgzfBlockDesc *h_blk = nullptr; pdk::BgzfSummary *h_sum = nullptr; uint32_t *h_totals = nullptr; size_t h_blk_cap = 0;   // pinned
+    cudaStream_t stream = nullptr;                                // decode + pack of this slot (slots decode concurrently)
+    cudaEvent_t copied = nullptr, in_free = nullptr, decoded = nullptr, consumed = nullptr;
+    bool in_used = false, out_used = false, pending = false;
+    uint32_t n_blocks = 0;
+};
+constexpr int N_BZ = PD_BGZF_DEPTH + 1;
 
 }  // namespace
 
@@ -65,6 +84,9 @@ struct pd_engine {
 
     cudaStream_t own_stream = nullptr, copy_stream = nullptr, stream = nullptr;
     Slot slot[N_SLOTS]; int next_slot = 0;
+    BzSlot bz[N_BZ]; int bz_next = 0;
+    uint8_t *d_owned = nullptr;
+    int bz_grid = 148 * 4;
 
     // reduce scratch
     void *d_red = nullptr; size_t red_cap = 0;
@@ -96,19 +118,21 @@ namespace {
 int fail(pd_engine *e, int code, const char *msg) { if (e) e->err = msg; return code; }
 
 template <typename F>
-int launch(pd_engine *e, int k, F &&f)
+int launch_on(pd_engine *e, cudaStream_t st, int k, F &&f)
 {
     cudaEvent_t a = nullptr, b = nullptr;
     if (e->profiling) {
         CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
-        CK(cudaEventRecord(a, e->stream));
+        CK(cudaEventRecord(a, st));
     }
     f();
     CK(cudaGetLastError());
-    if (e->profiling) { CK(cudaEventRecord(b, e->stream)); e->pending.push_back({k, a, b}); }
+    if (e->profiling) { CK(cudaEventRecord(b, st)); e->pending.push_back({k, a, b}); }
     e->stats.kernel_launches++;
     return PD_OK;
 }
+template <typename F>
+int launch(pd_engine *e, int k, F &&f) { return launch_on(e, e->stream, k, static_cast<F &&>(f)); }
 
 int drain_profile(pd_engine *e)
 {
@@ -208,9 +232,155 @@ int check_device_flags(pd_engine *e)
     int h[2] = {0, 0};
     CK(cudaMemcpyAsync(h, e->d_flags, sizeof h, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
+    if (h[1]) e->host_delta_used = true;        // before the error returns: pd_reset must know the tile kernel wrote far-run deltas
     if (h[0] & pdk::ERR_UNSORTED) return fail(e, PD_ERR_UNSORTED, "a batch pushed with PD_SORTED was not sorted by pos");
     if (h[0] & pdk::ERR_RANGE) return fail(e, PD_ERR_UNSORTED, "a PD_SORTED batch had positions outside their segment (unsorted input)");
-    if (h[1]) e->host_delta_used = true;
+    return PD_OK;
+}
+
+// ---- device-side BGZF decode (pd_push_bgzf) ------------------------------------------------------------------------------
+template <typename T>
+int bz_grow(pd_engine *e, T *&p, size_t &cap, size_t need, size_t *cap_out = nullptr)
+{
+    (void)cap_out;
+    if (need <= cap) return PD_OK;
+    if (p) { CK(cudaDeviceSynchronize()); cudaFree(p); p = nullptr; }
+    const size_t c = need + need / 4 + 1024;
+    CK(cudaMalloc(&p, c * sizeof(T)));
+    e->stats.hbm_bytes_allocated += c * sizeof(T);
+    cap = c;
+    return PD_OK;
+}
+
+int bz_ensure(pd_engine *e, BzSlot &s, size_t in_bytes, uint64_t out_total, uint32_t n_blocks, bool device_input)
+{
+    if (!s.copied) {
+        CK(cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&s.in_free, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&s.decoded, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&s.consumed, cudaEventDisableTiming));
+        CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        CK(cudaMalloc(&s.d_totals, 16)); CK(cudaMalloc(&s.d_ticket, 4));
+        CK(cudaHostAlloc(&s.h_totals, 16, cudaHostAllocDefault));
+    }
+    int rc;
+    if (!device_input) { rc = bz_grow(e, s.d_in, s.in_cap, in_bytes + 64); if (rc) return rc; }
+    rc = bz_grow(e, s.d_out, s.out_cap, (size_t)out_total + 64); if (rc) return rc;
+    if (n_blocks > s.blk_cap) {
+        if (s.d_blk) CK(cudaDeviceSynchronize());
+        cudaFree(s.d_blk); cudaFree(s.d_sum); cudaFree(s.d_r0); cudaFree(s.d_c0);
+        s.d_blk = nullptr; s.d_sum = nullptr; s.d_r0 = s.d_c0 = nullptr;
+        const size_t c = (size_t)n_blocks + n_blocks / 4 + 256;
+        CK(cudaMalloc(&s.d_blk, c * sizeof(pdk::BgzfBlockDesc))); CK(cudaMalloc(&s.d_sum, c * sizeof(pdk::BgzfSummary)));
+        CK(cudaMalloc(&s.d_r0, c * 4)); CK(cudaMalloc(&s.d_c0, c * 4));
+        s.blk_cap = c;
+    }
+    if (n_blocks > s.h_blk_cap) {
+        if (s.h_blk) { cudaFreeHost(s.h_blk); cudaFreeHost(s.h_sum); s.h_blk = nullptr; s.h_sum = nullptr; }
+        const size_t c = (size_t)n_blocks + n_blocks / 4 + 256;
+        CK(cudaHostAlloc(&s.h_blk, c * sizeof(pdk::BgzfBlockDesc), cudaHostAllocDefault));
+        CK(cudaHostAlloc(&s.h_sum, c * sizeof(pdk::BgzfSummary), cudaHostAllocDefault));
+        s.h_blk_cap = c;
+    }
+    // staging (block-local) and dense outputs: sized by what the inflated bytes can hold at most
+    const size_t st_rec = (size_t)(out_total / 32) + 2ull * n_blocks + 64, st_cig = (size_t)(out_total / 4) + n_blocks + 64;
+    const size_t n_rec = (size_t)(out_total / 36) + 64, n_cig = (size_t)(out_total / 4) + 64;
+    if (st_rec > s.st_rec_cap) {
+        size_t c0 = s.st_rec_cap, c1 = s.st_rec_cap, c2 = s.st_rec_cap;
+        rc = bz_grow(e, s.st_pos, c0, st_rec); if (rc) return rc;
+        rc = bz_grow(e, s.st_tid, c1, st_rec); if (rc) return rc;
+        rc = bz_grow(e, s.st_coff, c2, st_rec); if (rc) return rc;
+        s.st_rec_cap = c0;
+    }
+    rc = bz_grow(e, s.st_cig, s.st_cig_cap, st_cig); if (rc) return rc;
+    if (n_rec + 1 > s.rec_cap) {
+        size_t c0 = s.rec_cap, c1 = s.rec_cap, c2 = s.rec_cap;
+        rc = bz_grow(e, s.pos, c0, n_rec + 1); if (rc) return rc;
+        rc = bz_grow(e, s.tid, c1, n_rec + 1); if (rc) return rc;
+        rc = bz_grow(e, s.coff, c2, n_rec + 1); if (rc) return rc;
+        s.rec_cap = c0;
+    }
+    rc = bz_grow(e, s.cig, s.cig_cap, n_cig); if (rc) return rc;
+    return PD_OK;
+}
+
+// Drop whatever the decoder still has in flight (error paths, pd_reset).
+int bz_cancel(pd_engine *e)
+{
+    bool any = false;
+    for (auto &s : e->bz) { any = any || s.pending; s.pending = false; }
+    if (any) { CK(cudaStreamSynchronize(e->copy_stream)); for (auto &s : e->bz) if (s.stream) CK(cudaStreamSynchronize(s.stream)); CK(cudaStreamSynchronize(e->stream)); }
+    return PD_OK;
+}
+
+// Second half of a chunk: its per-block summaries are back on the host -> check them, cut the records into contig runs and
+// queue the accumulate kernels.  Sorted single-contig runs take the tile path; blocks holding a contig change or records out
+// of order go through the per-record-tid delta scatter.
+int bz_finish(pd_engine *e, BzSlot &s)
+{
+    if (!s.pending) return PD_OK;
+    s.pending = false;
+    CK(cudaEventSynchronize(s.decoded));
+    const uint32_t n_reads = s.h_totals[0], n_cigar = s.h_totals[1], fl = s.h_totals[2];
+    if (fl & pdk::BZ_INFLATE) { bz_cancel(e); return fail(e, PD_ERR_ARG, "pd_push_bgzf: a BGZF block does not inflate to its ISIZE (corrupt or truncated block)"); }
+    if (fl & (pdk::BZ_MALFORMED | pdk::BZ_STRADDLE | pdk::BZ_CG_TAG)) {
+        bz_cancel(e);
+        return fail(e, PD_ERR_FALLBACK, (fl & pdk::BZ_CG_TAG) ? "pd_push_bgzf: a CIGAR may live in the CG tag (host path needed)"
+                                                               : "pd_push_bgzf: records do not start on BGZF block boundaries (host path needed)");
+    }
+    if (!n_reads) return PD_OK;
+    CK(cudaStreamWaitEvent(e->stream, s.decoded, 0));          // the accumulate kernels below read the slot's dense arrays
+    const bool single_op = !(fl & pdk::BZ_MULTI_OP);           // every record has exactly one CIGAR word: cigar[i] belongs to read i
+    if (e->delta_stale) { CK(cudaMemsetAsync(e->d_delta, 0, e->total * 4, e->stream)); e->delta_stale = false; }
+    const pdk::BgzfSummary *sm = s.h_sum;
+    // exclusive prefix of reads per block (the device computed the same; recomputed here to avoid another copy)
+    uint32_t r = 0;
+    struct Run { int32_t tid; uint32_t r0, r1; int32_t p0, p1; bool sorted; };
+    Run cur{0, 0, 0, 0, 0, false}; bool open = false;
+    uint32_t irr0 = 0, irr1 = 0; bool irr_open = false;
+    int32_t prev_tid = INT32_MIN, prev_pos = INT32_MIN;
+    int rc = PD_OK;
+    auto flush_run = [&]() -> int {
+        if (!open) return PD_OK;
+        open = false;
+        const int32_t t = cur.tid;
+        if (t < 0 || t >= e->n_targets || !e->owned[t] || e->tlen[t] == 0) return PD_OK;
+        const int64_t max_seg = ((int64_t)e->tlen[t]) / pdk::SEG;
+        int64_t p0 = std::max<int32_t>(cur.p0, 0), p1 = std::max<int32_t>(cur.p1, 0);
+        int64_t seg_a = std::min<int64_t>(p0 / pdk::SEG, max_seg), seg_b = std::min<int64_t>((p1 + pdk::HALO) / pdk::SEG, max_seg);
+        if (seg_b < seg_a) seg_b = seg_a;
+        return run_batch(e, t, cur.r1 - cur.r0, s.pos + cur.r0, nullptr, nullptr, single_op ? nullptr : s.coff + cur.r0,
+                         single_op ? s.cig + cur.r0 : s.cig, true, seg_a, seg_b);
+    };
+    auto flush_irr = [&]() -> int {
+        if (!irr_open) return PD_OK;
+        irr_open = false;
+        const uint32_t n = irr1 - irr0;
+        pdk::ScatterMultiArgs m{s.tid + irr0, s.pos + irr0, s.cig, s.coff + irr0, n, e->d_off, e->d_tlen, e->d_owned, e->n_targets, e->d_delta};
+        int rc2 = launch(e, K_SCATTER, [&] { pdk::k_delta_scatter_multi<<<(n + 255) / 256, 256, 0, e->stream>>>(m); });
+        if (rc2) return rc2;
+        e->host_delta_used = true; e->stats.delta_path_batches++; e->stats.reads_pushed += n;
+        e->finalized = false; e->pushed_since_reset = true;
+        return PD_OK;
+    };
+    for (uint32_t b = 0; b < s.n_blocks; b++) {
+        const uint32_t n = sm[b].n_reads;
+        if (!n) continue;
+        const bool regular = !(sm[b].flags & pdk::BZ_UNSORTED) && sm[b].first_tid == sm[b].last_tid;
+        if (regular) {
+            if ((rc = flush_irr())) return rc;
+            const bool cont = open && cur.tid == sm[b].first_tid && sm[b].first_pos >= prev_pos && prev_tid == cur.tid;
+            if (cont) { cur.r1 = r + n; cur.p1 = sm[b].last_pos; }
+            else { if ((rc = flush_run())) return rc; cur = Run{sm[b].first_tid, r, r + n, sm[b].first_pos, sm[b].last_pos, true}; open = true; }
+        } else {
+            if ((rc = flush_run())) return rc;
+            if (irr_open && irr1 == r) irr1 = r + n; else { if ((rc = flush_irr())) return rc; irr0 = r; irr1 = r + n; irr_open = true; }
+        }
+        prev_tid = sm[b].last_tid; prev_pos = sm[b].last_pos;
+        r += n;
+    }
+    if ((rc = flush_run())) return rc;
+    if ((rc = flush_irr())) return rc;
+    CK(cudaEventRecord(s.consumed, e->stream)); s.out_used = true;
+    (void)n_cigar;
     return PD_OK;
 }
 
@@ -242,6 +412,20 @@ void pd_destroy(pd_engine *e)
         if (s.copied) cudaEventDestroy(s.copied);
         if (s.consumed) cudaEventDestroy(s.consumed);
     }
+    for (auto &s : e->bz) {
+        cudaFree(s.d_in); cudaFree(s.d_out); cudaFree(s.d_blk); cudaFree(s.d_sum); cudaFree(s.d_r0); cudaFree(s.d_c0);
+        cudaFree(s.st_pos); cudaFree(s.st_tid); cudaFree(s.st_coff); cudaFree(s.st_cig);
+        cudaFree(s.pos); cudaFree(s.tid); cudaFree(s.coff); cudaFree(s.cig); cudaFree(s.d_totals); cudaFree(s.d_ticket);
+        if (s.h_blk) cudaFreeHost(s.h_blk);
+        if (s.h_sum) cudaFreeHost(s.h_sum);
+        if (s.h_totals) cudaFreeHost(s.h_totals);
+        if (s.copied) cudaEventDestroy(s.copied);
+        if (s.in_free) cudaEventDestroy(s.in_free);
+        if (s.decoded) cudaEventDestroy(s.decoded);
+        if (s.consumed) cudaEventDestroy(s.consumed);
+        if (s.stream) cudaStreamDestroy(s.stream);
+    }
+    cudaFree(e->d_owned);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     delete e;
@@ -288,6 +472,8 @@ pd_engine *pd_create(int device, int n_targets, const uint32_t *target_len, cons
     e->stats.hbm_bytes_allocated = total * 8 + e->n_seg * 13 + (total / pdk::SCAN_TILE) * 8;
     if ((ce = cudaMemcpy(e->d_off, e->off.data(), (size_t)n_targets * 8, cudaMemcpyHostToDevice)) != cudaSuccess) return bail("memcpy", ce);
     if ((ce = cudaMemcpy(e->d_tlen, e->tlen.data(), (size_t)n_targets * 4, cudaMemcpyHostToDevice)) != cudaSuccess) return bail("memcpy", ce);
+    if ((ce = cudaMalloc(&e->d_owned, (size_t)n_targets)) != cudaSuccess) return bail("cudaMalloc", ce);
+    if ((ce = cudaMemcpy(e->d_owned, e->owned.data(), (size_t)n_targets, cudaMemcpyHostToDevice)) != cudaSuccess) return bail("memcpy", ce);
     if ((ce = cudaMemsetAsync(e->d_delta, 0, total * 4, e->stream)) != cudaSuccess) return bail("memset", ce);
     if ((ce = cudaMemsetAsync(e->d_seg_state, 0, e->n_seg, e->stream)) != cudaSuccess) return bail("memset", ce);
     if ((ce = cudaMemsetAsync(e->d_flags, 0, 8, e->stream)) != cudaSuccess) return bail("memset", ce);
@@ -303,6 +489,8 @@ pd_engine *pd_create(int device, int n_targets, const uint32_t *target_len, cons
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pdk::k_tile_accumulate<false, false>, pdk::WPC * 32, pdk::WPC * pdk::TILE_SMEM_WORDS * 4) == cudaSuccess && n_sm > 0 && per_sm > 0)
             e->tile_resident_warps = n_sm * per_sm * pdk::WPC;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pdk::k_bgzf_decode, pdk::BZ_WPC * 32, 0) == cudaSuccess && n_sm > 0 && per_sm > 0)
+            e->bz_grid = n_sm * per_sm;
     }
     if ((ce = cudaStreamSynchronize(e->stream)) != cudaSuccess) return bail("sync", ce);
     return e;
@@ -330,6 +518,7 @@ int pd_reset(pd_engine *e)
 {
     if (!e) return PD_ERR_ARG;
     CK(cudaSetDevice(e->device));
+    { int rc = bz_cancel(e); if (rc) return rc; }
     if (!e->finalized) {                  // un-finalized pushes may have queued far-run deltas on the device
         CK(cudaStreamSynchronize(e->copy_stream));
         (void)check_device_flags(e);      // stale errors are dropped
@@ -431,17 +620,78 @@ int pd_push(pd_engine *e, int64_t n_reads, const int32_t *tid, const int32_t *po
     return PD_OK;
 }
 
-int pd_push_bgzf(pd_engine *e, const uint8_t *, size_t, const pd_bgzf_block *, int64_t, uint32_t, uint32_t)
+int pd_push_bgzf(pd_engine *e, const uint8_t *bytes, size_t n_bytes, const pd_bgzf_block *blocks, int64_t n_blocks,
+                 uint32_t first_skip, uint32_t flags)
 {
-    // the device decoder (pd_inflate.cuh / pd_decode.hpp) is not wired in yet: callers take their host decode path
     if (!e) return PD_ERR_ARG;
-    return fail(e, PD_ERR_FALLBACK, "pd_push_bgzf: device-side BGZF decode is not enabled in this build");
+    if (n_blocks < 0 || (n_blocks > 0 && (!bytes || !blocks)) || n_blocks > 0x7fffffffll) return fail(e, PD_ERR_ARG, "pd_push_bgzf: bad arguments");
+    CK(cudaSetDevice(e->device));
+    const bool dev = (flags & PD_DEVICE) != 0;
+    int rc = PD_OK;
+    if (n_blocks > 0) {
+        BzSlot &s = e->bz[e->bz_next];
+        e->bz_next = (e->bz_next + 1) % N_BZ;
+        if (s.pending) { rc = bz_finish(e, s); if (rc) return rc; }
+        // block table with inflated offsets; the bytes that travel are [first payload, end of last payload)
+        uint64_t lo = UINT64_MAX, hi = 0, out_total = 0;
+        for (int64_t b = 0; b < n_blocks; b++) {
+            const pd_bgzf_block &k = blocks[b];
+            if (k.in_off > n_bytes || k.in_len > n_bytes - k.in_off || k.out_len > 65536u) return fail(e, PD_ERR_ARG, "pd_push_bgzf: block outside the buffer or ISIZE > 64 KB");
+            lo = std::min<uint64_t>(lo, k.in_off); hi = std::max<uint64_t>(hi, k.in_off + k.in_len);
+            out_total += k.out_len;
+        }
+        if (out_total > 0xf0000000ull) return fail(e, PD_ERR_ARG, "pd_push_bgzf: chunk inflates to more than 3.75 GB; pass smaller chunks");
+        rc = bz_ensure(e, s, (size_t)(hi - lo), out_total + 8ull * (uint64_t)n_blocks, (uint32_t)n_blocks, dev); if (rc) return rc;
+        uint64_t oo = 0;
+        for (int64_t b = 0; b < n_blocks; b++) {
+            s.h_blk[b] = pdk::BgzfBlockDesc{blocks[b].in_off - lo, blocks[b].in_len, blocks[b].out_len, oo};
+            oo += (blocks[b].out_len + 7u) & ~7u;                 // every block's output starts 8-byte aligned
+        }
+        s.n_blocks = (uint32_t)n_blocks;
+        const uint8_t *d_in = dev ? bytes + lo : s.d_in;
+        if (!dev) {
+            if (s.in_used) CK(cudaStreamWaitEvent(e->copy_stream, s.in_free, 0));
+            CK(cudaMemcpyAsync(s.d_in, bytes + lo, (size_t)(hi - lo), cudaMemcpyHostToDevice, e->copy_stream));
+            e->stats.h2d_bytes += hi - lo;
+        }
+        CK(cudaMemcpyAsync(s.d_blk, s.h_blk, (size_t)n_blocks * sizeof(pdk::BgzfBlockDesc), cudaMemcpyHostToDevice, e->copy_stream));
+        e->stats.h2d_bytes += (uint64_t)n_blocks * sizeof(pdk::BgzfBlockDesc);
+        CK(cudaEventRecord(s.copied, e->copy_stream));
+        CK(cudaStreamWaitEvent(s.stream, s.copied, 0));
+        if (s.out_used) CK(cudaStreamWaitEvent(s.stream, s.consumed, 0));     // the slot's previous arrays have been accumulated
+        CK(cudaMemsetAsync(s.d_ticket, 0, 4, s.stream));
+        pdk::BzArgs a{d_in, s.d_out, s.d_blk, (uint32_t)n_blocks, first_skip, e->n_targets, e->xflags, e->min_mapq,
+                      s.st_pos, s.st_tid, s.st_coff, s.st_cig, s.d_sum, s.d_ticket};
+        const unsigned grid = (unsigned)std::min<int64_t>((n_blocks + pdk::BZ_WPC - 1) / pdk::BZ_WPC, e->bz_grid);
+        rc = launch_on(e, s.stream, K_BGZF, [&] { pdk::k_bgzf_decode<<<grid, pdk::BZ_WPC * 32, 0, s.stream>>>(a); }); if (rc) return rc;
+        CK(cudaEventRecord(s.in_free, s.stream)); s.in_used = true;
+        pdk::BzCompactArgs c{s.d_blk, s.d_sum, s.d_r0, s.d_c0, (uint32_t)n_blocks, s.st_pos, s.st_tid, s.st_coff, s.st_cig, s.pos, s.tid, s.coff, s.cig};
+        rc = launch_on(e, s.stream, K_BGZF_PACK, [&] {
+            pdk::k_bgzf_offsets<<<1, 1024, 0, s.stream>>>(s.d_sum, (uint32_t)n_blocks, s.d_r0, s.d_c0, s.d_totals);
+            pdk::k_bgzf_compact<<<(unsigned)((n_blocks + 7) / 8), 256, 0, s.stream>>>(c);
+        });
+        if (rc) return rc;
+        e->stats.kernel_launches++;
+        CK(cudaMemcpyAsync(s.h_sum, s.d_sum, (size_t)n_blocks * sizeof(pdk::BgzfSummary), cudaMemcpyDeviceToHost, s.stream));
+        CK(cudaMemcpyAsync(s.h_totals, s.d_totals, 16, cudaMemcpyDeviceToHost, s.stream));
+        e->stats.d2h_bytes += (uint64_t)n_blocks * sizeof(pdk::BgzfSummary) + 16;
+        CK(cudaEventRecord(s.decoded, s.stream));
+        s.pending = true;
+        e->finalized = false; e->pushed_since_reset = true;
+        // the oldest chunk in flight has had whole decodes to finish: plan and queue its accumulate kernels now
+        // (PD_BGZF_DEPTH chunks stay in flight; without PD_ASYNC everything is drained)
+        if (!(flags & PD_ASYNC)) { for (int k = 0; k < N_BZ; k++) { rc = bz_finish(e, e->bz[(e->bz_next + k) % N_BZ]); if (rc) return rc; } }
+        else { BzSlot &oldest = e->bz[e->bz_next]; if (oldest.pending) { rc = bz_finish(e, oldest); if (rc) return rc; } }
+    }
+    if (!(flags & PD_ASYNC)) CK(cudaStreamSynchronize(e->copy_stream));
+    return PD_OK;
 }
 
 int pd_sync(pd_engine *e)
 {
     if (!e) return PD_ERR_ARG;
     CK(cudaSetDevice(e->device));
+    for (int k = 0; k < N_BZ; k++) { int rc = bz_finish(e, e->bz[(e->bz_next + k) % N_BZ]); if (rc) return rc; }
     CK(cudaStreamSynchronize(e->copy_stream));
     CK(cudaStreamSynchronize(e->stream));
     return check_device_flags(e);
@@ -451,6 +701,7 @@ int pd_finalize(pd_engine *e)
 {
     if (!e) return PD_ERR_ARG;
     CK(cudaSetDevice(e->device));
+    for (int k = 0; k < N_BZ; k++) { int rc = bz_finish(e, e->bz[(e->bz_next + k) % N_BZ]); if (rc) return rc; }
     if (e->finalized) return PD_OK;
     int rc = check_device_flags(e); if (rc) return rc;
     if (e->host_delta_used) {

@@ -53,6 +53,8 @@ def load_library() -> ctypes.CDLL:
     L.pd_push_contig.argtypes = [vp, i32, i64, vp, vp, vp, vp, vp, u32]
     L.pd_push.restype = ctypes.c_int
     L.pd_push.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, u32]
+    L.pd_push_bgzf.restype = ctypes.c_int
+    L.pd_push_bgzf.argtypes = [vp, vp, ctypes.c_size_t, vp, i64, u32, u32]
     L.pd_sync.restype = ctypes.c_int; L.pd_sync.argtypes = [vp]
     L.pd_finalize.restype = ctypes.c_int; L.pd_finalize.argtypes = [vp]
     L.pd_reduce.restype = ctypes.c_int
@@ -146,6 +148,17 @@ class Engine:
         flag = _arr(flag, np.uint16); mapq = _arr(mapq, np.uint8); cigar_off = _arr(cigar_off, np.uint32)
         self._keep = (tid, pos, cigar, flag, mapq, cigar_off)
         self._ck(self._L.pd_push(self._h, int(tid.size), _p(tid), _p(pos), _p(flag), _p(mapq), _p(cigar_off), _p(cigar), flags))
+
+    def push_bgzf(self, data, blocks, first_skip: int = 0, flags: int = 0, n_bytes: Optional[int] = None):
+        """Compressed BGZF chunk -> inflate + record walk + accumulate on the device.  `data` is a uint8 numpy array (or, with
+        PD_DEVICE, an integer device pointer plus n_bytes); `blocks` a structured array (in_off u64, in_len u32, out_len u32)."""
+        blocks = np.ascontiguousarray(blocks)
+        assert blocks.dtype.itemsize == 16
+        if not (flags & PD_DEVICE):
+            data = _arr(data, np.uint8)
+            n_bytes = int(data.size)
+        self._keep = (data, blocks)
+        self._ck(self._L.pd_push_bgzf(self._h, _p(data), int(n_bytes), _p(blocks), int(blocks.size), first_skip, flags))
 
     def sync(self):
         self._ck(self._L.pd_sync(self._h))

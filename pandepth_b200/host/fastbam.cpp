@@ -134,6 +134,7 @@ bool BamRangeScanner::inflate_next_block()
         const uint8_t *cdata = h + 12 + xlen;
         const size_t clen = bsize - xlen - 12 - 8;
         const uint32_t isize = le32(h + bsize - 4);
+        if (isize > (1u << 16)) { err_ = "BGZF block claims more than 64 KB"; return false; }
         raw_pos_ += bsize;
         if (isize == 0) continue;                                             // empty block (EOF marker)
         // keep the unconsumed tail, append this block
@@ -155,6 +156,7 @@ bool BamRangeScanner::inflate_next_block()
         inflateEnd(&zs);
         if (rc != Z_STREAM_END || zs.avail_out != 0) { err_ = "inflate failed"; return false; }
 #endif
+        if ((uint32_t)crc32(0L, buf_.data() + blen_, isize) != le32(h + bsize - 8)) { err_ = "BGZF block CRC mismatch"; return false; }   // htslib checks it too
         blen_ += isize;
         return true;
     }
@@ -234,9 +236,11 @@ struct Inflater {
 #endif
 };
 
-// BGZF block at h (avail bytes): > 0 total size (payload in cdata/clen, inflated size in isize); 0 = more bytes needed
-// (header or block not complete within avail); -1 = not a BGZF block
-int64_t bgzf_block(const uint8_t *h, size_t avail, const uint8_t **cdata, size_t *clen, uint32_t *isize)
+int64_t bgzf_block(const uint8_t *h, size_t avail, const uint8_t **cdata, size_t *clen, uint32_t *isize) { return bgzf_block_at(h, avail, cdata, clen, isize); }
+
+}  // namespace
+
+int64_t bgzf_block_at(const uint8_t *h, size_t avail, const uint8_t **cdata, size_t *clen, uint32_t *isize)
 {
     if (avail < 18) return 0;
     if (h[0] != 31 || h[1] != 139 || h[2] != 8 || !(h[3] & 4)) return -1;
@@ -252,10 +256,9 @@ int64_t bgzf_block(const uint8_t *h, size_t avail, const uint8_t **cdata, size_t
     if (bsize < 12 + xlen + 8) return -1;
     if (bsize > avail) return 0;
     *cdata = h + 12 + xlen; *clen = bsize - xlen - 12 - 8; *isize = le32(h + bsize - 4);
+    if (*isize > (1u << 16)) return -1;                      // BGZF blocks inflate to at most 64 KB: a larger ISIZE is corruption, not a size to allocate
     return bsize;
 }
-
-}  // namespace
 
 // Groups of consecutive BGZF blocks (up to ~4 MB inflated / 2 MB compressed) are cut by whoever asks for work next: the cut
 // needs the block headers, a sequential walk, so it happens under the lock on a shared read-ahead buffer and copies only the
@@ -325,7 +328,9 @@ struct BamStreamScanner::Impl {
             // the slot is free: seq < consumed + ring.size() means its previous tenant (seq - ring.size()) was released
             Slot &s = ring[seq % ring.size()];
             if (s.out.size() < out_len) s.out.resize(out_len);
-            if (!bad) for (const Blk &b : blks) if (b.isize && !inf.run(raw.data() + b.off, b.clen, s.out.data() + b.out_off, b.isize)) { bad = true; break; }
+            // inflate, then the CRC32 that follows every payload (htslib verifies it too)
+            if (!bad) for (const Blk &b : blks) if (b.isize && (!inf.run(raw.data() + b.off, b.clen, s.out.data() + b.out_off, b.isize) ||
+                                                            (uint32_t)crc32(0L, s.out.data() + b.out_off, b.isize) != le32(raw.data() + b.off + b.clen))) { bad = true; break; }
             {
                 std::lock_guard<std::mutex> g(mu);
                 s.len = bad ? 0 : out_len; s.seq = seq; s.bad = bad; s.last = last; s.ready = true;

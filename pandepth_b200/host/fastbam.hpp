@@ -96,9 +96,14 @@ public:
     // next chunk of up to max_bytes compressed bytes (whole blocks, at least one); false at the end of the file
     bool next(size_t max_bytes, std::vector<uint8_t> &bytes, std::vector<Block> &blocks);
     const std::string &error() const { return err_; }
+    uint64_t position() const { return pos_; }          // file offset of the next block next() would return
 private:
     int fd_ = -1; uint64_t pos_ = 0; std::string err_;
 };
+
+// BGZF block at h (avail bytes): > 0 total size (payload in cdata / clen, inflated size in isize); 0 = more bytes needed
+// (header or block not complete within avail); -1 = not a BGZF block (bad magic, size fields, or ISIZE > 64 KB)
+int64_t bgzf_block_at(const uint8_t *h, size_t avail, const uint8_t **cdata, size_t *clen, uint32_t *isize);
 
 // long CIGAR (> 65535 ops) kept in the CG:B,I tag behind a `<l_seq>S<ref_len>N` placeholder (SAMv1 4.2.2): fills r from it
 bool resolve_long_cigar_tag(const uint8_t *rec, uint32_t block_size, uint32_t l_read_name, uint32_t n_cigar, int32_t l_seq,

@@ -3,6 +3,7 @@
 #pragma once
 #include "pd_host.hpp"
 #include "fastbam.hpp"
+#include "bgzf_feed.hpp"
 #include "../../include/pandepth_b200.h"
 
 #include "sam.h"
@@ -149,7 +150,9 @@ struct Feeder {
     std::atomic<uint64_t> ns_decode{0}, ns_wait{0}, ns_push{0}, n_push{0}, dry_digest{0};
     const BaiLinear *bai = nullptr;                      // non-null: scan raw BAM records directly (fastbam.hpp)
     std::string input;                                   // the file being fed (multi-file mode feeds several in turn)
-    bool used_fast = false;
+    bool used_fast = false, used_device_decode = false;
+    ChunkPool chunk_pool;                                // pinned buffers of the device-decode path (bgzf_feed.hpp)
+    bool hint_set = false; uint32_t hint_min_dep = 1, hint_mask = 0xFFFFFFFFu;   // reduce hint to restore after a pd_reset
     PinnedPool *pool = nullptr;                          // pinned staging (exists once the CUDA context does)
     const std::vector<Target> *targets = nullptr;        // contig table (names, lengths)
     bool dry = getenv("PANDEPTH_DRY") != nullptr;
@@ -394,42 +397,36 @@ struct Feeder {
         }
     };
 
-    // PANDEPTH_GPU_DECODE=1, whole-genome modes, BAM input: the compressed file goes to the engine chunk by chunk
-    // (pd_push_bgzf: inflate + record walk + accumulate on the device).  Returns 1 = the whole file was accumulated this way,
+    // Whole-genome modes, BAM input: the compressed file goes to the engine piece by piece (bgzf_feed.hpp -> pd_push_bgzf:
+    // inflate + record walk + accumulate on the device).  Returns 1 = the whole file was accumulated this way,
     // 0 = not applicable or the engine asked for the host path (nothing of this file is accumulated: the engine was reset if
     // needed), -1 = failed.
     int stream_bgzf()
     {
         if (dry) return 0;
-        uint32_t first_skip = 0;
-        BgzfChunker ch;
-        if (!ch.open(input, first_skip)) return 0;
         eng_future.wait();
         {
             std::lock_guard<std::mutex> g(eng_mu);
             if (!eng) { eng = eng_future.get(); if (!eng) { fail(std::string("Error: ") + pd_last_error(nullptr)); return -1; } }
             eng_ok = true;
         }
-        std::vector<uint8_t> bytes; std::vector<BgzfChunker::Block> blocks; std::vector<pd_bgzf_block> pb;
-        size_t n_chunks = 0;
-        while (ch.next(16u << 20, bytes, blocks)) {
-            if (blocks.empty()) continue;
-            pb.resize(blocks.size());
-            for (size_t i = 0; i < blocks.size(); i++) pb[i] = pd_bgzf_block{blocks[i].in_off, blocks[i].in_len, blocks[i].out_len};
+        const auto t0 = std::chrono::steady_clock::now();
+        const BgzfFeedResult r = bgzf_feed_file(eng, &eng_mu, input, std::max(1, o.threads), chunk_pool);
+        ns_decode += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
+        n_push += r.pieces;
+        if (r.status < 0) { fail(r.err.empty() ? "Error: device decode failed on " + input : r.err); return -1; }
+        if (r.status == 0) {
+            // (records that do not start on block boundaries, CG-tag CIGARs.)  Depth is additive but the pieces already
+            // accumulated cannot be taken back one by one, so this file starts over on the host path from a clean engine;
+            // only valid while this is the first input file
             std::lock_guard<std::mutex> g(eng_mu);
-            const int rc = pd_push_bgzf(eng, bytes.data(), bytes.size(), pb.data(), (int64_t)pb.size(), n_chunks == 0 ? first_skip : 0u, 0u);
-            if (rc == PD_ERR_FALLBACK) {
-                // (typically the very first chunk: reads larger than a block.)  Depth is additive but the chunks already
-                // accumulated cannot be taken back one by one, so this file starts over on the host path from a clean engine;
-                // only valid while this is the first input file
-                if (n_chunks && pd_reset(eng) != PD_OK) { fail(std::string("pd_reset: ") + pd_last_error(eng)); return -1; }
-                return 0;
-            }
-            if (rc != PD_OK) { fail(std::string("pd_push_bgzf: ") + pd_last_error(eng)); return -1; }
-            n_chunks++;
+            if (r.pieces && pd_reset(eng) != PD_OK) { fail(std::string("pd_reset: ") + pd_last_error(eng)); return -1; }
+            if (r.pieces && hint_set && pd_set_reduce_hint(eng, hint_min_dep, hint_mask) != PD_OK) { fail(std::string("pd_set_reduce_hint: ") + pd_last_error(eng)); return -1; }
+            return 0;
         }
-        if (!ch.error().empty()) { fail("Error: malformed BAM while reading " + input + ": " + ch.error()); return -1; }
-        used_fast = true;
+        pd_stats st;
+        if (pd_get_stats(eng, &st) == PD_OK) reads_pushed = st.reads_pushed;
+        used_fast = true; used_device_decode = true;
         return 1;
     }
 

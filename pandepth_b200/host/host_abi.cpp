@@ -1,0 +1,33 @@
+// host_abi.cpp -- libpandepth_host.so: the feeder's C entry points (include/pandepth_host.h).
+#include "../../include/pandepth_host.h"
+#include "bgzf_feed.hpp"
+
+#include <cstdio>
+#include <memory>
+
+namespace {
+std::mutex g_mu;
+std::unique_ptr<pdh::ChunkPool> g_pool;
+}
+
+extern "C" int pdh_feed_bam(pd_engine *e, const char *path, int threads, pdh_feed_stats *stats, char *err, size_t err_cap)
+{
+    if (!e || !path) return PD_ERR_ARG;
+    std::lock_guard<std::mutex> g(g_mu);
+    if (!g_pool) g_pool.reset(new pdh::ChunkPool);
+    pd_stats before{}, after{};
+    pd_get_stats(e, &before);
+    const pdh::BgzfFeedResult r = pdh::bgzf_feed_file(e, nullptr, path, threads < 1 ? 1 : threads, *g_pool);
+    pd_get_stats(e, &after);
+    if (stats) { stats->file_bytes = r.bytes; stats->pieces = r.pieces; stats->bgzf_blocks = r.blocks; stats->reads = after.reads_pushed - before.reads_pushed; }
+    if (err && err_cap) snprintf(err, err_cap, "%s", r.err.c_str());
+    if (r.status == 1) return PD_OK;
+    if (r.status == 0) { pd_reset(e); return PD_ERR_FALLBACK; }
+    return PD_ERR_ARG;
+}
+
+extern "C" void pdh_release(void)
+{
+    std::lock_guard<std::mutex> g(g_mu);
+    g_pool.reset();
+}

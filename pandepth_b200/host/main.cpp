@@ -253,9 +253,11 @@ void feed_hts_file(Feeder &feeder, const Options &o, const std::string &path, bo
                    const RegionsByContig &merged, const std::vector<uint32_t> &tlen, size_t n_targets, bool first_file)
 {
     const bool f_indexed = has_index(path) && o.use_index;
-    // experimental (off by default): device-side decode of the whole file -- whole-genome modes, first input file only, and
-    // not where the reference's no-index region cursor decides which reads count (sorted header without an index)
-    if (getenv("PANDEPTH_GPU_DECODE") && f_bam && !region_modes && first_file && (f_indexed || !f_sorted)) {
+    // device-side decode of the whole file (PANDEPTH_GPU_DECODE=0 turns it off): whole-genome modes -- with -g / -b the index
+    // lets the host skip most of the file --, first input file only (a fallback restarts from a clean engine), and not where
+    // the reference's no-index region cursor decides which reads count (sorted header without an index)
+    const char *gd = getenv("PANDEPTH_GPU_DECODE");
+    if (!(gd && gd[0] == '0') && f_bam && !region_modes && first_file && (f_indexed || !f_sorted)) {
         const int r = feeder.stream_bgzf();
         if (r != 0) return;
     }
@@ -523,6 +525,7 @@ int main(int argc, char **argv)
     Feeder feeder(o, eng_future, merged, false);
     feeder.pool = &pool;
     feeder.targets = &targets;
+    feeder.hint_set = hint_reduce; feeder.hint_min_dep = (uint32_t)o.min_dep; feeder.hint_mask = mask;
     for (size_t fi = 0; fi < o.inputs.size() && !feeder.failed; fi++) {
         const std::string &path = o.inputs[fi];
         feeder.input = path;
@@ -547,8 +550,9 @@ int main(int argc, char **argv)
         return 0;
     }
     feeder.finish();
-    if (tm.on) fprintf(stderr, "[timing] workers: total %.3f thread-s, of which mutex wait %.3f s, inside push %.3f s (%llu pushes, %llu reads)\n",
-                       feeder.ns_decode / 1e9, feeder.ns_wait / 1e9, feeder.ns_push / 1e9, (unsigned long long)feeder.n_push.load(), (unsigned long long)feeder.reads_pushed.load());
+    if (tm.on) fprintf(stderr, "[timing] workers: total %.3f thread-s, of which mutex wait %.3f s, inside push %.3f s (%llu pushes, %llu reads)%s\n",
+                       feeder.ns_decode / 1e9, feeder.ns_wait / 1e9, feeder.ns_push / 1e9, (unsigned long long)feeder.n_push.load(), (unsigned long long)feeder.reads_pushed.load(),
+                       feeder.used_device_decode ? " [device-side BGZF decode]" : "");
     pd_engine *eng = eng_future.get();
     if (!eng) { std::cerr << "Error: " << pd_last_error(nullptr) << std::endl; return 1; }
     tm.mark("decode+push");

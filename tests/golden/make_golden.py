@@ -169,6 +169,14 @@ def main():
     add("k.a", "k.sam", ["-a"])
     add("k.a.w100", "k.sam", ["-a", "-w", "100"])
     add("k.s", "k.sam", ["-s"], kinds=("bam",))
+    # -a together with regions: the per-site dump covers the contigs that carry regions, from the reads the region path keeps
+    add("k.a.bed4", "k.sam", ["-a", "-b", "@k.bed4"])
+    add("k.a.gff", "k.sam", ["-a", "-g", "@k.gff"])
+    add("mix.a.bed", "mix.sam", ["-a", "-b", "@mix.bed"])
+    # mode-6 widths that take the five-load lanes of k_reduce_windows (129..149) and the first mode-5 width
+    add("k.w129", "k.sam", ["-w", "129"])
+    add("mix.w129", "mix.sam", ["-w", "129"])
+    add("mix.w149d2", "mix.sam", ["-w", "149", "-d", "2"])
     add("mix.default", "mix.sam", [])
     add("mix.w100", "mix.sam", ["-w", "100"])
     add("mix.w1000", "mix.sam", ["-w", "1000"])

@@ -49,9 +49,9 @@ def inputs(workdir):
     return res
 
 
-def _run(binary, inp, args, workdir, tag):
+def _run(binary, inp, args, workdir, tag, env=None):
     pre = os.path.join(workdir, tag)
-    r = subprocess.run([binary, "-i", inp, "-o", pre] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+    r = subprocess.run([binary, "-i", inp, "-o", pre] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600, env=env)
     assert r.returncode == 0, (r.stdout, r.stderr)
     outs = {}
     for fn in sorted(os.listdir(workdir)):
@@ -83,14 +83,12 @@ def test_cli_matches_golden(case, inputs, workdir):
     outs, _ = _run(CLI, inp, args + ["-t", "4"], workdir, "our_" + case)
     assert sorted(outs) == sorted(c["outputs"]), (sorted(outs), sorted(c["outputs"]))
     for k, want in c["outputs"].items():
-        if k == ".SiteDepth.gz" and ("-b" in c["args"] or "-g" in c["args"]):
-            continue                     # -a with regions: the reference's two read paths disagree with each other
         assert_matches(want, outs[k], f"{case}{k}")
 
 
 OPTION_SETS = [
     [], ["-w", "100"], ["-w", "1000"], ["-w", "33"], ["-q", "20", "-d", "2"], ["-x", "0"], ["-x", "3844", "-q", "1"],
-    ["-s"], ["-a"], ["-t", "1"], ["-t", "16", "-d", "5"],
+    ["-s"], ["-a"], ["-t", "1"], ["-t", "16", "-d", "5"], ["-w", "129"], ["-w", "149", "-d", "2"], ["-w", "150"],
 ]
 
 
@@ -125,12 +123,14 @@ def test_cli_matches_reference_binary_on_random_bams(seed, contigs, reads, workd
     if seed != 11:
         # every option set runs against the reference on the CPU as well (tests/test_cli_cpu.py, host program + stand-in); on
         # the GPU the larger genomes keep the sets that differ in what they ask of the engine (each run pays a CUDA start-up)
-        sets = [[], ["-w", "100"], ["-w", "1000"], ["-q", "20", "-d", "2"], ["-s"], ["-t", "16", "-d", "5"], ["-b", bed], ["-g", gff, "-s"]]
+        sets = [[], ["-w", "100"], ["-w", "1000"], ["-q", "20", "-d", "2"], ["-s"], ["-t", "16", "-d", "5"], ["-b", bed], ["-g", gff, "-s"], ["-w", "129"]]
     for k, opts in enumerate(sets):
         if "-a" in opts and sum(lens) > 5_000_000:
             continue                     # keep the suite quick: the per-site dump is one line per base
+        # whole-genome modes decode the BAM on the device by default; every other option set also runs the host decode path
+        env = dict(os.environ, PANDEPTH_GPU_DECODE="0") if k % 2 else None
         ref, _ = _run(REF, bam, opts + (["-t", "4"] if "-t" not in opts else []), workdir, f"ref{seed}_{k}")
-        our, _ = _run(CLI, bam, opts + (["-t", "4"] if "-t" not in opts else []), workdir, f"our{seed}_{k}")
+        our, _ = _run(CLI, bam, opts + (["-t", "4"] if "-t" not in opts else []), workdir, f"our{seed}_{k}", env)
         assert sorted(ref) == sorted(our), (opts, sorted(ref), sorted(our))
         for name in ref:
             assert ref[name] == our[name], f"seed {seed} opts {opts}: {name} differs from the reference binary"
@@ -160,6 +160,33 @@ def test_cli_matches_reference_binary_on_cram(workdir):
         assert sorted(ref) == sorted(our), (opts, sorted(ref), sorted(our))
         for name in ref:
             assert ref[name] == our[name], f"cram opts {opts}: {name} differs from the reference binary"
+
+
+def test_cli_cfg1_one_contig_one_million_reads(workdir):
+    """BASELINE config 1: one 10 Mb contig, 1 M sorted 150 bp reads, per-chr mode, reference `-t 1` -- byte-identical output,
+    with the device decoder (default) and with the host decoder."""
+    bam = os.path.join(workdir, "cfg1.bam")
+    subprocess.run([BAMGEN, "-o", bam, "-c", "chr1:10000000", "-n", "1000000", "-s", "12345", "-l", "150"], check=True)
+    ref, _ = _run(REF, bam, ["-t", "1"], workdir, "cfg1_ref")
+    our, _ = _run(CLI, bam, ["-t", "1"], workdir, "cfg1_our")
+    host, _ = _run(CLI, bam, ["-t", "4"], workdir, "cfg1_host", dict(os.environ, PANDEPTH_GPU_DECODE="0"))
+    assert sorted(ref) == sorted(our) == sorted(host) == [".chr.stat.gz"]
+    assert ref[".chr.stat.gz"] == our[".chr.stat.gz"] == host[".chr.stat.gz"]
+    row = ref[".chr.stat.gz"].splitlines()[1].split("\t")
+    assert row[0] == "chr1" and row[1] == "10000000" and row[3] == "150000000"      # every aligned base counted once
+
+
+def test_cli_device_decode_is_the_default_path(workdir):
+    """PANDEPTH_TIMING names the decode path: whole-genome BAM input goes through pd_push_bgzf unless it is switched off."""
+    bam = os.path.join(workdir, "cfg1.bam")
+    if not os.path.exists(bam):
+        subprocess.run([BAMGEN, "-o", bam, "-c", "chr1:10000000", "-n", "1000000", "-s", "12345", "-l", "150"], check=True)
+    r = subprocess.run([CLI, "-i", bam, "-o", os.path.join(workdir, "dd"), "-t", "4"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                       env=dict(os.environ, PANDEPTH_TIMING="1"))
+    assert r.returncode == 0 and "device-side BGZF decode" in r.stderr, r.stderr
+    r = subprocess.run([CLI, "-i", bam, "-o", os.path.join(workdir, "dh"), "-t", "4"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                       env=dict(os.environ, PANDEPTH_TIMING="1", PANDEPTH_GPU_DECODE="0"))
+    assert r.returncode == 0 and "device-side BGZF decode" not in r.stderr, r.stderr
 
 
 def test_cli_usage_errors_exit_zero_like_the_reference(workdir):

@@ -78,9 +78,11 @@ def test_depth_matches_oracle_on_fixtures(fixture, path):
 def test_printed_output_matches_reference(case):
     """Engine depth + engine reduce -> the exact text the reference binary printed for this case."""
     c = _CASES[case]
-    targets, rec, _ = load_fixture(c["fixture"], c["args"])
+    targets, rec, sorted_hdr = load_fixture(c["fixture"], c["args"])
     opts = options_from_args(c["args"], c["kind"], c["fixture"])
     tlen = np.array([t[1] for t in targets], np.uint32)
+    if opts.site_output:
+        rec = rec.select(model.reads_reaching_depth(targets, rec, opts, sorted_hdr))    # -a with -g / -b: only the reads the region path keeps
     r = rec.select(_sorted_order(rec))
     with _engine(tlen, xflags=opts.xflags, min_mapq=opts.min_mapq) as eng:
         _push_all(eng, r, sorted_flag=True, chunks=2)
@@ -88,6 +90,8 @@ def test_printed_output_matches_reference(case):
         depth = [eng.depth(t) if tlen[t] else np.zeros(0, np.uint32) for t in range(len(targets))]
         res = model.run_model(targets, rec, opts, depth_override=depth)
         assert_matches(c["outputs"][res["suffix"]], res["stat"], case)
+        if ".SiteDepth.gz" in c["outputs"]:
+            assert_matches(c["outputs"][".SiteDepth.gz"], res["site"], case + " site")
         # and the device-side reducers against the oracle's on the same depth
         whole = (not opts.indexed) or opts.site_output or res["mode"] == 6
         mask = 0x3FFFF if whole else 0xFFFFFFFF
@@ -226,6 +230,73 @@ def test_18bit_wrap_and_uint32_paths():
         assert (int(cov[0]), int(tot[0])) == (10, 50)
         cov, tot = eng.reduce_windows(0, 0, 100, 10, 1, 0x3FFFF)
         assert cov.tolist()[:2] == [1, 9] and tot.tolist()[:2] == [5, 45]
+
+
+@pytest.mark.parametrize("mask", [0xFFFFFFFF, 0x3FFFF])
+@pytest.mark.parametrize("min_dep", [1, 3])
+def test_reduce_windows_every_width_branch(mask, min_dep):
+    """k_reduce_windows on the device at the widths each of its branches covers: lane-per-window (< 32), the 4-window groups
+    with 128-bit loads (multiples of 4 up to 128), the five-load lanes (129..160, reachable from the CLI with -w 129..149),
+    the 32-bit lane-strided branch (161..512) and the generic 64-bit one (> 512) -- against the oracle's interval reduce,
+    on a contig whose length leaves a ragged last window and a depth profile that crosses the 18-bit wrap."""
+    import pandepth_b200 as pd
+    rng = np.random.default_rng(77)
+    L = 300_007
+    tlen = np.array([L, 1000], np.uint32)
+    pos, cig = _uniform_reads(rng, L, 30_000, 150)
+    # a pile of 262150 stacked reads: depth there exceeds 2^18, so the two masks disagree
+    pile_pos = np.full(262_150, 150_000, np.int32); pile_cig = np.full(262_150, (40 << 4), np.uint32)
+    with _engine(tlen) as eng:
+        eng.push_contig(0, pos, cig, flags=pd.PD_SORTED)
+        eng.push_contig(0, pile_pos, pile_cig, flags=pd.PD_SORTED)
+        eng.push_contig(1, np.array([5, 900], np.int32), np.array([(200 << 4), (200 << 4)], np.uint32), flags=pd.PD_SORTED)
+        eng.finalize()
+        depth = [eng.depth(0), eng.depth(1)]
+        rec = model.Records(np.zeros(pos.size, np.int32), pos, np.zeros(pos.size, np.uint16), np.zeros(pos.size, np.uint8),
+                            np.arange(pos.size + 1, dtype=np.uint32), cig)
+        want0 = model.accumulate(tlen, rec)[0]
+        want0[150_000:150_040] += 262_150
+        assert np.array_equal(depth[0], want0)
+        for win in (1, 7, 31, 32, 33, 64, 100, 128, 129, 130, 149, 150, 159, 160, 161, 200, 511, 512, 513, 1000, 4096, 70_001):
+            for t, ln in ((0, L), (1, 1000)):
+                s0, e0 = model.mode6_windows(ln, win)
+                cov_o, sum_o = model.reduce_intervals(depth[t], s0, e0, min_dep, mask)
+                cov_w, sum_w = eng.reduce_windows(t, 0, win, s0.size, min_dep, mask)
+                assert np.array_equal(cov_o, cov_w.astype(np.uint64)), (win, t, "cov")
+                assert np.array_equal(sum_o, sum_w), (win, t, "sum")
+            # a start that is not 16-byte aligned takes the scalar lanes of the same branches
+            n = (L - 3) // win
+            s0 = 3 + np.arange(n, dtype=np.int64) * win
+            cov_o, sum_o = model.reduce_intervals(depth[0], s0.astype(np.int32), np.minimum(s0 + win, L).astype(np.int32), min_dep, mask)
+            cov_w, sum_w = eng.reduce_windows(0, 3, win, n, min_dep, mask)
+            assert np.array_equal(cov_o, cov_w.astype(np.uint64)) and np.array_equal(sum_o, sum_w), (win, "offset start")
+
+
+def test_reset_after_an_unsorted_error_clears_far_run_deltas():
+    """A PD_SORTED batch whose tile kernel wrote far-run deltas, then a batch that trips PD_ERR_UNSORTED, then pd_reset:
+    the deltas of the first batch must not leak into the next input (the device flag is folded before the error returns)."""
+    import pandepth_b200 as pd
+    rng = np.random.default_rng(41)
+    L = 200_000
+    tlen = np.array([L], np.uint32)
+    rows = [(0, 0, int(p) + 1, 60, f"50M{rng.integers(3000, 9000)}N50M") for p in np.sort(rng.integers(0, L - 20_000, 5000))]
+    far = model.records_from_tuples(rows, ["a"])
+    with _engine(tlen) as eng:
+        _push_all(eng, far, True, 1)
+        bad_pos = np.array([5000, 100, 90_000, 7], np.int32)
+        with pytest.raises(pd.PDError) as ei:
+            eng.push_contig(0, bad_pos, np.full(4, (50 << 4), np.uint32), flags=pd.PD_SORTED)
+            eng.finalize()
+        assert ei.value.code == 4
+        eng.reset()
+        pos, cig = _uniform_reads(rng, L, 10_000)
+        rec = model.Records(np.zeros(pos.size, np.int32), pos, np.zeros(pos.size, np.uint16), np.zeros(pos.size, np.uint8),
+                            np.arange(pos.size + 1, dtype=np.uint32), cig)
+        # an unsorted batch forces the scan, which would fold any stale deltas into depth
+        perm = rng.permutation(pos.size)
+        eng.push_contig(0, pos[perm], cig[perm], flags=0)
+        eng.finalize()
+        _check_depth(eng, tlen, model.accumulate(tlen, rec))
 
 
 def test_empty_ragged_and_reset():

@@ -19,9 +19,9 @@ with open(os.path.join(GOLD, "expected.json")) as _fh:
 @pytest.mark.parametrize("case", sorted(_CASES))
 def test_model_matches_reference(case):
     c = _CASES[case]
-    targets, rec, _ = load_fixture(c["fixture"], c["args"])
+    targets, rec, sorted_hdr = load_fixture(c["fixture"], c["args"])
     opts = options_from_args(c["args"], c["kind"], c["fixture"])
-    res = model.run_model(targets, rec, opts)
+    res = model.run_model(targets, rec, opts, sorted_hdr=sorted_hdr)
     outs = c["outputs"]
     assert res["suffix"] in outs, (res["suffix"], list(outs))
     assert_matches(outs[res["suffix"]], res["stat"], case)
