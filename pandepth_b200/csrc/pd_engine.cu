@@ -13,6 +13,8 @@
 #include "pd_kernels.cuh"
 #include "pd_bgzf.cuh"
 
+#include <nvtx3/nvToolsExt.h>      // header-only NVTX v3: ranges show up in nsys / ncu timelines, no-ops without a tool attached
+
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
@@ -116,6 +118,8 @@ namespace {
     } while (0)
 
 int fail(pd_engine *e, int code, const char *msg) { if (e) e->err = msg; return code; }
+
+struct NvtxRange { explicit NvtxRange(const char *name) { nvtxRangePushA(name); } ~NvtxRange() { nvtxRangePop(); } };
 
 template <typename F>
 int launch_on(pd_engine *e, cudaStream_t st, int k, F &&f)
@@ -516,6 +520,7 @@ int pd_set_reduce_hint(pd_engine *e, uint32_t min_dep, uint32_t depth_mask)
 
 int pd_reset(pd_engine *e)
 {
+    NvtxRange nvtx_("pd_reset");
     if (!e) return PD_ERR_ARG;
     CK(cudaSetDevice(e->device));
     { int rc = bz_cancel(e); if (rc) return rc; }
@@ -540,6 +545,7 @@ int pd_reset(pd_engine *e)
 int pd_push_contig(pd_engine *e, int32_t tid, int64_t n_reads, const int32_t *pos, const uint16_t *flag, const uint8_t *mapq,
                    const uint32_t *cigar_off, const uint32_t *cigar, uint32_t flags)
 {
+    NvtxRange nvtx_("pd_push_contig");
     if (!e) return PD_ERR_ARG;
     if (tid < 0 || tid >= e->n_targets || n_reads < 0 || (n_reads > 0 && (!pos || !cigar))) return fail(e, PD_ERR_ARG, "pd_push_contig: bad arguments");
     if (!e->owned[tid] || n_reads == 0 || e->tlen[tid] == 0) return PD_OK;
@@ -623,6 +629,7 @@ int pd_push(pd_engine *e, int64_t n_reads, const int32_t *tid, const int32_t *po
 int pd_push_bgzf(pd_engine *e, const uint8_t *bytes, size_t n_bytes, const pd_bgzf_block *blocks, int64_t n_blocks,
                  uint32_t first_skip, uint32_t flags)
 {
+    NvtxRange nvtx_("pd_push_bgzf");
     if (!e) return PD_ERR_ARG;
     if (n_blocks < 0 || (n_blocks > 0 && (!bytes || !blocks)) || n_blocks > 0x7fffffffll) return fail(e, PD_ERR_ARG, "pd_push_bgzf: bad arguments");
     CK(cudaSetDevice(e->device));
@@ -689,6 +696,7 @@ int pd_push_bgzf(pd_engine *e, const uint8_t *bytes, size_t n_bytes, const pd_bg
 
 int pd_sync(pd_engine *e)
 {
+    NvtxRange nvtx_("pd_sync");
     if (!e) return PD_ERR_ARG;
     CK(cudaSetDevice(e->device));
     for (int k = 0; k < N_BZ; k++) { int rc = bz_finish(e, e->bz[(e->bz_next + k) % N_BZ]); if (rc) return rc; }
@@ -699,6 +707,7 @@ int pd_sync(pd_engine *e)
 
 int pd_finalize(pd_engine *e)
 {
+    NvtxRange nvtx_("pd_finalize");
     if (!e) return PD_ERR_ARG;
     CK(cudaSetDevice(e->device));
     for (int k = 0; k < N_BZ; k++) { int rc = bz_finish(e, e->bz[(e->bz_next + k) % N_BZ]); if (rc) return rc; }
@@ -737,6 +746,7 @@ static int ensure_red(pd_engine *e, size_t bytes)
 int pd_reduce(pd_engine *e, int64_t n_iv, const int32_t *tid, const int32_t *start0, const int32_t *end0_excl,
               uint32_t min_dep, uint32_t depth_mask, uint64_t *cov, uint64_t *sum, uint32_t flags)
 {
+    NvtxRange nvtx_("pd_reduce");
     if (!e) return PD_ERR_ARG;
     if (n_iv < 0 || (n_iv > 0 && (!tid || !start0 || !end0_excl || !cov || !sum))) return fail(e, PD_ERR_ARG, "pd_reduce: bad arguments");
     if (flags & PD_DEVICE) return fail(e, PD_ERR_ARG, "pd_reduce: interval tables are host pointers");
@@ -788,6 +798,7 @@ int pd_reduce(pd_engine *e, int64_t n_iv, const int32_t *tid, const int32_t *sta
 int pd_reduce_windows(pd_engine *e, int32_t tid, int32_t start0, int32_t win, int64_t n_win, uint32_t min_dep, uint32_t depth_mask,
                       uint32_t *cov, uint64_t *sum, uint32_t flags)
 {
+    NvtxRange nvtx_("pd_reduce_windows");
     if (!e) return PD_ERR_ARG;
     if (tid < 0 || tid >= e->n_targets || win < 1 || start0 < 0 || n_win < 0 || (n_win > 0 && (!cov || !sum))) return fail(e, PD_ERR_ARG, "pd_reduce_windows: bad arguments");
     CK(cudaSetDevice(e->device));
@@ -820,6 +831,7 @@ int pd_reduce_windows(pd_engine *e, int32_t tid, int32_t start0, int32_t win, in
 
 int pd_depth_read(pd_engine *e, int32_t tid, int32_t start0, int32_t n, uint32_t *out, uint32_t flags)
 {
+    NvtxRange nvtx_("pd_depth_read");
     if (!e) return PD_ERR_ARG;
     if (tid < 0 || tid >= e->n_targets || start0 < 0 || n < 0 || (n > 0 && !out)) return fail(e, PD_ERR_ARG, "pd_depth_read: bad arguments");
     if ((int64_t)start0 + n > (int64_t)e->tlen[tid]) return fail(e, PD_ERR_ARG, "pd_depth_read: range beyond the contig");

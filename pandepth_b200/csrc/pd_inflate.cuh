@@ -1,15 +1,13 @@
 // pd_inflate.cuh -- DEFLATE (RFC 1951) decoder and BAM record walker written as host+device functions.
 //
-// Groundwork for moving the decode side of the feeder (role of PanDepth.cpp:633-661 / :725-734) onto
-// the GPU: a BGZF file is a sequence of independent <= 64 KB deflate streams, and htslib's writer starts every block on a
-// record boundary unless a single record is larger than a block (bam_write1 flushes first), so blocks can be inflated AND
-// parsed independently -- one decoder per block, tens of thousands of blocks in flight.  On realistic BAMs (SEQ + QUAL)
-// the whole program is bounded by Huffman decoding on the host cores; this is the part a B200 can take.
+// The sequential restatement of what pd_bgzf.cuh does warp-cooperatively on the device: one function inflates a raw deflate
+// stream, one walks the BAM records of an inflated block.  A BGZF file is a sequence of independent <= 64 KB deflate streams,
+// and htslib's writer starts every block on a record boundary unless a single record is larger than a block (bam_write1
+// flushes first), so blocks can be inflated AND parsed independently.
 //
-// Status: the functions below are exercised on the CPU (tests/cpp/inflate_check.cpp: every BGZF block of generated BAMs and
-// of zlib streams at all levels / strategies, against zlib) -- they compile for both sides, so the arithmetic is verified
-// here; the kernels that call them (one decoder per warp) are NOT yet wired into the engine or measured.  Nothing in the
-// product path calls this file yet.
+// TEST INFRASTRUCTURE: used by tests/cpp (inflate_check, decode_check, bgzf_emu_check: the reference the emulated device
+// kernels are compared with) and by the CPU stand-in engine of tests/stand_in.  Verified against zlib on every BGZF block of
+// generated BAMs and on zlib streams at all levels / strategies.  The product path (pd_engine.cu) does not include this file.
 #pragma once
 #include <stdint.h>
 
@@ -224,40 +222,3 @@ PD_HD int64_t walk_bam_block(const uint8_t *buf, uint32_t len, Emit &&emit)
 
 }  // namespace pdk
 
-#ifdef __CUDACC__
-namespace pdk {
-
-// One BGZF block per warp: lane 0 decodes (tables in the warp's slice of shared memory), the other lanes are idle in this
-// first version (candidates for later: cooperative table build, lane-parallel match copies, double-buffered input).
-struct BgzfBlock { uint64_t in_off; uint32_t in_len; uint32_t out_len; uint64_t out_off; };
-
-constexpr int INFLATE_WPC = 8;      // warps (decoders) per CTA: 8 x 3.5 KB of tables
-
-__global__ void __launch_bounds__(INFLATE_WPC * 32) k_inflate_blocks(const uint8_t *__restrict__ in, uint8_t *__restrict__ out,
-                                                                     const BgzfBlock *__restrict__ blocks, uint32_t n_blocks, int *status)
-{
-    __shared__ InflateTables tabs[INFLATE_WPC];
-    const uint32_t b = blockIdx.x * INFLATE_WPC + (threadIdx.x >> 5);
-    if (b >= n_blocks || (threadIdx.x & 31) != 0) return;
-    const BgzfBlock k = blocks[b];
-    const int r = k.out_len ? inflate_raw(in + k.in_off, k.in_len, out + k.out_off, k.out_len, tabs[threadIdx.x >> 5]) : 0;
-    if (r != (int)k.out_len) atomicMin(status, r < 0 ? r : INF_ERR_OUTPUT);
-}
-
-// One block per thread: number of records that start in the block and the offset just past the last one, assuming the block
-// starts on a record boundary (htslib's writer guarantees it unless a record is larger than a block).  A block whose
-// `used` differs from its length hands the remainder to its successor; the host checks that before trusting the counts.
-__global__ void __launch_bounds__(128) k_count_records(const uint8_t *__restrict__ data, const BgzfBlock *__restrict__ blocks, uint32_t n_blocks,
-                                                       uint32_t first_block_skip, uint32_t *n_rec, uint32_t *used)
-{
-    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= n_blocks) return;
-    const BgzfBlock k = blocks[b];
-    const uint32_t skip = b == 0 ? first_block_skip : 0;     // BAM header bytes at the start of the first block handed over
-    uint32_t n = 0;
-    const int64_t u = walk_bam_block(data + k.out_off + skip, k.out_len - skip, [&](int32_t, int32_t, uint16_t, uint8_t, uint32_t, const uint8_t *) { n++; });
-    n_rec[b] = n; used[b] = u < 0 ? 0xffffffffu : (uint32_t)u + skip;
-}
-
-}  // namespace pdk
-#endif

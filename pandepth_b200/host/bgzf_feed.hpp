@@ -67,7 +67,9 @@ struct ChunkPool {
 struct BgzfFeedResult { int status = 0; std::string err; uint64_t bytes = 0, pieces = 0, blocks = 0; };   // status 1 = whole file fed, 0 = host path needed, -1 = failed
 
 // Feeds every record of `path` (a BAM in BGZF blocks) to `eng`.  `eng_mu` (nullable) serialises engine calls with other users.
-inline BgzfFeedResult bgzf_feed_file(pd_engine *eng, std::mutex *eng_mu, const std::string &path, int threads, ChunkPool &pool)
+// strict_eof: a file that ends inside a BGZF block is an error (what the indexed host scanner reports); otherwise the stream
+// ends quietly at the last complete block, like the reference's `while (sam_read1(...) >= 0)` loop (:4608).
+inline BgzfFeedResult bgzf_feed_file(pd_engine *eng, std::mutex *eng_mu, const std::string &path, int threads, ChunkPool &pool, bool strict_eof = true)
 {
     BgzfFeedResult res;
     uint32_t first_skip = 0;
@@ -145,12 +147,12 @@ inline BgzfFeedResult bgzf_feed_file(pd_engine *eng, std::mutex *eng_mu, const s
             if (state.load() != 1) { pool.release(id); break; }
             blocks.clear();
             uint64_t p = s0 - a;                                                // s0 >= a: a block is shorter than a piece
-            bool bad = false;
+            bool bad = false, cut = false;
             while (a + p < z) {
                 const uint8_t *cd; size_t cl; uint32_t is;
                 const int64_t b = bgzf_block_at(buf + p, got > p ? got - (size_t)p : 0, &cd, &cl, &is);
                 if (b < 0) { bad = true; break; }
-                if (b == 0) { p = z - a + (1u << 20); break; }                  // truncated last block: the stream ends here (quietly, like sam_read1)
+                if (b == 0) { cut = true; p = z - a + (1u << 20); break; }      // the file ends inside this block: the stream ends here
                 if (is) blocks.push_back(pd_bgzf_block{(uint64_t)(cd - buf), (uint32_t)cl, is});
                 p += (uint64_t)b;
             }
@@ -160,6 +162,7 @@ inline BgzfFeedResult bgzf_feed_file(pd_engine *eng, std::mutex *eng_mu, const s
             }
             chain_cv.notify_all();
             if (bad) { set_state(-1, "Error: malformed BAM while reading " + path + ": not a BGZF block"); pool.release(id); break; }
+            if (cut && strict_eof) { set_state(-1, "Error: malformed BAM while reading " + path + ": unexpected end of file inside a BGZF block"); pool.release(id); break; }
             if (blocks.empty()) { pool.release(id); continue; }
             int rc;
             {

@@ -401,7 +401,7 @@ struct Feeder {
     // inflate + record walk + accumulate on the device).  Returns 1 = the whole file was accumulated this way,
     // 0 = not applicable or the engine asked for the host path (nothing of this file is accumulated: the engine was reset if
     // needed), -1 = failed.
-    int stream_bgzf()
+    int stream_bgzf(bool strict_eof)
     {
         if (dry) return 0;
         eng_future.wait();
@@ -411,7 +411,7 @@ struct Feeder {
             eng_ok = true;
         }
         const auto t0 = std::chrono::steady_clock::now();
-        const BgzfFeedResult r = bgzf_feed_file(eng, &eng_mu, input, std::max(1, o.threads), chunk_pool);
+        const BgzfFeedResult r = bgzf_feed_file(eng, &eng_mu, input, std::max(1, o.threads), chunk_pool, strict_eof);
         ns_decode += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
         n_push += r.pieces;
         if (r.status < 0) { fail(r.err.empty() ? "Error: device decode failed on " + input : r.err); return -1; }

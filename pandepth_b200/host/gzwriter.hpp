@@ -87,6 +87,8 @@ struct GzWriter {
             for (size_t k = 0; k < m; k++) emit(z[k]);
         }
     }
+    // a failed run: close and remove the partial file (a truncated .gz at the output path reads as a result)
+    void abandon() { if (fp) { fclose(fp); fp = nullptr; } if (!path.empty()) ::remove(path.c_str()); }
     // false if anything could not be written; the caller reports it and exits non-zero
     bool close()
     {

@@ -258,7 +258,7 @@ void feed_hts_file(Feeder &feeder, const Options &o, const std::string &path, bo
     // the reference's no-index region cursor decides which reads count (sorted header without an index)
     const char *gd = getenv("PANDEPTH_GPU_DECODE");
     if (!(gd && gd[0] == '0') && f_bam && !region_modes && first_file && (f_indexed || !f_sorted)) {
-        const int r = feeder.stream_bgzf();
+        const int r = feeder.stream_bgzf(f_indexed);         // no index: a cut file ends quietly, like the reference's sam_read1 loop
         if (r != 0) return;
     }
     feeder.filter_by_region = f_indexed && region_modes;
@@ -442,7 +442,11 @@ bool report_genes(pd_engine *eng, GzWriter &out, const Options &o, const std::ve
 int main(int argc, char **argv)
 {
     Options o;
-    if (parse_args(argc, argv, o) != 0) return 0;
+    {
+        const int pa = parse_args(argc, argv, o);
+        if (pa == 2) return 1;                               // an option this build does not provide (-c): not a silent success
+        if (pa != 0) return 0;                               // usage / argument errors leave with 0, like the reference (:3449-3450)
+    }
     Timer tm;
     if (!getenv("PANDEPTH_NO_CLAMP")) {
         const int cpus = usable_cpus();
@@ -521,6 +525,9 @@ int main(int argc, char **argv)
     if (const char *path = getenv("PANDEPTH_DUMP_REGIONS")) dump_regions(path, o, targets, genes, merged, mode, mask);
     if (const char *pre = getenv("PANDEPTH_SELFTEST_ROWS")) selftest_rows(pre, o.threads);
 
+    // a failed run must not leave a truncated .gz behind at the output path
+    auto drop_outputs = [&] { out.abandon(); if (o.site_output) unlink((prefix + ".SiteDepth.gz").c_str()); };
+
     // ---- feed ---------------------------------------------------------------------------------------------------
     Feeder feeder(o, eng_future, merged, false);
     feeder.pool = &pool;
@@ -533,7 +540,7 @@ int main(int argc, char **argv)
         bool f_bam = in.is_bam, f_cram = in.is_cram, f_sorted = in.sorted_hdr;
         if (fi > 0) {                                        // later files: own format / sort order, the first file's targets (:2701-2862)
             htsFile *fp = hts_open(path.c_str(), "r");
-            if (!fp) { std::cerr << "Error: Failed to open the BAM/CRAM file: " << path << std::endl; continue; }
+            if (!fp) { feeder.fail("Error: Failed to open the BAM/CRAM file: " + path); break; }        // partial totals are not a result
             if (fp->format.format == cram) hts_set_fai_filename(fp, o.reference.c_str());
             f_bam = fp->format.format == bam; f_cram = fp->format.format == cram;
             sam_hdr_t *h2 = sam_hdr_read(fp);
@@ -546,6 +553,7 @@ int main(int argc, char **argv)
     if (dry) {
         tm.mark("decode (dry)");
         std::cout << "dry: reads=" << feeder.reads_pushed.load() << " digest=" << feeder.dry_digest.load() << " path=" << (feeder.used_fast ? "fastbam" : "htslib") << std::endl;
+        drop_outputs();                                      // a dry run writes nothing
         if (feeder.failed) { std::cerr << feeder.err << std::endl; return 1; }
         return 0;
     }
@@ -554,13 +562,13 @@ int main(int argc, char **argv)
                        feeder.ns_decode / 1e9, feeder.ns_wait / 1e9, feeder.ns_push / 1e9, (unsigned long long)feeder.n_push.load(), (unsigned long long)feeder.reads_pushed.load(),
                        feeder.used_device_decode ? " [device-side BGZF decode]" : "");
     pd_engine *eng = eng_future.get();
-    if (!eng) { std::cerr << "Error: " << pd_last_error(nullptr) << std::endl; return 1; }
+    if (!eng) { std::cerr << "Error: " << pd_last_error(nullptr) << std::endl; drop_outputs(); return 1; }
     tm.mark("decode+push");
-    if (feeder.failed) { std::cerr << feeder.err << std::endl; pd_destroy(eng); return 1; }
-    if (pd_finalize(eng) != PD_OK) { engine_error(eng); pd_destroy(eng); return 1; }
+    if (feeder.failed) { std::cerr << feeder.err << std::endl; drop_outputs(); pd_destroy(eng); return 1; }
+    if (pd_finalize(eng) != PD_OK) { engine_error(eng); drop_outputs(); pd_destroy(eng); return 1; }
     std::cout << "INFO: Input data read done" << std::endl;                                                                        // :4879
 
-    if (o.site_output && !write_site_depth(eng, prefix + ".SiteDepth.gz", targets, genes, o.threads)) return 1;
+    if (o.site_output && !write_site_depth(eng, prefix + ".SiteDepth.gz", targets, genes, o.threads)) { drop_outputs(); return 1; }
     tm.mark("finalize(+site dump)");
 
     // ---- reduce + report -----------------------------------------------------------------------------------------
@@ -569,7 +577,7 @@ int main(int argc, char **argv)
     const bool ok = mode == 6 ? report_windows(eng, out, o, targets, genes, tot)
                   : mode == 5 ? report_tiles(eng, out, o, targets, genes, mask, tot)
                               : report_genes(eng, out, o, targets, genes, merged, mode, whole, mask, tot);
-    if (!ok) return 1;
+    if (!ok) { drop_outputs(); return 1; }
     {
         char row[512];
         const double Coverage = tot.cov * 100.0 / tot.len, MeanDepth = tot.depth * 1.0 / tot.len;   // :5119-5122
@@ -577,7 +585,7 @@ int main(int argc, char **argv)
                          (unsigned long long)tot.len, (unsigned long long)tot.cov, Coverage, MeanDepth);
         out.put(std::string(row, (size_t)m));
     }
-    if (!out.close()) return 1;
+    if (!out.close()) { drop_outputs(); return 1; }
     tm.mark("reduce+report");
     // every output is flushed and closed: leave without the teardown of the CUDA context, 24 GB of device memory and the
     // parked/pinned host buffers -- the OS reclaims all of it, and the orderly teardown only costs wall time

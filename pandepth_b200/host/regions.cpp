@@ -158,7 +158,7 @@ int parse_args(int argc, char **argv, Options &o)
         in.next(l1); in.next(l2);
         if (split_any(l1, " \t").size() == 4 || split_any(l2, " \t").size() == 4) o.region_mode = 4;
     }
-    if (o.gc) { std::cerr << "Error: GC content (-c) is not part of the depth path and is not supported by pandepth-b200" << std::endl; return 1; }
+    if (o.gc) { std::cerr << "Error: GC content (-c) is not part of the depth path and is not supported by pandepth-b200" << std::endl; return 2; }   // exit status 1
     if (o.threads < 1) o.threads = 1;
     return 0;
 }

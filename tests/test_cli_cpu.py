@@ -227,3 +227,29 @@ def test_device_decode_entry_point_through_the_host_program(workdir, standin_env
             assert ref == our, (name, opts)
             calls = open(trace).read().split()[0::3] if os.path.exists(trace) else []
             assert calls == (["bgzf_fallback"] if "long" in name else ["bgzf_ok"]), (name, opts, calls)     # the decoder ran / the fallback ran
+
+
+def test_failed_runs_leave_no_partial_outputs(workdir, standin_env, inputs):
+    """A truncated BAM fails with exit status 1 and leaves no (truncated) .gz at the output path; so does a list with an
+    unreadable member (partial totals are not a result); -c (GC content, not provided) exits 1 instead of a silent 0."""
+    src = inputs["big.sam"]["bam"]
+    data = open(src, "rb").read()
+    cut = os.path.join(workdir, "cut.bam")
+    with open(cut, "wb") as fh:
+        fh.write(data[:len(data) * 2 // 3])
+    subprocess.run([BAMGEN, "-I", inputs["big.sam"]["sam"], "-o", os.path.join(workdir, "cutidx.bam")], check=True)
+    os.replace(os.path.join(workdir, "cutidx.bam.bai"), cut + ".bai")
+    # with an index both decode paths report the truncation (the reference itself crashes on this file) ...
+    for mode_env in ({}, {"PANDEPTH_GPU_DECODE": "0"}):
+        pre = os.path.join(workdir, "cutout")
+        r = subprocess.run([CLI, "-i", cut, "-o", pre, "-t", "2"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=dict(standin_env, **mode_env))
+        assert r.returncode == 1, (r.stdout, r.stderr)
+        assert not os.path.exists(pre + ".chr.stat.gz")
+    lst = os.path.join(workdir, "broken.list")
+    with open(lst, "w") as fh:
+        fh.write(inputs["k.sam"]["bam"] + "\n" + os.path.join(workdir, "does_not_exist.bam") + "\n")
+    pre = os.path.join(workdir, "listout")
+    r = subprocess.run([CLI, "-i", lst, "-o", pre], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=standin_env)
+    assert r.returncode == 1 and not os.path.exists(pre + ".chr.stat.gz"), (r.stdout, r.stderr)
+    r = subprocess.run([CLI, "-i", inputs["k.sam"]["bam"], "-o", os.path.join(workdir, "gc"), "-c"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=standin_env)
+    assert r.returncode == 1 and "GC content" in r.stderr
