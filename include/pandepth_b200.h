@@ -49,6 +49,14 @@ enum {
  * (pd_last_error(NULL) has the reason). */
 pd_engine *pd_create(int device, int n_targets, const uint32_t *target_len, const uint8_t *owned,
                      uint32_t xflags, int min_mapq);
+/* Range sharding ("genomic ranges are independent if reads overlapping a boundary are fed to both
+ * owners and each owner clips to its range"): the engine owns [own_beg[t], own_end[t]) of contig t (own_end <= own_beg: nothing)
+ * and holds depth only for that.  Every call keeps speaking contig coordinates: pushes may carry any reads -- what falls
+ * outside the owned range is clipped away, on both sides --, pd_reduce clips its intervals to the owned range and
+ * pd_depth_read returns zeros outside it, so the results of engines with disjoint ranges ADD UP to the single-engine
+ * result (one all-reduce of the cov / sum arrays, or a host-side sum).  pd_reduce_windows needs wholly owned contigs. */
+pd_engine *pd_create_ranges(int device, int n_targets, const uint32_t *target_len, const uint32_t *own_beg, const uint32_t *own_end,
+                            uint32_t xflags, int min_mapq);
 void pd_destroy(pd_engine *e);
 const char *pd_last_error(pd_engine *e);
 

@@ -29,6 +29,17 @@ typedef struct pdh_feed_stats {
  * accumulated); PD_ERR_ARG for an unreadable / corrupt file.  `err` (nullable) receives the message. */
 int pdh_feed_bam(pd_engine *e, const char *path, int threads, pdh_feed_stats *stats, char *err, size_t err_cap);
 
+/* Range sharding over several engines / GPUs: feed only the BGZF blocks that start in the byte range [file_beg, file_end) of
+ * the file (file_beg = 0: from the first record; file_end = UINT64_MAX: to the end).  The engine (pd_create_ranges) clips
+ * whatever falls outside the range it owns, so neighbouring ranks may overlap by a few blocks. */
+int pdh_feed_bam_range(pd_engine *e, const char *path, int threads, uint64_t file_beg, uint64_t file_end,
+                       pdh_feed_stats *stats, char *err, size_t err_cap);
+
+/* File offset of the BGZF block holding the first read that overlaps the 16 kb window of position `pos` (0-based) of contig
+ * `tid`, from the linear index of `path`.bai -- every read of that contig starting at or after `pos` (and every read that
+ * overlaps it) lies at or after this offset in a coordinate-sorted file.  UINT64_MAX: no such read (or no usable index). */
+uint64_t pdh_bai_block_offset(const char *path, int32_t tid, int64_t pos);
+
 /* Free the pinned buffers kept between calls. */
 void pdh_release(void);
 

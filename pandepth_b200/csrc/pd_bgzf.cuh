@@ -495,9 +495,9 @@ __global__ void __launch_bounds__(256) k_bgzf_compact(BzCompactArgs a)
 struct ScatterMultiArgs {
     const int32_t *tid; const int32_t *pos; const uint32_t *cigar; const uint32_t *cigar_off;
     uint32_t n;
-    const uint64_t *contig_off; const uint32_t *contig_len; const uint8_t *owned; int32_t n_targets;
+    const uint64_t *contig_off; const uint32_t *contig_len; const uint32_t *contig_org; const uint8_t *owned; int32_t n_targets;
     uint32_t *delta;   // array base
-};
+};                     // contig_len / contig_org: owned length and first owned base per contig (range sharding)
 
 __global__ void __launch_bounds__(256) k_delta_scatter_multi(ScatterMultiArgs a)
 {
@@ -510,10 +510,10 @@ __global__ void __launch_bounds__(256) k_delta_scatter_multi(ScatterMultiArgs a)
     const uint32_t c0 = a.cigar_off[i], nops = a.cigar_off[i + 1] - c0;
     const int64_t clen = a.contig_len[t];
     uint32_t *delta = a.delta + a.contig_off[t];
-    int64_t q = p, rs = -1, re = -1;
+    int64_t q = (int64_t)p - (int64_t)a.contig_org[t], rs = 0, re = 0; bool open = false;
     auto flush = [&]() {
-        if (rs < 0) return;
-        const int64_t s = rs, e = re > clen ? clen : re;
+        if (!open) return;
+        const int64_t s = rs < 0 ? 0 : rs, e = re > clen ? clen : re;
         if (s >= e) return;
 #ifndef PD_WARP_EMU
         asm volatile("red.global.add.u32 [%0], %1;" ::"l"(delta + s), "r"(1u) : "memory");
@@ -527,7 +527,7 @@ __global__ void __launch_bounds__(256) k_delta_scatter_multi(ScatterMultiArgs a)
         const uint32_t op = w & 15u;
         const int64_t n = w >> 4;
         if ((0x181u >> op) & 1u) {                               // M = X
-            if (rs >= 0 && re == q) re = q + n; else { flush(); rs = q; re = q + n; }
+            if (open && re == q) re = q + n; else { flush(); rs = q; re = q + n; open = true; }
             q += n;
         } else if ((0x00cu >> op) & 1u) q += n;                  // D N
     }

@@ -66,7 +66,9 @@ constexpr int N_BZ = PD_BGZF_DEPTH + 1;
 struct pd_engine {
     int device = 0;
     int n_targets = 0;
-    std::vector<uint32_t> tlen;
+    std::vector<uint32_t> tlen;      // contig lengths (the header's)
+    std::vector<uint32_t> org, elen; // owned range of contig t: [org[t], org[t] + elen[t]) (range sharding; whole contig: 0, tlen[t])
+    bool has_ranges = false;         // some contig is owned only in part
     std::vector<uint8_t> owned;
     std::vector<uint64_t> off;       // element offset of contig t (valid when owned)
     uint64_t total = 0;              // elements in depth/delta
@@ -75,7 +77,7 @@ struct pd_engine {
 
     uint32_t *d_depth = nullptr, *d_delta = nullptr;
     uint8_t *d_seg_state = nullptr;
-    uint64_t *d_off = nullptr; uint32_t *d_tlen = nullptr;
+    uint64_t *d_off = nullptr; uint32_t *d_tlen = nullptr, *d_org = nullptr;     // d_tlen holds the OWNED lengths
     uint32_t *d_lo = nullptr, *d_hi = nullptr, *d_coarse = nullptr; size_t cut_cap = 0;
     int *d_flags = nullptr;          // [0] err bits, [1] delta_used
     uint32_t *d_part_cov = nullptr; unsigned long long *d_part_sum = nullptr;   // per-segment reduce partials (hint)
@@ -172,7 +174,7 @@ int run_batch(pd_engine *e, int32_t tid, uint32_t n, const int32_t *pos, const u
     if (sorted) {
         const int32_t nseg = (int32_t)(seg_b - seg_a + 1);
         int rc = ensure_cut(e, (size_t)nseg + 1); if (rc) return rc;
-        pdk::CutArgs c{pos, n, (int32_t)seg_a, nseg, e->d_lo, e->d_hi};
+        pdk::CutArgs c{pos, n, (int32_t)seg_a, nseg, e->d_lo, e->d_hi, (int64_t)e->org[tid]};
         const int32_t ncoarse = (nseg + pdk::CUT_COARSE - 1) / pdk::CUT_COARSE;
         rc = launch(e, K_CUT, [&] {
             pdk::k_cut_coarse<<<(ncoarse + 127) / 128, 128, 0, e->stream>>>(c, e->d_coarse, ncoarse);
@@ -180,11 +182,18 @@ int run_batch(pd_engine *e, int32_t tid, uint32_t n, const int32_t *pos, const u
         });
         if (rc) return rc;
         e->stats.kernel_launches++;
-        pdk::TileArgs t{pos, cigar, cigar_off, flag, mapq, e->d_lo, e->d_hi, n, (int32_t)seg_a, nseg, (int32_t)e->tlen[tid],
+        if (e->org[tid] != 0 && seg_a == 0) {
+            // range sharding: reads that start more than HALO bases left of the owned range are seen by no segment; the ones
+            // among them that reach into the range are the first lo[0] reads of the batch (a device-side count, usually 0)
+            pdk::ScatterArgs sp{pos, cigar, cigar_off, flag, mapq, n, (int32_t)e->elen[tid], e->d_delta + off, e->xflags, e->min_mapq,
+                                (int32_t)e->org[tid], e->d_lo, e->d_flags + 1};
+            rc = launch(e, K_SCATTER, [&] { pdk::k_delta_scatter<<<148, 256, 0, e->stream>>>(sp); }); if (rc) return rc;
+        }
+        pdk::TileArgs t{pos, cigar, cigar_off, flag, mapq, e->d_lo, e->d_hi, n, (int32_t)seg_a, nseg, (int32_t)e->elen[tid],
                         e->d_depth + off, e->d_delta + off, e->d_seg_state + off / pdk::SEG, e->xflags, e->min_mapq,
                         e->d_flags, e->d_flags + 1,
                         e->hint_on ? 1u : 0u, e->hint_min_dep, e->hint_mask, e->d_part_cov + off / pdk::SEG, e->d_part_sum + off / pdk::SEG,
-                        e->tile_resident_warps};
+                        e->tile_resident_warps, (int32_t)e->org[tid]};
         const size_t smem = (size_t)pdk::WPC * pdk::TILE_SMEM_WORDS * 4;
         const unsigned grid = (nseg + pdk::WPC - 1) / pdk::WPC, blk = pdk::WPC * 32;
         const bool has_off = cigar_off != nullptr, has_filter = flag != nullptr || mapq != nullptr;
@@ -195,7 +204,8 @@ int run_batch(pd_engine *e, int32_t tid, uint32_t n, const int32_t *pos, const u
         if (rc) return rc;
         e->stats.tile_path_batches++;
     } else {
-        pdk::ScatterArgs s{pos, cigar, cigar_off, flag, mapq, n, (int32_t)e->tlen[tid], e->d_delta + off, e->xflags, e->min_mapq};
+        pdk::ScatterArgs s{pos, cigar, cigar_off, flag, mapq, n, (int32_t)e->elen[tid], e->d_delta + off, e->xflags, e->min_mapq,
+                           (int32_t)e->org[tid], nullptr, nullptr};
         int rc = launch(e, K_SCATTER, [&] { pdk::k_delta_scatter<<<(n + 255) / 256, 256, 0, e->stream>>>(s); }); if (rc) return rc;
         e->host_delta_used = true;
         e->stats.delta_path_batches++;
@@ -346,9 +356,9 @@ int bz_finish(pd_engine *e, BzSlot &s)
         if (!open) return PD_OK;
         open = false;
         const int32_t t = cur.tid;
-        if (t < 0 || t >= e->n_targets || !e->owned[t] || e->tlen[t] == 0) return PD_OK;
-        const int64_t max_seg = ((int64_t)e->tlen[t]) / pdk::SEG;
-        int64_t p0 = std::max<int32_t>(cur.p0, 0), p1 = std::max<int32_t>(cur.p1, 0);
+        if (t < 0 || t >= e->n_targets || !e->owned[t] || e->elen[t] == 0) return PD_OK;
+        const int64_t max_seg = ((int64_t)e->elen[t]) / pdk::SEG;
+        int64_t p0 = std::max<int64_t>((int64_t)cur.p0 - e->org[t], 0), p1 = std::max<int64_t>((int64_t)cur.p1 - e->org[t], 0);
         int64_t seg_a = std::min<int64_t>(p0 / pdk::SEG, max_seg), seg_b = std::min<int64_t>((p1 + pdk::HALO) / pdk::SEG, max_seg);
         if (seg_b < seg_a) seg_b = seg_a;
         return run_batch(e, t, cur.r1 - cur.r0, s.pos + cur.r0, nullptr, nullptr, single_op ? nullptr : s.coff + cur.r0,
@@ -358,7 +368,7 @@ int bz_finish(pd_engine *e, BzSlot &s)
         if (!irr_open) return PD_OK;
         irr_open = false;
         const uint32_t n = irr1 - irr0;
-        pdk::ScatterMultiArgs m{s.tid + irr0, s.pos + irr0, s.cig, s.coff + irr0, n, e->d_off, e->d_tlen, e->d_owned, e->n_targets, e->d_delta};
+        pdk::ScatterMultiArgs m{s.tid + irr0, s.pos + irr0, s.cig, s.coff + irr0, n, e->d_off, e->d_tlen, e->d_org, e->d_owned, e->n_targets, e->d_delta};
         int rc2 = launch(e, K_SCATTER, [&] { pdk::k_delta_scatter_multi<<<(n + 255) / 256, 256, 0, e->stream>>>(m); });
         if (rc2) return rc2;
         e->host_delta_used = true; e->stats.delta_path_batches++; e->stats.reads_pushed += n;
@@ -429,7 +439,7 @@ void pd_destroy(pd_engine *e)
         if (s.consumed) cudaEventDestroy(s.consumed);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
-    cudaFree(e->d_owned);
+    cudaFree(e->d_owned); cudaFree(e->d_org);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     delete e;
@@ -438,6 +448,15 @@ void pd_destroy(pd_engine *e)
 pd_engine *pd_create(int device, int n_targets, const uint32_t *target_len, const uint8_t *owned, uint32_t xflags, int min_mapq)
 {
     if (n_targets <= 0 || !target_len) { g_create_error = "pd_create: bad arguments"; return nullptr; }
+    std::vector<uint32_t> beg((size_t)n_targets, 0), end(target_len, target_len + n_targets);
+    if (owned) for (int t = 0; t < n_targets; ++t) if (!owned[t]) end[(size_t)t] = 0;
+    return pd_create_ranges(device, n_targets, target_len, beg.data(), end.data(), xflags, min_mapq);
+}
+
+pd_engine *pd_create_ranges(int device, int n_targets, const uint32_t *target_len, const uint32_t *own_beg, const uint32_t *own_end,
+                            uint32_t xflags, int min_mapq)
+{
+    if (n_targets <= 0 || !target_len || !own_beg || !own_end) { g_create_error = "pd_create: bad arguments"; return nullptr; }
     pd_engine *e = new pd_engine;
     auto bail = [&](const char *what, cudaError_t ce) -> pd_engine * {
         g_create_error = std::string("pd_create: ") + what + ": " + cudaGetErrorString(ce);
@@ -446,15 +465,17 @@ pd_engine *pd_create(int device, int n_targets, const uint32_t *target_len, cons
     };
     e->device = device; e->n_targets = n_targets; e->xflags = xflags; e->min_mapq = min_mapq;
     e->tlen.assign(target_len, target_len + n_targets);
-    e->owned.assign(n_targets, 1);
-    if (owned) e->owned.assign(owned, owned + n_targets);
+    e->owned.assign(n_targets, 0); e->org.assign(n_targets, 0); e->elen.assign(n_targets, 0);
     e->off.assign(n_targets, 0);
     uint64_t total = 0;
     for (int t = 0; t < n_targets; ++t) {
-        if (!e->owned[t]) continue;
         if (e->tlen[t] > 0x7fffffffu) { g_create_error = "pd_create: contig longer than 2^31-1"; delete e; return nullptr; }
+        const uint32_t b = std::min(own_beg[t], e->tlen[t]), z = std::min(own_end[t], e->tlen[t]);
+        if (z <= b) continue;                                  // nothing of this contig is owned: pushes for it are ignored
+        e->owned[t] = 1; e->org[t] = b; e->elen[t] = z - b;
+        if (b != 0 || z != e->tlen[t]) e->has_ranges = true;
         e->off[t] = total;
-        total += ((uint64_t)e->tlen[t] + 1 + PAD_ELEMS - 1) / PAD_ELEMS * PAD_ELEMS;
+        total += ((uint64_t)e->elen[t] + 1 + PAD_ELEMS - 1) / PAD_ELEMS * PAD_ELEMS;
     }
     if (total == 0) total = PAD_ELEMS;
     e->total = total; e->n_seg = total / pdk::SEG;
@@ -475,7 +496,9 @@ pd_engine *pd_create(int device, int n_targets, const uint32_t *target_len, cons
     if ((ce = cudaMalloc(&e->d_part_sum, e->n_seg * 8)) != cudaSuccess) return bail("cudaMalloc", ce);
     e->stats.hbm_bytes_allocated = total * 8 + e->n_seg * 13 + (total / pdk::SCAN_TILE) * 8;
     if ((ce = cudaMemcpy(e->d_off, e->off.data(), (size_t)n_targets * 8, cudaMemcpyHostToDevice)) != cudaSuccess) return bail("memcpy", ce);
-    if ((ce = cudaMemcpy(e->d_tlen, e->tlen.data(), (size_t)n_targets * 4, cudaMemcpyHostToDevice)) != cudaSuccess) return bail("memcpy", ce);
+    if ((ce = cudaMemcpy(e->d_tlen, e->elen.data(), (size_t)n_targets * 4, cudaMemcpyHostToDevice)) != cudaSuccess) return bail("memcpy", ce);
+    if ((ce = cudaMalloc(&e->d_org, (size_t)n_targets * 4)) != cudaSuccess) return bail("cudaMalloc", ce);
+    if ((ce = cudaMemcpy(e->d_org, e->org.data(), (size_t)n_targets * 4, cudaMemcpyHostToDevice)) != cudaSuccess) return bail("memcpy", ce);
     if ((ce = cudaMalloc(&e->d_owned, (size_t)n_targets)) != cudaSuccess) return bail("cudaMalloc", ce);
     if ((ce = cudaMemcpy(e->d_owned, e->owned.data(), (size_t)n_targets, cudaMemcpyHostToDevice)) != cudaSuccess) return bail("memcpy", ce);
     if ((ce = cudaMemsetAsync(e->d_delta, 0, total * 4, e->stream)) != cudaSuccess) return bail("memset", ce);
@@ -548,10 +571,11 @@ int pd_push_contig(pd_engine *e, int32_t tid, int64_t n_reads, const int32_t *po
     NvtxRange nvtx_("pd_push_contig");
     if (!e) return PD_ERR_ARG;
     if (tid < 0 || tid >= e->n_targets || n_reads < 0 || (n_reads > 0 && (!pos || !cigar))) return fail(e, PD_ERR_ARG, "pd_push_contig: bad arguments");
-    if (!e->owned[tid] || n_reads == 0 || e->tlen[tid] == 0) return PD_OK;
+    if (!e->owned[tid] || n_reads == 0 || e->elen[tid] == 0) return PD_OK;
     CK(cudaSetDevice(e->device));
     const bool sorted = (flags & PD_SORTED) != 0;
-    const int64_t max_seg = ((int64_t)e->tlen[tid]) / pdk::SEG;      // segment of the padding element
+    const int64_t max_seg = ((int64_t)e->elen[tid]) / pdk::SEG;      // segment of the padding element
+    const int64_t org = e->org[tid];
 
     if (flags & PD_DEVICE) {
         for (int64_t b = 0; b < n_reads; b += 0x7fff0000ll) {
@@ -585,6 +609,7 @@ int pd_push_contig(pd_engine *e, int32_t tid, int64_t n_reads, const int32_t *po
             // sorted => first/last positions bound the segments this chunk can touch (+HALO of look-ahead for the halo readers)
             int64_t p0 = pos[b], p1 = pos[b + n - 1];
             if (p1 < p0) return fail(e, PD_ERR_UNSORTED, "a batch pushed with PD_SORTED was not sorted by pos (last < first)");
+            p0 -= org; p1 -= org;                               // positions relative to the owned range
             if (p0 < 0) p0 = 0;
             if (p1 < 0) p1 = 0;
             seg_a = std::min<int64_t>(p0 / pdk::SEG, max_seg);
@@ -762,7 +787,7 @@ int pd_reduce(pd_engine *e, int64_t n_iv, const int32_t *tid, const int32_t *sta
         const int32_t t = tid[i];
         if (t < 0 || t >= e->n_targets) return fail(e, PD_ERR_ARG, "pd_reduce: tid out of range");
         if (!e->owned[t]) continue;
-        int64_t s = std::max<int64_t>(start0[i], 0), en = std::min<int64_t>(end0_excl[i], e->tlen[t]);
+        int64_t s = std::max<int64_t>((int64_t)start0[i] - e->org[t], 0), en = std::min<int64_t>((int64_t)end0_excl[i] - e->org[t], e->elen[t]);
         if (s >= en) continue;
         n_units += (uint64_t)((en - 1) / pdk::REDUCE_CHUNK - s / pdk::REDUCE_CHUNK + 1);      // REDUCE_CHUNK-aligned pieces
     }
@@ -775,6 +800,16 @@ int pd_reduce(pd_engine *e, int64_t n_iv, const int32_t *tid, const int32_t *sta
     rc = ensure_red(e, need); if (rc) return rc;
     char *base = (char *)e->d_red;
     CK(cudaMemcpyAsync(base + a_tid, tid, iv_bytes, cudaMemcpyHostToDevice, e->stream));
+    std::vector<int32_t> sh_s, sh_e;                         // range sharding: intervals relative to the owned ranges (clipped by the kernel)
+    if (e->has_ranges) {
+        sh_s.resize((size_t)n_iv); sh_e.resize((size_t)n_iv);
+        for (int64_t i = 0; i < n_iv; ++i) {
+            const int64_t o = e->org[tid[i]];
+            sh_s[(size_t)i] = (int32_t)std::max<int64_t>((int64_t)start0[i] - o, INT32_MIN);
+            sh_e[(size_t)i] = (int32_t)std::max<int64_t>((int64_t)end0_excl[i] - o, INT32_MIN);
+        }
+        start0 = sh_s.data(); end0_excl = sh_e.data();
+    }
     CK(cudaMemcpyAsync(base + a_s, start0, iv_bytes, cudaMemcpyHostToDevice, e->stream));
     CK(cudaMemcpyAsync(base + a_e, end0_excl, iv_bytes, cudaMemcpyHostToDevice, e->stream));
     CK(cudaMemcpyAsync(base + a_units, prefix.data(), prefix.size() * 8, cudaMemcpyHostToDevice, e->stream));
@@ -810,6 +845,8 @@ int pd_reduce_windows(pd_engine *e, int32_t tid, int32_t start0, int32_t win, in
         else { memset(cov, 0, (size_t)n_win * 4); memset(sum, 0, (size_t)n_win * 8); }
         return PD_OK;
     }
+    if (e->org[tid] != 0 || e->elen[tid] != e->tlen[tid])
+        return fail(e, PD_ERR_STATE, "pd_reduce_windows: contig owned only in part (range sharding): use pd_reduce, whose results add up across engines");
     uint32_t *d_cov = cov; unsigned long long *d_sum = (unsigned long long *)sum;
     if (!dev) {
         const size_t a_sum = ((size_t)n_win * 4 + 15) & ~15ull;
@@ -843,7 +880,10 @@ int pd_depth_read(pd_engine *e, int32_t tid, int32_t start0, int32_t n, uint32_t
         if (dev) CK(cudaMemsetAsync(out, 0, (size_t)n * 4, e->stream)); else memset(out, 0, (size_t)n * 4);
         return PD_OK;
     }
-    CK(cudaMemcpyAsync(out, e->d_depth + e->off[tid] + start0, (size_t)n * 4, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, e->stream));
+    // the part of [start0, start0 + n) inside the owned range; the rest reads as zero (depth adds up across engines)
+    const int64_t a = std::max<int64_t>(start0, e->org[tid]), z = std::min<int64_t>((int64_t)start0 + n, (int64_t)e->org[tid] + e->elen[tid]);
+    if (a > start0 || z < (int64_t)start0 + n) { if (dev) CK(cudaMemsetAsync(out, 0, (size_t)n * 4, e->stream)); else memset(out, 0, (size_t)n * 4); }
+    if (z > a) CK(cudaMemcpyAsync(out + (a - start0), e->d_depth + e->off[tid] + (a - e->org[tid]), (size_t)(z - a) * 4, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, e->stream));
     if (!dev) { e->stats.d2h_bytes += (uint64_t)n * 4; CK(cudaStreamSynchronize(e->stream)); }
     return PD_OK;
 }

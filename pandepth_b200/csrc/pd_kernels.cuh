@@ -90,6 +90,7 @@ struct CutArgs {
     const int32_t *pos;
     uint32_t n; int32_t seg0; int32_t nseg;
     uint32_t *lo; uint32_t *hi;
+    int64_t shift;      // contig coordinate of the engine's first owned base (range sharding): segment s covers [shift + s*SEG, ...)
 };
 
 constexpr int CUT_COARSE = 64;   // segments per coarse search key
@@ -126,7 +127,7 @@ __global__ void __launch_bounds__(128) k_cut_coarse(CutArgs a, uint32_t *coarse,
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= ncoarse) return;
-    const int64_t key = (int64_t)(a.seg0 + (int64_t)k * CUT_COARSE) * SEG - HALO;
+    const int64_t key = (int64_t)(a.seg0 + (int64_t)k * CUT_COARSE) * SEG - HALO + a.shift;
     const uint32_t g = (uint32_t)(((uint64_t)a.n * (uint32_t)k) / (uint32_t)ncoarse);
     coarse[k] = lower_bound_near(a.pos, a.n, key, g);
 }
@@ -137,7 +138,7 @@ __global__ void __launch_bounds__(256) k_cut(CutArgs a, const uint32_t *coarse, 
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j > a.nseg) return;
-    const int64_t s0 = (int64_t)(a.seg0 + j) * SEG;
+    const int64_t s0 = (int64_t)(a.seg0 + j) * SEG + a.shift;
     int k = j / CUT_COARSE; if (k >= ncoarse) k = ncoarse - 1;
     const uint32_t ca = coarse[k];
     const uint32_t cb = (k + 1 < ncoarse) ? coarse[k + 1] : a.n;
@@ -178,6 +179,7 @@ struct TileArgs {
     uint32_t hint_on, hint_min_dep, hint_mask;
     uint32_t *part_cov; unsigned long long *part_sum;     // contig base, one entry per segment
     int32_t pf_dist;      // PD_PREFETCH: segments between a warp's own segment and the one whose reads it prefetches
+    int32_t shift;        // contig coordinate of depth[0] (range sharding: this engine owns [shift, shift + contig_len) of the contig)
 };
 
 constexpr int TILE_UNROLL = PD_TILE_UNROLL;   // 32-read chunks whose loads are issued together (memory-level parallelism)
@@ -220,8 +222,9 @@ __global__ void __launch_bounds__(WPC * 32, TILE_MIN_CTAS) k_tile_accumulate(Til
         if (i_hi < a.n) chk_r = ldg_i32(a.pos + i_hi);
         if (j + 1 < a.nseg) chk_n = a.lo[j + 1];
     }
+    const int64_t shift = a.shift;
     if (i_lo >= i_hi || bad) {
-        if (lane == 0 && (bad || (int64_t)chk_l >= hbase || (int64_t)chk_r < send || chk_n > i_hi)) atomicOr(a.err, ERR_UNSORTED);
+        if (lane == 0 && (bad || (int64_t)chk_l - shift >= hbase || (int64_t)chk_r - shift < send || chk_n > i_hi)) atomicOr(a.err, ERR_UNSORTED);
         return;
     }
 
@@ -242,10 +245,13 @@ __global__ void __launch_bounds__(WPC * 32, TILE_MIN_CTAS) k_tile_accumulate(Til
     uint32_t carry_reg = 0;        // per-lane part of "depth just left of the segment"
     int32_t carry_p = INT32_MIN;   // last position of the previous chunk (sortedness check)
     uint32_t idx_max = 0;          // largest window index seen: anything >= WIN means a read outside the window (inconsistent cut)
-    const int32_t win0 = (int32_t)hbase;                                  // position of window index 0 (>= -HALO)
+    const uint32_t win0 = (uint32_t)(hbase + shift);                      // contig position of window index 0 (modular: hbase >= -HALO)
+    // reads that start left of an owned range (segment 0 of a range that does not begin at the contig start) have no owner
+    // segment in this engine: segment 0 scatters their far runs itself
+    const bool own_halo = (a.seg0 + j) == 0 && shift != 0;
     const int64_t clen_w64 = clen - hbase;                                // contig end as a window index
     const uint32_t clen_w = (uint32_t)(clen_w64 > 0x7fffffff ? 0x7fffffff : clen_w64);
-    const int32_t pad_pos = (int32_t)(send - 1);                          // filler for lanes past the last read: in window, sorts last
+    const int32_t pad_pos = (int32_t)(send - 1 + shift);                  // filler for lanes past the last read: in window, sorts last
     // delta v applies to every base >= window index x (anything at or beyond WIN belongs to a later segment)
     auto emit = [&](int64_t x, uint32_t v) {
         if (x < TOFF) carry_reg += v;
@@ -302,7 +308,7 @@ __global__ void __launch_bounds__(WPC * 32, TILE_MIN_CTAS) k_tile_accumulate(Til
             const int32_t p = pv[u];
             const uint32_t c = cv[u];
             const uint32_t nops = HAS_OFF ? nv[u] : 1u;
-            const uint32_t w = (uint32_t)p - (uint32_t)win0;   // window index: < WIN for a consistent cut
+            const uint32_t w = (uint32_t)p - win0;             // window index: < WIN for a consistent cut
             const bool in_win = w < (uint32_t)WIN;
             idx_max = max(idx_max, w);                         // checked once after the loop
             bool pass = in_win && p >= 0;
@@ -319,7 +325,7 @@ __global__ void __launch_bounds__(WPC * 32, TILE_MIN_CTAS) k_tile_accumulate(Til
                 if (ok && e > (uint32_t)WIN) {                                      // the run leaves the segment (7% of 150M reads)
                     // first base (window index) that no segment seeing this read owns: segments see reads up to HALO to their left
                     const uint32_t far_w = (w >= (uint32_t)SEG) ? 2 * SEG + HALO : SEG + HALO;
-                    if (w >= (uint32_t)HALO && e > far_w) {                         // rare: run longer than HALO, applied by its owner
+                    if ((w >= (uint32_t)HALO || own_halo) && e > far_w) {           // rare: run longer than HALO, applied by its owner
                         red_add_u32(a.delta + hbase + far_w, 1u);
                         red_add_u32(a.delta + hbase + e, 0xffffffffu);
                         *a.delta_used = 1;
@@ -327,7 +333,7 @@ __global__ void __launch_bounds__(WPC * 32, TILE_MIN_CTAS) k_tile_accumulate(Til
                 }
             } else if (pass) {
                 const uint32_t c0 = ov[u];
-                const bool owner = w >= (uint32_t)HALO;
+                const bool owner = w >= (uint32_t)HALO || own_halo;
                 const int64_t far_w = (w >= (uint32_t)SEG) ? 2 * SEG + HALO : SEG + HALO;
                 int64_t q = w, rs = INT64_MIN, re = INT64_MIN;
                 auto flush = [&]() {
@@ -448,7 +454,7 @@ __global__ void __launch_bounds__(WPC * 32, TILE_MIN_CTAS) k_tile_accumulate(Til
         if (lane == 0) *st_ptr = 2;
     }
     bad = __any_sync(FULL, bad || idx_max >= (uint32_t)WIN);
-    if (lane == 0 && (bad || (int64_t)chk_l >= hbase || (int64_t)chk_r < send || chk_n > i_hi)) atomicOr(a.err, ERR_UNSORTED);
+    if (lane == 0 && (bad || (int64_t)chk_l - shift >= hbase || (int64_t)chk_r - shift < send || chk_n > i_hi)) atomicOr(a.err, ERR_UNSORTED);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -461,12 +467,13 @@ struct ScatterArgs {
     uint32_t n; int32_t contig_len;
     uint32_t *delta;   // contig base
     uint32_t xflags; int32_t min_mapq;
+    int32_t shift;     // contig coordinate of delta[0] (range sharding); runs are clipped to [0, contig_len) after the shift
+    const uint32_t *n_dev;   // non-null: only reads [0, *n_dev) (a device-side count: the reads left of a sorted batch's first cut)
+    int *delta_used;         // with n_dev: set when anything was scattered (the engine then runs the scan at finalize)
 };
 
-__global__ void __launch_bounds__(256) k_delta_scatter(ScatterArgs a)
+__device__ __forceinline__ void scatter_one(const ScatterArgs &a, uint32_t i)
 {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.n) return;
     if (a.flag && (a.flag[i] & a.xflags)) return;
     if (a.mapq && (int)a.mapq[i] < a.min_mapq) return;
     const int32_t p = a.pos[i];
@@ -474,10 +481,10 @@ __global__ void __launch_bounds__(256) k_delta_scatter(ScatterArgs a)
     uint32_t c0 = i, nops = 1;
     if (a.cigar_off) { c0 = a.cigar_off[i]; nops = a.cigar_off[i + 1] - c0; }
     const int64_t clen = a.contig_len;
-    int64_t q = p, rs = -1, re = -1;
+    int64_t q = (int64_t)p - a.shift, rs = 0, re = 0; bool open = false;
     auto flush = [&]() {
-        if (rs < 0) return;
-        const int64_t s = rs, e = re > clen ? clen : re;
+        if (!open) return;
+        const int64_t s = rs < 0 ? 0 : rs, e = re > clen ? clen : re;
         if (s >= e) return;
         red_add_u32(a.delta + s, 1u);
         red_add_u32(a.delta + e, 0xffffffffu);
@@ -487,11 +494,24 @@ __global__ void __launch_bounds__(256) k_delta_scatter(ScatterArgs a)
         const uint32_t op = w & 15u;
         const int64_t n = w >> 4;
         if (is_match_op(op)) {
-            if (rs >= 0 && re == q) re = q + n; else { flush(); rs = q; re = q + n; }
+            if (open && re == q) re = q + n; else { flush(); rs = q; re = q + n; open = true; }
             q += n;
         } else if (is_skip_op(op)) q += n;
     }
     flush();
+}
+
+__global__ void __launch_bounds__(256) k_delta_scatter(ScatterArgs a)
+{
+    if (a.n_dev) {                                              // grid-stride over a device-side count (usually zero)
+        const uint32_t n = min(*a.n_dev, a.n);
+        if (n && a.delta_used && blockIdx.x == 0 && threadIdx.x == 0) *a.delta_used = 1;
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) scatter_one(a, i);
+        return;
+    }
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    scatter_one(a, i);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -44,6 +44,8 @@ def load_library() -> ctypes.CDLL:
     vp, i32, i64, u32 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_uint32
     L.pd_create.restype = vp
     L.pd_create.argtypes = [ctypes.c_int, ctypes.c_int, vp, vp, u32, ctypes.c_int]
+    L.pd_create_ranges.restype = vp
+    L.pd_create_ranges.argtypes = [ctypes.c_int, ctypes.c_int, vp, vp, vp, u32, ctypes.c_int]
     L.pd_destroy.restype = None; L.pd_destroy.argtypes = [vp]
     L.pd_last_error.restype = ctypes.c_char_p; L.pd_last_error.argtypes = [vp]
     L.pd_set_stream.restype = ctypes.c_int; L.pd_set_stream.argtypes = [vp, vp]
@@ -96,11 +98,16 @@ class Engine:
     """One engine per GPU (see include/pandepth_b200.h for the contract of every call)."""
 
     def __init__(self, target_len: Sequence[int], device: int = 0, owned: Optional[Sequence[int]] = None,
-                 xflags: int = 1796, min_mapq: int = -1):
+                 xflags: int = 1796, min_mapq: int = -1, own_beg: Optional[Sequence[int]] = None, own_end: Optional[Sequence[int]] = None):
+        """owned: per-contig 0/1 mask (contig sharding); own_beg / own_end: per-contig owned range (range sharding)."""
         self._L = load_library()
         self.target_len = np.ascontiguousarray(target_len, dtype=np.uint32)
-        own = None if owned is None else np.ascontiguousarray(owned, dtype=np.uint8)
-        self._h = self._L.pd_create(device, int(self.target_len.size), _p(self.target_len), _p(own), xflags, min_mapq)
+        if own_beg is not None:
+            b = np.ascontiguousarray(own_beg, dtype=np.uint32); z = np.ascontiguousarray(own_end, dtype=np.uint32)
+            self._h = self._L.pd_create_ranges(device, int(self.target_len.size), _p(self.target_len), _p(b), _p(z), xflags, min_mapq)
+        else:
+            own = None if owned is None else np.ascontiguousarray(owned, dtype=np.uint8)
+            self._h = self._L.pd_create(device, int(self.target_len.size), _p(self.target_len), _p(own), xflags, min_mapq)
         if not self._h:
             raise PDError(-1, self._L.pd_last_error(None).decode())
 

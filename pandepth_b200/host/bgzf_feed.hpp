@@ -16,6 +16,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstdlib>
 #include <cstring>
@@ -64,22 +65,31 @@ struct ChunkPool {
     ~ChunkPool() { for (auto &b : bufs) pd_host_free(b.p); }
 };
 
-struct BgzfFeedResult { int status = 0; std::string err; uint64_t bytes = 0, pieces = 0, blocks = 0; };   // status 1 = whole file fed, 0 = host path needed, -1 = failed
+struct BgzfFeedResult {
+    int status = 0; std::string err; uint64_t bytes = 0, pieces = 0, blocks = 0;   // status 1 = whole file fed, 0 = host path needed, -1 = failed
+    double s_alloc = 0, s_read = 0, s_chain = 0, s_push = 0, s_sync = 0;           // thread-seconds: pinned buffers, pread, block-table hand-over + hop, pd_push_bgzf, final pd_sync
+    size_t piece_bytes = 0; int threads = 0;
+};
 
 // Feeds every record of `path` (a BAM in BGZF blocks) to `eng`.  `eng_mu` (nullable) serialises engine calls with other users.
 // strict_eof: a file that ends inside a BGZF block is an error (what the indexed host scanner reports); otherwise the stream
 // ends quietly at the last complete block, like the reference's `while (sam_read1(...) >= 0)` loop (:4608).
-inline BgzfFeedResult bgzf_feed_file(pd_engine *eng, std::mutex *eng_mu, const std::string &path, int threads, ChunkPool &pool, bool strict_eof = true)
+// [range_beg, range_end): only the BGZF blocks that START in this byte range of the file are fed (range sharding over GPUs: the
+// offsets come from the .bai, see pdh_bai_block_offset); range_beg = 0 means "from the first record".
+inline BgzfFeedResult bgzf_feed_file(pd_engine *eng, std::mutex *eng_mu, const std::string &path, int threads, ChunkPool &pool, bool strict_eof = true,
+                                     uint64_t range_beg = 0, uint64_t range_end = UINT64_MAX)
 {
     BgzfFeedResult res;
     uint32_t first_skip = 0;
     BgzfChunker ch;
     if (!ch.open(path, first_skip)) { res.status = 0; return res; }            // not a BAM this path understands
-    const uint64_t data_start = ch.position();
+    uint64_t data_start = ch.position();
+    if (range_beg > data_start) { data_start = range_beg; first_skip = 0; }    // a block boundary inside the file: records start at offset 0
     const int fd = ::open(path.c_str(), O_RDONLY);
     struct stat st;
     if (fd < 0 || fstat(fd, &st) != 0) { if (fd >= 0) close(fd); res.status = -1; res.err = "cannot open " + path; return res; }
-    const uint64_t file_size = (uint64_t)st.st_size;
+    const uint64_t true_size = (uint64_t)st.st_size;
+    const uint64_t file_size = std::min<uint64_t>(true_size, range_end);      // blocks starting at or after this offset belong to someone else
     // piece size from the compression ratio of the first blocks: ~384 MB inflated, 8..96 MB compressed
     double ratio = 4.0;
     {
@@ -97,8 +107,10 @@ inline BgzfFeedResult bgzf_feed_file(pd_engine *eng, std::mutex *eng_mu, const s
     size_t piece = (size_t)(384.0 * 1048576.0 / std::max(1.0, ratio));
     if (const char *e = getenv("PANDEPTH_BGZF_PIECE_MB")) piece = (size_t)(atof(e) * 1048576.0);
     piece = std::max<size_t>(1u << 20, std::min<size_t>(96u << 20, piece));
-    piece = std::max<size_t>(piece, 1u << 17);
     const uint64_t span = file_size > data_start ? file_size - data_start : 0;
+    // small inputs: more, smaller pieces (pinned memory costs ~0.3 ms per MB to allocate and as much again to release at exit)
+    if (!getenv("PANDEPTH_BGZF_PIECE_MB")) piece = std::min<size_t>(piece, std::max<size_t>(8u << 20, (size_t)(span / (4 * (uint64_t)std::max(1, threads)))));
+    piece = std::max<size_t>(piece, 1u << 17);
     const size_t n_pieces = (size_t)((span + piece - 1) / piece);
     if (n_pieces == 0) { close(fd); res.status = 1; return res; }
     const int T = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(1, threads), n_pieces));
@@ -120,23 +132,34 @@ inline BgzfFeedResult bgzf_feed_file(pd_engine *eng, std::mutex *eng_mu, const s
         if (state.load() == 1) { state = s; err = m; }
         chain_cv.notify_all();
     };
+    res.piece_bytes = piece; res.threads = T;
+    std::mutex stat_mu;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
     auto worker = [&] {
         std::vector<pd_bgzf_block> blocks;
+        double t_alloc = 0, t_read = 0, t_chain = 0, t_push = 0;
+        struct Fold { double &a, &r, &c, &p; BgzfFeedResult &res; std::mutex &mu; ~Fold() { std::lock_guard<std::mutex> g(mu); res.s_alloc += a; res.s_read += r; res.s_chain += c; res.s_push += p; } } fold{t_alloc, t_read, t_chain, t_push, res, stat_mu};
         for (;;) {
             const size_t j = next.fetch_add(1);
             if (j >= n_pieces || state.load() != 1) break;
             const uint64_t a = data_start + (uint64_t)j * piece, z = std::min<uint64_t>(file_size, a + piece);
+            auto t0 = now();
             const int id = pool.acquire();
+            t_alloc += secs(t0, now());
             if (id < 0) { set_state(-1, "out of pinned host memory"); break; }
             uint8_t *buf = pool.ptr(id);
-            const size_t want = (size_t)std::min<uint64_t>(file_size - a, (uint64_t)piece + (1u << 16) + 64);
+            const size_t want = (size_t)std::min<uint64_t>(true_size - a, (uint64_t)piece + (1u << 16) + 64);   // the last block may end past the range
             size_t got = 0;
+            t0 = now();
             while (got < want) {
                 const ssize_t k = pread(fd, buf + got, want - got, (off_t)(a + got));
                 if (k < 0) { set_state(-1, "read error on " + path); break; }
                 if (k == 0) break;
                 got += (size_t)k;
             }
+            t_read += secs(t0, now());
+            t0 = now();
             // my first block: handed over by the previous piece
             uint64_t s0;
             {
@@ -164,6 +187,8 @@ inline BgzfFeedResult bgzf_feed_file(pd_engine *eng, std::mutex *eng_mu, const s
             if (bad) { set_state(-1, "Error: malformed BAM while reading " + path + ": not a BGZF block"); pool.release(id); break; }
             if (cut && strict_eof) { set_state(-1, "Error: malformed BAM while reading " + path + ": unexpected end of file inside a BGZF block"); pool.release(id); break; }
             if (blocks.empty()) { pool.release(id); continue; }
+            t_chain += secs(t0, now());
+            t0 = now();
             int rc;
             {
                 std::lock_guard<std::mutex> g(emu);
@@ -179,6 +204,7 @@ inline BgzfFeedResult bgzf_feed_file(pd_engine *eng, std::mutex *eng_mu, const s
                     if (rc == PD_ERR_FALLBACK) set_state(0, m); else set_state(-1, m);
                 }
             }
+            t_push += secs(t0, now());
             if (rc != PD_OK) break;
         }
     };
@@ -188,6 +214,8 @@ inline BgzfFeedResult bgzf_feed_file(pd_engine *eng, std::mutex *eng_mu, const s
     for (auto &t : th) t.join();
     {
         std::lock_guard<std::mutex> g(emu);
+        const auto t0 = now();
+        struct S { double &d; std::chrono::steady_clock::time_point t; ~S() { d += std::chrono::duration<double>(std::chrono::steady_clock::now() - t).count(); } } sy{res.s_sync, t0};
         if (state.load() == 1) {
             const int rc = pd_sync(eng);
             if (rc == PD_ERR_FALLBACK) set_state(0, std::string("pd_push_bgzf: ") + pd_last_error(eng));

@@ -414,6 +414,9 @@ struct Feeder {
         const BgzfFeedResult r = bgzf_feed_file(eng, &eng_mu, input, std::max(1, o.threads), chunk_pool, strict_eof);
         ns_decode += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
         n_push += r.pieces;
+        if (getenv("PANDEPTH_TIMING"))
+            fprintf(stderr, "[timing] bgzf feed: %llu pieces of %.1f MB, %d readers; thread-seconds: pinned alloc/wait %.3f, pread %.3f, block tables %.3f, pd_push_bgzf %.3f; final pd_sync %.3f s\n",
+                    (unsigned long long)r.pieces, r.piece_bytes / 1048576.0, r.threads, r.s_alloc, r.s_read, r.s_chain, r.s_push, r.s_sync);
         if (r.status < 0) { fail(r.err.empty() ? "Error: device decode failed on " + input : r.err); return -1; }
         if (r.status == 0) {
             // (records that do not start on block boundaries, CG-tag CIGARs.)  Depth is additive but the pieces already

@@ -17,6 +17,7 @@ def read_bgzf_blocks(data):
     """-> list of (in_off, in_len, out_len) for every non-empty block."""
     out = []
     p = 0
+    data = memoryview(data).cast("B")           # plain Python ints whatever the caller holds (numpy uint8 scalars would wrap)
     n = len(data)
     while p + 18 <= n:
         if data[p] != 31 or data[p + 1] != 139:

@@ -16,7 +16,7 @@ def _declared():
 
 def test_header_declares_the_boundary():
     names = _declared()
-    for must in ("pd_create", "pd_push", "pd_push_contig", "pd_push_bgzf", "pd_finalize", "pd_reduce", "pd_reduce_windows",
+    for must in ("pd_create", "pd_create_ranges", "pd_push", "pd_push_contig", "pd_push_bgzf", "pd_finalize", "pd_reduce", "pd_reduce_windows",
                  "pd_depth_read", "pd_destroy", "pd_last_error"):
         assert must in names
 
@@ -26,6 +26,20 @@ def test_library_exports_every_declared_symbol():
     lib = pd.load_library()
     for n in _declared():
         assert hasattr(lib, n), f"libpandepth_b200.so does not export {n}"
+
+
+def test_host_library_exports_every_declared_symbol():
+    """include/pandepth_host.h (the feeder's C entry points) against libpandepth_host.so."""
+    src = open(os.path.join(ROOT, "include", "pandepth_host.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = sorted(set(re.findall(r"\b(pdh_[a-z_0-9]+)\s*\(", src)))
+    assert "pdh_feed_bam" in names and "pdh_feed_bam_range" in names and "pdh_bai_block_offset" in names
+    path = os.path.join(ROOT, "pandepth_b200", "libpandepth_host.so")
+    if not os.path.exists(path):
+        pytest.skip("host library not built")
+    lib = ctypes.CDLL(path)
+    for n in names:
+        assert hasattr(lib, n), f"libpandepth_host.so does not export {n}"
 
 
 def test_no_cpu_fallback_without_gpu():

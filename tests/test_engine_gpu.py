@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 from oracle import model
-from tests.helpers import GOLD, assert_matches, load_fixture, options_from_args
+from tests.helpers import GOLD, ROOT, assert_matches, load_fixture, options_from_args
 
 pytestmark = pytest.mark.gpu
 
@@ -462,3 +462,85 @@ def test_batches_after_a_scan_see_a_clean_delta_array(second):
         _push_all(eng, third, True, 1)
         eng.finalize()
         _check_depth(eng, tlen, [a + b + c for a, b, c in zip(both, add, model.accumulate(tlen, third))])
+
+
+@pytest.mark.parametrize("style", ["sorted", "chunked", "unsorted", "device_decode"])
+def test_range_sharded_engines_add_up_to_one_engine(style, tmp_path):
+    """Range sharding (pd_create_ranges): three engines own disjoint thirds of the concatenated genome, every engine is
+    fed ALL reads -- boundary reads included, also spliced reads that start thousands of bases left of a range and reach
+    into it -- clips to its range, and the depth pieces / reduce results add up to the single-engine result."""
+    import pandepth_b200 as pd
+    from pandepth_b200.shard import assign_ranges
+    rng = np.random.default_rng(17)
+    lens = [200_003, 50_000, 1, 120_000]
+    names = [f"c{i}" for i in range(len(lens))]
+    rows = []
+    for t, ln in enumerate(lens):
+        n = 0 if ln < 10 else ln // 4
+        for p in np.sort(rng.integers(0, ln, n)).tolist():
+            k = rng.integers(0, 8)
+            cs = "150M" if k < 5 else (f"{rng.integers(10, 80)}M{rng.integers(300, 9000)}N{rng.integers(10, 80)}M" if k < 7 else f"{rng.integers(1, 3000)}M")
+            rows.append((0, t, p + 1, 60, cs))
+    rec = model.records_from_tuples(rows, names)
+    tlen = np.array(lens, np.uint32)
+    want = model.accumulate(tlen, rec)
+    world = 3
+    beg, end = assign_ranges(lens, world)
+    iv = []
+    for t, ln in enumerate(lens):
+        if ln < 2:
+            continue
+        iv.append((t, 0, ln))
+        for s in range(0, ln, 9_000):
+            iv.append((t, s, min(ln, s + 9_000)))
+    it = np.array([x[0] for x in iv], np.int32); s0 = np.array([x[1] for x in iv], np.int32); e0 = np.array([x[2] for x in iv], np.int32)
+    bam = None
+    if style == "device_decode":
+        import subprocess
+        from tests import bgzf_util as bu
+        sam = str(tmp_path / "r.sam")
+        with open(sam, "w") as fh:
+            fh.write("@HD\tVN:1.6\tSO:coordinate\n" + "".join(f"@SQ\tSN:{n}\tLN:{l}\n" for n, l in zip(names, lens)))
+            for fl, t, p1, mq, cs in rows:
+                fh.write(f"r\t{fl}\t{names[t]}\t{p1}\t{mq}\t{cs}\t*\t0\t0\t*\t*\n")
+        bampath = str(tmp_path / "r.bam")
+        subprocess.run([os.path.join(ROOT, "oracle", "_ref", "bamgen"), "-I", sam, "-o", bampath], check=True)
+        bam = open(bampath, "rb").read()
+    cov_sum = np.zeros(len(iv), np.uint64); tot_sum = np.zeros(len(iv), np.uint64)
+    depth_sum = [np.zeros(int(n), np.uint64) for n in lens]
+    for r in range(world):
+        with pd.Engine(tlen, own_beg=beg[r], own_end=end[r]) as eng:
+            eng.set_reduce_hint(1, 0xFFFFFFFF)
+            if style == "sorted":
+                _push_all(eng, rec, True, 1)
+            elif style == "chunked":
+                _push_all(eng, rec, True, 11)
+            elif style == "unsorted":
+                _push_all(eng, rec.select(rng.permutation(rec.n)), False, 2)
+            else:
+                from tests import bgzf_util as bu
+                raw, first, recs, _ = bu.bam_payload(bam)
+                tab = bu.block_table(bam)
+                acc = 0; b0 = 0
+                while b0 < tab.size and acc + int(tab["out_len"][b0]) <= first:
+                    acc += int(tab["out_len"][b0]); b0 += 1
+                buf = np.frombuffer(bam, np.uint8)
+                for a in range(b0, tab.size, 5):
+                    eng.push_bgzf(buf, tab[a:a + 5].copy(), first_skip=(first - acc) if a == b0 else 0, flags=pd.PD_ASYNC)
+            cov, tot = eng.reduce(it, s0, e0, 1, 0xFFFFFFFF)
+            cov_sum += cov; tot_sum += tot
+            for t, ln in enumerate(lens):
+                if ln == 0:
+                    continue
+                d = eng.depth(t)
+                lo, hi = int(beg[r, t]), int(end[r, t])
+                assert not d[:lo].any() and not d[max(hi, lo):].any(), (style, r, t, "depth outside the owned range")
+                depth_sum[t] += d
+            with pytest.raises(pd.PDError):
+                t_part = next(t for t in range(len(lens)) if 0 < int(end[r, t]) - int(beg[r, t]) < lens[t])
+                eng.reduce_windows(t_part, 0, 100, 10)
+    for t in range(len(lens)):
+        assert np.array_equal(depth_sum[t], want[t].astype(np.uint64)), (style, t)
+    for k, (t, a, b) in enumerate(iv):
+        co, so = model.reduce_intervals(want[t], [a], [b], 1, 0xFFFFFFFF)
+        assert (int(cov_sum[k]), int(tot_sum[k])) == (int(co[0]), int(so[0])), (style, iv[k])

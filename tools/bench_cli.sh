@@ -2,11 +2,11 @@
 # real end-to-end: pandepth (ours) vs the reference binary on the same BAM, decode included, whole-process wall time.
 # usage: bench_cli.sh <genome_mb> <flavour A|B> [extra args...]     env: REPS (3), THREADS ("16"), REF_T (52)
 MB=${1:-300}; FL=${2:-A}; shift 2
-D=/tmp/pdcli_${MB}_${FL}; mkdir -p $D gpurun_out
+D=/tmp/pdcliP_${MB}_${FL}; mkdir -p $D gpurun_out
 L=$((MB*1000000/9)); SPEC=""; for i in 1 2 3 4 5 6 7 8 9; do SPEC="$SPEC,chr$i:$L"; done; SPEC=${SPEC:1}
 READS=$((MB*1000000*50/150))
 if [ ! -f $D/s.bam.bai ]; then
-  t0=$(date +%s.%N); oracle/_ref/bamgen -o $D/s.bam -c $SPEC -n $READS -s 7 -t 16 $([ $FL = B ] && echo -q); t1=$(date +%s.%N)
+  t0=$(date +%s.%N); oracle/_ref/bamgen -P -o $D/s.bam -c $SPEC -n $READS -s 7 -t 16 $([ $FL = B ] && echo -q); t1=$(date +%s.%N)
   echo "bamgen: $READS reads, $(du -h $D/s.bam | cut -f1), $(python -c "print('%.1f' % ($t1-$t0))") s"
 fi
 run() { # name cmd...
