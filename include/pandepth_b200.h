@@ -41,6 +41,8 @@ enum {
 #define PD_SORTED 1u   /* records are sorted by pos within each tid (coordinate-sorted BAM order): enables the tile path */
 #define PD_DEVICE 2u   /* every pointer argument is a device pointer on the engine's GPU */
 #define PD_ASYNC  4u   /* host buffers are pinned and stay valid until pd_sync(): copies are not waited for */
+#define PD_READY  8u   /* with PD_DEVICE: the arrays are complete NOW (not merely ordered by the engine's stream), so the engine may
+                          index the batch on a side stream while earlier batches are still being accumulated */
 
 /* Create an engine on CUDA device `device` for the BAM header's targets (sam_hdr_t::target_len,
  * read at PanDepth.cpp:684).  `owned` (nullable) selects the contigs this engine accumulates (multi-GPU

@@ -44,9 +44,10 @@ __host__ __device__ __forceinline__ uint64_t bz_cig_base(uint64_t out_off, uint3
 
 constexpr int BZ_LIT_BITS = 10, BZ_DIST_BITS = 8;
 constexpr int BZ_WPC = 8;            // warps (decoders) per CTA
+constexpr uint16_t BZ_MISS = 0xffffu;
 
 struct BzTables {                    // per warp, shared memory
-    uint16_t lit_fast[1 << BZ_LIT_BITS];     // (symbol << 4) | code length, 0 = longer than the table
+    uint16_t lit_fast[1 << BZ_LIT_BITS];     // (symbol << 4) | code length; BZ_MISS = code longer than the table.  A literal hit is e < 4096.
     uint16_t dist_fast[1 << BZ_DIST_BITS];
     uint16_t lit_sym[288];                   // symbols in canonical code order
     uint16_t dist_sym[32];
@@ -67,31 +68,31 @@ struct BzArgs {
 };
 
 // ---- bit reader over aligned 32-bit words (lane 0 only) -----------------------------------------------------------
+// A 64-bit window (lo = word k, hi = word k+1) and a bit offset sh < 32 into it: peek32() is ONE funnel shift and always
+// returns 32 valid bits, dropping bits is one add, and a refill (every >= 3 symbols) slides the window by a word.
+// (The first version kept a 64-bit buffer: two 64-bit shifts + a counter update per symbol, 36 warp instructions per
+// literal on SEQ+QUAL data -- the kernel is issue-bound, so the instruction count IS the throughput.)
 struct BzBits {
-    const uint32_t *w; uint32_t wi, wlimit; uint64_t buf; int cnt; int mis;
+    const uint32_t *w; uint32_t wi, wlimit; uint32_t lo, hi; uint32_t sh; int mis;
+    __device__ __forceinline__ uint32_t word(uint32_t i) const { return i < wlimit ? w[i] : 0u; }   // beyond the stream: zeros
     __device__ __forceinline__ void init(const uint8_t *p, uint32_t n)
     {
         mis = (int)((uintptr_t)p & 3);
         w = reinterpret_cast<const uint32_t *>(p - mis);
-        wlimit = (uint32_t)((mis + n + 3) >> 2);                 // words holding stream bytes; beyond them zeros are fed
-        buf = (uint64_t)(wlimit ? w[0] : 0u) >> (8 * mis);
-        cnt = 32 - 8 * mis; wi = 1;
+        wlimit = (uint32_t)((mis + n + 3) >> 2);                 // words holding stream bytes
+        lo = word(0); hi = word(1); wi = 2; sh = 8u * (uint32_t)mis;
     }
-    __device__ __forceinline__ void refill()                      // >= 33 valid bits afterwards
-    {
-        if (cnt <= 32) { const uint32_t x = wi < wlimit ? w[wi] : 0u; buf |= (uint64_t)x << cnt; wi++; cnt += 32; }
-    }
-    __device__ __forceinline__ uint32_t peek(int n) const { return (uint32_t)buf & ((1u << n) - 1u); }
-    __device__ __forceinline__ void drop(int n) { buf >>= n; cnt -= n; }
-    __device__ __forceinline__ uint32_t bits(int n) { refill(); const uint32_t v = peek(n); drop(n); return v; }
-    // bytes of the stream consumed so far (rounded up to whole bytes)
-    __device__ __forceinline__ int64_t consumed_bits() const { return (int64_t)wi * 32 - 8 * mis - cnt; }
+    __device__ __forceinline__ void norm() { if (sh >= 32u) { lo = hi; hi = word(wi); wi++; sh -= 32u; } }   // sh < 64 on entry
+    __device__ __forceinline__ uint32_t peek32() const { return __funnelshift_r(lo, hi, sh); }               // needs sh < 32
+    __device__ __forceinline__ void drop(uint32_t n) { sh += n; }                                            // then norm() before the next peek
+    __device__ __forceinline__ uint32_t bits(int n) { norm(); const uint32_t v = peek32() & ((1u << n) - 1u); sh += (uint32_t)n; return v; }   // n <= 16
+    __device__ __forceinline__ int64_t consumed_bits() const { return ((int64_t)wi - 2) * 32 + (int64_t)sh - 8 * mis; }
+    __device__ __forceinline__ void align_byte() { sh = (sh + 7u) & ~7u; }
     __device__ __forceinline__ void seek_bytes(uint32_t byte_pos)  // continue at stream byte `byte_pos`
     {
         const uint32_t a = (uint32_t)mis + byte_pos;
-        wi = a >> 2;
-        const int sh = (int)(a & 3) * 8;
-        buf = (uint64_t)(wi < wlimit ? w[wi] : 0u) >> sh; cnt = 32 - sh; wi++;
+        const uint32_t idx = a >> 2;
+        lo = word(idx); hi = word(idx + 1); wi = idx + 2; sh = (a & 3u) * 8u;
     }
 };
 
@@ -101,7 +102,7 @@ __device__ __forceinline__ int bz_build(const uint8_t *lens, int n, uint32_t *cn
                                         uint32_t *aux, int lane)
 {
     if (lane < 16) cnt[lane] = 0;
-    for (int i = lane; i < (1 << fast_bits); i += 32) fast[i] = 0;
+    for (int i = lane; i < (1 << fast_bits); i += 32) fast[i] = BZ_MISS;
     __syncwarp();
     for (int s = lane; s < n; s += 32) atomicAdd(&cnt[lens[s]], 1u);
     __syncwarp();
@@ -148,15 +149,16 @@ __device__ __forceinline__ int bz_build(const uint8_t *lens, int n, uint32_t *cn
 // one symbol (lane 0): first-level hit, else canonical bit-by-bit decode (RFC 1951 3.2.2)
 __device__ __forceinline__ int bz_symbol(BzBits &br, const uint32_t *cnt, const uint16_t *sym, const uint16_t *fast, int fast_bits)
 {
-    br.refill();
-    const uint16_t e = fast[br.peek(fast_bits)];
-    if (e) { br.drop(e & 15); return e >> 4; }
+    br.norm();
+    const uint32_t b32 = br.peek32();
+    const uint16_t e = fast[b32 & ((1u << fast_bits) - 1u)];
+    if (e != BZ_MISS) { br.drop(e & 15u); return e >> 4; }
     int code = 0, first = 0, index = 0;
-    uint64_t b = br.buf;
+    uint32_t b = b32;
     for (int l = 1; l < 16; l++) {
-        code |= (int)(b & 1); b >>= 1;
+        code |= (int)(b & 1u); b >>= 1;
         const int c = (int)cnt[l];
-        if (code - c < first) { br.drop(l); return sym[index + (code - first)]; }
+        if (code - c < first) { br.drop((uint32_t)l); return sym[index + (code - first)]; }
         index += c; first += c; first <<= 1; code <<= 1;
     }
     return -1;
@@ -187,7 +189,7 @@ __device__ __forceinline__ int bz_inflate(const uint8_t *in, uint32_t in_len, ui
         if (type == 0) {                                         // stored block: copied by all lanes
             uint32_t n = 0, p = 0; int bad = 0;
             if (lane == 0) {
-                br.drop(br.cnt & 7);
+                br.align_byte();
                 n = br.bits(16); const uint32_t nn = br.bits(16);
                 if ((n ^ nn) != 0xffffu) bad = 1;
                 p = (uint32_t)(br.consumed_bits() >> 3);         // byte position of the payload in the stream
@@ -253,22 +255,22 @@ __device__ __forceinline__ int bz_inflate(const uint8_t *in, uint32_t in_len, ui
                 uint32_t mlen = 0, dist = 0;
                 if (lane == 0) {
                     for (;;) {
-                        // one refill leaves >= 33 bits: enough for three first-level literal hits (<= 10 bits each) in a row
-                        br.refill();
-                        uint16_t e = T.lit_fast[br.peek(BZ_LIT_BITS)];
-                        if (e && e < (256u << 4)) {
-                            if (o >= out_cap) { cmd = 3; break; }
-                            br.drop(e & 15); out[o++] = (uint8_t)(e >> 4);
-                            e = T.lit_fast[br.peek(BZ_LIT_BITS)];
-                            if (e && e < (256u << 4)) {
-                                if (o >= out_cap) { cmd = 3; break; }
-                                br.drop(e & 15); out[o++] = (uint8_t)(e >> 4);
-                                e = T.lit_fast[br.peek(BZ_LIT_BITS)];
-                                if (e && e < (256u << 4)) {
-                                    if (o >= out_cap) { cmd = 3; break; }
-                                    br.drop(e & 15); out[o++] = (uint8_t)(e >> 4);
-                                }
-                            }
+                        // 32 window bits hold three first-level literal hits (<= 10 bits each): one funnel shift, then 32-bit
+                        // shifts; the output bound is checked once per group (a group writes at most 3 bytes)
+                        br.norm();
+                        uint32_t wnd = br.peek32();
+                        uint32_t e = T.lit_fast[wnd & ((1u << BZ_LIT_BITS) - 1u)];
+                        if (e < 4096u && o + 3u <= out_cap) {
+                            uint32_t used = e & 15u;
+                            out[o] = (uint8_t)(e >> 4); wnd >>= used;
+                            e = T.lit_fast[wnd & ((1u << BZ_LIT_BITS) - 1u)];
+                            if (e < 4096u) {
+                                out[o + 1] = (uint8_t)(e >> 4); wnd >>= (e & 15u); used += e & 15u;
+                                e = T.lit_fast[wnd & ((1u << BZ_LIT_BITS) - 1u)];
+                                if (e < 4096u) { out[o + 2] = (uint8_t)(e >> 4); used += e & 15u; o += 3; }
+                                else o += 2;
+                            } else o += 1;
+                            br.drop(used);
                             continue;
                         }
                         int s = bz_symbol(br, T.lit_cnt, T.lit_sym, T.lit_fast, BZ_LIT_BITS);
@@ -299,6 +301,7 @@ __device__ __forceinline__ int bz_inflate(const uint8_t *in, uint32_t in_len, ui
                 // byte o+k of a match equals byte o-dist+(k mod dist): every source lies before o, so all lanes copy at once
                 const uint8_t *src = out + o - dist;
                 if (dist >= mlen) { for (uint32_t k = lane; k < mlen; k += 32) out[o + k] = src[k]; }
+                else if (mlen <= 2u * dist) { for (uint32_t k = lane; k < mlen; k += 32) out[o + k] = src[k >= dist ? k - dist : k]; }   // one wrap at most
                 else { for (uint32_t k = lane; k < mlen; k += 32) out[o + k] = src[k % dist]; }
                 o += mlen;
                 __syncwarp();

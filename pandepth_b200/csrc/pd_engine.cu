@@ -16,7 +16,9 @@
 #include <nvtx3/nvToolsExt.h>      // header-only NVTX v3: ranges show up in nsys / ncu timelines, no-ops without a tool attached
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -78,7 +80,10 @@ struct pd_engine {
     uint32_t *d_depth = nullptr, *d_delta = nullptr;
     uint8_t *d_seg_state = nullptr;
     uint64_t *d_off = nullptr; uint32_t *d_tlen = nullptr, *d_org = nullptr;     // d_tlen holds the OWNED lengths
-    uint32_t *d_lo = nullptr, *d_hi = nullptr, *d_coarse = nullptr; size_t cut_cap = 0;
+    // per-batch cut arrays, double-buffered: the cut kernels of batch k+1 run on cut_stream under batch k's tile kernel
+    struct CutBuf { uint32_t *lo = nullptr, *hi = nullptr, *coarse = nullptr; size_t cap = 0; cudaEvent_t ready = nullptr, released = nullptr; bool used = false; };
+    CutBuf cut[2]; int cut_next = 0;
+    cudaStream_t cut_stream = nullptr; cudaEvent_t cut_input = nullptr;
     int *d_flags = nullptr;          // [0] err bits, [1] delta_used
     uint32_t *d_part_cov = nullptr; unsigned long long *d_part_sum = nullptr;   // per-segment reduce partials (hint)
     bool hint_on = false; uint32_t hint_min_dep = 1, hint_mask = 0xFFFFFFFFu;
@@ -152,19 +157,23 @@ int drain_profile(pd_engine *e)
     return PD_OK;
 }
 
-int ensure_cut(pd_engine *e, size_t nseg)
+int ensure_cut(pd_engine *e, pd_engine::CutBuf &c, size_t nseg)
 {
-    if (nseg <= e->cut_cap) return PD_OK;
-    if (e->d_lo) { CK(cudaStreamSynchronize(e->stream)); cudaFree(e->d_lo); cudaFree(e->d_hi); cudaFree(e->d_coarse); e->d_lo = e->d_hi = e->d_coarse = nullptr; }
+    if (!c.ready) { CK(cudaEventCreateWithFlags(&c.ready, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&c.released, cudaEventDisableTiming)); }
+    if (nseg <= c.cap) return PD_OK;
+    if (c.lo) { CK(cudaStreamSynchronize(e->stream)); CK(cudaStreamSynchronize(e->cut_stream)); cudaFree(c.lo); cudaFree(c.hi); cudaFree(c.coarse); c.lo = c.hi = c.coarse = nullptr; }
     size_t cap = nseg + nseg / 4 + 1024;
-    CK(cudaMalloc(&e->d_lo, cap * 4)); CK(cudaMalloc(&e->d_hi, cap * 4)); CK(cudaMalloc(&e->d_coarse, (cap / pdk::CUT_COARSE + 2) * 4));
-    e->cut_cap = cap;
+    CK(cudaMalloc(&c.lo, cap * 4)); CK(cudaMalloc(&c.hi, cap * 4)); CK(cudaMalloc(&c.coarse, (cap / pdk::CUT_COARSE + 2) * 4));
+    c.cap = cap;
     return PD_OK;
 }
 
 // Queue the kernels for one contig batch whose arrays are on the device.  seg range [seg_a, seg_b].
+// input_ready: the event after which the batch's arrays are complete (a copy / decode on another stream); nullptr = they are
+// ordered by the main stream (a caller's device batch), unless ready_now says they are complete already (PD_READY).
 int run_batch(pd_engine *e, int32_t tid, uint32_t n, const int32_t *pos, const uint16_t *flag, const uint8_t *mapq,
-              const uint32_t *cigar_off, const uint32_t *cigar, bool sorted, int64_t seg_a, int64_t seg_b)
+              const uint32_t *cigar_off, const uint32_t *cigar, bool sorted, int64_t seg_a, int64_t seg_b,
+              cudaEvent_t input_ready = nullptr, bool ready_now = false)
 {
     const uint64_t off = e->off[tid];
     if (e->delta_stale) {            // a batch after a scan (rare): both paths may write deltas, so the consumed ones go first
@@ -173,23 +182,32 @@ int run_batch(pd_engine *e, int32_t tid, uint32_t n, const int32_t *pos, const u
     }
     if (sorted) {
         const int32_t nseg = (int32_t)(seg_b - seg_a + 1);
-        int rc = ensure_cut(e, (size_t)nseg + 1); if (rc) return rc;
-        pdk::CutArgs c{pos, n, (int32_t)seg_a, nseg, e->d_lo, e->d_hi, (int64_t)e->org[tid]};
+        // The cut kernels (binary searches: pure latency, a handful of CTAs) run on their own stream: they only need the batch's
+        // positions (whatever the main stream had queued when this call was made) and a free pair of cut arrays, so they
+        // overlap the previous batch's tile kernel instead of sitting between two tile kernels.
+        pd_engine::CutBuf &cb = e->cut[e->cut_next]; e->cut_next ^= 1;
+        int rc = ensure_cut(e, cb, (size_t)nseg + 1); if (rc) return rc;
+        pdk::CutArgs c{pos, n, (int32_t)seg_a, nseg, cb.lo, cb.hi, (int64_t)e->org[tid]};
         const int32_t ncoarse = (nseg + pdk::CUT_COARSE - 1) / pdk::CUT_COARSE;
-        rc = launch(e, K_CUT, [&] {
-            pdk::k_cut_coarse<<<(ncoarse + 127) / 128, 128, 0, e->stream>>>(c, e->d_coarse, ncoarse);
-            pdk::k_cut<<<(nseg + 1 + 255) / 256, 256, 0, e->stream>>>(c, e->d_coarse, ncoarse);
+        if (input_ready) CK(cudaStreamWaitEvent(e->cut_stream, input_ready, 0));
+        else if (!ready_now) { CK(cudaEventRecord(e->cut_input, e->stream)); CK(cudaStreamWaitEvent(e->cut_stream, e->cut_input, 0)); }
+        if (cb.used) CK(cudaStreamWaitEvent(e->cut_stream, cb.released, 0));      // the tile kernel that last read these arrays
+        rc = launch_on(e, e->cut_stream, K_CUT, [&] {
+            pdk::k_cut_coarse<<<(ncoarse + 127) / 128, 128, 0, e->cut_stream>>>(c, cb.coarse, ncoarse);
+            pdk::k_cut<<<(nseg + 1 + 255) / 256, 256, 0, e->cut_stream>>>(c, cb.coarse, ncoarse);
         });
         if (rc) return rc;
         e->stats.kernel_launches++;
+        CK(cudaEventRecord(cb.ready, e->cut_stream));
+        CK(cudaStreamWaitEvent(e->stream, cb.ready, 0));
         if (e->org[tid] != 0 && seg_a == 0) {
             // range sharding: reads that start more than HALO bases left of the owned range are seen by no segment; the ones
             // among them that reach into the range are the first lo[0] reads of the batch (a device-side count, usually 0)
             pdk::ScatterArgs sp{pos, cigar, cigar_off, flag, mapq, n, (int32_t)e->elen[tid], e->d_delta + off, e->xflags, e->min_mapq,
-                                (int32_t)e->org[tid], e->d_lo, e->d_flags + 1};
+                                (int32_t)e->org[tid], cb.lo, e->d_flags + 1};
             rc = launch(e, K_SCATTER, [&] { pdk::k_delta_scatter<<<148, 256, 0, e->stream>>>(sp); }); if (rc) return rc;
         }
-        pdk::TileArgs t{pos, cigar, cigar_off, flag, mapq, e->d_lo, e->d_hi, n, (int32_t)seg_a, nseg, (int32_t)e->elen[tid],
+        pdk::TileArgs t{pos, cigar, cigar_off, flag, mapq, cb.lo, cb.hi, n, (int32_t)seg_a, nseg, (int32_t)e->elen[tid],
                         e->d_depth + off, e->d_delta + off, e->d_seg_state + off / pdk::SEG, e->xflags, e->min_mapq,
                         e->d_flags, e->d_flags + 1,
                         e->hint_on ? 1u : 0u, e->hint_min_dep, e->hint_mask, e->d_part_cov + off / pdk::SEG, e->d_part_sum + off / pdk::SEG,
@@ -202,6 +220,7 @@ int run_batch(pd_engine *e, int32_t tid, uint32_t n, const int32_t *pos, const u
             else { if (has_filter) pdk::k_tile_accumulate<false, true><<<grid, blk, smem, e->stream>>>(t); else pdk::k_tile_accumulate<false, false><<<grid, blk, smem, e->stream>>>(t); }
         });
         if (rc) return rc;
+        CK(cudaEventRecord(cb.released, e->stream)); cb.used = true;
         e->stats.tile_path_batches++;
     } else {
         pdk::ScatterArgs s{pos, cigar, cigar_off, flag, mapq, n, (int32_t)e->elen[tid], e->d_delta + off, e->xflags, e->min_mapq,
@@ -362,7 +381,7 @@ int bz_finish(pd_engine *e, BzSlot &s)
         int64_t seg_a = std::min<int64_t>(p0 / pdk::SEG, max_seg), seg_b = std::min<int64_t>((p1 + pdk::HALO) / pdk::SEG, max_seg);
         if (seg_b < seg_a) seg_b = seg_a;
         return run_batch(e, t, cur.r1 - cur.r0, s.pos + cur.r0, nullptr, nullptr, single_op ? nullptr : s.coff + cur.r0,
-                         single_op ? s.cig + cur.r0 : s.cig, true, seg_a, seg_b);
+                         single_op ? s.cig + cur.r0 : s.cig, true, seg_a, seg_b, s.decoded);
     };
     auto flush_irr = [&]() -> int {
         if (!irr_open) return PD_OK;
@@ -419,7 +438,10 @@ void pd_destroy(pd_engine *e)
     cudaDeviceSynchronize();
     for (auto &p : e->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     cudaFree(e->d_depth); cudaFree(e->d_delta); cudaFree(e->d_seg_state); cudaFree(e->d_off); cudaFree(e->d_tlen);
-    cudaFree(e->d_lo); cudaFree(e->d_hi); cudaFree(e->d_coarse); cudaFree(e->d_flags); cudaFree(e->d_desc); cudaFree(e->d_counter);
+    for (auto &c : e->cut) { cudaFree(c.lo); cudaFree(c.hi); cudaFree(c.coarse); if (c.ready) cudaEventDestroy(c.ready); if (c.released) cudaEventDestroy(c.released); }
+    if (e->cut_stream) cudaStreamDestroy(e->cut_stream);
+    if (e->cut_input) cudaEventDestroy(e->cut_input);
+    cudaFree(e->d_flags); cudaFree(e->d_desc); cudaFree(e->d_counter);
     cudaFree(e->d_red); cudaFree(e->d_part_cov); cudaFree(e->d_part_sum);
     for (auto &s : e->slot) {
         cudaFree(s.pos); cudaFree(s.cigar); cudaFree(s.cigar_off); cudaFree(s.flag); cudaFree(s.mapq);
@@ -480,12 +502,22 @@ pd_engine *pd_create_ranges(int device, int n_targets, const uint32_t *target_le
     if (total == 0) total = PAD_ELEMS;
     e->total = total; e->n_seg = total / pdk::SEG;
     cudaError_t ce;
+    const bool timing = getenv("PANDEPTH_TIMING") != nullptr;           // phase times of the engine start-up on stderr
+    const auto t_start = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (timing) fprintf(stderr, "[timing] pd_create: %-28s +%.3f s\n", what, std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count());
+    };
     if ((ce = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", ce);
+    if ((ce = cudaFree(0)) != cudaSuccess) return bail("context", ce);
+    lap("CUDA context");
     if ((ce = cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", ce);
     if ((ce = cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", ce);
+    if ((ce = cudaStreamCreateWithFlags(&e->cut_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", ce);
+    if ((ce = cudaEventCreateWithFlags(&e->cut_input, cudaEventDisableTiming)) != cudaSuccess) return bail("event", ce);
     e->stream = e->own_stream;
     if ((ce = cudaMalloc(&e->d_depth, total * 4)) != cudaSuccess) return bail("cudaMalloc(depth)", ce);
     if ((ce = cudaMalloc(&e->d_delta, total * 4)) != cudaSuccess) return bail("cudaMalloc(delta)", ce);
+    lap("cudaMalloc depth + delta");
     if ((ce = cudaMalloc(&e->d_seg_state, e->n_seg)) != cudaSuccess) return bail("cudaMalloc(seg_state)", ce);
     if ((ce = cudaMalloc(&e->d_off, (size_t)n_targets * 8)) != cudaSuccess) return bail("cudaMalloc", ce);
     if ((ce = cudaMalloc(&e->d_tlen, (size_t)n_targets * 4)) != cudaSuccess) return bail("cudaMalloc", ce);
@@ -520,6 +552,7 @@ pd_engine *pd_create_ranges(int device, int n_targets, const uint32_t *target_le
             e->bz_grid = n_sm * per_sm;
     }
     if ((ce = cudaStreamSynchronize(e->stream)) != cudaSuccess) return bail("sync", ce);
+    lap("tables, memsets, attributes");
     return e;
 }
 
@@ -582,7 +615,7 @@ int pd_push_contig(pd_engine *e, int32_t tid, int64_t n_reads, const int32_t *po
             const uint32_t n = (uint32_t)std::min<int64_t>(0x7fff0000ll, n_reads - b);
             if (cigar_off && b) return fail(e, PD_ERR_ARG, "pd_push_contig: device batches with cigar_off must have < 2^31 reads");
             int rc = run_batch(e, tid, n, pos + b, flag ? flag + b : nullptr, mapq ? mapq + b : nullptr, cigar_off,
-                               cigar_off ? cigar : cigar + b, sorted, 0, max_seg);
+                               cigar_off ? cigar : cigar + b, sorted, 0, max_seg, nullptr, (flags & PD_READY) != 0);
             if (rc) return rc;
         }
         return PD_OK;
@@ -619,7 +652,7 @@ int pd_push_contig(pd_engine *e, int32_t tid, int64_t n_reads, const int32_t *po
         // cigar offsets on the device are absolute: rebase the cigar pointer instead of rewriting them
         const uint32_t *d_cig = cigar_off ? s.cigar - cg0 : s.cigar;
         rc = run_batch(e, tid, (uint32_t)n, s.pos, flag ? s.flag : nullptr, mapq ? s.mapq : nullptr,
-                       cigar_off ? s.cigar_off : nullptr, d_cig, sorted, seg_a, seg_b);
+                       cigar_off ? s.cigar_off : nullptr, d_cig, sorted, seg_a, seg_b, s.copied);
         if (rc) return rc;
         CK(cudaEventRecord(s.consumed, e->stream));
         s.used = true;

@@ -184,6 +184,23 @@ struct TileArgs {
 
 constexpr int TILE_UNROLL = PD_TILE_UNROLL;   // 32-read chunks whose loads are issued together (memory-level parallelism)
 
+#ifndef PD_TILE_BULK
+#define PD_TILE_BULK 0       // 1: flush a finished segment with ONE TMA bulk copy from shared memory (cp.async.bulk, and
+#endif                       //    cp.reduce.async.bulk .add.u32 for a segment that already holds depth) instead of 64 STG.128 per
+                             //    warp; 2: only the add case (no 4 B/base re-read of depth at batch boundaries), first writes
+                             //    stay register stores.  A/B on B200 (cfg2): see DESIGN.md section 3 for the measured outcome.
+
+// TMA 1-D bulk copy shared::cta -> global of one segment (8 KB), issued by one lane; `add` folds into what is there
+__device__ __forceinline__ void bulk_flush_segment(uint32_t *gdst, const uint32_t *ssrc, bool add)
+{
+    const uint32_t sa = (uint32_t)__cvta_generic_to_shared(ssrc);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the generic-proxy stores of the scan are visible to the async proxy
+    if (add) asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.u32 [%0], [%1], %2;" :: "l"(gdst), "r"(sa), "n"(SEG * 4) : "memory");
+    else asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(gdst), "r"(sa), "n"(SEG * 4) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory may be reused / the CTA may retire
+}
+
 template <bool HAS_OFF, bool HAS_FILTER>
 __global__ void __launch_bounds__(WPC * 32, TILE_MIN_CTAS) k_tile_accumulate(TileArgs a)
 {
@@ -402,8 +419,12 @@ __global__ void __launch_bounds__(WPC * 32, TILE_MIN_CTAS) k_tile_accumulate(Til
                 const int b = r * 128 + lane * 4;
                 uint4 v, w;
                 scan_pair(b, v, w);
+#if PD_TILE_BULK == 1
+                *reinterpret_cast<uint4 *>(E + b) = v; *reinterpret_cast<uint4 *>(E + b + 128) = w;
+#else
                 __stcs(reinterpret_cast<uint4 *>(out + b), v);
                 __stcs(reinterpret_cast<uint4 *>(out + b + 128), w);
+#endif
                 pc += nonzero4(v) + nonzero4(w);
                 ps += ((unsigned long long)v.x + v.y + v.z + v.w) + ((unsigned long long)w.x + w.y + w.z + w.w);
             }
@@ -420,11 +441,19 @@ __global__ void __launch_bounds__(WPC * 32, TILE_MIN_CTAS) k_tile_accumulate(Til
                 const int b = r * 128 + lane * 4;
                 uint4 v, w;
                 scan_pair(b, v, w);
+#if PD_TILE_BULK == 1
+                *reinterpret_cast<uint4 *>(E + b) = v; *reinterpret_cast<uint4 *>(E + b + 128) = w;
+#else
                 __stcs(reinterpret_cast<uint4 *>(out + b), v);
                 __stcs(reinterpret_cast<uint4 *>(out + b + 128), w);
+#endif
                 acc(v); acc(w);
             }
         }
+#if PD_TILE_BULK == 1
+        __syncwarp();
+        if (lane == 0) bulk_flush_segment(out, E, false);
+#endif
         pc = __reduce_add_sync(FULL, pc);
 #pragma unroll
         for (int o = 16; o; o >>= 1) ps += __shfl_xor_sync(FULL, ps, o);
@@ -435,11 +464,31 @@ __global__ void __launch_bounds__(WPC * 32, TILE_MIN_CTAS) k_tile_accumulate(Til
             const int b = r * 128 + lane * 4;
             uint4 v, w;
             scan_pair(b, v, w);
+#if PD_TILE_BULK == 1
+            *reinterpret_cast<uint4 *>(E + b) = v; *reinterpret_cast<uint4 *>(E + b + 128) = w;
+#else
             __stcs(reinterpret_cast<uint4 *>(out + b), v);
             __stcs(reinterpret_cast<uint4 *>(out + b + 128), w);
+#endif
         }
+#if PD_TILE_BULK == 1
+        __syncwarp();
+        if (lane == 0) bulk_flush_segment(out, E, false);
+#endif
         if (lane == 0) *st_ptr = 2;
     } else {
+#if PD_TILE_BULK >= 1
+        // the segment already holds depth: the scanned rows are ADDED by the copy engine (no 4 B/base read of depth)
+#pragma unroll 2
+        for (int r = 0; r < SEG / 128; r += 2) {
+            const int b = r * 128 + lane * 4;
+            uint4 v, w;
+            scan_pair(b, v, w);
+            *reinterpret_cast<uint4 *>(E + b) = v; *reinterpret_cast<uint4 *>(E + b + 128) = w;
+        }
+        __syncwarp();
+        if (lane == 0) bulk_flush_segment(out, E, true);
+#else
 #pragma unroll 1
         for (int r = 0; r < SEG / 128; r += 2) {
             const int b = r * 128 + lane * 4;
@@ -451,6 +500,7 @@ __global__ void __launch_bounds__(WPC * 32, TILE_MIN_CTAS) k_tile_accumulate(Til
             w.x += oB.x; w.y += oB.y; w.z += oB.z; w.w += oB.w;
             dst[0] = v; dst[32] = w;
         }
+#endif
         if (lane == 0) *st_ptr = 2;
     }
     bad = __any_sync(FULL, bad || idx_max >= (uint32_t)WIN);

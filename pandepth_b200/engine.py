@@ -7,7 +7,7 @@ from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 
-PD_SORTED, PD_DEVICE, PD_ASYNC = 1, 2, 4
+PD_SORTED, PD_DEVICE, PD_ASYNC, PD_READY = 1, 2, 4, 8
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
