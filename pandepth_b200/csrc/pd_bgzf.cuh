@@ -74,7 +74,9 @@ struct BzArgs {
 // literal on SEQ+QUAL data -- the kernel is issue-bound, so the instruction count IS the throughput.)
 struct BzBits {
     const uint32_t *w; uint32_t wi, wlimit; uint32_t lo, hi; uint32_t sh; int mis;
-    __device__ __forceinline__ uint32_t word(uint32_t i) const { return i < wlimit ? w[i] : 0u; }   // beyond the stream: zeros
+    // beyond the stream every read returns the word just behind it (the chunk buffer is padded): garbage bits there only ever
+    // feed a decode that the consumed_bits() checks reject, and the clamp keeps a corrupt stream from running off the buffer
+    __device__ __forceinline__ uint32_t word(uint32_t i) const { return w[i < wlimit ? i : wlimit]; }
     __device__ __forceinline__ void init(const uint8_t *p, uint32_t n)
     {
         mis = (int)((uintptr_t)p & 3);
@@ -261,13 +263,14 @@ __device__ __forceinline__ int bz_inflate(const uint8_t *in, uint32_t in_len, ui
                         uint32_t wnd = br.peek32();
                         uint32_t e = T.lit_fast[wnd & ((1u << BZ_LIT_BITS) - 1u)];
                         if (e < 4096u && o + 3u <= out_cap) {
+                            uint8_t *op = out + o;                       // one address per group, immediate offsets for the stores
                             uint32_t used = e & 15u;
-                            out[o] = (uint8_t)(e >> 4); wnd >>= used;
+                            op[0] = (uint8_t)(e >> 4); wnd >>= used;
                             e = T.lit_fast[wnd & ((1u << BZ_LIT_BITS) - 1u)];
                             if (e < 4096u) {
-                                out[o + 1] = (uint8_t)(e >> 4); wnd >>= (e & 15u); used += e & 15u;
+                                op[1] = (uint8_t)(e >> 4); wnd >>= (e & 15u); used += e & 15u;
                                 e = T.lit_fast[wnd & ((1u << BZ_LIT_BITS) - 1u)];
-                                if (e < 4096u) { out[o + 2] = (uint8_t)(e >> 4); used += e & 15u; o += 3; }
+                                if (e < 4096u) { op[2] = (uint8_t)(e >> 4); used += e & 15u; o += 3; }
                                 else o += 2;
                             } else o += 1;
                             br.drop(used);

@@ -94,6 +94,7 @@ struct pd_engine {
     cudaStream_t own_stream = nullptr, copy_stream = nullptr, stream = nullptr;
     Slot slot[N_SLOTS]; int next_slot = 0;
     BzSlot bz[N_BZ]; int bz_next = 0;
+    int32_t bz_prog_tid = -1, bz_prog_pos = -1;   // first record of the last block (with records) of the last chunk that was planned
     uint8_t *d_owned = nullptr;
     int bz_grid = 148 * 4;
 
@@ -193,8 +194,8 @@ int run_batch(pd_engine *e, int32_t tid, uint32_t n, const int32_t *pos, const u
         else if (!ready_now) { CK(cudaEventRecord(e->cut_input, e->stream)); CK(cudaStreamWaitEvent(e->cut_stream, e->cut_input, 0)); }
         if (cb.used) CK(cudaStreamWaitEvent(e->cut_stream, cb.released, 0));      // the tile kernel that last read these arrays
         rc = launch_on(e, e->cut_stream, K_CUT, [&] {
-            pdk::k_cut_coarse<<<(ncoarse + 127) / 128, 128, 0, e->cut_stream>>>(c, cb.coarse, ncoarse);
-            pdk::k_cut<<<(nseg + 1 + 255) / 256, 256, 0, e->cut_stream>>>(c, cb.coarse, ncoarse);
+            pdk::k_cut_coarse<<<(ncoarse + pdk::CUT_THREADS - 1) / pdk::CUT_THREADS, pdk::CUT_THREADS, 0, e->cut_stream>>>(c, cb.coarse, ncoarse);
+            pdk::k_cut<<<(nseg + 1 + pdk::CUT_THREADS - 1) / pdk::CUT_THREADS, pdk::CUT_THREADS, 0, e->cut_stream>>>(c, cb.coarse, ncoarse);
         });
         if (rc) return rc;
         e->stats.kernel_launches++;
@@ -412,6 +413,7 @@ int bz_finish(pd_engine *e, BzSlot &s)
     }
     if ((rc = flush_run())) return rc;
     if ((rc = flush_irr())) return rc;
+    for (uint32_t b = s.n_blocks; b-- > 0;) if (sm[b].n_reads) { e->bz_prog_tid = sm[b].first_tid; e->bz_prog_pos = sm[b].first_pos; break; }
     CK(cudaEventRecord(s.consumed, e->stream)); s.out_used = true;
     (void)n_cigar;
     return PD_OK;
@@ -592,6 +594,7 @@ int pd_reset(pd_engine *e)
     e->delta_stale = false;
     e->finalized = false;
     e->pushed_since_reset = false;
+    e->bz_prog_tid = -1; e->bz_prog_pos = -1;
     uint64_t keep = e->stats.hbm_bytes_allocated;
     e->stats = pd_stats{};
     e->stats.hbm_bytes_allocated = keep;
@@ -749,6 +752,13 @@ int pd_push_bgzf(pd_engine *e, const uint8_t *bytes, size_t n_bytes, const pd_bg
         else { BzSlot &oldest = e->bz[e->bz_next]; if (oldest.pending) { rc = bz_finish(e, oldest); if (rc) return rc; } }
     }
     if (!(flags & PD_ASYNC)) CK(cudaStreamSynchronize(e->copy_stream));
+    return PD_OK;
+}
+
+int pd_bgzf_progress(pd_engine *e, int32_t *tid, int32_t *pos)
+{
+    if (!e || !tid || !pos) return PD_ERR_ARG;
+    *tid = e->bz_prog_tid; *pos = e->bz_prog_pos;
     return PD_OK;
 }
 

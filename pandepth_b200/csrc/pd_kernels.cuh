@@ -94,6 +94,8 @@ struct CutArgs {
 };
 
 constexpr int CUT_COARSE = 64;   // segments per coarse search key
+constexpr int CUT_THREADS = 64;  // small CTAs: the cut kernels of batch k+1 run UNDER batch k's tile kernel (own stream) and must fit the
+                                 // few registers three resident tile CTAs leave free on an SM instead of displacing one of them
 
 // lower_bound(pos, n, key) found by galloping outwards from a guess, then bisecting the bracket: O(log distance) probes,
 // all close to the answer (the plain bisection touches ~30 different 32-byte sectors per key).
@@ -123,7 +125,7 @@ __device__ __forceinline__ uint32_t lower_bound_near(const int32_t *pos, uint32_
 // pass A: one thread per CUT_COARSE segments: coarse[k] = lower_bound(pos, (seg0 + k*CUT_COARSE)*SEG - HALO), searched outwards
 // from the position a uniform batch would have it at (a handful of dependent probes instead of the ~27 of a plain bisection
 // over 10^8 reads; any guess gives the same answer -- lower_bound_near is exact)
-__global__ void __launch_bounds__(128) k_cut_coarse(CutArgs a, uint32_t *coarse, int32_t ncoarse)
+__global__ void __launch_bounds__(CUT_THREADS) k_cut_coarse(CutArgs a, uint32_t *coarse, int32_t ncoarse)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= ncoarse) return;
@@ -134,7 +136,7 @@ __global__ void __launch_bounds__(128) k_cut_coarse(CutArgs a, uint32_t *coarse,
 
 // pass B: thread j < nseg: lo[j] = lower_bound(s0_j - HALO) from an interpolated guess inside its coarse bracket, and
 // mid[j] = lower_bound(s0_j) a few reads to its right; thread nseg: mid[nseg].  Segment j's reads are [lo[j], mid[j+1]).
-__global__ void __launch_bounds__(256) k_cut(CutArgs a, const uint32_t *coarse, int32_t ncoarse)
+__global__ void __launch_bounds__(CUT_THREADS) k_cut(CutArgs a, const uint32_t *coarse, int32_t ncoarse)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j > a.nseg) return;
@@ -185,10 +187,12 @@ struct TileArgs {
 constexpr int TILE_UNROLL = PD_TILE_UNROLL;   // 32-read chunks whose loads are issued together (memory-level parallelism)
 
 #ifndef PD_TILE_BULK
-#define PD_TILE_BULK 0       // 1: flush a finished segment with ONE TMA bulk copy from shared memory (cp.async.bulk, and
-#endif                       //    cp.reduce.async.bulk .add.u32 for a segment that already holds depth) instead of 64 STG.128 per
-                             //    warp; 2: only the add case (no 4 B/base re-read of depth at batch boundaries), first writes
-                             //    stay register stores.  A/B on B200 (cfg2): see DESIGN.md section 3 for the measured outcome.
+#define PD_TILE_BULK 2       // TMA 1-D bulk flush of a finished segment from shared memory.  Measured on B200 (tools/bench_tile.py,
+#endif                       // one cfg2 contig, profiles/r02_tile_ab.txt):
+                             //   0  register stores; a segment that already holds depth is load+add+store   first write 0.455 ms, add pass 0.652 ms
+                             //   1  cp.async.bulk for first writes too (8 KB shared -> global per segment)    first write 0.478 ms, add pass 0.550 ms
+                             //   2  (default) first writes stay register stores; segments that already hold depth are ADDED by the copy
+                             //      engine (cp.reduce.async.bulk .add.u32): no 4 B/base re-read of depth         first write 0.457 ms, add pass 0.550 ms
 
 // TMA 1-D bulk copy shared::cta -> global of one segment (8 KB), issued by one lane; `add` folds into what is there
 __device__ __forceinline__ void bulk_flush_segment(uint32_t *gdst, const uint32_t *ssrc, bool add)

@@ -76,8 +76,10 @@ struct BgzfFeedResult {
 // ends quietly at the last complete block, like the reference's `while (sam_read1(...) >= 0)` loop (:4608).
 // [range_beg, range_end): only the BGZF blocks that START in this byte range of the file are fed (range sharding over GPUs: the
 // offsets come from the .bai, see pdh_bai_block_offset); range_beg = 0 means "from the first record".
+// stop_tid / stop_pos (range sharding, coordinate-sorted files): stop pushing once the engine reports a block whose first
+// record lies at or beyond (stop_tid, stop_pos) -- every read that starts before that position has been pushed by then.
 inline BgzfFeedResult bgzf_feed_file(pd_engine *eng, std::mutex *eng_mu, const std::string &path, int threads, ChunkPool &pool, bool strict_eof = true,
-                                     uint64_t range_beg = 0, uint64_t range_end = UINT64_MAX)
+                                     uint64_t range_beg = 0, uint64_t range_end = UINT64_MAX, int32_t stop_tid = INT32_MAX, int32_t stop_pos = INT32_MAX)
 {
     BgzfFeedResult res;
     uint32_t first_skip = 0;
@@ -198,6 +200,11 @@ inline BgzfFeedResult bgzf_feed_file(pd_engine *eng, std::mutex *eng_mu, const s
                 // the engine has finished reading the bytes of a chunk once PD_BGZF_DEPTH later pushes have returned
                 while (!in_flight.empty() && in_flight.front().first + PD_BGZF_DEPTH <= push_seq) { pool.release(in_flight.front().second); in_flight.pop_front(); }
                 res.bytes += got; res.pieces++; res.blocks += blocks.size();
+                if (rc == PD_OK && stop_tid != INT32_MAX) {
+                    int32_t pt = -1, pp = -1;
+                    pd_bgzf_progress(eng, &pt, &pp);
+                    if (pt > stop_tid || (pt == stop_tid && pp >= stop_pos)) next.store(n_pieces);     // no further pieces: the rest belongs to others
+                }
                 if (rc != PD_OK) {
                     // this chunk or an earlier one: depth already accumulated cannot be taken back piecewise, the caller starts over
                     const std::string m = std::string("pd_push_bgzf: ") + pd_last_error(eng);

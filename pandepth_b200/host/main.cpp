@@ -295,6 +295,24 @@ struct Totals { uint64_t len = 0, cov = 0, depth = 0; };     // SS_Len, SS_Cov, 
 
 bool engine_error(pd_engine *eng) { std::cerr << "Error: " << pd_last_error(eng) << std::endl; return false; }
 
+// One engine, or several that own disjoint genomic ranges (PANDEPTH_DEVICES, range sharding): interval results add up.
+struct Engines {
+    std::vector<pd_engine *> v;
+    pd_engine *first() const { return v[0]; }
+    pd_engine *failed = nullptr;
+    bool reduce(int64_t n_iv, const int32_t *tid, const int32_t *s0, const int32_t *e0, uint32_t min_dep, uint32_t mask, uint64_t *cov, uint64_t *sum)
+    {
+        if (v.size() == 1) { if (pd_reduce(v[0], n_iv, tid, s0, e0, min_dep, mask, cov, sum, 0) != PD_OK) { failed = v[0]; return false; } return true; }
+        std::vector<uint64_t> c((size_t)n_iv), d((size_t)n_iv);
+        std::fill(cov, cov + n_iv, 0); std::fill(sum, sum + n_iv, 0);
+        for (pd_engine *e : v) {
+            if (pd_reduce(e, n_iv, tid, s0, e0, min_dep, mask, c.data(), d.data(), 0) != PD_OK) { failed = e; return false; }
+            for (int64_t i = 0; i < n_iv; i++) { cov[i] += c[(size_t)i]; sum[i] += d[(size_t)i]; }
+        }
+        return true;
+    }
+};
+
 // -a per-site dump (:4264-4284): D2H in 4 M-base pieces, rows formatted + compressed by the thread pool
 bool write_site_depth(pd_engine *eng, const std::string &path, const std::vector<Target> &targets, const GeneMap &genes, int threads)
 {
@@ -345,7 +363,7 @@ bool report_windows(pd_engine *eng, GzWriter &out, const Options &o, const std::
 // mode 5 (-w >= 150): the pseudo-gene tiles are enumerated arithmetically (pd_host.hpp n_tiles) -- one pd_reduce over all of
 // them, rows formatted and compressed in parallel.  Same rows, same order (GeneStart) and same totals as report_genes would
 // produce from materialised genes (:5080-5118); every tile counts exactly once (pd_host.hpp).
-bool report_tiles(pd_engine *eng, GzWriter &out, const Options &o, const std::vector<Target> &targets, const GeneMap &genes, uint32_t mask, Totals &tot)
+bool report_tiles(Engines &engs, GzWriter &out, const Options &o, const std::vector<Target> &targets, const GeneMap &genes, uint32_t mask, Totals &tot)
 {
     const long long W = o.tile_win;
     std::vector<int> tids;
@@ -362,7 +380,7 @@ bool report_tiles(pd_engine *eng, GzWriter &out, const Options &o, const std::ve
         }
     }
     std::vector<uint64_t> cov(n_iv), sum(n_iv);
-    if (pd_reduce(eng, (int64_t)n_iv, iv_t.data(), iv_s.data(), iv_e.data(), (uint32_t)o.min_dep, mask, cov.data(), sum.data(), 0) != PD_OK) return engine_error(eng);
+    if (!engs.reduce((int64_t)n_iv, iv_t.data(), iv_s.data(), iv_e.data(), (uint32_t)o.min_dep, mask, cov.data(), sum.data())) return engine_error(engs.failed);
     for (size_t ci = 0; ci < tids.size(); ci++) {
         const long long len = targets[(size_t)tids[ci]].len, nt = n_tiles(len, W);
         const std::string &chr = targets[(size_t)tids[ci]].name;
@@ -383,7 +401,7 @@ bool report_tiles(pd_engine *eng, GzWriter &out, const Options &o, const std::ve
 
 // modes 0-4: every CDS interval of every gene in one pd_reduce call (StatChrDepthWin / StatChrDepthLowMEM), then one row per
 // contig (mode 0, :5051-5079) or per gene (:5011-5050), rows ordered by (tid, GeneStart, GeneID)
-bool report_genes(pd_engine *eng, GzWriter &out, const Options &o, const std::vector<Target> &targets, GeneMap &genes, const RegionsByContig &merged,
+bool report_genes(Engines &engs, GzWriter &out, const Options &o, const std::vector<Target> &targets, GeneMap &genes, const RegionsByContig &merged,
                   int mode, bool whole, uint32_t mask, Totals &tot)
 {
     std::vector<int32_t> iv_t, iv_s, iv_e;
@@ -397,7 +415,7 @@ bool report_genes(pd_engine *eng, GzWriter &out, const Options &o, const std::ve
         }
     }
     std::vector<uint64_t> cov(iv_t.size()), sum(iv_t.size());
-    if (pd_reduce(eng, (int64_t)iv_t.size(), iv_t.data(), iv_s.data(), iv_e.data(), (uint32_t)o.min_dep, mask, cov.data(), sum.data(), 0) != PD_OK) return engine_error(eng);
+    if (!engs.reduce((int64_t)iv_t.size(), iv_t.data(), iv_s.data(), iv_e.data(), (uint32_t)o.min_dep, mask, cov.data(), sum.data())) return engine_error(engs.failed);
     for (size_t i = 0; i < iv_g.size(); i++) { iv_g[i]->cover += (int64_t)cov[i]; iv_g[i]->depth += sum[i]; }
 
     std::vector<int> tids;
@@ -435,6 +453,69 @@ bool report_genes(pd_engine *eng, GzWriter &out, const Options &o, const std::ve
     });
     for (size_t ci = 0; ci < tids.size(); ci++) { tot.len += pL[ci]; tot.cov += pC[ci]; tot.depth += pD[ci]; }
     return true;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// several GPUs in one process (PANDEPTH_DEVICES=0,1,...): range sharding
+// ---------------------------------------------------------------------------------------------------------------
+// The concatenated genome (the contigs that carry regions) is cut into equal ranges, one engine per device owns one range
+// (pd_create_ranges) and decodes, through the .bai, the part of the file that can hold reads overlapping it: from the
+// first read overlapping its first base up to the first block that starts behind its last base (pd_bgzf_progress).
+// Boundary blocks go to both neighbours; the engines clip.  Returns the engines (empty: not handled, e.g. a file the device
+// decoder cannot take -- the caller continues on one GPU).
+std::vector<pd_engine *> feed_multi_gpu(const Options &o, const std::string &path, const std::vector<int> &devices, const std::vector<uint32_t> &tlen,
+                                        const std::vector<uint8_t> &owned, uint32_t hint_min_dep, uint32_t hint_mask, bool hint, Timer &tm, std::string &err)
+{
+    const size_t K = devices.size(), T = tlen.size();
+    BaiLinear bai;
+    if (!bai.load(path + ".bai") || bai.refs.size() != T) return {};
+    uint64_t G = 0;
+    std::vector<uint64_t> start(T + 1, 0);
+    for (size_t t = 0; t < T; t++) { start[t] = G; if (owned[t]) G += tlen[t]; }
+    start[T] = G;
+    std::vector<std::vector<uint32_t>> beg(K, std::vector<uint32_t>(T, 0)), end(K, std::vector<uint32_t>(T, 0));
+    for (size_t k = 0; k < K; k++) {
+        const uint64_t a = G * k / K, z = G * (k + 1) / K;
+        for (size_t t = 0; t < T; t++) {
+            if (!owned[t]) continue;
+            const uint64_t lo = std::max(a, start[t]), hi = std::min(z, start[t] + tlen[t]);
+            if (hi > lo) { beg[k][t] = (uint32_t)(lo - start[t]); end[k][t] = (uint32_t)(hi - start[t]); }
+        }
+    }
+    std::vector<pd_engine *> eng(K, nullptr);
+    std::vector<BgzfFeedResult> res(K);
+    std::vector<ChunkPool> pools(K);
+    std::vector<std::thread> th;
+    const int thr = std::max(1, o.threads / (int)K);
+    for (size_t k = 0; k < K; k++)
+        th.emplace_back([&, k] {
+            eng[k] = pd_create_ranges(devices[k], (int)T, tlen.data(), beg[k].data(), end[k].data(), o.xflags, o.min_mapq);
+            if (!eng[k]) { res[k].status = -1; res[k].err = std::string("Error: ") + pd_last_error(nullptr); return; }
+            if (hint) pd_set_reduce_hint(eng[k], hint_min_dep, hint_mask);
+            int t0 = -1, t1 = -1;
+            for (size_t t = 0; t < T; t++) if (end[k][t] > beg[k][t]) { if (t0 < 0) t0 = (int)t; t1 = (int)t; }
+            if (t0 < 0) { res[k].status = 1; return; }           // more devices than bases
+            uint64_t f_beg = 0;
+            if (k > 0) {
+                f_beg = UINT64_MAX;
+                for (size_t t = (size_t)t0; t < T; t++) { const uint64_t v = bai.start_voffset((int)t, (int)t == t0 ? (int64_t)beg[k][t] : 0); if (v) { f_beg = v >> 16; break; } }
+                if (f_beg == UINT64_MAX) { res[k].status = 1; return; }     // no read at or behind my first base
+            }
+            const bool last = k + 1 == K;
+            res[k] = bgzf_feed_file(eng[k], nullptr, path, thr, pools[k], true, f_beg, UINT64_MAX, last ? INT32_MAX : t1, last ? INT32_MAX : (int32_t)end[k][(size_t)t1]);
+        });
+    for (auto &t : th) t.join();
+    bool ok = true, fallback = false;
+    for (size_t k = 0; k < K; k++) { if (res[k].status < 0) { ok = false; if (err.empty()) err = res[k].err; } if (res[k].status == 0) fallback = true; }
+    if (tm.on) for (size_t k = 0; k < K; k++)
+        fprintf(stderr, "[timing] device %d: %llu pieces, %.1f MB fed, pread %.3f s, pd_push_bgzf %.3f s (thread-seconds)\n", devices[k],
+                (unsigned long long)res[k].pieces, res[k].bytes / 1048576.0, res[k].s_read, res[k].s_push);
+    if (!ok || fallback) {
+        for (pd_engine *e : eng) if (e) pd_destroy(e);
+        if (ok) err.clear();                                    // fallback only: not an error, the single-GPU path takes over
+        return {};
+    }
+    return eng;
 }
 
 }  // namespace
@@ -502,6 +583,9 @@ int main(int argc, char **argv)
     // the CUDA context (~0.5 s) is created in the background while the host threads already decode
     int device = 0;
     if (const char *d = getenv("PANDEPTH_DEVICE")) device = atoi(d);
+    std::vector<int> devices;                                // PANDEPTH_DEVICES=0,1,2,...: several GPUs, range sharding
+    if (const char *d = getenv("PANDEPTH_DEVICES")) { for (const char *q = d; *q;) { if (*q >= '0' && *q <= '9') { devices.push_back(atoi(q)); while (*q >= '0' && *q <= '9') q++; } else q++; } }
+    if (!devices.empty()) device = devices[0];
     std::vector<uint32_t> tlen(targets.size());
     std::vector<uint8_t> owned(targets.size(), 0);
     for (size_t t = 0; t < targets.size(); t++) { tlen[t] = targets[t].len; owned[t] = genes.count((int)t) ? 1 : 0; }
@@ -509,8 +593,20 @@ int main(int argc, char **argv)
     const bool dry = getenv("PANDEPTH_DRY") != nullptr;      // decode only: no GPU is touched (diagnostics)
     // -d and the depth width are known before the first read: let the engine keep per-segment partials for pd_reduce
     const bool hint_reduce = mode != 6;
+    // Several GPUs: whole-genome interval modes (per-chr rows, -w >= 150 tiles) of one indexed BAM, decoded on the devices.
+    // Everything else (regions, -a, -w < 150, SAM / CRAM / PAF / lists) runs on the first device.
+    Engines engs;
+    {
+        const char *gd = getenv("PANDEPTH_GPU_DECODE");
+        if (devices.size() > 1 && !dry && !multi && in.is_bam && indexed && !region_modes && (mode == 0 || mode == 5) && !o.site_output && !(gd && gd[0] == '0')) {
+            std::string merr;
+            engs.v = feed_multi_gpu(o, o.input, devices, tlen, owned, (uint32_t)o.min_dep, mask, hint_reduce, tm, merr);
+            if (!merr.empty()) { std::cerr << merr << std::endl; return 1; }
+        }
+    }
+    const bool multi_gpu = !engs.v.empty();
     std::shared_future<pd_engine *> eng_future = std::async(std::launch::async, [&]() -> pd_engine * {
-        if (dry) return nullptr;
+        if (dry || multi_gpu) return nullptr;
         pd_engine *e = pd_create(device, (int)targets.size(), tlen.data(), owned.data(), o.xflags, o.min_mapq);
         if (e && hint_reduce) pd_set_reduce_hint(e, (uint32_t)o.min_dep, mask);
         if (e) pool.init(8, (1u << 20) + 1024, (1u << 20) + (1u << 18));      // 8 x 13 MB pinned; bigger batches go pageable
@@ -533,7 +629,7 @@ int main(int argc, char **argv)
     feeder.pool = &pool;
     feeder.targets = &targets;
     feeder.hint_set = hint_reduce; feeder.hint_min_dep = (uint32_t)o.min_dep; feeder.hint_mask = mask;
-    for (size_t fi = 0; fi < o.inputs.size() && !feeder.failed; fi++) {
+    for (size_t fi = 0; fi < o.inputs.size() && !feeder.failed && !multi_gpu; fi++) {
         const std::string &path = o.inputs[fi];
         feeder.input = path;
         if (in.is_paf) { feeder.paf_stream(in.paf_chr2int, targets.size()); continue; }
@@ -557,15 +653,16 @@ int main(int argc, char **argv)
         if (feeder.failed) { std::cerr << feeder.err << std::endl; return 1; }
         return 0;
     }
-    feeder.finish();
-    if (tm.on) fprintf(stderr, "[timing] workers: total %.3f thread-s, of which mutex wait %.3f s, inside push %.3f s (%llu pushes, %llu reads)%s\n",
+    if (!multi_gpu) feeder.finish();
+    if (tm.on && !multi_gpu) fprintf(stderr, "[timing] workers: total %.3f thread-s, of which mutex wait %.3f s, inside push %.3f s (%llu pushes, %llu reads)%s\n",
                        feeder.ns_decode / 1e9, feeder.ns_wait / 1e9, feeder.ns_push / 1e9, (unsigned long long)feeder.n_push.load(), (unsigned long long)feeder.reads_pushed.load(),
                        feeder.used_device_decode ? " [device-side BGZF decode]" : "");
-    pd_engine *eng = eng_future.get();
+    pd_engine *eng = multi_gpu ? engs.v[0] : eng_future.get();
     if (!eng) { std::cerr << "Error: " << pd_last_error(nullptr) << std::endl; drop_outputs(); return 1; }
-    tm.mark("decode+push");
+    if (!multi_gpu) engs.v.assign(1, eng);
+    tm.mark(multi_gpu ? "decode+push (multi-GPU)" : "decode+push");
     if (feeder.failed) { std::cerr << feeder.err << std::endl; drop_outputs(); pd_destroy(eng); return 1; }
-    if (pd_finalize(eng) != PD_OK) { engine_error(eng); drop_outputs(); pd_destroy(eng); return 1; }
+    for (pd_engine *e : engs.v) if (pd_finalize(e) != PD_OK) { engine_error(e); drop_outputs(); return 1; }
     std::cout << "INFO: Input data read done" << std::endl;                                                                        // :4879
 
     if (o.site_output && !write_site_depth(eng, prefix + ".SiteDepth.gz", targets, genes, o.threads)) { drop_outputs(); return 1; }
@@ -575,8 +672,8 @@ int main(int argc, char **argv)
     Totals tot;
     out.put(stat_header(mode));
     const bool ok = mode == 6 ? report_windows(eng, out, o, targets, genes, tot)
-                  : mode == 5 ? report_tiles(eng, out, o, targets, genes, mask, tot)
-                              : report_genes(eng, out, o, targets, genes, merged, mode, whole, mask, tot);
+                  : mode == 5 ? report_tiles(engs, out, o, targets, genes, mask, tot)
+                              : report_genes(engs, out, o, targets, genes, merged, mode, whole, mask, tot);
     if (!ok) { drop_outputs(); return 1; }
     {
         char row[512];
@@ -591,7 +688,7 @@ int main(int argc, char **argv)
     // parked/pinned host buffers -- the OS reclaims all of it, and the orderly teardown only costs wall time
     fflush(stdout); fflush(stderr);
     if (!getenv("PANDEPTH_ORDERLY_EXIT")) _exit(0);
-    pd_destroy(eng);
+    for (pd_engine *e : engs.v) pd_destroy(e);
     if (in.hdr) sam_hdr_destroy(in.hdr);
     tm.mark("pd_destroy");
     return 0;

@@ -15,6 +15,7 @@
 #include "../../oracle/pd_oracle.h"
 #include "../../pandepth_b200/csrc/pd_decode.hpp"      // the block-parallel decoder, here on a host backend
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -24,6 +25,8 @@
 struct pd_engine {
     std::vector<uint32_t> tlen;
     std::vector<uint8_t> owned;
+    std::vector<uint32_t> own_beg, own_end;              // range sharding: depth is kept whole, results are clipped to the owned range
+    int32_t prog_tid = -1, prog_pos = -1;
     std::vector<std::vector<uint32_t>> depth;
     uint32_t xflags; int min_mapq;
     bool pushed = false;
@@ -47,6 +50,18 @@ void *pd_host_alloc(size_t bytes) { return malloc(bytes ? bytes : 1); }
 void pd_host_free(void *p) { free(p); }
 void pd_destroy(pd_engine *e) { delete e; }
 
+pd_engine *pd_create_ranges(int, int n_targets, const uint32_t *target_len, const uint32_t *own_beg, const uint32_t *own_end, uint32_t xflags, int min_mapq)
+{
+    if (n_targets <= 0 || !target_len || !own_beg || !own_end) { g_err = "pd_create: bad arguments"; return nullptr; }
+    std::vector<uint8_t> owned((size_t)n_targets);
+    for (int t = 0; t < n_targets; t++) owned[(size_t)t] = own_end[t] > own_beg[t];
+    pd_engine *e = pd_create(0, n_targets, target_len, owned.data(), xflags, min_mapq);
+    if (e) for (int t = 0; t < n_targets; t++) { e->own_beg[(size_t)t] = std::min(own_beg[t], target_len[t]); e->own_end[(size_t)t] = std::min(own_end[t], target_len[t]); }
+    return e;
+}
+
+int pd_bgzf_progress(pd_engine *e, int32_t *tid, int32_t *pos) { if (!e || !tid || !pos) return PD_ERR_ARG; *tid = e->prog_tid; *pos = e->prog_pos; return PD_OK; }
+
 pd_engine *pd_create(int, int n_targets, const uint32_t *target_len, const uint8_t *owned, uint32_t xflags, int min_mapq)
 {
     if (n_targets <= 0 || !target_len) { g_err = "pd_create: bad arguments"; return nullptr; }
@@ -54,6 +69,7 @@ pd_engine *pd_create(int, int n_targets, const uint32_t *target_len, const uint8
     e->tlen.assign(target_len, target_len + n_targets);
     e->owned.assign((size_t)n_targets, 1);
     if (owned) e->owned.assign(owned, owned + n_targets);
+    e->own_beg.assign((size_t)n_targets, 0); e->own_end.assign(target_len, target_len + n_targets);
     e->depth.resize((size_t)n_targets);
     for (int t = 0; t < n_targets; t++) if (e->owned[(size_t)t]) e->depth[(size_t)t].assign(e->tlen[(size_t)t], 0u);
     e->xflags = xflags; e->min_mapq = min_mapq;
@@ -73,7 +89,7 @@ int pd_reset(pd_engine *e)
 {
     if (!e) return PD_ERR_ARG;
     for (auto &d : e->depth) std::fill(d.begin(), d.end(), 0u);
-    e->pushed = false; e->stats = pd_stats{}; e->err.clear();
+    e->pushed = false; e->stats = pd_stats{}; e->err.clear(); e->prog_tid = e->prog_pos = -1;
     return PD_OK;
 }
 
@@ -121,7 +137,7 @@ struct HostBackend {
     int inflate(const uint8_t *in, size_t, const pdk::ChunkBlock *blk, const uint64_t *out_off, uint32_t n, uint64_t out_total)
     {
         inflated_v.assign(out_total + 8, 0); inflated = inflated_v.data();
-        static pdk::InflateTables T;
+        static thread_local pdk::InflateTables T;       // (several stand-in engines may decode at once: PANDEPTH_DEVICES)
         for (uint32_t b = 0; b < n; b++)
             if (blk[b].out_len && pdk::inflate_raw(in + blk[b].in_off, blk[b].in_len, inflated + out_off[b], blk[b].out_len, T) != (int)blk[b].out_len) return -1;
         return 0;
@@ -157,6 +173,7 @@ int pd_push_bgzf(pd_engine *e, const uint8_t *bytes, size_t n_bytes, const pd_bg
         const int prc = pd_push_contig(e, r.tid, (int64_t)(r.r1 - r.r0), be.pos.data() + r.r0, nullptr, nullptr, be.cigar_off.data() + r.r0, be.cigar.data(), r.sorted ? PD_SORTED : 0u);
         if (prc) return prc;
     }
+    for (int64_t b = n_blocks; b-- > 0;) if (be.counts_host[b].n_reads) { e->prog_tid = be.counts_host[b].first_tid; e->prog_pos = be.counts_host[b].first_pos; break; }
     trace("bgzf_ok", n_blocks, n_reads);
     return PD_OK;
 }
@@ -173,7 +190,9 @@ int pd_reduce(pd_engine *e, int64_t n_iv, const int32_t *tid, const int32_t *s0,
         if (tid[i] < 0 || tid[i] >= (int32_t)e->tlen.size()) return fail(e, PD_ERR_ARG, "pd_reduce: tid out of range");
         const auto &d = e->depth[(size_t)tid[i]];
         if (d.empty()) continue;
-        pdo_reduce(d.data(), (uint32_t)d.size(), 1, s0 + i, e0 + i, min_dep, mask, cov + i, sum + i);
+        const int32_t a = std::max<int32_t>(s0[i], (int32_t)e->own_beg[(size_t)tid[i]]), z = std::min<int32_t>(e0[i], (int32_t)e->own_end[(size_t)tid[i]]);
+        if (a >= z) continue;                                // (clipped to the owned range: results of disjoint engines add up)
+        pdo_reduce(d.data(), (uint32_t)d.size(), 1, &a, &z, min_dep, mask, cov + i, sum + i);
     }
     return PD_OK;
 }

@@ -253,3 +253,21 @@ def test_failed_runs_leave_no_partial_outputs(workdir, standin_env, inputs):
     assert r.returncode == 1 and not os.path.exists(pre + ".chr.stat.gz"), (r.stdout, r.stderr)
     r = subprocess.run([CLI, "-i", inputs["k.sam"]["bam"], "-o", os.path.join(workdir, "gc"), "-c"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=standin_env)
     assert r.returncode == 1 and "GC content" in r.stderr
+
+
+@pytest.mark.parametrize("case", ["k.default.bam", "k.w150.bam", "mix.default.bam", "mix.w1000.bam", "mix.w151.bam", "big.default.bam", "big.w1000.bam", "k.q10d2.bam", "mix.q20d3x3844.bam"])
+@pytest.mark.parametrize("devices", ["0,1", "0,1,2,3,4"])
+def test_host_program_multi_device_range_sharding(case, devices, inputs, workdir, standin_env):
+    """PANDEPTH_DEVICES: one engine per device, each owning an equal range of the concatenated genome (pd_create_ranges), fed
+    through the .bai with the part of the file that can touch its range, reduce results summed -- same bytes as one device.
+    (The stand-in ignores the device numbers; the host-side routing, ranges and sums are what is under test here.)"""
+    c = _CASES[case]
+    args = [os.path.join(GOLD, a[1:]) if a.startswith("@") else a for a in c["args"]]
+    env = dict(standin_env, PANDEPTH_DEVICES=devices, PANDEPTH_TIMING="1")
+    pre = os.path.join(workdir, "md_" + devices.replace(",", "") + case)
+    r = subprocess.run([CLI, "-i", inputs[c["fixture"]]["bam"], "-o", pre] + args + ["-t", "4"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600, env=env)
+    assert r.returncode == 0, (r.stdout, r.stderr)
+    assert "decode+push (multi-GPU)" in r.stderr, r.stderr
+    for k, want in c["outputs"].items():
+        with gzip.open(pre + k, "rt") as fh:
+            assert_matches(want, fh.read(), f"{case}{k} devices={devices}")
