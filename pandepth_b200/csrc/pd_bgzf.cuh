@@ -44,10 +44,15 @@ __host__ __device__ __forceinline__ uint64_t bz_cig_base(uint64_t out_off, uint3
 
 constexpr int BZ_LIT_BITS = 10, BZ_DIST_BITS = 8;
 constexpr int BZ_WPC = 8;            // warps (decoders) per CTA
+// First-level table entry (16 bits): symbol in the LOW byte (a literal is stored to memory straight from the entry), code
+// length in bits 8..11, bit 12 = "symbol is 256 + low byte" (end of block / length codes), 0xFFFF = code longer than the table.
+// A literal hit is therefore e < 0x1000.
 constexpr uint16_t BZ_MISS = 0xffffu;
+__host__ __device__ __forceinline__ uint16_t bz_entry(uint32_t sym, uint32_t len) { return (uint16_t)((sym & 0xffu) | (len << 8) | (sym >= 256u ? 0x1000u : 0u)); }
+__host__ __device__ __forceinline__ int bz_entry_sym(uint32_t e) { return (int)((e & 0xffu) + ((e & 0x1000u) >> 4)); }
+__host__ __device__ __forceinline__ uint32_t bz_entry_len(uint32_t e) { return (e >> 8) & 15u; }
 
 struct BzTables {                    // per warp, shared memory
-    uint16_t lit_fast[1 << BZ_LIT_BITS];     // (symbol << 4) | code length; BZ_MISS = code longer than the table.  A literal hit is e < 4096.
     uint16_t dist_fast[1 << BZ_DIST_BITS];
     uint16_t lit_sym[288];                   // symbols in canonical code order
     uint16_t dist_sym[32];
@@ -140,7 +145,7 @@ __device__ __forceinline__ int bz_build(const uint8_t *lens, int n, uint32_t *cn
         if (l <= (uint32_t)fast_bits) {
             const uint32_t code = aux[16 + l] + ((uint32_t)i - aux[32 + l]);
             const uint32_t rev = __brev(code) >> (32 - l);
-            const uint16_t e = (uint16_t)((s << 4) | l);
+            const uint16_t e = bz_entry(s, l);
             for (uint32_t p = rev; p < (1u << fast_bits); p += 1u << l) fast[p] = e;
         }
     }
@@ -154,7 +159,7 @@ __device__ __forceinline__ int bz_symbol(BzBits &br, const uint32_t *cnt, const 
     br.norm();
     const uint32_t b32 = br.peek32();
     const uint16_t e = fast[b32 & ((1u << fast_bits) - 1u)];
-    if (e != BZ_MISS) { br.drop(e & 15u); return e >> 4; }
+    if (e != BZ_MISS) { br.drop(bz_entry_len(e)); return bz_entry_sym(e); }
     int code = 0, first = 0, index = 0;
     uint32_t b = b32;
     for (int l = 1; l < 16; l++) {
@@ -175,7 +180,29 @@ __device__ __forceinline__ uint32_t bz_ld32(const uint8_t *p)     // little-endi
 }
 
 // Inflate one raw deflate stream with the whole warp.  Returns (to every lane) bytes written, or < 0 on a malformed stream.
-__device__ __forceinline__ int bz_inflate(const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_t out_cap, BzTables &T, int lane)
+__device__ __forceinline__ uint32_t bz_shared_addr(const void *p)
+{
+#ifndef PD_WARP_EMU
+    return (uint32_t)__cvta_generic_to_shared(p);
+#else
+    return emu_shared_addr(p);
+#endif
+}
+
+__device__ __forceinline__ uint32_t bz_lds_u16(uint32_t saddr)
+{
+#ifndef PD_WARP_EMU
+    uint16_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(saddr));
+    return v;
+#else
+    return *reinterpret_cast<const uint16_t *>(emu_shared_ptr(saddr));
+#endif
+}
+
+// lit_fast: this warp's 1024-entry literal/length table, 2 KB aligned in shared memory (lit_sa = its shared-window address):
+// a lookup is ONE logic op -- lit_sa | (bits << 1 & 0x7fe) -- and the load.
+__device__ __forceinline__ int bz_inflate(const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_t out_cap, BzTables &T, uint16_t *lit_fast, uint32_t lit_sa, int lane)
 {
     constexpr unsigned FULLM = 0xffffffffu;
     BzBits br; br.init(in, in_len);
@@ -247,7 +274,7 @@ __device__ __forceinline__ int bz_inflate(const uint8_t *in, uint32_t in_len, ui
                 if (bad) return -1;
                 __syncwarp();
             }
-            int r = bz_build(T.lens + 24, nlen, T.lit_cnt, T.lit_sym, T.lit_fast, BZ_LIT_BITS, T.aux, lane);
+            int r = bz_build(T.lens + 24, nlen, T.lit_cnt, T.lit_sym, lit_fast, BZ_LIT_BITS, T.aux, lane);
             if (r < 0 || (r > 0 && (type == 1 ? false : nlen - (int)T.lit_cnt[0] != 1))) return -1;
             r = bz_build(T.lens + 24 + nlen, ndist, T.dist_cnt, T.dist_sym, T.dist_fast, BZ_DIST_BITS, T.aux, lane);
             if (r < 0 || (r > 0 && (type == 1 ? false : ndist - (int)T.dist_cnt[0] != 1))) return -1;
@@ -260,23 +287,23 @@ __device__ __forceinline__ int bz_inflate(const uint8_t *in, uint32_t in_len, ui
                         // 32 window bits hold three first-level literal hits (<= 10 bits each): one funnel shift, then 32-bit
                         // shifts; the output bound is checked once per group (a group writes at most 3 bytes)
                         br.norm();
-                        uint32_t wnd = br.peek32();
-                        uint32_t e = T.lit_fast[wnd & ((1u << BZ_LIT_BITS) - 1u)];
-                        if (e < 4096u && o + 3u <= out_cap) {
+                        uint32_t wnd1 = br.peek32() << 1;             // kept shifted left by one: (wnd1 & 0x7fe) is the byte offset of the entry
+                        uint32_t e = bz_lds_u16(lit_sa | (wnd1 & 0x7feu));
+                        if (e < 0x1000u && o + 3u <= out_cap) {
                             uint8_t *op = out + o;                       // one address per group, immediate offsets for the stores
-                            uint32_t used = e & 15u;
-                            op[0] = (uint8_t)(e >> 4); wnd >>= used;
-                            e = T.lit_fast[wnd & ((1u << BZ_LIT_BITS) - 1u)];
-                            if (e < 4096u) {
-                                op[1] = (uint8_t)(e >> 4); wnd >>= (e & 15u); used += e & 15u;
-                                e = T.lit_fast[wnd & ((1u << BZ_LIT_BITS) - 1u)];
-                                if (e < 4096u) { op[2] = (uint8_t)(e >> 4); used += e & 15u; o += 3; }
+                            uint32_t used = e >> 8;
+                            op[0] = (uint8_t)e; wnd1 >>= used;
+                            e = bz_lds_u16(lit_sa | (wnd1 & 0x7feu));
+                            if (e < 0x1000u) {
+                                op[1] = (uint8_t)e; wnd1 >>= (e >> 8); used += e >> 8;
+                                e = bz_lds_u16(lit_sa | (wnd1 & 0x7feu));
+                                if (e < 0x1000u) { op[2] = (uint8_t)e; used += e >> 8; o += 3; }
                                 else o += 2;
                             } else o += 1;
                             br.drop(used);
                             continue;
                         }
-                        int s = bz_symbol(br, T.lit_cnt, T.lit_sym, T.lit_fast, BZ_LIT_BITS);
+                        int s = bz_symbol(br, T.lit_cnt, T.lit_sym, lit_fast, BZ_LIT_BITS);
                         if (s < 0) { cmd = 3; break; }
                         if (s < 256) { if (o >= out_cap) { cmd = 3; break; } out[o++] = (uint8_t)s; continue; }
                         if (s == 256) { cmd = 2; break; }
@@ -327,9 +354,12 @@ __device__ __forceinline__ int bz_inflate(const uint8_t *in, uint32_t in_len, ui
 __global__ void __launch_bounds__(BZ_WPC * 32, 4) k_bgzf_decode(BzArgs a)
 {
     constexpr unsigned FULLM = 0xffffffffu;
+    __shared__ __align__(2048) uint16_t lit_tabs[BZ_WPC][1 << BZ_LIT_BITS];
     __shared__ BzTables tabs[BZ_WPC];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     BzTables &T = tabs[warp];
+    uint16_t *lit_fast = lit_tabs[warp];
+    const uint32_t lit_sa = bz_shared_addr(lit_fast);
     for (;;) {
         uint32_t b = 0;
         if (lane == 0) b = atomicAdd(a.ticket, 1u);
@@ -338,7 +368,7 @@ __global__ void __launch_bounds__(BZ_WPC * 32, 4) k_bgzf_decode(BzArgs a)
         const BgzfBlockDesc k = a.blk[b];
         uint8_t *out = a.out + k.out_off;
         uint32_t flags = 0;
-        const int got = k.out_len ? bz_inflate(a.in + k.in_off, k.in_len, out, k.out_len, T, lane) : 0;
+        const int got = k.out_len ? bz_inflate(a.in + k.in_off, k.in_len, out, k.out_len, T, lit_fast, lit_sa, lane) : 0;
         if (got != (int)k.out_len) flags |= BZ_INFLATE;
         __syncwarp();
 

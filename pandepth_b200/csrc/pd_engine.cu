@@ -28,8 +28,9 @@ namespace {
 
 std::string g_create_error;
 
-constexpr uint64_t PAD_ELEMS = pdk::SCAN_TILE > 4096 ? pdk::SCAN_TILE : 4096;   // contig offsets / total are multiples of this (and of SCAN_TILE)
-static_assert(PAD_ELEMS % pdk::SCAN_TILE == 0 && PAD_ELEMS % 4096 == 0, "padding must hold whole scan tiles");
+constexpr uint64_t PAD_ELEMS = pdk::SCAN_TILE > pdk::REDUCE_CHUNK ? pdk::SCAN_TILE : pdk::REDUCE_CHUNK;   // contig offsets / total are multiples of this
+static_assert(PAD_ELEMS % pdk::SCAN_TILE == 0 && PAD_ELEMS % pdk::REDUCE_CHUNK == 0 && PAD_ELEMS % 4096 == 0,
+              "padding must hold whole scan tiles, and a contig's reduce chunks must start on 4-segment boundaries of the whole array");
 constexpr int64_t HOST_CHUNK_READS = 8 << 20;            // staging chunk for host-resident pushes
 constexpr int N_SLOTS = 2;
 
@@ -100,6 +101,7 @@ struct pd_engine {
 
     // reduce scratch
     void *d_red = nullptr; size_t red_cap = 0;
+    uint32_t *d_todo = nullptr; size_t todo_cap = 0;   // pd_reduce with the hint: units that still need depth after the partials pass
 
     bool finalized = false;
     bool host_delta_used = false;    // a scatter-path batch was queued since the last scan
@@ -444,7 +446,7 @@ void pd_destroy(pd_engine *e)
     if (e->cut_stream) cudaStreamDestroy(e->cut_stream);
     if (e->cut_input) cudaEventDestroy(e->cut_input);
     cudaFree(e->d_flags); cudaFree(e->d_desc); cudaFree(e->d_counter);
-    cudaFree(e->d_red); cudaFree(e->d_part_cov); cudaFree(e->d_part_sum);
+    cudaFree(e->d_red); cudaFree(e->d_todo); cudaFree(e->d_part_cov); cudaFree(e->d_part_sum);
     for (auto &s : e->slot) {
         cudaFree(s.pos); cudaFree(s.cigar); cudaFree(s.cigar_off); cudaFree(s.flag); cudaFree(s.mapq);
         if (s.copied) cudaEventDestroy(s.copied);
@@ -794,10 +796,20 @@ int pd_finalize(pd_engine *e)
         e->delta_stale = true;
         e->stats.scan_passes++;
     } else {
-        rc = launch(e, K_FILL, [&] { pdk::k_fill_untouched<<<(unsigned)((e->n_seg + 7) / 8), 256, 0, e->stream>>>(e->d_depth, e->d_seg_state, e->n_seg, e->hint_on ? 1u : 0u, e->d_part_cov, e->d_part_sum); });
+        rc = launch(e, K_FILL, [&] { pdk::k_fill_untouched<<<(unsigned)((e->n_seg + 255) / 256), 256, 0, e->stream>>>(e->d_depth, e->d_seg_state, e->n_seg, e->hint_on ? 1u : 0u, e->d_part_cov, e->d_part_sum); });
         if (rc) return rc;
     }
     e->finalized = true;
+    return PD_OK;
+}
+
+static int ensure_todo(pd_engine *e, size_t n)
+{
+    if (n <= e->todo_cap) return PD_OK;
+    if (e->d_todo) { CK(cudaStreamSynchronize(e->stream)); cudaFree(e->d_todo); e->d_todo = nullptr; }
+    const size_t cap = n + n / 4 + 1024;
+    CK(cudaMalloc(&e->d_todo, cap * 4));
+    e->todo_cap = cap;
     return PD_OK;
 }
 
@@ -859,11 +871,21 @@ int pd_reduce(pd_engine *e, int64_t n_iv, const int32_t *tid, const int32_t *sta
     CK(cudaMemsetAsync(base + a_cov, 0, (size_t)n_iv * 16, e->stream));
     e->stats.h2d_bytes += iv_bytes * 3 + prefix.size() * 8;
     if (n_units) {
+        const bool use_part = e->hint_on && min_dep == e->hint_min_dep && depth_mask == e->hint_mask;
+        uint32_t *d_todo = nullptr;
+        if (use_part && pdk::SEG == 2048) {
+            rc = ensure_todo(e, (size_t)n_units); if (rc) return rc;
+            d_todo = e->d_todo;
+            CK(cudaMemsetAsync(d_todo, 0, (size_t)n_units * 4, e->stream));
+        }
         pdk::ReduceArgs r{e->d_depth, e->d_off, e->d_tlen, (const int32_t *)(base + a_tid), (const int32_t *)(base + a_s),
                           (const int32_t *)(base + a_e), (const uint64_t *)(base + a_units), (uint64_t)n_iv, n_units, min_dep, depth_mask,
                           (unsigned long long *)(base + a_cov), (unsigned long long *)(base + a_sum),
-                          (e->hint_on && min_dep == e->hint_min_dep && depth_mask == e->hint_mask) ? 1u : 0u, e->d_seg_state, e->d_part_cov, e->d_part_sum};
-        rc = launch(e, K_REDUCE, [&] { pdk::k_reduce_units<<<(unsigned)((n_units + 7) / 8), 256, 0, e->stream>>>(r); });
+                          use_part ? 1u : 0u, e->d_seg_state, e->d_part_cov, e->d_part_sum, d_todo};
+        rc = launch(e, K_REDUCE, [&] {
+            if (d_todo) pdk::k_reduce_units_part<<<(unsigned)((n_units + 255) / 256), 256, 0, e->stream>>>(r, d_todo);
+            pdk::k_reduce_units<<<(unsigned)((n_units + 7) / 8), 256, 0, e->stream>>>(r);
+        });
         if (rc) return rc;
     }
     CK(cudaMemcpyAsync(cov, base + a_cov, (size_t)n_iv * 8, cudaMemcpyDeviceToHost, e->stream));

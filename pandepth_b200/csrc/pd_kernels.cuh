@@ -689,23 +689,29 @@ __global__ void __launch_bounds__(SCAN_THREADS, PD_SCAN_MIN_CTAS) k_scan_add(uin
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// k_fill_untouched: one warp per segment; segments never written by a batch become zeros.
+// k_fill_untouched: segments never written by a batch become zeros.  A warp looks at the states of 32 segments at once (one
+// per lane) and zero-fills, all lanes together, the few that need it -- at 50x every segment has been written and the kernel
+// only reads n_seg bytes (one warp per segment cost 0.11 ms per 3 Gb just to find that out).
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_fill_untouched(uint32_t *depth, uint8_t *seg_state, uint64_t n_seg,
                                                         uint32_t hint_on, uint32_t *part_cov, unsigned long long *part_sum)
 {
-    const uint64_t s = (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (s >= n_seg) return;
-    if (seg_state[s] != 0) return;
     const int lane = threadIdx.x & 31;
-    uint4 *p = reinterpret_cast<uint4 *>(depth + s * SEG);
-    const uint4 z = make_uint4(0, 0, 0, 0);
-#pragma unroll
-    for (int k = lane; k < SEG / 4; k += 32) p[k] = z;
-    __syncwarp();
-    if (lane == 0) {
+    const uint64_t s0 = ((uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5)) * 32;
+    if (s0 >= n_seg) return;
+    const uint64_t s = s0 + lane;
+    const bool untouched = s < n_seg && seg_state[s] == 0;
+    unsigned todo = __ballot_sync(FULL, untouched);
+    if (untouched) {
         if (hint_on) { part_cov[s] = 0; part_sum[s] = 0; seg_state[s] = 1; }     // min_dep >= 1: zero depth covers nothing
         else seg_state[s] = 2;
+    }
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    while (todo) {
+        const int k = __ffs(todo) - 1; todo &= todo - 1;
+        uint4 *p = reinterpret_cast<uint4 *>(depth + (s0 + k) * SEG);
+#pragma unroll
+        for (int q = lane; q < SEG / 4; q += 32) p[q] = z;
     }
 }
 
@@ -714,7 +720,7 @@ __global__ void __launch_bounds__(256) k_fill_untouched(uint32_t *depth, uint8_t
 // 64-bit atomic pair per unit.   if (depth >= minDep) { Cover++; Depth += depth; }   (:319-323, :340-344)
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int REDUCE_CHUNK = 8192;
-static_assert(REDUCE_CHUNK % SEG == 0, "reduce chunks are whole segments");
+static_assert(REDUCE_CHUNK % SEG == 0 && REDUCE_CHUNK / SEG == 4, "a reduce chunk is four segments (k_reduce_units_part reads their states as one word)");
 
 struct ReduceArgs {
     const uint32_t *depth;           // array base
@@ -727,6 +733,7 @@ struct ReduceArgs {
     unsigned long long *cov; unsigned long long *sum;
     // partials written by k_tile_accumulate for (hint_min_dep, hint_mask); used when use_part (the caller asked for the same pair)
     uint32_t use_part; const uint8_t *seg_state; const uint32_t *part_cov; const unsigned long long *part_sum;
+    const uint32_t *todo;            // non-null: only units flagged here (the others were served from the partials)
 };
 
 __device__ __forceinline__ void warp_reduce_range(const uint32_t *__restrict__ d, int64_t a, int64_t b, uint32_t min_dep,
@@ -755,10 +762,56 @@ __device__ __forceinline__ void warp_reduce_range(const uint32_t *__restrict__ d
     if (lane < n - done) { const uint32_t x = __ldg(p + done + lane) & mask; if (x >= min_dep) { cov++; sum += x; } }
 }
 
+// With the reduce hint most units need no depth at all: four written-once segments, four partials.  One LANE per unit then
+// (a warp covers 32 consecutive units, which nearly always belong to one interval: one shuffle reduction, one atomic pair);
+// units that do need depth (interval edges, re-written segments) are left to k_reduce_units, flagged in `todo`.
+__global__ void __launch_bounds__(256) k_reduce_units_part(ReduceArgs a, uint32_t *todo)
+{
+    const int lane = threadIdx.x & 31;
+    const uint64_t u = ((uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5)) * 32 + lane;
+    const bool live = u < a.n_units;
+    uint64_t iv = 0; uint32_t cov = 0; unsigned long long sum = 0; bool slow = false;
+    if (live) {
+        uint64_t lo_i = 0, hi_i = a.n_iv;
+        while (hi_i - lo_i > 1) {
+            const uint64_t m = (lo_i + hi_i) >> 1;
+            if (__ldg(a.unit_prefix + m) <= u) lo_i = m; else hi_i = m;
+        }
+        iv = lo_i;
+        const int64_t c = (int64_t)(u - __ldg(a.unit_prefix + iv));
+        const int32_t t = a.tid[iv];
+        int64_t s = a.start0[iv], e = a.end0[iv];
+        const int64_t len = a.contig_len[t];
+        if (s < 0) s = 0;
+        if (e > len) e = len;
+        const int64_t chunk0 = (s / REDUCE_CHUNK + c) * REDUCE_CHUNK;
+        const uint64_t sg0 = (a.contig_off[t] + (uint64_t)chunk0) / SEG;
+        if (s <= chunk0 && e >= chunk0 + REDUCE_CHUNK) {
+            // the whole chunk lies inside the interval: four segment partials, if all four were written exactly once
+            const uint32_t st4 = *reinterpret_cast<const uint32_t *>(a.seg_state + sg0);       // REDUCE_CHUNK / SEG == 4 states, 4-byte aligned
+            if (st4 == 0x01010101u) {
+#pragma unroll
+                for (int q = 0; q < REDUCE_CHUNK / SEG; q++) { cov += a.part_cov[sg0 + q]; sum += a.part_sum[sg0 + q]; }
+            } else slow = true;
+        } else slow = true;
+    }
+    if (slow) todo[u] = 1;
+    // 32 consecutive units of one interval (the common case): reduce in the warp, one atomic pair
+    const uint64_t iv0 = __shfl_sync(FULL, iv, 0);
+    const bool uniform = __all_sync(FULL, !live || iv == iv0);
+    if (uniform) {
+        cov = __reduce_add_sync(FULL, cov);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(FULL, sum, o);
+        if (lane == 0 && (cov | (sum != 0))) { atomicAdd(a.cov + iv0, (unsigned long long)cov); atomicAdd(a.sum + iv0, sum); }
+    } else if (live && (cov | (sum != 0))) { atomicAdd(a.cov + iv, (unsigned long long)cov); atomicAdd(a.sum + iv, sum); }
+}
+
 __global__ void __launch_bounds__(256) k_reduce_units(ReduceArgs a)
 {
     const uint64_t u = (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (u >= a.n_units) return;
+    if (a.todo && a.todo[u] == 0) return;                      // k_reduce_units_part took this unit from the partials
     const int lane = threadIdx.x & 31;
     // interval of this unit: last i with unit_prefix[i] <= u
     uint64_t lo_i = 0, hi_i = a.n_iv;

@@ -586,6 +586,14 @@ int main(int argc, char **argv)
     std::vector<int> devices;                                // PANDEPTH_DEVICES=0,1,2,...: several GPUs, range sharding
     if (const char *d = getenv("PANDEPTH_DEVICES")) { for (const char *q = d; *q;) { if (*q >= '0' && *q <= '9') { devices.push_back(atoi(q)); while (*q >= '0' && *q <= '9') q++; } else q++; } }
     if (!devices.empty()) device = devices[0];
+    // cuInit brings up every VISIBLE GPU (0.5 s for one, 2+ s on a multi-GPU node): show the driver only the devices this run uses
+    if (!getenv("CUDA_VISIBLE_DEVICES")) {
+        std::string vis;
+        if (devices.empty()) vis = std::to_string(device);
+        else for (size_t k = 0; k < devices.size(); k++) vis += (k ? "," : "") + std::to_string(devices[k]);
+        setenv("CUDA_VISIBLE_DEVICES", vis.c_str(), 1);
+        if (devices.empty()) device = 0; else for (size_t k = 0; k < devices.size(); k++) devices[k] = (int)k;
+    }
     std::vector<uint32_t> tlen(targets.size());
     std::vector<uint8_t> owned(targets.size(), 0);
     for (size_t t = 0; t < targets.size(); t++) { tlen[t] = targets[t].len; owned[t] = genes.count((int)t) ? 1 : 0; }
