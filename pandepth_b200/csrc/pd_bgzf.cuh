@@ -58,7 +58,6 @@ struct BzTables {                    // per warp, shared memory
     uint16_t dist_sym[32];
     uint32_t lit_cnt[16], dist_cnt[16];      // codes per length
     uint32_t aux[48];                        // table build: running offsets / first code / first index per length
-    uint32_t rec_off[32];                    // record walk: offsets of the 32 records being parsed
     uint8_t lens[320 + 24];                  // code-length code (19, padded to 24) then literal/length + distance lengths
 };
 
@@ -188,6 +187,21 @@ __device__ __forceinline__ uint32_t bz_shared_addr(const void *p)
     return emu_shared_addr(p);
 #endif
 }
+
+__device__ __forceinline__ void *bz_shared_ptr(uint32_t sa)
+{
+#ifndef PD_WARP_EMU
+    return __cvta_shared_to_generic(sa);
+#else
+    return const_cast<void *>(emu_shared_ptr(sa));
+#endif
+}
+
+// First-level literal tables live in a raw shared array that is 2 KB larger than needed and are placed at the first 2 KB
+// boundary OF THE SHARED WINDOW inside it, at run time: `__align__(2048)` on a static shared variable only aligns it inside
+// the kernel's own section, and that section starts behind the 1 KB the system reserves at the bottom of the window
+// (sm_90 and later) -- found the hard way: lookups formed with OR read the wrong entries on the device.
+__device__ __forceinline__ uint32_t bz_align_tables(const void *raw) { return (bz_shared_addr(raw) + 2047u) & ~2047u; }
 
 __device__ __forceinline__ uint32_t bz_lds_u16(uint32_t saddr)
 {
@@ -349,17 +363,112 @@ __device__ __forceinline__ int bz_inflate(const uint8_t *in, uint32_t in_len, ui
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// k_bgzf_decode
+// BAM records of one inflated block (SAMv1 4.2: block_size, refID, pos, l_read_name, mapq, bin, n_cigar_op, flag, ...), walked by
+// the whole warp: lane 0 follows the block_size chain 32 records at a time, every lane parses one record, applies the filter
+// (PanDepth.cpp:732-733) and writes the records that pass into the block's staging region; one summary per block.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bz_walk_block(const BzArgs &a, uint32_t b, const BgzfBlockDesc &k, uint8_t *out, int got, uint32_t *rec_off, int lane)
+{
+    constexpr unsigned FULLM = 0xffffffffu;
+    uint32_t flags = 0;
+    if (got != (int)k.out_len) flags |= BZ_INFLATE;
+    // ---- BAM records of the block (SAMv1 4.2): block_size, refID, pos, l_read_name, mapq, bin, n_cigar_op, flag, ... ----
+    const uint64_t rb = bz_rec_base(k.out_off, b), cb = bz_cig_base(k.out_off, b);
+    const uint32_t len = k.out_len;
+    uint32_t p = b == 0 ? a.first_skip : 0u;                 // lane 0's chain position
+    uint32_t n_reads = 0, n_cig = 0;
+    int32_t first_tid = INT32_MIN, first_pos = 0, last_tid = INT32_MIN, last_pos = INT32_MIN;
+    bool chain_end = (flags != 0) || p > len;
+    if (p > len) flags |= BZ_MALFORMED;
+    while (!chain_end) {
+        // lane 0 follows the block_size chain for up to 32 records
+        uint32_t nrec = 0;
+        if (lane == 0) {
+            while (nrec < 32 && p + 4 <= len) {
+                const uint32_t bs = bz_ld32(out + p);
+                if (bs < 32 || bs > (1u << 30)) { nrec |= 0x100u; break; }       // malformed
+                if ((uint64_t)p + 4 + bs > len) { nrec |= 0x200u; break; }       // continues in the next block
+                rec_off[nrec++] = p;
+                p += 4 + bs;
+            }
+            if (!(nrec & 0x300u) && p + 4 > len) nrec |= 0x400u;                 // end of the block reached
+        }
+        nrec = __shfl_sync(FULLM, nrec, 0);
+        if (nrec & 0x100u) flags |= BZ_MALFORMED;
+        if (nrec & 0x700u) chain_end = true;
+        nrec &= 0xffu;
+        __syncwarp();
+        // every lane parses one record
+        bool keep = false; int32_t tid = 0, pos = 0; uint32_t ncg = 0; const uint8_t *cig = nullptr;
+        if ((uint32_t)lane < nrec) {
+            const uint8_t *rec = out + rec_off[lane] + 4;
+            const uint32_t bs = bz_ld32(rec - 4);
+            tid = (int32_t)bz_ld32(rec); pos = (int32_t)bz_ld32(rec + 4);
+            const uint32_t w8 = bz_ld32(rec + 8), w12 = bz_ld32(rec + 12);
+            const uint32_t l_name = w8 & 0xffu, mapq = (w8 >> 8) & 0xffu;
+            ncg = w12 & 0xffffu;
+            const uint32_t flag = w12 >> 16;
+            if (32 + l_name + 4 * ncg > bs) flags |= BZ_MALFORMED;
+            else {
+                cig = rec + 32 + l_name;
+                keep = tid >= 0 && tid < a.n_targets && !(flag & a.xflags) && (int32_t)mapq >= a.min_mapq;   // :732-733
+                if (keep && ncg == 2 && (bz_ld32(cig) & 15u) == 4u && (bz_ld32(cig + 4) & 15u) == 3u) flags |= BZ_CG_TAG;   // `<l_seq>S<ref_len>N`: CIGAR may be in the CG tag
+                if (keep && ncg != 1) flags |= BZ_MULTI_OP;
+            }
+        }
+        const unsigned km = __ballot_sync(FULLM, keep);
+        if (km) {
+            // order among the records that pass: each compares with the previous passing one
+            const unsigned before = km & ((1u << lane) - 1u);
+            const int src = before ? 31 - __clz(before) : lane;
+            const int32_t ptid = __shfl_sync(FULLM, tid, src), ppos = __shfl_sync(FULLM, pos, src);
+            if (keep) {
+                const int32_t qt = before ? ptid : last_tid, qp = before ? ppos : last_pos;
+                if (tid < qt || (tid == qt && pos < qp)) flags |= BZ_UNSORTED;
+            }
+            // staging: record rank and CIGAR word offset by warp prefix sums
+            const uint32_t rank = n_reads + __popc(before);
+            uint32_t c = keep ? ncg : 0u, incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(FULLM, incl, o); if (lane >= o) incl += y; }
+            const uint32_t coff = n_cig + incl - c;
+            if (keep) {
+                a.st_pos[rb + rank] = pos; a.st_tid[rb + rank] = tid; a.st_coff[rb + rank] = coff;
+                for (uint32_t j = 0; j < ncg; j++) a.st_cig[cb + coff + j] = bz_ld32(cig + 4 * j);
+            }
+            const int lo_lane = __ffs(km) - 1, hi_lane = 31 - __clz(km);
+            if (first_tid == INT32_MIN) { first_tid = __shfl_sync(FULLM, tid, lo_lane); first_pos = __shfl_sync(FULLM, pos, lo_lane); }
+            last_tid = __shfl_sync(FULLM, tid, hi_lane); last_pos = __shfl_sync(FULLM, pos, hi_lane);
+            n_reads += __popc(km);
+            n_cig += __shfl_sync(FULLM, incl, 31);
+        }
+        __syncwarp();
+    }
+    p = __shfl_sync(FULLM, p, 0);
+    // flags raised by single lanes
+    flags = __reduce_or_sync(FULLM, flags);
+    if (!(flags & (BZ_INFLATE | BZ_MALFORMED)) && p != len) flags |= BZ_STRADDLE;
+    if (lane == 0) {
+        BgzfSummary s;
+        s.n_reads = n_reads; s.n_cigar = n_cig; s.used = p; s.flags = flags;
+        s.first_tid = first_tid; s.last_tid = last_tid; s.first_pos = first_pos; s.last_pos = last_tid == INT32_MIN ? 0 : last_pos;
+        a.sum[b] = s;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// k_bgzf_decode: one decoder per warp (match-dominated streams: SEQ-less BAMs, ratio >= 4)
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(BZ_WPC * 32, 4) k_bgzf_decode(BzArgs a)
 {
     constexpr unsigned FULLM = 0xffffffffu;
-    __shared__ __align__(2048) uint16_t lit_tabs[BZ_WPC][1 << BZ_LIT_BITS];
+    __shared__ uint16_t lit_raw[(BZ_WPC + 1) << BZ_LIT_BITS];
     __shared__ BzTables tabs[BZ_WPC];
+    __shared__ uint32_t rec_offs[BZ_WPC][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     BzTables &T = tabs[warp];
-    uint16_t *lit_fast = lit_tabs[warp];
-    const uint32_t lit_sa = bz_shared_addr(lit_fast);
+    const uint32_t lit_sa = bz_align_tables(lit_raw) + (uint32_t)warp * (2u << BZ_LIT_BITS);
+    uint16_t *lit_fast = static_cast<uint16_t *>(bz_shared_ptr(lit_sa));
     for (;;) {
         uint32_t b = 0;
         if (lane == 0) b = atomicAdd(a.ticket, 1u);
@@ -367,92 +476,218 @@ __global__ void __launch_bounds__(BZ_WPC * 32, 4) k_bgzf_decode(BzArgs a)
         if (b >= a.n_blocks) return;
         const BgzfBlockDesc k = a.blk[b];
         uint8_t *out = a.out + k.out_off;
-        uint32_t flags = 0;
         const int got = k.out_len ? bz_inflate(a.in + k.in_off, k.in_len, out, k.out_len, T, lit_fast, lit_sa, lane) : 0;
-        if (got != (int)k.out_len) flags |= BZ_INFLATE;
         __syncwarp();
+        bz_walk_block(a, b, k, out, got, rec_offs[warp], lane);
+    }
+}
 
-        // ---- BAM records of the block (SAMv1 4.2): block_size, refID, pos, l_read_name, mapq, bin, n_cigar_op, flag, ... ----
-        const uint64_t rb = bz_rec_base(k.out_off, b), cb = bz_cig_base(k.out_off, b);
-        const uint32_t len = k.out_len;
-        uint32_t p = b == 0 ? a.first_skip : 0u;                 // lane 0's chain position
-        uint32_t n_reads = 0, n_cig = 0;
-        int32_t first_tid = INT32_MIN, first_pos = 0, last_tid = INT32_MIN, last_pos = INT32_MIN;
-        bool chain_end = (flags != 0) || p > len;
-        if (p > len) flags |= BZ_MALFORMED;
-        while (!chain_end) {
-            // lane 0 follows the block_size chain for up to 32 records
-            uint32_t nrec = 0;
-            if (lane == 0) {
-                while (nrec < 32 && p + 4 <= len) {
-                    const uint32_t bs = bz_ld32(out + p);
-                    if (bs < 32 || bs > (1u << 30)) { nrec |= 0x100u; break; }       // malformed
-                    if ((uint64_t)p + 4 + bs > len) { nrec |= 0x200u; break; }       // continues in the next block
-                    T.rec_off[nrec++] = p;
-                    p += 4 + bs;
-                }
-                if (!(nrec & 0x300u) && p + 4 > len) nrec |= 0x400u;                 // end of the block reached
-            }
-            nrec = __shfl_sync(FULLM, nrec, 0);
-            if (nrec & 0x100u) flags |= BZ_MALFORMED;
-            if (nrec & 0x700u) chain_end = true;
-            nrec &= 0xffu;
-            __syncwarp();
-            // every lane parses one record
-            bool keep = false; int32_t tid = 0, pos = 0; uint32_t ncg = 0; const uint8_t *cig = nullptr;
-            if ((uint32_t)lane < nrec) {
-                const uint8_t *rec = out + T.rec_off[lane] + 4;
-                const uint32_t bs = bz_ld32(rec - 4);
-                tid = (int32_t)bz_ld32(rec); pos = (int32_t)bz_ld32(rec + 4);
-                const uint32_t w8 = bz_ld32(rec + 8), w12 = bz_ld32(rec + 12);
-                const uint32_t l_name = w8 & 0xffu, mapq = (w8 >> 8) & 0xffu;
-                ncg = w12 & 0xffffu;
-                const uint32_t flag = w12 >> 16;
-                if (32 + l_name + 4 * ncg > bs) flags |= BZ_MALFORMED;
-                else {
-                    cig = rec + 32 + l_name;
-                    keep = tid >= 0 && tid < a.n_targets && !(flag & a.xflags) && (int32_t)mapq >= a.min_mapq;   // :732-733
-                    if (keep && ncg == 2 && (bz_ld32(cig) & 15u) == 4u && (bz_ld32(cig + 4) & 15u) == 3u) flags |= BZ_CG_TAG;   // `<l_seq>S<ref_len>N`: CIGAR may be in the CG tag
-                    if (keep && ncg != 1) flags |= BZ_MULTI_OP;
-                }
-            }
-            const unsigned km = __ballot_sync(FULLM, keep);
-            if (km) {
-                // order among the records that pass: each compares with the previous passing one
-                const unsigned before = km & ((1u << lane) - 1u);
-                const int src = before ? 31 - __clz(before) : lane;
-                const int32_t ptid = __shfl_sync(FULLM, tid, src), ppos = __shfl_sync(FULLM, pos, src);
-                if (keep) {
-                    const int32_t qt = before ? ptid : last_tid, qp = before ? ppos : last_pos;
-                    if (tid < qt || (tid == qt && pos < qp)) flags |= BZ_UNSORTED;
-                }
-                // staging: record rank and CIGAR word offset by warp prefix sums
-                const uint32_t rank = n_reads + __popc(before);
-                uint32_t c = keep ? ncg : 0u, incl = c;
+// ---------------------------------------------------------------------------------------------------------------
+// K decoders per warp (literal-dominated streams: BAMs with SEQ + QUAL).
+//
+// With one decoder per warp the symbol loop runs on ONE lane: 31 of 32 issue slots of every instruction are empty, and the
+// kernel is issue-bound (32 resident warps x ~0.16 IPC each > 4 IPC per SM).  Here a warp inflates K blocks at once: the
+// leaders of K lane groups run the literal loop in SIMT lockstep (same instructions, K lanes active), leave it when their
+// stream shows a match / end of block, and the warp then serves those events one decoder at a time with all 32 lanes (match
+// copy, block header, table build).  Per-decoder progress lives in its leader's registers; a small state machine
+// (HEADER -> SYMBOLS -> ... -> DONE) replaces the nested loops of bz_inflate.  K = 1 is bz_inflate's behaviour.
+// ---------------------------------------------------------------------------------------------------------------
+enum { BZS_HEADER = 0, BZS_SYMBOLS = 1, BZS_DONE = 2, BZS_ERROR = 3 };
+
+template <int K>
+__device__ __forceinline__ void bz_inflate_multi(const BzArgs &a, uint32_t b0, BzTables *T, uint32_t lit_sa0, int lane, int *got)
+{
+    constexpr unsigned FULLM = 0xffffffffu;
+    constexpr int STRIDE = 32 / K;
+    const int my = lane / STRIDE;                                // the decoder this lane's registers describe
+    const bool leader = (lane % STRIDE) == 0;
+    const uint8_t *inp[K]; uint8_t *outp[K];
+    BzBits br; br.init(a.in, 0);
+    uint32_t o = 0, cap = 0, last = 0, in_len = 0; int state = BZS_DONE;
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(FULLM, incl, o); if (lane >= o) incl += y; }
-                const uint32_t coff = n_cig + incl - c;
-                if (keep) {
-                    a.st_pos[rb + rank] = pos; a.st_tid[rb + rank] = tid; a.st_coff[rb + rank] = coff;
-                    for (uint32_t j = 0; j < ncg; j++) a.st_cig[cb + coff + j] = bz_ld32(cig + 4 * j);
+    for (int j = 0; j < K; j++) {
+        const bool v = b0 + j < a.n_blocks;
+        const BgzfBlockDesc d = a.blk[v ? b0 + j : b0];
+        inp[j] = a.in + d.in_off; outp[j] = a.out + d.out_off;
+        if (my == j && v) { br.init(inp[j], d.in_len); in_len = d.in_len; cap = d.out_len; state = d.out_len ? BZS_HEADER : BZS_DONE; }
+    }
+    const int64_t in_bits = (int64_t)in_len * 8;
+    BzTables &Tm = T[my];
+    const uint32_t lit_sa = lit_sa0 + (uint32_t)my * (2u << BZ_LIT_BITS);          // decoder j's table: 2 KB aligned in the shared window
+    const uint16_t *lit_m = static_cast<const uint16_t *>(bz_shared_ptr(lit_sa));
+    for (;;) {
+        // ---- block headers and tables, one decoder at a time, all lanes ----
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+            const int L = j * STRIDE;
+            if (__shfl_sync(FULLM, state, L) != BZS_HEADER) continue;
+            BzTables &Tj = T[j];
+            uint16_t *lit_j = static_cast<uint16_t *>(bz_shared_ptr(lit_sa0 + (uint32_t)j * (2u << BZ_LIT_BITS)));
+            uint32_t hdr = 0;
+            if (lane == L) { hdr = br.bits(3); if (br.consumed_bits() > in_bits + 64) hdr |= 8u; }
+            hdr = __shfl_sync(FULLM, hdr, L);
+            if (hdr & 8u) { if (lane == L) state = BZS_ERROR; continue; }
+            const uint32_t lastj = hdr & 1u, type = (hdr >> 1) & 3u;
+            if (lane == L) last = lastj;
+            if (type == 0) {                                     // stored block: copied by all lanes
+                uint32_t n = 0, p = 0, oo = 0; int bad = 0;
+                if (lane == L) {
+                    br.align_byte();
+                    n = br.bits(16); const uint32_t nn = br.bits(16);
+                    if ((n ^ nn) != 0xffffu) bad = 1;
+                    p = (uint32_t)(br.consumed_bits() >> 3);
+                    if ((uint64_t)p + n > in_len || o + n > cap) bad = 1;
+                    oo = o;
                 }
-                const int lo_lane = __ffs(km) - 1, hi_lane = 31 - __clz(km);
-                if (first_tid == INT32_MIN) { first_tid = __shfl_sync(FULLM, tid, lo_lane); first_pos = __shfl_sync(FULLM, pos, lo_lane); }
-                last_tid = __shfl_sync(FULLM, tid, hi_lane); last_pos = __shfl_sync(FULLM, pos, hi_lane);
-                n_reads += __popc(km);
-                n_cig += __shfl_sync(FULLM, incl, 31);
+                bad = __shfl_sync(FULLM, bad, L);
+                if (bad) { if (lane == L) state = BZS_ERROR; continue; }
+                n = __shfl_sync(FULLM, n, L); p = __shfl_sync(FULLM, p, L); oo = __shfl_sync(FULLM, oo, L);
+                for (uint32_t q = lane; q < n; q += 32) outp[j][oo + q] = inp[j][p + q];
+                if (lane == L) { o += n; br.seek_bytes(p + n); state = lastj ? BZS_DONE : BZS_HEADER; }
+                __syncwarp();
+                continue;
             }
-            __syncwarp();
+            if (type == 3) { if (lane == L) state = BZS_ERROR; continue; }
+            int nlen = 288, ndist = 30;
+            if (type == 1) {                                     // fixed code (RFC 1951 3.2.6)
+                for (int i = lane; i < 288; i += 32) Tj.lens[24 + i] = i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : 8;
+                if (lane < 30) Tj.lens[24 + 288 + lane] = 5;
+                __syncwarp();
+            } else {                                             // dynamic code (3.2.7)
+                uint32_t h = 0;
+                if (lane == L) h = br.bits(14);
+                h = __shfl_sync(FULLM, h, L);
+                nlen = (int)(h & 31u) + 257; ndist = (int)((h >> 5) & 31u) + 1;
+                const int ncode = (int)(h >> 10) + 4;
+                if (nlen > 286 || ndist > 30) { if (lane == L) state = BZS_ERROR; continue; }
+                if (lane < 24) Tj.lens[lane] = 0;
+                __syncwarp();
+                if (lane == L) {
+                    const uint8_t ORDER[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+                    for (int i = 0; i < ncode; i++) Tj.lens[ORDER[i]] = (uint8_t)br.bits(3);
+                }
+                __syncwarp();
+                if (bz_build(Tj.lens, 19, Tj.dist_cnt, Tj.dist_sym, Tj.dist_fast, BZ_DIST_BITS, Tj.aux, lane) != 0) { if (lane == L) state = BZS_ERROR; continue; }
+                int bad = 0;
+                if (lane == L) {
+                    int idx = 0;
+                    while (idx < nlen + ndist) {
+                        const int sy = bz_symbol(br, Tj.dist_cnt, Tj.dist_sym, Tj.dist_fast, BZ_DIST_BITS);
+                        if (sy < 0) { bad = 1; break; }
+                        if (sy < 16) { Tj.lens[24 + idx++] = (uint8_t)sy; continue; }
+                        int rep, val = 0;
+                        if (sy == 16) { if (idx == 0) { bad = 1; break; } val = Tj.lens[24 + idx - 1]; rep = 3 + (int)br.bits(2); }
+                        else if (sy == 17) rep = 3 + (int)br.bits(3);
+                        else rep = 11 + (int)br.bits(7);
+                        if (idx + rep > nlen + ndist) { bad = 1; break; }
+                        while (rep--) Tj.lens[24 + idx++] = (uint8_t)val;
+                    }
+                    if (!bad && Tj.lens[24 + 256] == 0) bad = 1;
+                    if (br.consumed_bits() > in_bits + 64) bad = 1;
+                }
+                bad = __shfl_sync(FULLM, bad, L);
+                if (bad) { if (lane == L) state = BZS_ERROR; continue; }
+                __syncwarp();
+            }
+            int r = bz_build(Tj.lens + 24, nlen, Tj.lit_cnt, Tj.lit_sym, lit_j, BZ_LIT_BITS, Tj.aux, lane);
+            bool okb = !(r < 0 || (r > 0 && type == 2 && nlen - (int)Tj.lit_cnt[0] != 1));
+            if (okb) {
+                r = bz_build(Tj.lens + 24 + nlen, ndist, Tj.dist_cnt, Tj.dist_sym, Tj.dist_fast, BZ_DIST_BITS, Tj.aux, lane);
+                okb = !(r < 0 || (r > 0 && type == 2 && ndist - (int)Tj.dist_cnt[0] != 1));
+            }
+            if (lane == L) state = okb ? BZS_SYMBOLS : BZS_ERROR;
         }
-        p = __shfl_sync(FULLM, p, 0);
-        // flags raised by single lanes
-        flags = __reduce_or_sync(FULLM, flags);
-        if (!(flags & (BZ_INFLATE | BZ_MALFORMED)) && p != len) flags |= BZ_STRADDLE;
-        if (lane == 0) {
-            BgzfSummary s;
-            s.n_reads = n_reads; s.n_cigar = n_cig; s.used = p; s.flags = flags;
-            s.first_tid = first_tid; s.last_tid = last_tid; s.first_pos = first_pos; s.last_pos = last_tid == INT32_MIN ? 0 : last_pos;
-            a.sum[b] = s;
+        // ---- symbols: the leaders that are inside a block decode until their stream shows a match or the end of the block ----
+        int cmd = 0;                                             // 1 = match, 2 = end of block, 3 = error
+        uint32_t mlen = 0, dist = 0;
+        if (leader && state == BZS_SYMBOLS) {
+            uint8_t *out = outp[0];
+#pragma unroll
+            for (int j = 1; j < K; j++) if (my == j) out = outp[j];
+            for (;;) {
+                br.norm();
+                uint32_t wnd1 = br.peek32() << 1;
+                uint32_t e = bz_lds_u16(lit_sa | (wnd1 & 0x7feu));
+                if (e < 0x1000u && o + 3u <= cap) {
+                    uint8_t *op = out + o;
+                    uint32_t used = e >> 8;
+                    op[0] = (uint8_t)e; wnd1 >>= used;
+                    e = bz_lds_u16(lit_sa | (wnd1 & 0x7feu));
+                    if (e < 0x1000u) {
+                        op[1] = (uint8_t)e; wnd1 >>= (e >> 8); used += e >> 8;
+                        e = bz_lds_u16(lit_sa | (wnd1 & 0x7feu));
+                        if (e < 0x1000u) { op[2] = (uint8_t)e; used += e >> 8; o += 3; }
+                        else o += 2;
+                    } else o += 1;
+                    br.drop(used);
+                    continue;
+                }
+                int sy = bz_symbol(br, Tm.lit_cnt, Tm.lit_sym, lit_m, BZ_LIT_BITS);
+                if (sy < 0) { cmd = 3; break; }
+                if (sy < 256) { if (o >= cap) { cmd = 3; break; } out[o++] = (uint8_t)sy; continue; }
+                if (sy == 256) { cmd = 2; break; }
+                sy -= 257;
+                if (sy >= 29) { cmd = 3; break; }
+                if (sy < 8) mlen = 3u + (uint32_t)sy;
+                else if (sy == 28) mlen = 258u;
+                else { const int x = (sy - 4) >> 2; mlen = 3u + ((4u + ((uint32_t)sy & 3u)) << x) + br.bits(x); }
+                const int d = bz_symbol(br, Tm.dist_cnt, Tm.dist_sym, Tm.dist_fast, BZ_DIST_BITS);
+                if (d < 0 || d >= 30) { cmd = 3; break; }
+                if (d < 4) dist = 1u + (uint32_t)d;
+                else { const int x = (d - 2) >> 1; dist = 1u + ((2u + ((uint32_t)d & 1u)) << x) + br.bits(x); }
+                if (dist > o || o + mlen > cap) { cmd = 3; break; }
+                cmd = 1;
+                break;
+            }
+        }
+        // ---- events, one decoder at a time, all lanes ----
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+            const int L = j * STRIDE;
+            const int cj = __shfl_sync(FULLM, cmd, L);           // (also orders the leader's literal stores before the copy below)
+            if (cj == 0) continue;
+            if (cj == 1) {
+                const uint32_t m = __shfl_sync(FULLM, mlen, L), dd = __shfl_sync(FULLM, dist, L), oo = __shfl_sync(FULLM, o, L);
+                __syncwarp();
+                uint8_t *dst = outp[j] + oo;
+                const uint8_t *src = dst - dd;
+                if (dd >= m) { for (uint32_t q = lane; q < m; q += 32) dst[q] = src[q]; }
+                else if (m <= 2u * dd) { for (uint32_t q = lane; q < m; q += 32) dst[q] = src[q >= dd ? q - dd : q]; }
+                else { for (uint32_t q = lane; q < m; q += 32) dst[q] = src[q % dd]; }
+                if (lane == L) o += m;
+                __syncwarp();
+            } else if (cj == 2) {
+                if (lane == L) state = br.consumed_bits() > in_bits + 7 ? BZS_ERROR : (last ? BZS_DONE : BZS_HEADER);
+            } else if (lane == L) state = BZS_ERROR;
+        }
+        if (!__ballot_sync(FULLM, leader && (state == BZS_HEADER || state == BZS_SYMBOLS))) break;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < K; j++) got[j] = __shfl_sync(FULLM, (state == BZS_DONE && o == cap) ? (int)o : -1, j * STRIDE);
+}
+
+template <int K, int WPC>
+__global__ void __launch_bounds__(WPC * 32, 4) k_bgzf_decode_multi(BzArgs a)
+{
+    constexpr unsigned FULLM = 0xffffffffu;
+    __shared__ uint16_t lit_raw[(WPC * K + 1) << BZ_LIT_BITS];
+    __shared__ BzTables tabs[WPC][K];
+    __shared__ uint32_t rec_offs[WPC][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lit_sa0 = bz_align_tables(lit_raw) + (uint32_t)(warp * K) * (2u << BZ_LIT_BITS);
+    for (;;) {
+        uint32_t b0 = 0;
+        if (lane == 0) b0 = atomicAdd(a.ticket, (uint32_t)K);
+        b0 = __shfl_sync(FULLM, b0, 0);
+        if (b0 >= a.n_blocks) return;
+        int got[K];
+        bz_inflate_multi<K>(a, b0, tabs[warp], lit_sa0, lane, got);
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+            if (b0 + j >= a.n_blocks) break;
+            const BgzfBlockDesc k = a.blk[b0 + j];
+            bz_walk_block(a, b0 + j, k, a.out + k.out_off, got[j], rec_offs[warp], lane);
         }
     }
 }

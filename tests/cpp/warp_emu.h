@@ -129,25 +129,15 @@ inline unsigned __reduce_add_sync(unsigned, unsigned v)
     w.bar.wait();
     return r;
 }
-// "shared window" addresses: the kernels under test form them with bit operations on 2 KB-aligned tables, so the emulation keeps
-// the offset inside a 2 KB frame and a frame table for the rest of the pointer
+// "shared window" addresses: the kernels under test do arithmetic on them (2 KB alignment, OR-ed offsets), so the emulation
+// uses the distance from a 2 KB-aligned anchor near the static objects that stand in for shared memory: linear, and the low
+// 11 bits are those of the host address
 namespace emu {
-static std::mutex frames_mu;
-static std::vector<uintptr_t> frames;
+static char anchor;
+inline uintptr_t shared_base() { return (((uintptr_t)&anchor) - (uintptr_t)(512u << 20)) & ~(uintptr_t)2047; }
 }
-inline uint32_t emu_shared_addr(const void *p)
-{
-    const uintptr_t a = (uintptr_t)p, frame = a >> 11;
-    std::lock_guard<std::mutex> g(emu::frames_mu);
-    for (size_t i = 0; i < emu::frames.size(); i++) if (emu::frames[i] == frame) return (uint32_t)(i << 11 | (a & 2047));
-    emu::frames.push_back(frame);
-    return (uint32_t)((emu::frames.size() - 1) << 11 | (a & 2047));
-}
-inline const void *emu_shared_ptr(uint32_t sa)
-{
-    std::lock_guard<std::mutex> g(emu::frames_mu);
-    return (const void *)((emu::frames[sa >> 11] << 11) | (sa & 2047));
-}
+inline uint32_t emu_shared_addr(const void *p) { return (uint32_t)((uintptr_t)p - emu::shared_base()); }
+inline const void *emu_shared_ptr(uint32_t sa) { return (const void *)(emu::shared_base() + sa); }
 #define __align__(n) __attribute__((aligned(n)))
 inline uint32_t atomicAdd(uint32_t *p, uint32_t v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }

@@ -71,7 +71,9 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("K", [1, 2, 4])
 @pytest.mark.parametrize("name,blocks,xflags,q,warps", CASES)
-def test_emulated_decoder_matches_zlib_and_sequential_walk(name, blocks, xflags, q, warps, checker, bams):
-    r = subprocess.run([checker, bams[name], str(blocks), str(xflags), str(q), str(warps)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900)
+def test_emulated_decoder_matches_zlib_and_sequential_walk(name, blocks, xflags, q, warps, K, checker, bams):
+    """K = 1: k_bgzf_decode; K = 2, 4: k_bgzf_decode_multi<K> (K decoders per warp in SIMT lockstep)."""
+    r = subprocess.run([checker, bams[name], str(blocks), str(xflags), str(q), str(warps), "0", str(K)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900)
     assert r.returncode == 0 and r.stdout.strip().endswith(": ok"), (r.stdout[-2000:], r.stderr[-2000:])

@@ -232,3 +232,21 @@ def test_corrupt_block_is_an_error(mixed):
                 eng.push_bgzf(buf, t, first_skip=skip)
             eng.finalize()
         assert ei.value.code in (1, 6)          # does not inflate to ISIZE (PD_ERR_ARG) or garbage records (PD_ERR_FALLBACK)
+
+
+@pytest.mark.parametrize("K", ["1", "2", "4"])
+def test_device_decode_with_k_decoders_per_warp(K, mixed, monkeypatch):
+    """PANDEPTH_BGZF_K forces the number of decoders per warp (1: k_bgzf_decode; 2 / 4: k_bgzf_decode_multi, the lockstep
+    decoder the engine picks by itself for streams that inflate by less than 4x): same depth from every variant, on the
+    mixed BAM as written, re-compressed Huffman-only (literal runs only) and as stored blocks."""
+    import pandepth_b200 as pd
+    monkeypatch.setenv("PANDEPTH_BGZF_K", K)
+    data, tlen, rec = mixed
+    raw, first, recs, _ = bu.bam_payload(data)
+    want = model.accumulate(tlen, rec, 1796, -1)
+    got, _ = _decode_depth(data, tlen, 1796, -1, per_chunk=17, flags=pd.PD_ASYNC)
+    _assert_depth(got, want, f"K={K} as written")
+    for name in ("huffman_only", "stored", "fixed"):
+        re = bu.rewrite_bgzf(raw, bu.record_cuts(raw, first, recs, max_block=15000), **VARIANTS[name])
+        got, _ = _decode_depth(re, tlen, 1796, -1, per_chunk=23)
+        _assert_depth(got, want, f"K={K} {name}")
