@@ -77,18 +77,19 @@ struct BzArgs {
 // (The first version kept a 64-bit buffer: two 64-bit shifts + a counter update per symbol, 36 warp instructions per
 // literal on SEQ+QUAL data -- the kernel is issue-bound, so the instruction count IS the throughput.)
 struct BzBits {
-    const uint32_t *w; uint32_t wi, wlimit; uint32_t lo, hi; uint32_t sh; int mis;
+    const uint32_t *w; uint32_t wi, wlimit; uint32_t lo, hi, nx; uint32_t sh; int mis;
     // beyond the stream every read returns the word just behind it (the chunk buffer is padded): garbage bits there only ever
     // feed a decode that the consumed_bits() checks reject, and the clamp keeps a corrupt stream from running off the buffer
     __device__ __forceinline__ uint32_t word(uint32_t i) const { return w[i < wlimit ? i : wlimit]; }
+    // nx = word wi is loaded one refill AHEAD of its use, so the load's latency is off the symbol chain
     __device__ __forceinline__ void init(const uint8_t *p, uint32_t n)
     {
         mis = (int)((uintptr_t)p & 3);
         w = reinterpret_cast<const uint32_t *>(p - mis);
         wlimit = (uint32_t)((mis + n + 3) >> 2);                 // words holding stream bytes
-        lo = word(0); hi = word(1); wi = 2; sh = 8u * (uint32_t)mis;
+        lo = word(0); hi = word(1); nx = word(2); wi = 2; sh = 8u * (uint32_t)mis;
     }
-    __device__ __forceinline__ void norm() { if (sh >= 32u) { lo = hi; hi = word(wi); wi++; sh -= 32u; } }   // sh < 64 on entry
+    __device__ __forceinline__ void norm() { if (sh >= 32u) { lo = hi; hi = nx; wi++; nx = word(wi); sh -= 32u; } }   // sh < 64 on entry
     __device__ __forceinline__ uint32_t peek32() const { return __funnelshift_r(lo, hi, sh); }               // needs sh < 32
     __device__ __forceinline__ void drop(uint32_t n) { sh += n; }                                            // then norm() before the next peek
     __device__ __forceinline__ uint32_t bits(int n) { norm(); const uint32_t v = peek32() & ((1u << n) - 1u); sh += (uint32_t)n; return v; }   // n <= 16
@@ -98,7 +99,7 @@ struct BzBits {
     {
         const uint32_t a = (uint32_t)mis + byte_pos;
         const uint32_t idx = a >> 2;
-        lo = word(idx); hi = word(idx + 1); wi = idx + 2; sh = (a & 3u) * 8u;
+        lo = word(idx); hi = word(idx + 1); nx = word(idx + 2); wi = idx + 2; sh = (a & 3u) * 8u;
     }
 };
 
@@ -485,35 +486,49 @@ __global__ void __launch_bounds__(BZ_WPC * 32, 4) k_bgzf_decode(BzArgs a)
 // ---------------------------------------------------------------------------------------------------------------
 // K decoders per warp (literal-dominated streams: BAMs with SEQ + QUAL).
 //
-// With one decoder per warp the symbol loop runs on ONE lane: 31 of 32 issue slots of every instruction are empty, and the
-// kernel is issue-bound (32 resident warps x ~0.16 IPC each > 4 IPC per SM).  Here a warp inflates K blocks at once: the
-// leaders of K lane groups run the literal loop in SIMT lockstep (same instructions, K lanes active), leave it when their
-// stream shows a match / end of block, and the warp then serves those events one decoder at a time with all 32 lanes (match
-// copy, block header, table build).  Per-decoder progress lives in its leader's registers; a small state machine
-// (HEADER -> SYMBOLS -> ... -> DONE) replaces the nested loops of bz_inflate.  K = 1 is bz_inflate's behaviour.
+// With one decoder per warp the symbol loop runs on ONE lane: every instruction spends a whole issue slot on one literal, and
+// the kernel is issue-bound (about 13 warp instructions per literal).  Here a warp inflates K blocks at once.  The K lane-group
+// leaders run the symbol loop TOGETHER: the loop itself is warp-uniform (every lane iterates, a warp vote closes each
+// iteration, so the leaders re-converge after every step -- a loop that only the leaders execute does not: after their first
+// divergence the hardware schedules them one after the other until the loop's exit, which is what the first version of this
+// kernel did and why it was slower than one decoder per warp), and one step decodes up to three literals per leader.  A leader
+// also serves most of its own matches (short, source before the destination: random SEQ coincidences and the record header
+// fields -- 86 % of the matches of such a stream) and the rare codes longer than the first-level table.  What needs the whole
+// warp -- long or overlapping matches, block headers and table builds -- stops the loop at the first such event and is served
+// one decoder at a time with all 32 lanes.  Per-decoder progress lives in its leader's registers.
 // ---------------------------------------------------------------------------------------------------------------
 enum { BZS_HEADER = 0, BZS_SYMBOLS = 1, BZS_DONE = 2, BZS_ERROR = 3 };
 
+__device__ __forceinline__ bool bz_any(bool p)
+{
+    return __ballot_sync(0xffffffffu, p) != 0u;
+}
+
+template <typename P>
+__device__ __forceinline__ P *bz_shfl_ptr(P *p, int src)
+{
+    return reinterpret_cast<P *>((uintptr_t)__shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)p, src));
+}
+
+constexpr uint32_t BZ_SELF_MAX = 64;     // longest match a leader copies itself (source entirely before the destination)
+
+// returns, to every lane, the result of the decoder its lane group describes: bytes written (== the block's ISIZE) or -1
 template <int K>
-__device__ __forceinline__ void bz_inflate_multi(const BzArgs &a, uint32_t b0, BzTables *T, uint32_t lit_sa0, int lane, int *got)
+__device__ __forceinline__ int bz_inflate_multi(const BzArgs &a, uint32_t b0, BzTables *T, uint32_t lit_sa0, int lane)
 {
     constexpr unsigned FULLM = 0xffffffffu;
     constexpr int STRIDE = 32 / K;
     const int my = lane / STRIDE;                                // the decoder this lane's registers describe
     const bool leader = (lane % STRIDE) == 0;
-    const uint8_t *inp[K]; uint8_t *outp[K];
-    BzBits br; br.init(a.in, 0);
-    uint32_t o = 0, cap = 0, last = 0, in_len = 0; int state = BZS_DONE;
-#pragma unroll
-    for (int j = 0; j < K; j++) {
-        const bool v = b0 + j < a.n_blocks;
-        const BgzfBlockDesc d = a.blk[v ? b0 + j : b0];
-        inp[j] = a.in + d.in_off; outp[j] = a.out + d.out_off;
-        if (my == j && v) { br.init(inp[j], d.in_len); in_len = d.in_len; cap = d.out_len; state = d.out_len ? BZS_HEADER : BZS_DONE; }
-    }
+    const bool valid = b0 + (uint32_t)my < a.n_blocks;
+    const BgzfBlockDesc d = a.blk[valid ? b0 + (uint32_t)my : b0];
+    const uint8_t *in_my = a.in + d.in_off; uint8_t *out_my = a.out + d.out_off;
+    const uint32_t in_len = valid ? d.in_len : 0u, cap = valid ? d.out_len : 0u;
+    BzBits br; br.init(in_my, in_len);
+    uint32_t o = 0, last = 0; int state = (valid && cap) ? BZS_HEADER : BZS_DONE;
     const int64_t in_bits = (int64_t)in_len * 8;
     BzTables &Tm = T[my];
-    const uint32_t lit_sa = lit_sa0 + (uint32_t)my * (2u << BZ_LIT_BITS);          // decoder j's table: 2 KB aligned in the shared window
+    const uint32_t lit_sa = lit_sa0 + (uint32_t)my * (2u << BZ_LIT_BITS);          // decoder `my`'s table: 2 KB aligned in the shared window
     const uint16_t *lit_m = static_cast<const uint16_t *>(bz_shared_ptr(lit_sa));
     for (;;) {
         // ---- block headers and tables, one decoder at a time, all lanes ----
@@ -542,7 +557,8 @@ __device__ __forceinline__ void bz_inflate_multi(const BzArgs &a, uint32_t b0, B
                 bad = __shfl_sync(FULLM, bad, L);
                 if (bad) { if (lane == L) state = BZS_ERROR; continue; }
                 n = __shfl_sync(FULLM, n, L); p = __shfl_sync(FULLM, p, L); oo = __shfl_sync(FULLM, oo, L);
-                for (uint32_t q = lane; q < n; q += 32) outp[j][oo + q] = inp[j][p + q];
+                const uint8_t *in_j = bz_shfl_ptr(in_my, L); uint8_t *out_j = bz_shfl_ptr(out_my, L);
+                for (uint32_t q = lane; q < n; q += 32) out_j[oo + q] = in_j[p + q];
                 if (lane == L) { o += n; br.seek_bytes(p + n); state = lastj ? BZS_DONE : BZS_HEADER; }
                 __syncwarp();
                 continue;
@@ -597,48 +613,84 @@ __device__ __forceinline__ void bz_inflate_multi(const BzArgs &a, uint32_t b0, B
             }
             if (lane == L) state = okb ? BZS_SYMBOLS : BZS_ERROR;
         }
-        // ---- symbols: the leaders that are inside a block decode until their stream shows a match or the end of the block ----
-        int cmd = 0;                                             // 1 = match, 2 = end of block, 3 = error
+        // ---- symbols: a warp-uniform loop; the leaders inside a block advance together until one of them needs the warp ----
+        int cmd = 0;                                             // 1 = match for the warp, 2 = end of block, 3 = error
         uint32_t mlen = 0, dist = 0;
-        if (leader && state == BZS_SYMBOLS) {
-            uint8_t *out = outp[0];
-#pragma unroll
-            for (int j = 1; j < K; j++) if (my == j) out = outp[j];
-            for (;;) {
-                br.norm();
-                uint32_t wnd1 = br.peek32() << 1;
-                uint32_t e = bz_lds_u16(lit_sa | (wnd1 & 0x7feu));
-                if (e < 0x1000u && o + 3u <= cap) {
-                    uint8_t *op = out + o;
-                    uint32_t used = e >> 8;
-                    op[0] = (uint8_t)e; wnd1 >>= used;
-                    e = bz_lds_u16(lit_sa | (wnd1 & 0x7feu));
-                    if (e < 0x1000u) {
-                        op[1] = (uint8_t)e; wnd1 >>= (e >> 8); used += e >> 8;
+        const bool act = leader && state == BZS_SYMBOLS;
+        if (bz_any(act)) {
+            do {
+                if (act) {
+                    br.norm();
+                    uint32_t wnd1 = br.peek32() << 1;
+                    uint32_t e = bz_lds_u16(lit_sa | (wnd1 & 0x7feu));
+                    if (e < 0x1000u && o + 3u <= cap) {              // up to three first-level literal hits out of one 32-bit window
+                        uint8_t *op = out_my + o;
+                        uint32_t used = e >> 8;
+                        op[0] = (uint8_t)e; wnd1 >>= used;
                         e = bz_lds_u16(lit_sa | (wnd1 & 0x7feu));
-                        if (e < 0x1000u) { op[2] = (uint8_t)e; used += e >> 8; o += 3; }
-                        else o += 2;
-                    } else o += 1;
-                    br.drop(used);
-                    continue;
+                        if (e < 0x1000u) {
+                            op[1] = (uint8_t)e; wnd1 >>= (e >> 8); used += e >> 8;
+                            e = bz_lds_u16(lit_sa | (wnd1 & 0x7feu));
+                            if (e < 0x1000u) { op[2] = (uint8_t)e; used += e >> 8; o += 3; }
+                            else o += 2;
+                        } else o += 1;
+                        br.drop(used);
+                    } else {
+                        int sy = bz_symbol(br, Tm.lit_cnt, Tm.lit_sym, lit_m, BZ_LIT_BITS);
+                        if (sy < 0) cmd = 3;
+                        else if (sy < 256) { if (o >= cap) cmd = 3; else out_my[o++] = (uint8_t)sy; }
+                        else if (sy == 256) cmd = 2;
+                        else if (sy >= 257 + 29) cmd = 3;
+                        else {
+                            sy -= 257;
+                            if (sy < 8) mlen = 3u + (uint32_t)sy;
+                            else if (sy == 28) mlen = 258u;
+                            else { const int x = (sy - 4) >> 2; mlen = 3u + ((4u + ((uint32_t)sy & 3u)) << x) + br.bits(x); }
+                            const int dc = bz_symbol(br, Tm.dist_cnt, Tm.dist_sym, Tm.dist_fast, BZ_DIST_BITS);
+                            if (dc < 0 || dc >= 30) cmd = 3;
+                            else {
+                                if (dc < 4) dist = 1u + (uint32_t)dc;
+                                else { const int x = (dc - 2) >> 1; dist = 1u + ((2u + ((uint32_t)dc & 1u)) << x) + br.bits(x); }
+                                if (dist > o || o + mlen > cap) cmd = 3;
+                                else if (dist >= mlen && mlen <= BZ_SELF_MAX) {
+                                    // the leader's own copy: all loads of a piece before its stores (one memory round trip per piece).
+                                    // Away from the block's end a piece is stored whole -- the bytes behind the match are garbage that
+                                    // the following symbols overwrite (output is strictly sequential) -- so no per-byte predicates;
+                                    // the loads may read up to 19 bytes past the match, inside the padded buffer.
+                                    const uint8_t *src = out_my + o - dist; uint8_t *dst = out_my + o;
+                                    if (mlen <= 8u && o + 8u <= cap) {
+                                        const uint32_t *al = reinterpret_cast<const uint32_t *>((uintptr_t)src & ~(uintptr_t)3);
+                                        const uint32_t s8 = (uint32_t)((uintptr_t)src & 3) * 8;
+                                        const uint32_t a0 = al[0], a1 = al[1], a2 = al[2];
+                                        const uint32_t w0 = __funnelshift_r(a0, a1, s8), w1 = __funnelshift_r(a1, a2, s8);
+                                        dst[0] = (uint8_t)w0; dst[1] = (uint8_t)(w0 >> 8); dst[2] = (uint8_t)(w0 >> 16); dst[3] = (uint8_t)(w0 >> 24);
+                                        dst[4] = (uint8_t)w1; dst[5] = (uint8_t)(w1 >> 8); dst[6] = (uint8_t)(w1 >> 16); dst[7] = (uint8_t)(w1 >> 24);
+                                    } else {
+                                        uint32_t q = 0;
+                                        do {
+                                            const uint32_t *al = reinterpret_cast<const uint32_t *>((uintptr_t)(src + q) & ~(uintptr_t)3);
+                                            const uint32_t s8 = (uint32_t)((uintptr_t)(src + q) & 3) * 8;
+                                            const uint32_t a0 = al[0], a1 = al[1], a2 = al[2], a3 = al[3], a4 = al[4];
+                                            uint32_t wv[4] = {__funnelshift_r(a0, a1, s8), __funnelshift_r(a1, a2, s8), __funnelshift_r(a2, a3, s8), __funnelshift_r(a3, a4, s8)};
+                                            uint8_t *dp = dst + q;
+                                            if (o + q + 16u <= cap) {
+#pragma unroll
+                                                for (int k = 0; k < 16; k++) dp[k] = (uint8_t)(wv[k >> 2] >> (8 * (k & 3)));
+                                            } else {
+                                                const uint32_t n = mlen - q;
+#pragma unroll
+                                                for (int k = 0; k < 16; k++) if ((uint32_t)k < n) dp[k] = (uint8_t)(wv[k >> 2] >> (8 * (k & 3)));
+                                            }
+                                            q += 16;
+                                        } while (q < mlen);
+                                    }
+                                    o += mlen;
+                                } else cmd = 1;
+                            }
+                        }
+                    }
                 }
-                int sy = bz_symbol(br, Tm.lit_cnt, Tm.lit_sym, lit_m, BZ_LIT_BITS);
-                if (sy < 0) { cmd = 3; break; }
-                if (sy < 256) { if (o >= cap) { cmd = 3; break; } out[o++] = (uint8_t)sy; continue; }
-                if (sy == 256) { cmd = 2; break; }
-                sy -= 257;
-                if (sy >= 29) { cmd = 3; break; }
-                if (sy < 8) mlen = 3u + (uint32_t)sy;
-                else if (sy == 28) mlen = 258u;
-                else { const int x = (sy - 4) >> 2; mlen = 3u + ((4u + ((uint32_t)sy & 3u)) << x) + br.bits(x); }
-                const int d = bz_symbol(br, Tm.dist_cnt, Tm.dist_sym, Tm.dist_fast, BZ_DIST_BITS);
-                if (d < 0 || d >= 30) { cmd = 3; break; }
-                if (d < 4) dist = 1u + (uint32_t)d;
-                else { const int x = (d - 2) >> 1; dist = 1u + ((2u + ((uint32_t)d & 1u)) << x) + br.bits(x); }
-                if (dist > o || o + mlen > cap) { cmd = 3; break; }
-                cmd = 1;
-                break;
-            }
+            } while (!bz_any(cmd != 0));
         }
         // ---- events, one decoder at a time, all lanes ----
 #pragma unroll
@@ -648,8 +700,9 @@ __device__ __forceinline__ void bz_inflate_multi(const BzArgs &a, uint32_t b0, B
             if (cj == 0) continue;
             if (cj == 1) {
                 const uint32_t m = __shfl_sync(FULLM, mlen, L), dd = __shfl_sync(FULLM, dist, L), oo = __shfl_sync(FULLM, o, L);
+                uint8_t *dst = bz_shfl_ptr(out_my, L) + oo;
                 __syncwarp();
-                uint8_t *dst = outp[j] + oo;
+                // byte oo+q of a match equals byte oo-dd+(q mod dd): every source lies before oo, so all lanes copy at once
                 const uint8_t *src = dst - dd;
                 if (dd >= m) { for (uint32_t q = lane; q < m; q += 32) dst[q] = src[q]; }
                 else if (m <= 2u * dd) { for (uint32_t q = lane; q < m; q += 32) dst[q] = src[q >= dd ? q - dd : q]; }
@@ -660,17 +713,17 @@ __device__ __forceinline__ void bz_inflate_multi(const BzArgs &a, uint32_t b0, B
                 if (lane == L) state = br.consumed_bits() > in_bits + 7 ? BZS_ERROR : (last ? BZS_DONE : BZS_HEADER);
             } else if (lane == L) state = BZS_ERROR;
         }
-        if (!__ballot_sync(FULLM, leader && (state == BZS_HEADER || state == BZS_SYMBOLS))) break;
+        if (!bz_any(leader && (state == BZS_HEADER || state == BZS_SYMBOLS))) break;
     }
     __syncwarp();
-#pragma unroll
-    for (int j = 0; j < K; j++) got[j] = __shfl_sync(FULLM, (state == BZS_DONE && o == cap) ? (int)o : -1, j * STRIDE);
+    return __shfl_sync(FULLM, (state == BZS_DONE && o == cap) ? (int)o : -1, my * STRIDE);
 }
 
 template <int K, int WPC>
-__global__ void __launch_bounds__(WPC * 32, 4) k_bgzf_decode_multi(BzArgs a)
+__global__ void __launch_bounds__(WPC * 32, 6) k_bgzf_decode_multi(BzArgs a)
 {
     constexpr unsigned FULLM = 0xffffffffu;
+    constexpr int STRIDE = 32 / K;
     __shared__ uint16_t lit_raw[(WPC * K + 1) << BZ_LIT_BITS];
     __shared__ BzTables tabs[WPC][K];
     __shared__ uint32_t rec_offs[WPC][32];
@@ -681,13 +734,13 @@ __global__ void __launch_bounds__(WPC * 32, 4) k_bgzf_decode_multi(BzArgs a)
         if (lane == 0) b0 = atomicAdd(a.ticket, (uint32_t)K);
         b0 = __shfl_sync(FULLM, b0, 0);
         if (b0 >= a.n_blocks) return;
-        int got[K];
-        bz_inflate_multi<K>(a, b0, tabs[warp], lit_sa0, lane, got);
+        const int got_my = bz_inflate_multi<K>(a, b0, tabs[warp], lit_sa0, lane);
 #pragma unroll
         for (int j = 0; j < K; j++) {
             if (b0 + j >= a.n_blocks) break;
+            const int got = __shfl_sync(FULLM, got_my, j * STRIDE);
             const BgzfBlockDesc k = a.blk[b0 + j];
-            bz_walk_block(a, b0 + j, k, a.out + k.out_off, got[j], rec_offs[warp], lane);
+            bz_walk_block(a, b0 + j, k, a.out + k.out_off, got, rec_offs[warp], lane);
         }
     }
 }

@@ -97,8 +97,9 @@ struct pd_engine {
     BzSlot bz[N_BZ]; int bz_next = 0;
     int32_t bz_prog_tid = -1, bz_prog_pos = -1;   // first record of the last block (with records) of the last chunk that was planned
     uint8_t *d_owned = nullptr;
-    int bz_grid = 148 * 4, bz_grid_k2 = 148 * 4, bz_grid_k4 = 148 * 4;
-    int bz_force_k = 0;              // PANDEPTH_BGZF_K=1|2|4: decoders per warp (default: by compression ratio)
+    int bz_grid = 148 * 4, bz_grid_k2 = 148 * 6, bz_grid_k4 = 148 * 6, bz_grid_k8 = 148 * 6;
+    int bz_force_k = 0;              // PANDEPTH_BGZF_K=1|2|4|8: decoders per warp (default: by compression ratio)
+    int bz_lit_k = 4;                // decoders per warp for literal-dominated chunks (PANDEPTH_BGZF_LIT_K)
 
     // reduce scratch
     void *d_red = nullptr; size_t red_cap = 0;
@@ -555,11 +556,14 @@ pd_engine *pd_create_ranges(int device, int n_targets, const uint32_t *target_le
             e->tile_resident_warps = n_sm * per_sm * pdk::WPC;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pdk::k_bgzf_decode, pdk::BZ_WPC * 32, 0) == cudaSuccess && n_sm > 0 && per_sm > 0)
             e->bz_grid = n_sm * per_sm;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pdk::k_bgzf_decode_multi<2, 5>, 5 * 32, 0) == cudaSuccess && n_sm > 0 && per_sm > 0)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pdk::k_bgzf_decode_multi<2, 4>, 4 * 32, 0) == cudaSuccess && n_sm > 0 && per_sm > 0)
             e->bz_grid_k2 = n_sm * per_sm;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pdk::k_bgzf_decode_multi<4, 2>, 2 * 32, 0) == cudaSuccess && n_sm > 0 && per_sm > 0)
             e->bz_grid_k4 = n_sm * per_sm;
-        if (const char *fk = getenv("PANDEPTH_BGZF_K")) { const int v = atoi(fk); if (v == 1 || v == 2 || v == 4) e->bz_force_k = v; }
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pdk::k_bgzf_decode_multi<8, 1>, 1 * 32, 0) == cudaSuccess && n_sm > 0 && per_sm > 0)
+            e->bz_grid_k8 = n_sm * per_sm;
+        if (const char *fk = getenv("PANDEPTH_BGZF_K")) { const int v = atoi(fk); if (v == 1 || v == 2 || v == 4 || v == 8) e->bz_force_k = v; }
+        if (const char *fk = getenv("PANDEPTH_BGZF_LIT_K")) { const int v = atoi(fk); if (v == 1 || v == 2 || v == 4 || v == 8) e->bz_lit_k = v; }
     }
     if ((ce = cudaStreamSynchronize(e->stream)) != cudaSuccess) return bail("sync", ce);
     lap("tables, memsets, attributes");
@@ -738,12 +742,13 @@ int pd_push_bgzf(pd_engine *e, const uint8_t *bytes, size_t n_bytes, const pd_bg
         CK(cudaMemsetAsync(s.d_ticket, 0, 4, s.stream));
         pdk::BzArgs a{d_in, s.d_out, s.d_blk, (uint32_t)n_blocks, first_skip, e->n_targets, e->xflags, e->min_mapq,
                       s.st_pos, s.st_tid, s.st_coff, s.st_cig, s.d_sum, s.d_ticket};
-        // literal-dominated streams (BAMs with SEQ + QUAL inflate by less than 4x): K decoders per warp in SIMT lockstep
-        int K = out_total < 4 * (hi - lo) ? 2 : 1;
+        // literal-dominated streams (BAMs with SEQ + QUAL inflate by less than 4x): K decoders per warp, symbol loop in lockstep
+        int K = out_total < 4 * (hi - lo) ? e->bz_lit_k : 1;
         if (e->bz_force_k) K = e->bz_force_k;
         rc = launch_on(e, s.stream, K_BGZF, [&] {
-            if (K == 2) { const unsigned g = (unsigned)std::min<int64_t>((n_blocks + 9) / 10, e->bz_grid_k2); pdk::k_bgzf_decode_multi<2, 5><<<g, 5 * 32, 0, s.stream>>>(a); }
+            if (K == 2) { const unsigned g = (unsigned)std::min<int64_t>((n_blocks + 7) / 8, e->bz_grid_k2); pdk::k_bgzf_decode_multi<2, 4><<<g, 4 * 32, 0, s.stream>>>(a); }
             else if (K == 4) { const unsigned g = (unsigned)std::min<int64_t>((n_blocks + 7) / 8, e->bz_grid_k4); pdk::k_bgzf_decode_multi<4, 2><<<g, 2 * 32, 0, s.stream>>>(a); }
+            else if (K == 8) { const unsigned g = (unsigned)std::min<int64_t>((n_blocks + 7) / 8, e->bz_grid_k8); pdk::k_bgzf_decode_multi<8, 1><<<g, 1 * 32, 0, s.stream>>>(a); }
             else { const unsigned g = (unsigned)std::min<int64_t>((n_blocks + pdk::BZ_WPC - 1) / pdk::BZ_WPC, e->bz_grid); pdk::k_bgzf_decode<<<g, pdk::BZ_WPC * 32, 0, s.stream>>>(a); }
         });
         if (rc) return rc;

@@ -1,6 +1,6 @@
 // CPU check of the device BGZF decoder (pandepth_b200/csrc/pd_bgzf.cuh) through the warp emulator (warp_emu.h):
 //   bgzf_emu_check file.bam [max_blocks] [xflags] [min_mapq] [warps] [first_block] [K]
-//     K = 1: k_bgzf_decode (one decoder per warp); K = 2 / 4: k_bgzf_decode_multi<K> (K decoders per warp in lockstep)
+//     K = 1: k_bgzf_decode (one decoder per warp); K = 2 / 4 / 8: k_bgzf_decode_multi<K> (K decoders per warp, symbol loop in lockstep)
 // Every block: inflated bytes == zlib; dense pos / tid / cigar_off / cigar arrays, per-block summaries and totals == a plain
 // sequential walk (walk_bam_block of pd_inflate.cuh, itself pinned to htslib by tests/test_inflate_cpu.py).
 #define PD_WARP_EMU 1
@@ -85,8 +85,9 @@ int main(int argc, char **argv)
     uint32_t ticket = 0;
     BzArgs a{data.data(), out.data(), blk.data(), (uint32_t)nb, skip0, (int32_t)n_ref, xflags, min_mapq,
              st_pos.data(), st_tid.data(), st_coff.data(), st_cigv.data(), sum.data(), &ticket};
-    if (K == 2) emu::launch(1, 32 * std::min(warps, 5u), k_bgzf_decode_multi<2, 5>, a);
+    if (K == 2) emu::launch(1, 32 * std::min(warps, 4u), k_bgzf_decode_multi<2, 4>, a);
     else if (K == 4) emu::launch(1, 32 * std::min(warps, 2u), k_bgzf_decode_multi<4, 2>, a);
+    else if (K == 8) emu::launch(1, 32, k_bgzf_decode_multi<8, 1>, a);
     else emu::launch(1, 32 * warps, k_bgzf_decode, a);
     emu::launch(1, 1024, offsets_entry, OffArgs((const BgzfSummary *)sum.data(), (uint32_t)nb, r0.data(), c0.data(), totals.data()));
     BzCompactArgs c{blk.data(), sum.data(), r0.data(), c0.data(), (uint32_t)nb, st_pos.data(), st_tid.data(), st_coff.data(), st_cigv.data(),

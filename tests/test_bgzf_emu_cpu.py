@@ -66,14 +66,14 @@ def bams(tmp_path_factory):
 
 CASES = [
     # (file, max_blocks, xflags, min_mapq, warps)
-    ("A", 3, 1796, -1, 2), ("B", 2, 1796, -1, 1), ("M", 4, 1796, -1, 2), ("M", 3, 0, 20, 1), ("stored", 6, 1796, -1, 2), ("fixed", 5, 3844, 5, 1),
+    ("A", 3, 1796, -1, 2), ("B", 2, 1796, -1, 1), ("B", 7, 0, -1, 2), ("M", 4, 1796, -1, 2), ("M", 3, 0, 20, 1), ("stored", 6, 1796, -1, 2), ("fixed", 5, 3844, 5, 1),
     ("huff", 4, 1796, -1, 1), ("rle", 4, 0, 20, 2), ("l9", 5, 1796, -1, 1), ("tiny", 150, 1796, -1, 2), ("straddle", 6, 1796, -1, 1), ("shuffled", 5, 0, 20, 2),
 ]
 
 
-@pytest.mark.parametrize("K", [1, 2, 4])
+@pytest.mark.parametrize("K", [1, 2, 4, 8])
 @pytest.mark.parametrize("name,blocks,xflags,q,warps", CASES)
 def test_emulated_decoder_matches_zlib_and_sequential_walk(name, blocks, xflags, q, warps, K, checker, bams):
-    """K = 1: k_bgzf_decode; K = 2, 4: k_bgzf_decode_multi<K> (K decoders per warp in SIMT lockstep)."""
+    """K = 1: k_bgzf_decode; K = 2, 4, 8: k_bgzf_decode_multi<K> (K decoders per warp, warp-uniform symbol loop)."""
     r = subprocess.run([checker, bams[name], str(blocks), str(xflags), str(q), str(warps), "0", str(K)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900)
     assert r.returncode == 0 and r.stdout.strip().endswith(": ok"), (r.stdout[-2000:], r.stderr[-2000:])

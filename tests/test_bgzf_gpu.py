@@ -234,9 +234,9 @@ def test_corrupt_block_is_an_error(mixed):
         assert ei.value.code in (1, 6)          # does not inflate to ISIZE (PD_ERR_ARG) or garbage records (PD_ERR_FALLBACK)
 
 
-@pytest.mark.parametrize("K", ["1", "2", "4"])
+@pytest.mark.parametrize("K", ["1", "2", "4", "8"])
 def test_device_decode_with_k_decoders_per_warp(K, mixed, monkeypatch):
-    """PANDEPTH_BGZF_K forces the number of decoders per warp (1: k_bgzf_decode; 2 / 4: k_bgzf_decode_multi, the lockstep
+    """PANDEPTH_BGZF_K forces the number of decoders per warp (1: k_bgzf_decode; 2 / 4 / 8: k_bgzf_decode_multi, the lockstep
     decoder the engine picks by itself for streams that inflate by less than 4x): same depth from every variant, on the
     mixed BAM as written, re-compressed Huffman-only (literal runs only) and as stored blocks."""
     import pandepth_b200 as pd
@@ -250,3 +250,27 @@ def test_device_decode_with_k_decoders_per_warp(K, mixed, monkeypatch):
         re = bu.rewrite_bgzf(raw, bu.record_cuts(raw, first, recs, max_block=15000), **VARIANTS[name])
         got, _ = _decode_depth(re, tlen, 1796, -1, per_chunk=23)
         _assert_depth(got, want, f"K={K} {name}")
+
+
+@pytest.mark.parametrize("K", ["1", "2", "4", "8"])
+def test_device_decode_literal_dominated_bam_with_k_decoders(K, tmp_path, monkeypatch):
+    """Flavour B of SURVEY 8(d) (random SEQ + QUAL: literal runs, short matches the lane-group leaders copy themselves, 14-bit
+    codes behind the first-level table): every decoder variant against depth computed from the generator's records."""
+    import pandepth_b200 as pd
+    monkeypatch.setenv("PANDEPTH_BGZF_K", K)
+    bam = str(tmp_path / "b.bam")
+    subprocess.run([BAMGEN, "-P", "-q", "-o", bam, "-c", "c1:400000,c2:250000", "-n", "12000", "-s", "11", "-t", "2"], check=True)
+    data = open(bam, "rb").read()
+    raw, first, recs, _ = bu.bam_payload(data)
+    tlen = np.array([400000, 250000], np.uint32)
+    want = [np.zeros(int(n) + 1, np.int64) for n in tlen]
+    ends = recs[1:] + [len(raw)]
+    for a in recs:
+        tid, pos = np.frombuffer(raw, np.int32, 2, a + 4)
+        w = int(np.frombuffer(raw, np.uint32, 1, a + 36 + raw[a + 12])[0])       # the single CIGAR word (150M)
+        assert w & 15 == 0
+        want[tid][pos] += 1; want[tid][min(pos + (w >> 4), int(tlen[tid]))] -= 1
+    want = [np.cumsum(w)[:-1].astype(np.uint32) for w in want]
+    got, _ = _decode_depth(data, tlen, 1796, -1, per_chunk=5, flags=pd.PD_ASYNC)
+    _assert_depth(got, want, f"flavour B, K={K}")
+    assert sum(int(g.sum(dtype=np.uint64)) for g in got) == 150 * len(recs)
