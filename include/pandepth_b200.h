@@ -105,7 +105,9 @@ int pd_push(pd_engine *e, int64_t n_reads, const int32_t *tid, const int32_t *po
  * accumulated by earlier chunks stays in the engine: the caller resets it and feeds the file through pd_push_contig.
  * A block that does not inflate to its ISIZE is PD_ERR_ARG. */
 typedef struct pd_bgzf_block { uint64_t in_off; uint32_t in_len; uint32_t out_len; } pd_bgzf_block;
-#define PD_BGZF_DEPTH 3   /* PD_ASYNC: `bytes` of a call is no longer read once this many later pd_push_bgzf calls have returned */
+#ifndef PD_BGZF_DEPTH
+#define PD_BGZF_DEPTH 6   /* PD_ASYNC: `bytes` of a call is no longer read once this many later pd_push_bgzf calls have returned */
+#endif
 int pd_push_bgzf(pd_engine *e, const uint8_t *bytes, size_t n_bytes, const pd_bgzf_block *blocks, int64_t n_blocks,
                  uint32_t first_skip, uint32_t flags);
 

@@ -460,7 +460,10 @@ __device__ __forceinline__ void bz_walk_block(const BzArgs &a, uint32_t b, const
 // ---------------------------------------------------------------------------------------------------------------
 // k_bgzf_decode: one decoder per warp (match-dominated streams: SEQ-less BAMs, ratio >= 4)
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(BZ_WPC * 32, 4) k_bgzf_decode(BzArgs a)
+#ifndef PD_BZ_K1_CTAS
+#define PD_BZ_K1_CTAS 4               // resident CTAs per SM k_bgzf_decode is compiled for (register cap: 4 -> 64, 5 -> 48, 6 -> 40)
+#endif
+__global__ void __launch_bounds__(BZ_WPC * 32, PD_BZ_K1_CTAS) k_bgzf_decode(BzArgs a)
 {
     constexpr unsigned FULLM = 0xffffffffu;
     __shared__ uint16_t lit_raw[(BZ_WPC + 1) << BZ_LIT_BITS];
@@ -513,11 +516,12 @@ __device__ __forceinline__ P *bz_shfl_ptr(P *p, int src)
 constexpr uint32_t BZ_SELF_MAX = 64;     // longest match a leader copies itself (source entirely before the destination)
 
 // returns, to every lane, the result of the decoder its lane group describes: bytes written (== the block's ISIZE) or -1
-template <int K>
+template <int K, int LB>
 __device__ __forceinline__ int bz_inflate_multi(const BzArgs &a, uint32_t b0, BzTables *T, uint32_t lit_sa0, int lane)
 {
     constexpr unsigned FULLM = 0xffffffffu;
     constexpr int STRIDE = 32 / K;
+    constexpr uint32_t LMASK = ((1u << LB) - 1u) << 1;          // byte offset of a first-level entry: (window << 1) & LMASK
     const int my = lane / STRIDE;                                // the decoder this lane's registers describe
     const bool leader = (lane % STRIDE) == 0;
     const bool valid = b0 + (uint32_t)my < a.n_blocks;
@@ -528,7 +532,7 @@ __device__ __forceinline__ int bz_inflate_multi(const BzArgs &a, uint32_t b0, Bz
     uint32_t o = 0, last = 0; int state = (valid && cap) ? BZS_HEADER : BZS_DONE;
     const int64_t in_bits = (int64_t)in_len * 8;
     BzTables &Tm = T[my];
-    const uint32_t lit_sa = lit_sa0 + (uint32_t)my * (2u << BZ_LIT_BITS);          // decoder `my`'s table: 2 KB aligned in the shared window
+    const uint32_t lit_sa = lit_sa0 + (uint32_t)my * (2u << LB);          // decoder `my`'s table: 2 KB aligned in the shared window
     const uint16_t *lit_m = static_cast<const uint16_t *>(bz_shared_ptr(lit_sa));
     for (;;) {
         // ---- block headers and tables, one decoder at a time, all lanes ----
@@ -537,7 +541,7 @@ __device__ __forceinline__ int bz_inflate_multi(const BzArgs &a, uint32_t b0, Bz
             const int L = j * STRIDE;
             if (__shfl_sync(FULLM, state, L) != BZS_HEADER) continue;
             BzTables &Tj = T[j];
-            uint16_t *lit_j = static_cast<uint16_t *>(bz_shared_ptr(lit_sa0 + (uint32_t)j * (2u << BZ_LIT_BITS)));
+            uint16_t *lit_j = static_cast<uint16_t *>(bz_shared_ptr(lit_sa0 + (uint32_t)j * (2u << LB)));
             uint32_t hdr = 0;
             if (lane == L) { hdr = br.bits(3); if (br.consumed_bits() > in_bits + 64) hdr |= 8u; }
             hdr = __shfl_sync(FULLM, hdr, L);
@@ -605,7 +609,7 @@ __device__ __forceinline__ int bz_inflate_multi(const BzArgs &a, uint32_t b0, Bz
                 if (bad) { if (lane == L) state = BZS_ERROR; continue; }
                 __syncwarp();
             }
-            int r = bz_build(Tj.lens + 24, nlen, Tj.lit_cnt, Tj.lit_sym, lit_j, BZ_LIT_BITS, Tj.aux, lane);
+            int r = bz_build(Tj.lens + 24, nlen, Tj.lit_cnt, Tj.lit_sym, lit_j, LB, Tj.aux, lane);
             bool okb = !(r < 0 || (r > 0 && type == 2 && nlen - (int)Tj.lit_cnt[0] != 1));
             if (okb) {
                 r = bz_build(Tj.lens + 24 + nlen, ndist, Tj.dist_cnt, Tj.dist_sym, Tj.dist_fast, BZ_DIST_BITS, Tj.aux, lane);
@@ -622,21 +626,21 @@ __device__ __forceinline__ int bz_inflate_multi(const BzArgs &a, uint32_t b0, Bz
                 if (act) {
                     br.norm();
                     uint32_t wnd1 = br.peek32() << 1;
-                    uint32_t e = bz_lds_u16(lit_sa | (wnd1 & 0x7feu));
+                    uint32_t e = bz_lds_u16(lit_sa | (wnd1 & LMASK));
                     if (e < 0x1000u && o + 3u <= cap) {              // up to three first-level literal hits out of one 32-bit window
                         uint8_t *op = out_my + o;
                         uint32_t used = e >> 8;
                         op[0] = (uint8_t)e; wnd1 >>= used;
-                        e = bz_lds_u16(lit_sa | (wnd1 & 0x7feu));
+                        e = bz_lds_u16(lit_sa | (wnd1 & LMASK));
                         if (e < 0x1000u) {
                             op[1] = (uint8_t)e; wnd1 >>= (e >> 8); used += e >> 8;
-                            e = bz_lds_u16(lit_sa | (wnd1 & 0x7feu));
+                            e = bz_lds_u16(lit_sa | (wnd1 & LMASK));
                             if (e < 0x1000u) { op[2] = (uint8_t)e; used += e >> 8; o += 3; }
                             else o += 2;
                         } else o += 1;
                         br.drop(used);
                     } else {
-                        int sy = bz_symbol(br, Tm.lit_cnt, Tm.lit_sym, lit_m, BZ_LIT_BITS);
+                        int sy = bz_symbol(br, Tm.lit_cnt, Tm.lit_sym, lit_m, LB);
                         if (sy < 0) cmd = 3;
                         else if (sy < 256) { if (o >= cap) cmd = 3; else out_my[o++] = (uint8_t)sy; }
                         else if (sy == 256) cmd = 2;
@@ -719,22 +723,31 @@ __device__ __forceinline__ int bz_inflate_multi(const BzArgs &a, uint32_t b0, Bz
     return __shfl_sync(FULLM, (state == BZS_DONE && o == cap) ? (int)o : -1, my * STRIDE);
 }
 
+#ifndef PD_BZ_MULTI_LIT_BITS
+#define PD_BZ_MULTI_LIT_BITS 9       // first-level literal table of the K-decoder kernels: 1 KB per decoder.  Measured (B200, flavour B, K = 2,
+                                     // 6 chunks in flight): 10 bits / 6 CTAs per SM 103.8 ms, 9 bits / 9 CTAs 89.7 ms per 20 M reads -- resident
+                                     // decoders matter more than the few 10-bit codes that now take the slow path
+#endif
+#ifndef PD_BZ_MULTI_CTAS
+#define PD_BZ_MULTI_CTAS 9           // resident CTAs per SM the K-decoder kernels are compiled for (register cap)
+#endif
 template <int K, int WPC>
-__global__ void __launch_bounds__(WPC * 32, 6) k_bgzf_decode_multi(BzArgs a)
+__global__ void __launch_bounds__(WPC * 32, PD_BZ_MULTI_CTAS) k_bgzf_decode_multi(BzArgs a)
 {
     constexpr unsigned FULLM = 0xffffffffu;
     constexpr int STRIDE = 32 / K;
-    __shared__ uint16_t lit_raw[(WPC * K + 1) << BZ_LIT_BITS];
+    constexpr int LB = PD_BZ_MULTI_LIT_BITS;
+    __shared__ uint16_t lit_raw[(WPC * K << LB) + (1 << BZ_LIT_BITS)];   // + 2 KB: the tables start at a 2 KB boundary of the shared window
     __shared__ BzTables tabs[WPC][K];
     __shared__ uint32_t rec_offs[WPC][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t lit_sa0 = bz_align_tables(lit_raw) + (uint32_t)(warp * K) * (2u << BZ_LIT_BITS);
+    const uint32_t lit_sa0 = bz_align_tables(lit_raw) + (uint32_t)(warp * K) * (2u << LB);
     for (;;) {
         uint32_t b0 = 0;
         if (lane == 0) b0 = atomicAdd(a.ticket, (uint32_t)K);
         b0 = __shfl_sync(FULLM, b0, 0);
         if (b0 >= a.n_blocks) return;
-        const int got_my = bz_inflate_multi<K>(a, b0, tabs[warp], lit_sa0, lane);
+        const int got_my = bz_inflate_multi<K, LB>(a, b0, tabs[warp], lit_sa0, lane);
 #pragma unroll
         for (int j = 0; j < K; j++) {
             if (b0 + j >= a.n_blocks) break;

@@ -99,7 +99,8 @@ struct pd_engine {
     uint8_t *d_owned = nullptr;
     int bz_grid = 148 * 4, bz_grid_k2 = 148 * 6, bz_grid_k4 = 148 * 6, bz_grid_k8 = 148 * 6;
     int bz_force_k = 0;              // PANDEPTH_BGZF_K=1|2|4|8: decoders per warp (default: by compression ratio)
-    int bz_lit_k = 4;                // decoders per warp for literal-dominated chunks (PANDEPTH_BGZF_LIT_K)
+    int bz_lit_k = 2;                // decoders per warp for literal-dominated chunks (PANDEPTH_BGZF_LIT_K); measured on flavour B: K=1 116.1, K=2 89.7,
+                                     // K=4 108.4 ms per 20 M reads (K > 2: too few resident warps to hide the symbol chain's latency)
 
     // reduce scratch
     void *d_red = nullptr; size_t red_cap = 0;
@@ -399,10 +400,39 @@ int bz_finish(pd_engine *e, BzSlot &s)
         e->finalized = false; e->pushed_since_reset = true;
         return PD_OK;
     };
+    // Many-contig inputs (pan-genome assemblies): a chunk may hold thousands of contigs of a few blocks each, and a tile-path
+    // run costs three launches.  When a chunk has more than MANY_RUNS single-contig runs, the runs shorter than SHORT_RUN blocks
+    // join the per-record-tid scatter (one launch for any number of contigs); long runs keep the tile path.
+    constexpr uint32_t MANY_RUNS = 32, SHORT_RUN = 8;
+    std::vector<uint8_t> to_scatter;
+    {
+        std::vector<std::pair<uint32_t, uint32_t>> runs;       // [first block, last block] of every would-be tile run
+        bool o2 = false; int32_t ct = 0, pt = INT32_MIN, pp = INT32_MIN; uint32_t first = 0, lastb = 0;
+        for (uint32_t b = 0; b < s.n_blocks; b++) {
+            if (!sm[b].n_reads) continue;
+            const bool regular = !(sm[b].flags & pdk::BZ_UNSORTED) && sm[b].first_tid == sm[b].last_tid;
+            if (regular && o2 && ct == sm[b].first_tid && sm[b].first_pos >= pp && pt == ct) lastb = b;
+            else {
+                if (o2) runs.emplace_back(first, lastb);
+                o2 = regular;
+                if (regular) { ct = sm[b].first_tid; first = lastb = b; }
+            }
+            pt = sm[b].last_tid; pp = sm[b].last_pos;
+        }
+        if (o2) runs.emplace_back(first, lastb);
+        if (runs.size() > MANY_RUNS) {
+            to_scatter.assign(s.n_blocks, 0);
+            for (auto &q : runs) {
+                uint32_t nb = 0;
+                for (uint32_t b = q.first; b <= q.second; b++) nb += sm[b].n_reads ? 1u : 0u;
+                if (nb < SHORT_RUN) for (uint32_t b = q.first; b <= q.second; b++) to_scatter[b] = 1;
+            }
+        }
+    }
     for (uint32_t b = 0; b < s.n_blocks; b++) {
         const uint32_t n = sm[b].n_reads;
         if (!n) continue;
-        const bool regular = !(sm[b].flags & pdk::BZ_UNSORTED) && sm[b].first_tid == sm[b].last_tid;
+        const bool regular = !(sm[b].flags & pdk::BZ_UNSORTED) && sm[b].first_tid == sm[b].last_tid && !(to_scatter.size() && to_scatter[b]);
         if (regular) {
             if ((rc = flush_irr())) return rc;
             const bool cont = open && cur.tid == sm[b].first_tid && sm[b].first_pos >= prev_pos && prev_tid == cur.tid;

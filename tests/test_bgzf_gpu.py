@@ -193,6 +193,23 @@ def test_device_decode_many_small_contigs(tmp_path):
     assert st["kernel_launches"] < 400          # launches per chunk, not per contig
 
 
+def test_device_decode_contigs_of_a_few_blocks_each(tmp_path):
+    """Hundreds of contigs spanning two or three BGZF blocks each: more than 32 single-contig runs in a chunk, so the short
+    runs join the per-record-tid scatter (one launch) instead of three launches each; long runs keep the tile path."""
+    n_contigs = 300
+    contigs = ",".join(f"m{i}:{40000 + (i % 5) * 9000}" for i in range(n_contigs)) + ",big:2500000"
+    bam, sam = str(tmp_path / "mid.bam"), str(tmp_path / "mid.sam")
+    subprocess.run([BAMGEN, "-o", sam, "-c", contigs, "-n", "700000", "-s", "4", "-l", "100", "-S"], check=True)
+    subprocess.run([BAMGEN, "-I", sam, "-o", bam], check=True)
+    targets, rec, _ = model.parse_sam(sam)
+    tlen = np.array([t[1] for t in targets], np.uint32)
+    want = model.accumulate(tlen, rec, 1796, -1)
+    got, st = _decode_depth(open(bam, "rb").read(), tlen, 1796, -1)
+    _assert_depth(got, want, "contigs of a few blocks")
+    assert st["tile_path_batches"] >= 1 and st["delta_path_batches"] >= 1
+    assert st["kernel_launches"] < 200
+
+
 def test_records_straddling_blocks_ask_for_the_host_path(mixed):
     import pandepth_b200 as pd
     data, tlen, rec = mixed

@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--threads", type=int, default=16)
     ap.add_argument("--piece-mb", type=float, default=0.0)
     ap.add_argument("--no-resident", action="store_true")
+    ap.add_argument("--no-feed", action="store_true")
     args = ap.parse_args()
     import torch
     import pandepth_b200 as pd
@@ -90,7 +91,7 @@ def main():
         pad = torch.zeros(64, dtype=torch.uint8, device="cuda")
         d = torch.cat([d, pad])
         ratio = inflated / max(1, comp)
-        piece = int((args.piece_mb or min(96.0, max(1.0, 384.0 / ratio))) * (1 << 20))
+        piece = int((args.piece_mb or min(192.0, max(1.0, 768.0 / ratio))) * (1 << 20))
         # pieces of ~piece compressed bytes
         bounds = [0]
         start_off = int(tab["in_off"][0])
@@ -128,6 +129,11 @@ def main():
                             "total_depth": int(tot.sum()), "covered": int(cov.sum())}
         del d
         torch.cuda.empty_cache()
+
+    if args.no_feed:
+        line["parse_s"] = t_parse
+        print(json.dumps(line))
+        return
 
     # ---- feed: the product feeder, file in the page cache ----
     H = ctypes.CDLL(os.path.join(ROOT, "pandepth_b200", "libpandepth_host.so"))
