@@ -98,6 +98,8 @@ struct pd_engine {
     int32_t bz_prog_tid = -1, bz_prog_pos = -1;   // first record of the last block (with records) of the last chunk that was planned
     uint8_t *d_owned = nullptr;
     int bz_grid = 148 * 4, bz_grid_k2 = 148 * 6, bz_grid_k4 = 148 * 6, bz_grid_k8 = 148 * 6;
+    uint64_t scatter_stripe = 16ull << 20;          // elements (64 MB of deltas) per stripe of a striped scatter (PANDEPTH_SCATTER_STRIPE_MB)
+    uint64_t scatter_stripe_min_reads = 4ull << 20; // batches smaller than this scatter in one launch (PANDEPTH_SCATTER_STRIPE_MIN_READS)
     int bz_force_k = 0;              // PANDEPTH_BGZF_K=1|2|4|8: decoders per warp (default: by compression ratio)
     int bz_lit_k = 2;                // decoders per warp for literal-dominated chunks (PANDEPTH_BGZF_LIT_K); measured on flavour B: K=1 116.1, K=2 89.7,
                                      // K=4 108.4 ms per 20 M reads (K > 2: too few resident warps to hide the symbol chain's latency)
@@ -210,7 +212,7 @@ int run_batch(pd_engine *e, int32_t tid, uint32_t n, const int32_t *pos, const u
             // range sharding: reads that start more than HALO bases left of the owned range are seen by no segment; the ones
             // among them that reach into the range are the first lo[0] reads of the batch (a device-side count, usually 0)
             pdk::ScatterArgs sp{pos, cigar, cigar_off, flag, mapq, n, (int32_t)e->elen[tid], e->d_delta + off, e->xflags, e->min_mapq,
-                                (int32_t)e->org[tid], cb.lo, e->d_flags + 1};
+                                (int32_t)e->org[tid], cb.lo, e->d_flags + 1, 0, INT64_MAX};
             rc = launch(e, K_SCATTER, [&] { pdk::k_delta_scatter<<<148, 256, 0, e->stream>>>(sp); }); if (rc) return rc;
         }
         pdk::TileArgs t{pos, cigar, cigar_off, flag, mapq, cb.lo, cb.hi, n, (int32_t)seg_a, nseg, (int32_t)e->elen[tid],
@@ -230,8 +232,21 @@ int run_batch(pd_engine *e, int32_t tid, uint32_t n, const int32_t *pos, const u
         e->stats.tile_path_batches++;
     } else {
         pdk::ScatterArgs s{pos, cigar, cigar_off, flag, mapq, n, (int32_t)e->elen[tid], e->d_delta + off, e->xflags, e->min_mapq,
-                           (int32_t)e->org[tid], nullptr, nullptr};
-        int rc = launch(e, K_SCATTER, [&] { pdk::k_delta_scatter<<<(n + 255) / 256, 256, 0, e->stream>>>(s); }); if (rc) return rc;
+                           (int32_t)e->org[tid], nullptr, nullptr, 0, INT64_MAX};
+        // A big unsorted batch scatters 2 n run ends over the whole contig: every one a 32-byte read-modify-write in DRAM (the
+        // delta array is ten times the L2).  Striped: one launch per L2-sized stripe of the array applies only the ends that
+        // fall into it, so the reductions stay in L2 and each delta line goes to DRAM once; the price is re-reading the batch
+        // (8 B per read, streaming) once per stripe, which pays while the stripes are few and the batch is large.
+        const uint64_t n_stripes = ((uint64_t)e->elen[tid] + e->scatter_stripe - 1) / e->scatter_stripe;
+        const bool striped = n_stripes > 1 && n_stripes <= 48 && (uint64_t)n >= e->scatter_stripe_min_reads && (uint64_t)n >= n_stripes * std::max<uint64_t>(1, e->scatter_stripe_min_reads / 64);
+        int rc = launch(e, K_SCATTER, [&] {
+            if (!striped) { pdk::k_delta_scatter<<<(n + 255) / 256, 256, 0, e->stream>>>(s); return; }
+            for (uint64_t k = 0; k < n_stripes; k++) {
+                s.stripe_lo = (int64_t)(k * e->scatter_stripe); s.stripe_hi = k + 1 == n_stripes ? INT64_MAX : (int64_t)((k + 1) * e->scatter_stripe);
+                pdk::k_delta_scatter<<<(n + 255) / 256, 256, 0, e->stream>>>(s);
+            }
+        }); if (rc) return rc;
+        if (striped) e->stats.kernel_launches += n_stripes - 1;
         e->host_delta_used = true;
         e->stats.delta_path_batches++;
     }
@@ -593,6 +608,8 @@ pd_engine *pd_create_ranges(int device, int n_targets, const uint32_t *target_le
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pdk::k_bgzf_decode_multi<8, 1>, 1 * 32, 0) == cudaSuccess && n_sm > 0 && per_sm > 0)
             e->bz_grid_k8 = n_sm * per_sm;
         if (const char *fk = getenv("PANDEPTH_BGZF_K")) { const int v = atoi(fk); if (v == 1 || v == 2 || v == 4 || v == 8) e->bz_force_k = v; }
+        if (const char *v = getenv("PANDEPTH_SCATTER_STRIPE_MB")) { const double mb = atof(v); if (mb >= 0.001) e->scatter_stripe = std::max<uint64_t>(256, (uint64_t)(mb * 262144.0)); }
+        if (const char *v = getenv("PANDEPTH_SCATTER_STRIPE_MIN_READS")) e->scatter_stripe_min_reads = (uint64_t)std::max<long long>(1, atoll(v));
         if (const char *fk = getenv("PANDEPTH_BGZF_LIT_K")) { const int v = atoi(fk); if (v == 1 || v == 2 || v == 4 || v == 8) e->bz_lit_k = v; }
     }
     if ((ce = cudaStreamSynchronize(e->stream)) != cudaSuccess) return bail("sync", ce);

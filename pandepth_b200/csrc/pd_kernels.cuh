@@ -524,27 +524,30 @@ struct ScatterArgs {
     int32_t shift;     // contig coordinate of delta[0] (range sharding); runs are clipped to [0, contig_len) after the shift
     const uint32_t *n_dev;   // non-null: only reads [0, *n_dev) (a device-side count: the reads left of a sorted batch's first cut)
     int *delta_used;         // with n_dev: set when anything was scattered (the engine then runs the scan at finalize)
+    int64_t stripe_lo, stripe_hi;   // only run ends at delta indices in [stripe_lo, stripe_hi) are applied by this launch (striped
+                                    // scatter: one launch per L2-sized stripe of the delta array; 0 / INT64_MAX = everything)
 };
 
 __device__ __forceinline__ void scatter_one(const ScatterArgs &a, uint32_t i)
 {
     if (a.flag && (a.flag[i] & a.xflags)) return;
     if (a.mapq && (int)a.mapq[i] < a.min_mapq) return;
-    const int32_t p = a.pos[i];
-    if (p < 0) return;
+    const int32_t p = __ldcs(a.pos + i);                        // streaming loads: the reads pass through L2 once per stripe and
+    if (p < 0) return;                                          // must not push the stripe's delta lines out of it
     uint32_t c0 = i, nops = 1;
     if (a.cigar_off) { c0 = a.cigar_off[i]; nops = a.cigar_off[i + 1] - c0; }
     const int64_t clen = a.contig_len;
     int64_t q = (int64_t)p - a.shift, rs = 0, re = 0; bool open = false;
+    const int64_t slo = a.stripe_lo, shi = a.stripe_hi;
     auto flush = [&]() {
         if (!open) return;
         const int64_t s = rs < 0 ? 0 : rs, e = re > clen ? clen : re;
         if (s >= e) return;
-        red_add_u32(a.delta + s, 1u);
-        red_add_u32(a.delta + e, 0xffffffffu);
+        if (s >= slo && s < shi) red_add_u32(a.delta + s, 1u);
+        if (e >= slo && e < shi) red_add_u32(a.delta + e, 0xffffffffu);
     };
     for (uint32_t k = 0; k < nops; ++k) {
-        const uint32_t w = a.cigar[c0 + k];
+        const uint32_t w = __ldcs(a.cigar + c0 + k);
         const uint32_t op = w & 15u;
         const int64_t n = w >> 4;
         if (is_match_op(op)) {

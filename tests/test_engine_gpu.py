@@ -190,6 +190,32 @@ def test_random_mixed_cigars_all_paths(seed):
                 _check_depth(eng, tlen, want)
 
 
+def test_striped_scatter_applies_every_run_end_once(monkeypatch):
+    """Big unsorted batches scatter stripe by stripe (one launch per L2-sized stripe of the delta array, run ends outside the
+    stripe skipped): forced here with a 4 KB stripe, so runs straddle stripes, end on stripe boundaries and on the contig's
+    padding element.  Same depth as the oracle, multi-op CIGARs and the device-side filter included."""
+    monkeypatch.setenv("PANDEPTH_SCATTER_STRIPE_MB", str(1024 * 4 / (1 << 20)))     # 1024 elements per stripe
+    monkeypatch.setenv("PANDEPTH_SCATTER_STRIPE_MIN_READS", "64")
+    rng = np.random.default_rng(21)
+    L = 40_000                                                                       # 40 stripes (the cap is 48)
+    rows = []
+    for p in rng.integers(0, L, 30_000).tolist():
+        k = rng.integers(0, 6)
+        cs = ("150M", f"{rng.integers(1, 1100)}M", f"{rng.integers(1, 80)}M{rng.integers(1, 3000)}N{rng.integers(1, 80)}M",
+              f"{rng.integers(1, 40)}S{rng.integers(1, 120)}M", "1024M", f"{rng.integers(1, 60)}={rng.integers(1, 9)}I{rng.integers(1, 60)}X{rng.integers(1, 30)}D{rng.integers(1, 60)}M")[k]
+        rows.append((int(rng.choice([0, 16, 1024, 256])), 0, p + 1, int(rng.integers(0, 61)), cs))
+    rows += [(0, 0, 1, 60, "1024M"), (0, 0, L - 1023, 60, "1024M"), (0, 0, L, 60, "5M"), (0, 0, 1025, 60, "1024M")]   # stripe-aligned ends, contig end
+    rec = model.records_from_tuples(rows, ["c"])
+    tlen = np.array([L], np.uint32)
+    for xflags, q in ((1796, -1), (0, 30)):
+        want = model.accumulate(tlen, rec, xflags, q)
+        with _engine(tlen, xflags=xflags, min_mapq=q) as eng:
+            _push_all(eng, rec, False, 1)
+            eng.finalize()
+            _check_depth(eng, tlen, want)
+            assert eng.stats()["kernel_launches"] >= 40
+
+
 def test_other_read_lengths_and_no_common_span():
     """Read lengths above the modelled span (L > HALO) and batches with no dominant span fall back to corrections."""
     rng = np.random.default_rng(9)
