@@ -110,6 +110,7 @@ def main():
 
         cov, tot = step()
         reads = eng.stats()["reads_pushed"]
+        step()                       # second warm-up: every decode slot (PD_BGZF_DEPTH + 1 of them, used round-robin) has its buffers
         eng.profile_enable(True)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
