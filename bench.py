@@ -224,7 +224,9 @@ def reference_arm(args):
         "steps": args.steps, "warmup": max(1, args.warmup), "ms_per_step": 1e3 * total / len(times), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
         "gbases_per_s": value * READLEN / 1e3,
-        "config": {"workload": "cfg2 (9 contigs, 50x, sorted 150M reads, per-chr mode): " + sample,
+        "config": {"workload": ("cfg2 (9 contigs, 50x, sorted 150M reads, per-chr mode): " if args.gpus <= 1 else
+                                "cfg5's genome (9 contigs, 3 Gb, per-chr mode) on a bounded sample -- 50x instead of 200x, a quarter of the reads; "
+                                "the reference's Mreads/s does not depend on the coverage: ") + sample,
                    "cmd": f"pandepth_ref -i s.bam -o out -t {threads}"},
         "cpu_baseline": {"value": value, "unit": "Mreads/s", "cores": threads, "cpu_quota_cores": cpu_quota_cores(), "online_cpus": os.cpu_count(),
                          "kind": "reference", "sample": sample,

@@ -98,7 +98,7 @@ struct pd_engine {
     int32_t bz_prog_tid = -1, bz_prog_pos = -1;   // first record of the last block (with records) of the last chunk that was planned
     uint8_t *d_owned = nullptr;
     int bz_grid = 148 * 4, bz_grid_k2 = 148 * 6, bz_grid_k4 = 148 * 6, bz_grid_k8 = 148 * 6;
-    uint64_t scatter_stripe = 16ull << 20;          // elements (64 MB of deltas) per stripe of a striped scatter (PANDEPTH_SCATTER_STRIPE_MB)
+    uint64_t scatter_stripe = 32ull << 20;          // elements (128 MB of deltas) per stripe of a striped scatter (PANDEPTH_SCATTER_STRIPE_MB)
     uint64_t scatter_stripe_min_reads = 4ull << 20; // batches smaller than this scatter in one launch (PANDEPTH_SCATTER_STRIPE_MIN_READS)
     int bz_force_k = 0;              // PANDEPTH_BGZF_K=1|2|4|8: decoders per warp (default: by compression ratio)
     int bz_lit_k = 2;                // decoders per warp for literal-dominated chunks (PANDEPTH_BGZF_LIT_K); measured on flavour B: K=1 116.1, K=2 89.7,
@@ -234,11 +234,14 @@ int run_batch(pd_engine *e, int32_t tid, uint32_t n, const int32_t *pos, const u
         pdk::ScatterArgs s{pos, cigar, cigar_off, flag, mapq, n, (int32_t)e->elen[tid], e->d_delta + off, e->xflags, e->min_mapq,
                            (int32_t)e->org[tid], nullptr, nullptr, 0, INT64_MAX};
         // A big unsorted batch scatters 2 n run ends over the whole contig: every one a 32-byte read-modify-write in DRAM (the
-        // delta array is ten times the L2).  Striped: one launch per L2-sized stripe of the array applies only the ends that
-        // fall into it, so the reductions stay in L2 and each delta line goes to DRAM once; the price is re-reading the batch
-        // (8 B per read, streaming) once per stripe, which pays while the stripes are few and the batch is large.
+        // delta array is ten times the L2).  Striped: one launch per stripe of the array applies only the ends that fall into it,
+        // so each delta line goes to DRAM once; the price is re-reading the batch (8 B per read, streaming) once per stripe.
+        // Measured on B200 (111 M shuffled reads over 333 Mb, tools/bench_delta_path.py): unstriped 9.48 ms; stripes of 32 / 64 /
+        // 128 MB: 25.9 / 13.5 / 7.74 ms -- the reductions run at ~25 G/s whether their lines sit in L2 or not (the L2's atomic
+        // units are the limit, not DRAM), so only a few large stripes pay: -18 %.  A real fix needs fewer global reductions,
+        // i.e. sorted input for the tile kernel.
         const uint64_t n_stripes = ((uint64_t)e->elen[tid] + e->scatter_stripe - 1) / e->scatter_stripe;
-        const bool striped = n_stripes > 1 && n_stripes <= 48 && (uint64_t)n >= e->scatter_stripe_min_reads && (uint64_t)n >= n_stripes * std::max<uint64_t>(1, e->scatter_stripe_min_reads / 64);
+        const bool striped = n_stripes > 1 && n_stripes <= 16 && (uint64_t)n >= e->scatter_stripe_min_reads && (uint64_t)n >= n_stripes * std::max<uint64_t>(1, e->scatter_stripe_min_reads / 64);
         int rc = launch(e, K_SCATTER, [&] {
             if (!striped) { pdk::k_delta_scatter<<<(n + 255) / 256, 256, 0, e->stream>>>(s); return; }
             for (uint64_t k = 0; k < n_stripes; k++) {

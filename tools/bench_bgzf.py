@@ -110,7 +110,8 @@ def main():
 
         cov, tot = step()
         reads = eng.stats()["reads_pushed"]
-        step()                       # second warm-up: every decode slot (PD_BGZF_DEPTH + 1 of them, used round-robin) has its buffers
+        for _ in range(8):           # more warm-up: every decode slot (PD_BGZF_DEPTH + 1 of them, used round-robin) has seen the biggest
+            step()                   # piece and holds its final buffers (a slot that grows costs a device synchronisation + cudaMalloc)
         eng.profile_enable(True)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
