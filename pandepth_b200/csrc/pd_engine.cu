@@ -34,9 +34,9 @@ static_assert(PAD_ELEMS % pdk::SCAN_TILE == 0 && PAD_ELEMS % pdk::REDUCE_CHUNK =
 constexpr int64_t HOST_CHUNK_READS = 8 << 20;            // staging chunk for host-resident pushes
 constexpr int N_SLOTS = 2;
 
-enum KernelId { K_CUT = 0, K_TILE, K_SCATTER, K_SCAN, K_FILL, K_REDUCE, K_WINDOWS, K_BGZF, K_BGZF_PACK, K_COUNT };
+enum KernelId { K_CUT = 0, K_TILE, K_SCATTER, K_SCAN, K_FILL, K_REDUCE, K_WINDOWS, K_BGZF, K_BGZF_PACK, K_FILTER, K_COUNT };
 const char *const kKernelNames[K_COUNT] = {"k_cut", "k_tile_accumulate", "k_delta_scatter", "k_scan_add",
-                                           "k_fill_untouched", "k_reduce_units", "k_reduce_windows", "k_bgzf_decode", "k_bgzf_pack"};
+                                           "k_fill_untouched", "k_reduce_units", "k_reduce_windows", "k_bgzf_decode", "k_bgzf_pack", "k_filter_bits"};
 
 struct Slot {
     int32_t *pos = nullptr; uint32_t *cigar = nullptr; uint32_t *cigar_off = nullptr;
@@ -97,6 +97,7 @@ struct pd_engine {
     BzSlot bz[N_BZ]; int bz_next = 0;
     int32_t bz_prog_tid = -1, bz_prog_pos = -1;   // first record of the last block (with records) of the last chunk that was planned
     uint8_t *d_owned = nullptr;
+    uint32_t *d_pass_bits = nullptr; size_t bits_cap = 0;   // record filter of the current batch, one bit per read (k_filter_bits)
     int bz_grid = 148 * 4, bz_grid_k2 = 148 * 6, bz_grid_k4 = 148 * 6, bz_grid_k8 = 148 * 6;
     uint64_t scatter_stripe = 32ull << 20;          // elements (128 MB of deltas) per stripe of a striped scatter (PANDEPTH_SCATTER_STRIPE_MB)
     uint64_t scatter_stripe_min_reads = 4ull << 20; // batches smaller than this scatter in one launch (PANDEPTH_SCATTER_STRIPE_MIN_READS)
@@ -215,14 +216,25 @@ int run_batch(pd_engine *e, int32_t tid, uint32_t n, const int32_t *pos, const u
                                 (int32_t)e->org[tid], cb.lo, e->d_flags + 1, 0, INT64_MAX};
             rc = launch(e, K_SCATTER, [&] { pdk::k_delta_scatter<<<148, 256, 0, e->stream>>>(sp); }); if (rc) return rc;
         }
-        pdk::TileArgs t{pos, cigar, cigar_off, flag, mapq, cb.lo, cb.hi, n, (int32_t)seg_a, nseg, (int32_t)e->elen[tid],
+        const bool has_off = cigar_off != nullptr, has_filter = flag != nullptr || mapq != nullptr;
+        if (has_filter) {
+            // the record filter as one bit per read (the tile kernel reads a word per 32-read chunk)
+            const size_t n_words = (size_t)n / 32 + 34;
+            if (n_words > e->bits_cap) {
+                if (e->d_pass_bits) { CK(cudaStreamSynchronize(e->stream)); cudaFree(e->d_pass_bits); e->d_pass_bits = nullptr; }
+                const size_t cap = n_words + n_words / 4 + 1024;
+                CK(cudaMalloc(&e->d_pass_bits, cap * 4)); e->bits_cap = cap;
+            }
+            rc = launch(e, K_FILTER, [&] { pdk::k_filter_bits<<<(unsigned)((n_words * 32 + 255) / 256), 256, 0, e->stream>>>(flag, mapq, n, e->xflags, e->min_mapq, e->d_pass_bits, (uint32_t)n_words); });
+            if (rc) return rc;
+        }
+        pdk::TileArgs t{pos, cigar, cigar_off, flag, mapq, e->d_pass_bits, cb.lo, cb.hi, n, (int32_t)seg_a, nseg, (int32_t)e->elen[tid],
                         e->d_depth + off, e->d_delta + off, e->d_seg_state + off / pdk::SEG, e->xflags, e->min_mapq,
                         e->d_flags, e->d_flags + 1,
                         e->hint_on ? 1u : 0u, e->hint_min_dep, e->hint_mask, e->d_part_cov + off / pdk::SEG, e->d_part_sum + off / pdk::SEG,
                         e->tile_resident_warps, (int32_t)e->org[tid]};
         const size_t smem = (size_t)pdk::WPC * pdk::TILE_SMEM_WORDS * 4;
         const unsigned grid = (nseg + pdk::WPC - 1) / pdk::WPC, blk = pdk::WPC * 32;
-        const bool has_off = cigar_off != nullptr, has_filter = flag != nullptr || mapq != nullptr;
         rc = launch(e, K_TILE, [&] {
             if (has_off) { if (has_filter) pdk::k_tile_accumulate<true, true><<<grid, blk, smem, e->stream>>>(t); else pdk::k_tile_accumulate<true, false><<<grid, blk, smem, e->stream>>>(t); }
             else { if (has_filter) pdk::k_tile_accumulate<false, true><<<grid, blk, smem, e->stream>>>(t); else pdk::k_tile_accumulate<false, false><<<grid, blk, smem, e->stream>>>(t); }
@@ -515,7 +527,7 @@ void pd_destroy(pd_engine *e)
         if (s.consumed) cudaEventDestroy(s.consumed);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
-    cudaFree(e->d_owned); cudaFree(e->d_org);
+    cudaFree(e->d_owned); cudaFree(e->d_org); cudaFree(e->d_pass_bits);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     delete e;

@@ -166,9 +166,30 @@ __global__ void __launch_bounds__(CUT_THREADS) k_cut(CutArgs a, const uint32_t *
 // (Measured alternative, dropped: modelling reads as one common span and applying group counts with plain two-phase
 // read-modify-writes was 15% slower than the atomics on B200 -- see DESIGN.md.)
 // ---------------------------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------------------------
+// k_filter_bits: the record filter (:732-733) of a batch that brings flag[] / mapq[] arrays, as one bit per read.
+// The tile kernel then reads one word per 32-read chunk instead of a 2-byte and a 1-byte load per read (those loads were
+// consumed chunk by chunk and serialised sixteen DRAM round trips per group: 1.07 ms instead of 0.46 ms per cfg2 contig).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_filter_bits(const uint16_t *__restrict__ flag, const uint8_t *__restrict__ mapq, uint32_t n,
+                                                     uint32_t xflags, int32_t min_mapq, uint32_t *__restrict__ bits, uint32_t n_words)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;     // whole warps: n_words * 32 threads
+    if ((i >> 5) >= n_words) return;
+    bool pass = false;
+    if (i < n) {
+        pass = true;
+        if (flag && (__ldcs(flag + i) & xflags)) pass = false;                   // :732
+        if (mapq && (int)__ldcs(mapq + i) < min_mapq) pass = false;              // :733
+    }
+    const uint32_t m = __ballot_sync(FULL, pass);
+    if ((threadIdx.x & 31) == 0) bits[i >> 5] = m;
+}
+
 struct TileArgs {
     const int32_t *pos; const uint32_t *cigar; const uint32_t *cigar_off;
     const uint16_t *flag; const uint8_t *mapq;
+    const uint32_t *pass_bits;   // HAS_FILTER: bit i = read i passes the record filter (k_filter_bits), n/32 + 2 words
     const uint32_t *lo; const uint32_t *hi;
     uint32_t n;
     int32_t seg0; int32_t nseg; int32_t contig_len;
@@ -296,12 +317,18 @@ __global__ void __launch_bounds__(WPC * 32, TILE_MIN_CTAS) k_tile_accumulate(Til
             } else {
                 cv[u] = valid ? ldg_u32(pcig + u * 32) : 0u;
             }
-            if (HAS_FILTER) {
-                if (valid) {
-                    const uint32_t i = base + u * 32 + lane;
-                    if (a.flag && (__ldg(a.flag + i) & a.xflags)) failm |= 1u << u;           // :732
-                    if (a.mapq && (int)__ldg(a.mapq + i) < a.min_mapq) failm |= 1u << u;      // :733
-                }
+        }
+        if (HAS_FILTER) {
+            // filter bits of the group's reads [base, base + 32 U): lane l holds word (base >> 5) + l; chunk u's 32 bits straddle
+            // words u and u + 1 (two shuffles and a funnel shift per chunk)
+            const uint32_t wi = (base >> 5) + (uint32_t)lane;
+            const uint32_t bw = (lane <= U) ? ldg_u32(a.pass_bits + wi) : 0u;     // the array has two words of slack
+            const uint32_t sh = base & 31u;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const uint32_t w0 = __shfl_sync(FULL, bw, u), w1 = __shfl_sync(FULL, bw, u + 1);
+                const uint32_t x = __funnelshift_r(w0, w1, sh);
+                if (!((x >> lane) & 1u)) failm |= 1u << u;                          // :732-733 (filler lanes are never applied anyway)
             }
         }
         if (HAS_OFF) {

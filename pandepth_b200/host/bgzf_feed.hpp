@@ -92,8 +92,9 @@ inline BgzfFeedResult bgzf_feed_file(pd_engine *eng, std::mutex *eng_mu, const s
     if (fd < 0 || fstat(fd, &st) != 0) { if (fd >= 0) close(fd); res.status = -1; res.err = "cannot open " + path; return res; }
     const uint64_t true_size = (uint64_t)st.st_size;
     const uint64_t file_size = std::min<uint64_t>(true_size, range_end);      // blocks starting at or after this offset belong to someone else
-    // piece size from the compression ratio of the first blocks: ~768 MB inflated, at most 192 MB compressed (measured on B200:
-    // flavour A 18 -> 36 MB pieces +8 %, flavour B 96 -> 192 MB +1 %: a chunk should hold a few waves of BGZF blocks)
+    // piece size from the compression ratio of the first blocks: ~384 MB inflated, at most 96 MB compressed.  Measured on B200 through
+    // this feeder (gpurun_out/k_*feed*): flavour A (10^9 reads, 2.1 GB) 9 / 18 / 37 / 74 MB pieces -> 294 / 288 / 298 / 311 ms;
+    // flavour B (33 M reads, 5.4 GB) 48 / 96 / 192 MB -> 182 / 177 / 204 ms
     double ratio = 4.0;
     {
         std::vector<uint8_t> probe(1u << 20);
@@ -107,12 +108,12 @@ inline BgzfFeedResult bgzf_feed_file(pd_engine *eng, std::mutex *eng_mu, const s
         }
         if (in && out) ratio = (double)out / (double)in;
     }
-    size_t piece = (size_t)(768.0 * 1048576.0 / std::max(1.0, ratio));
+    size_t piece = (size_t)(384.0 * 1048576.0 / std::max(1.0, ratio));
     if (const char *e = getenv("PANDEPTH_BGZF_PIECE_MB")) piece = (size_t)(atof(e) * 1048576.0);
-    piece = std::max<size_t>(1u << 20, std::min<size_t>(192u << 20, piece));
+    piece = std::max<size_t>(1u << 20, std::min<size_t>(96u << 20, piece));
     const uint64_t span = file_size > data_start ? file_size - data_start : 0;
     // small inputs: more, smaller pieces (pinned memory costs ~0.3 ms per MB to allocate and as much again to release at exit)
-    if (!getenv("PANDEPTH_BGZF_PIECE_MB")) piece = std::min<size_t>(piece, std::max<size_t>(8u << 20, (size_t)(span / (2 * (uint64_t)std::max(1, threads)))));
+    if (!getenv("PANDEPTH_BGZF_PIECE_MB")) piece = std::min<size_t>(piece, std::max<size_t>(8u << 20, (size_t)(span / (4 * (uint64_t)std::max(1, threads)))));
     piece = std::max<size_t>(piece, 1u << 17);
     const size_t n_pieces = (size_t)((span + piece - 1) / piece);
     if (n_pieces == 0) { close(fd); res.status = 1; return res; }

@@ -91,7 +91,7 @@ def main():
         pad = torch.zeros(64, dtype=torch.uint8, device="cuda")
         d = torch.cat([d, pad])
         ratio = inflated / max(1, comp)
-        piece = int((args.piece_mb or min(192.0, max(1.0, 768.0 / ratio))) * (1 << 20))
+        piece = int((args.piece_mb or min(96.0, max(1.0, 384.0 / ratio))) * (1 << 20))
         # pieces of ~piece compressed bytes
         bounds = [0]
         start_off = int(tab["in_off"][0])

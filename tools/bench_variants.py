@@ -19,7 +19,7 @@ PEAK = 6550.1
 
 def main():
     ap = argparse.ArgumentParser(); ap.add_argument("--steps", type=int, default=10); ap.add_argument("--reads", type=int, default=111_111_111)
-    ap.add_argument("--len", type=int, default=333_333_333)
+    ap.add_argument("--len", type=int, default=333_333_333); ap.add_argument("--only", default="", help="run one variant (for ncu captures)")
     a = ap.parse_args()
     import torch
     import pandepth_b200 as pd
@@ -67,6 +67,8 @@ def main():
     F = pd.PD_SORTED | pd.PD_DEVICE | pd.PD_READY
     out = {"reads": R, "bases": G, "cigar_words_mixed": W, "multi_op_fraction": multi_frac, "peak_GBps": PK, "variants": {}}
     for name, use_mixed, use_filter in (("single_op", False, False), ("filter", False, True), ("mixed", True, False), ("mixed_filter", True, True)):
+        if a.only and name != a.only:
+            continue
         eng = pd.Engine(np.array([G], np.uint32), xflags=1796, min_mapq=20 if use_filter else -1)
         eng.set_reduce_hint(1, 0xFFFFFFFF)
         kw = dict(flags=F, n=R)
