@@ -233,7 +233,7 @@ int run_batch(pd_engine *e, int32_t tid, uint32_t n, const int32_t *pos, const u
                         e->d_flags, e->d_flags + 1,
                         e->hint_on ? 1u : 0u, e->hint_min_dep, e->hint_mask, e->d_part_cov + off / pdk::SEG, e->d_part_sum + off / pdk::SEG,
                         e->tile_resident_warps, (int32_t)e->org[tid]};
-        const size_t smem = (size_t)pdk::WPC * pdk::TILE_SMEM_WORDS * 4;
+        const size_t smem = (size_t)pdk::WPC * (pdk::TILE_SMEM_WORDS + (has_off ? pdk::TILE_QUEUE_WORDS : 0)) * 4;
         const unsigned grid = (nseg + pdk::WPC - 1) / pdk::WPC, blk = pdk::WPC * 32;
         rc = launch(e, K_TILE, [&] {
             if (has_off) { if (has_filter) pdk::k_tile_accumulate<true, true><<<grid, blk, smem, e->stream>>>(t); else pdk::k_tile_accumulate<true, false><<<grid, blk, smem, e->stream>>>(t); }
@@ -603,11 +603,11 @@ pd_engine *pd_create_ranges(int device, int n_targets, const uint32_t *target_le
     if ((ce = cudaMemsetAsync(e->d_seg_state, 0, e->n_seg, e->stream)) != cudaSuccess) return bail("memset", ce);
     if ((ce = cudaMemsetAsync(e->d_flags, 0, 8, e->stream)) != cudaSuccess) return bail("memset", ce);
     {
-        const int smem = pdk::WPC * pdk::TILE_SMEM_WORDS * 4;
+        const int smem = pdk::WPC * pdk::TILE_SMEM_WORDS * 4, smem_off = pdk::WPC * (pdk::TILE_SMEM_WORDS + pdk::TILE_QUEUE_WORDS) * 4;
         if ((ce = cudaFuncSetAttribute(pdk::k_tile_accumulate<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return bail("cudaFuncSetAttribute", ce);
         if ((ce = cudaFuncSetAttribute(pdk::k_tile_accumulate<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return bail("cudaFuncSetAttribute", ce);
-        if ((ce = cudaFuncSetAttribute(pdk::k_tile_accumulate<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return bail("cudaFuncSetAttribute", ce);
-        if ((ce = cudaFuncSetAttribute(pdk::k_tile_accumulate<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return bail("cudaFuncSetAttribute", ce);
+        if ((ce = cudaFuncSetAttribute(pdk::k_tile_accumulate<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_off)) != cudaSuccess) return bail("cudaFuncSetAttribute", ce);
+        if ((ce = cudaFuncSetAttribute(pdk::k_tile_accumulate<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_off)) != cudaSuccess) return bail("cudaFuncSetAttribute", ce);
     }
     {
         int n_sm = 0, per_sm = 0;

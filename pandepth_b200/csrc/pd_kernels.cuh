@@ -35,6 +35,7 @@ constexpr int WIN = SEG + HALO;              // bases a warp sees reads from: [s
 constexpr int TOFF = HALO;                   // window index of table entry 0: the table covers the segment itself
 constexpr int TLEN = WIN - TOFF;             // table entries (= SEG)
 constexpr int TILE_SMEM_WORDS = TLEN;        // per warp: 8 KB at SEG 2048
+constexpr int TILE_QUEUE_WORDS = 3 * 64;     // per warp, HAS_OFF kernels only: the ring of queued multi-op reads (768 B)
 constexpr int TILE_MIN_CTAS = PD_TILE_MIN_CTAS;   // resident CTAs per SM k_tile_accumulate is compiled for (register cap)
 constexpr unsigned FULL = 0xffffffffu;
 
@@ -299,6 +300,45 @@ __global__ void __launch_bounds__(WPC * 32, TILE_MIN_CTAS) k_tile_accumulate(Til
         if (x < TOFF) carry_reg += v;
         else if (x < WIN) atomicAdd(&E[(int)x - TOFF], v);
     };
+    // Multi-op reads (HAS_OFF) are not walked where they are met -- a per-read loop over the ops with a third of the lanes active
+    // and the rest waiting cost 5.4x the single-op time on 30 % multi-op input -- but queued in the warp's ring (64 entries of
+    // window index / first CIGAR word / op count behind the CTA's tables) and walked 32 at a time, one read per lane, all lanes busy.
+    uint32_t *Q = smem + WPC * TILE_SMEM_WORDS + warp * TILE_QUEUE_WORDS;
+    uint32_t qn = 0, qh = 0;
+    auto walk = [&](uint32_t w, uint32_t c0, uint32_t nops) {
+        const bool owner = w >= (uint32_t)HALO || own_halo;
+        const int64_t far_w = (w >= (uint32_t)SEG) ? 2 * SEG + HALO : SEG + HALO;
+        int64_t q = w, rs = INT64_MIN, re = INT64_MIN;
+        auto flush = [&]() {
+            if (rs == INT64_MIN) return;
+            const int64_t s = rs, e = re > clen_w64 ? clen_w64 : re;
+            if (s >= e) return;
+            emit(s, 1u);
+            emit(e, 0xffffffffu);
+            if (owner && e > far_w) {
+                const int64_t gs = s > far_w ? s : far_w;
+                red_add_u32(a.delta + hbase + gs, 1u);
+                red_add_u32(a.delta + hbase + e, 0xffffffffu);
+                *a.delta_used = 1;
+            }
+        };
+        for (uint32_t k = 0; k < nops; ++k) {
+            const uint32_t cw = ldg_u32(a.cigar + c0 + k);
+            const uint32_t op = cw & 15u;
+            const int64_t n = cw >> 4;
+            if (is_match_op(op)) {                                     // :745-752  adjacent M/=/X merge into one run
+                if (re == q && rs != INT64_MIN) re = q + n; else { flush(); rs = q; re = q + n; }
+                q += n;
+            } else if (is_skip_op(op)) q += n;                         // :754-757
+        }
+        flush();
+    };
+    auto drain = [&](uint32_t cnt) {                                   // the oldest `cnt` (<= 32) queued reads, one per lane
+        __syncwarp();
+        if ((uint32_t)lane < cnt) { const uint32_t s = (qh + (uint32_t)lane) & 63u; walk(Q[s], Q[64 + s], Q[128 + s]); }
+        __syncwarp();
+        qh = (qh + cnt) & 63u; qn -= cnt;
+    };
     for (uint32_t base = i_lo; base < i_hi; base += 32 * U) {
         // issue every load of TILE_UNROLL chunks before consuming any of them
         int32_t pv[U]; uint32_t cv[U]; uint32_t ov[U]; uint32_t nv[U];
@@ -361,10 +401,10 @@ __global__ void __launch_bounds__(WPC * 32, TILE_MIN_CTAS) k_tile_accumulate(Til
             idx_max = max(idx_max, w);                         // checked once after the loop
             bool pass = in_win && p >= 0;
             if (HAS_FILTER && ((failm >> u) & 1u)) pass = false;
-            if (!HAS_OFF || nops == 1) {
+            {
                 // one CIGAR op (the common case): M/=/X is one run [p, p+len)                      :745-752
                 const uint32_t e = min(w + (c >> 4), clen_w);                      // len < 2^28: no overflow
-                const bool ok = pass && ((0x181u >> (c & 15u)) & 1u) && e > w;
+                const bool ok = pass && (!HAS_OFF || nops == 1u) && ((0x181u >> (c & 15u)) & 1u) && e > w;
                 const bool s_tab = ok && w >= (uint32_t)TOFF;                      // start / end land in the table
                 const bool e_tab = ok && (e - (uint32_t)TOFF) < (uint32_t)TLEN;
                 carry_reg += (uint32_t)(ok && w < (uint32_t)TOFF) - (uint32_t)(ok && e < (uint32_t)TOFF);
@@ -379,37 +419,22 @@ __global__ void __launch_bounds__(WPC * 32, TILE_MIN_CTAS) k_tile_accumulate(Til
                         *a.delta_used = 1;
                     }
                 }
-            } else if (pass) {
-                const uint32_t c0 = ov[u];
-                const bool owner = w >= (uint32_t)HALO || own_halo;
-                const int64_t far_w = (w >= (uint32_t)SEG) ? 2 * SEG + HALO : SEG + HALO;
-                int64_t q = w, rs = INT64_MIN, re = INT64_MIN;
-                auto flush = [&]() {
-                    if (rs == INT64_MIN) return;
-                    const int64_t s = rs, e = re > clen_w64 ? clen_w64 : re;
-                    if (s >= e) return;
-                    emit(s, 1u);
-                    emit(e, 0xffffffffu);
-                    if (owner && e > far_w) {
-                        const int64_t gs = s > far_w ? s : far_w;
-                        red_add_u32(a.delta + hbase + gs, 1u);
-                        red_add_u32(a.delta + hbase + e, 0xffffffffu);
-                        *a.delta_used = 1;
+            }
+            if (HAS_OFF) {
+                const bool multi = pass && nops > 1u;
+                const unsigned mm = __ballot_sync(FULL, multi);
+                if (mm) {
+                    if (multi) {
+                        const uint32_t s = (qh + qn + (uint32_t)__popc(mm & ((1u << lane) - 1u))) & 63u;
+                        Q[s] = w; Q[64 + s] = ov[u]; Q[128 + s] = nops;
                     }
-                };
-                for (uint32_t k = 0; k < nops; ++k) {
-                    const uint32_t cw = (k == 0) ? c : ldg_u32(a.cigar + c0 + k);
-                    const uint32_t op = cw & 15u;
-                    const int64_t n = cw >> 4;
-                    if (is_match_op(op)) {                                     // :745-752  adjacent M/=/X merge into one run
-                        if (re == q && rs != INT64_MIN) re = q + n; else { flush(); rs = q; re = q + n; }
-                        q += n;
-                    } else if (is_skip_op(op)) q += n;                         // :754-757
+                    qn += (uint32_t)__popc(mm);
+                    if (qn >= 32u) drain(32u);
                 }
-                flush();
             }
         }
     }
+    if (HAS_OFF && qn) drain(qn);
     __syncwarp();
 
     // depth just left of the segment
