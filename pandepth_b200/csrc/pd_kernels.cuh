@@ -305,33 +305,34 @@ __global__ void __launch_bounds__(WPC * 32, TILE_MIN_CTAS) k_tile_accumulate(Til
     // window index / first CIGAR word / op count behind the CTA's tables) and walked 32 at a time, one read per lane, all lanes busy.
     uint32_t *Q = smem + WPC * TILE_SMEM_WORDS + warp * TILE_QUEUE_WORDS;
     uint32_t qn = 0, qh = 0;
+    bool far_flagged = false;                                          // this lane has raised *delta_used already
+    // One read's ops, 32-bit window arithmetic: positions saturate at 0x7fffffff (every position at or beyond the contig end
+    // -- clen_w <= 0x7fffffff -- is clipped away alike), op lengths are < 2^28.  One flush site: a run is closed when an M/=/X
+    // op does not continue it (re != q: a D/N lay between) and by the terminator step k == nops.
     auto walk = [&](uint32_t w, uint32_t c0, uint32_t nops) {
         const bool owner = w >= (uint32_t)HALO || own_halo;
-        const int64_t far_w = (w >= (uint32_t)SEG) ? 2 * SEG + HALO : SEG + HALO;
-        int64_t q = w, rs = INT64_MIN, re = INT64_MIN;
-        auto flush = [&]() {
-            if (rs == INT64_MIN) return;
-            const int64_t s = rs, e = re > clen_w64 ? clen_w64 : re;
-            if (s >= e) return;
-            emit(s, 1u);
-            emit(e, 0xffffffffu);
-            if (owner && e > far_w) {
-                const int64_t gs = s > far_w ? s : far_w;
-                red_add_u32(a.delta + hbase + gs, 1u);
-                red_add_u32(a.delta + hbase + e, 0xffffffffu);
-                *a.delta_used = 1;
+        const uint32_t far_w = (w >= (uint32_t)SEG) ? 2u * SEG + HALO : (uint32_t)(SEG + HALO);
+        uint32_t q = w, rs = 0, re = 0; bool open = false;
+        for (uint32_t k = 0; k <= nops; ++k) {
+            const uint32_t cw = k < nops ? ldg_u32(a.cigar + c0 + k) : 0xfu;       // 0xf: no op (terminator)
+            const uint32_t op = cw & 15u, n = cw >> 4;
+            const bool m = is_match_op(op);                                         // :745-752  adjacent M/=/X merge into one run
+            if (open && (k == nops || (m && re != q))) {
+                const uint32_t e = min(re, clen_w);
+                if (rs < e) {
+                    if (rs < (uint32_t)TOFF) carry_reg += 1u; else if (rs < (uint32_t)WIN) atomicAdd(&E[rs - TOFF], 1u);
+                    if (e < (uint32_t)TOFF) carry_reg -= 1u; else if (e < (uint32_t)WIN) atomicAdd(&E[e - TOFF], 0xffffffffu);
+                    if (owner && e > far_w) {
+                        red_add_u32(a.delta + hbase + max(rs, far_w), 1u);
+                        red_add_u32(a.delta + hbase + e, 0xffffffffu);
+                        if (!far_flagged) { *a.delta_used = 1; far_flagged = true; }
+                    }
+                }
+                open = false;
             }
-        };
-        for (uint32_t k = 0; k < nops; ++k) {
-            const uint32_t cw = ldg_u32(a.cigar + c0 + k);
-            const uint32_t op = cw & 15u;
-            const int64_t n = cw >> 4;
-            if (is_match_op(op)) {                                     // :745-752  adjacent M/=/X merge into one run
-                if (re == q && rs != INT64_MIN) re = q + n; else { flush(); rs = q; re = q + n; }
-                q += n;
-            } else if (is_skip_op(op)) q += n;                         // :754-757
+            if (m) { if (!open) { rs = q; open = true; } q = min(q + n, 0x7fffffffu); re = q; }
+            else if (is_skip_op(op)) q = min(q + n, 0x7fffffffu);                   // :754-757
         }
-        flush();
     };
     auto drain = [&](uint32_t cnt) {                                   // the oldest `cnt` (<= 32) queued reads, one per lane
         __syncwarp();
@@ -390,9 +391,18 @@ __global__ void __launch_bounds__(WPC * 32, TILE_MIN_CTAS) k_tile_accumulate(Til
             }
             carry_p = prev_last;
         }
+        // HAS_OFF: the unrolled chunk loop only queues multi-op reads; when 32 are waiting it is left (u0 = next chunk), the queue is
+        // drained at ONE code location below, and the loop is re-entered past the chunks already consumed -- a drain inlined
+        // behind every chunk made the kernel nine walks long and instruction-fetch bound (ncu: stall_no_instruction 10 per issue)
+        int u0 = 0;
+      consume_chunks:
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             if ((uint32_t)(u * 32) >= left) break;            // warp-uniform
+            if (HAS_OFF) {
+                if (u < u0) continue;                         // consumed before the last drain
+                if (qn >= 32u) { u0 = u; goto drain_queue; }
+            }
             const int32_t p = pv[u];
             const uint32_t c = cv[u];
             const uint32_t nops = HAS_OFF ? nv[u] : 1u;
@@ -416,7 +426,7 @@ __global__ void __launch_bounds__(WPC * 32, TILE_MIN_CTAS) k_tile_accumulate(Til
                     if ((w >= (uint32_t)HALO || own_halo) && e > far_w) {           // rare: run longer than HALO, applied by its owner
                         red_add_u32(a.delta + hbase + far_w, 1u);
                         red_add_u32(a.delta + hbase + e, 0xffffffffu);
-                        *a.delta_used = 1;
+                        if (!far_flagged) { *a.delta_used = 1; far_flagged = true; }
                     }
                 }
             }
@@ -429,12 +439,17 @@ __global__ void __launch_bounds__(WPC * 32, TILE_MIN_CTAS) k_tile_accumulate(Til
                         Q[s] = w; Q[64 + s] = ov[u]; Q[128 + s] = nops;
                     }
                     qn += (uint32_t)__popc(mm);
-                    if (qn >= 32u) drain(32u);
                 }
             }
         }
+        u0 = U;                                               // every chunk of the group is consumed
+      drain_queue:
+        if (HAS_OFF) {
+            const bool last_group = base + 32u * U >= i_hi;
+            while (qn >= 32u || (qn && u0 == U && last_group)) drain(qn < 32u ? qn : 32u);
+            if (u0 < U) goto consume_chunks;
+        }
     }
-    if (HAS_OFF && qn) drain(qn);
     __syncwarp();
 
     // depth just left of the segment
