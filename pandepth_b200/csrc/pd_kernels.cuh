@@ -313,11 +313,14 @@ __global__ void __launch_bounds__(WPC * 32, TILE_MIN_CTAS) k_tile_accumulate(Til
         const bool owner = w >= (uint32_t)HALO || own_halo;
         const uint32_t far_w = (w >= (uint32_t)SEG) ? 2u * SEG + HALO : (uint32_t)(SEG + HALO);
         uint32_t q = w, rs = 0, re = 0; bool open = false;
-        for (uint32_t k = 0; k <= nops; ++k) {
-            const uint32_t cw = k < nops ? ldg_u32(a.cigar + c0 + k) : 0xfu;       // 0xf: no op (terminator)
+        // the first four words are loaded together (independent loads: one memory round trip instead of one per op -- the
+        // dependent per-op load was the top stall of this path); reads with more ops continue with one load per op
+        const uint32_t *cp = a.cigar + c0;
+        const uint32_t p0 = ldg_u32(cp), p1 = nops > 1u ? ldg_u32(cp + 1) : 0xfu, p2 = nops > 2u ? ldg_u32(cp + 2) : 0xfu, p3 = nops > 3u ? ldg_u32(cp + 3) : 0xfu;
+        auto step = [&](uint32_t cw, bool term) {                                   // term: behind the read's last op
             const uint32_t op = cw & 15u, n = cw >> 4;
-            const bool m = is_match_op(op);                                         // :745-752  adjacent M/=/X merge into one run
-            if (open && (k == nops || (m && re != q))) {
+            const bool m = !term && is_match_op(op);                                // :745-752  adjacent M/=/X merge into one run
+            if (open && (term || (m && re != q))) {
                 const uint32_t e = min(re, clen_w);
                 if (rs < e) {
                     if (rs < (uint32_t)TOFF) carry_reg += 1u; else if (rs < (uint32_t)WIN) atomicAdd(&E[rs - TOFF], 1u);
@@ -331,7 +334,13 @@ __global__ void __launch_bounds__(WPC * 32, TILE_MIN_CTAS) k_tile_accumulate(Til
                 open = false;
             }
             if (m) { if (!open) { rs = q; open = true; } q = min(q + n, 0x7fffffffu); re = q; }
-            else if (is_skip_op(op)) q = min(q + n, 0x7fffffffu);                   // :754-757
+            else if (!term && is_skip_op(op)) q = min(q + n, 0x7fffffffu);          // :754-757
+        };
+        step(p0, nops < 1u);
+#pragma unroll 1
+        for (uint32_t k = 1; k <= nops; ++k) {
+            const uint32_t cw = k == 1u ? p1 : k == 2u ? p2 : k == 3u ? p3 : (k < nops ? ldg_u32(cp + k) : 0xfu);
+            step(cw, k >= nops);
         }
     };
     auto drain = [&](uint32_t cnt) {                                   // the oldest `cnt` (<= 32) queued reads, one per lane
