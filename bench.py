@@ -333,15 +333,24 @@ def ours(args):
         both = allreduce_sum_u64(np.stack([cov, tot]), world, device=dev)      # NCCL all-reduce (sum) of the triples' counters
         return both[0], both[1]
 
+    phase = {"reset": 0.0, "push": 0.0, "reduce": 0.0, "combine": 0.0, "n": 0}      # host-side wall time per phase of the device step
+
     def step_device():
+        t0 = time.perf_counter()
         eng.reset()
+        t1 = time.perf_counter()
         for t in mine:
             if n_reads[t]:
                 # (PD_READY -- cut kernels of batch k+1 on a side stream under batch k's tile kernel -- was measured on this
                 #  step: 5.10 -> 5.06 ms, because the tile kernel itself runs 10 % slower next to them; not used here)
                 eng.push_contig(t, d_pos[t].data_ptr(), d_cig[t].data_ptr(), flags=pd.PD_SORTED | pd.PD_DEVICE, n=n_reads[t])
-        cov, tot = eng.reduce(iv_t, iv_s, iv_e, 1, 0xFFFFFFFF)       # finalizes, reduces, copies the result back
-        return combine(cov, tot)
+        t2 = time.perf_counter()
+        cov, tot = eng.reduce(iv_t, iv_s, iv_e, 1, 0xFFFFFFFF)       # finalizes, reduces, copies the result back (synchronises)
+        t3 = time.perf_counter()
+        res = combine(cov, tot)
+        t4 = time.perf_counter()
+        phase["reset"] += t1 - t0; phase["push"] += t2 - t1; phase["reduce"] += t3 - t2; phase["combine"] += t4 - t3; phase["n"] += 1
+        return res
 
     def barrier():
         if world > 1:
@@ -376,7 +385,10 @@ def ours(args):
     for _ in range(args.warmup):
         step_device()
     eng.profile_enable(True)
+    for k in phase:
+        phase[k] = 0
     ms_dev, _, (cov, tot) = timed(step_device, args.steps, 0)
+    host_phase_ms = {k: 1e3 * v / max(1, phase["n"]) for k, v in phase.items() if k != "n"}
     clocks = sampler.stop() if sampler else None
     prof = eng.profile()
     eng.profile_enable(False)
@@ -558,6 +570,7 @@ def ours(args):
                          "peak_source": peak_src,
                          "kernel_share_of_step": kt["ms"] / ms_dev if ms_dev else None},
             "kernels_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items() if v["launches"]},
+            "host_phase_ms_per_step": host_phase_ms,
             "gpu_launches": int(launches_per_step),
             "clocks": clocks,
             "summary_row": {"RegionLength": int(table[:, 0].sum()), "CoveredSite": int(table[:, 1].sum()), "TotalDepth": int(table[:, 2].sum())},

@@ -29,7 +29,9 @@ constexpr int SEG = PD_SEG;   // bases owned by one warp of k_tile_accumulate (8
 constexpr int HALO = 256;   // look-back window in bases; also the largest "common span" L the fast path models
 constexpr int WPC = 8;      // warps per CTA in k_tile_accumulate
 #ifndef PD_TILE_AGG
-#define PD_TILE_AGG 1       // equal adjacent reads of a chunk are applied once with a weight (A/B: profiles/r02_tile_agg.txt)
+#define PD_TILE_AGG 0       // 1: runs of equal adjacent reads of a chunk are applied once with a weight.  Measured on B200 (one cfg2 contig,
+                            // profiles/r02_tile_agg.txt): 50x 0.465 -> 0.580 ms, 200x 1.420 -> 1.829 ms -- the shuffle + two ballots per chunk
+                            // cost more than the 15 % / 45 % of the shared atomics they save; off
 #endif
 #ifndef PD_PREFETCH
 #define PD_PREFETCH 1      // every warp prefetches (to L2) the reads of the segment one wave of resident warps ahead
@@ -429,9 +431,9 @@ __global__ void __launch_bounds__(WPC * 32, TILE_MIN_CTAS) k_tile_accumulate(Til
                 // one CIGAR op (the common case): M/=/X is one run [p, p+len)                      :745-752
                 const uint32_t e = min(w + (c >> 4), clen_w);                      // len < 2^28: no overflow
                 const bool ok = pass && (!HAS_OFF || nops == 1u) && ((0x181u >> (c & 15u)) & 1u) && e > w;
-                // Sorted input puts equal reads into adjacent lanes (duplicates, pile-ups, deep coverage: 15 % of the reads at 50x,
-                // 45 % at 200x): a run of lanes with the same (pos, op) is applied once, by its first lane, with the run length as
-                // the weight -- fewer shared atomics, and none of the same-address ones that serialise completely.
+                // PD_TILE_AGG (off, measured slower): sorted input puts equal reads into adjacent lanes (duplicates, pile-ups, deep
+                // coverage: 15 % of the reads at 50x, 45 % at 200x); a run of lanes with the same (pos, op) is applied once, by its
+                // first lane, with the run length as the weight.
                 uint32_t cnt = 1u; bool head = ok;
                 if (PD_TILE_AGG) {
                     const uint32_t cl = __shfl_up_sync(FULL, c, 1);

@@ -7,6 +7,10 @@ nvidia-smi --query-gpu=index,name --format=csv,noheader | head -n 8 > gpurun_out
 nproc >> gpurun_out/n${N}_env.log; cat /sys/fs/cgroup/cpu.max >> gpurun_out/n${N}_env.log 2>/dev/null
 ( timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 5 --warmup 3 ) > gpurun_out/n${N}_bench.log 2>&1; echo "rc=$?" >> gpurun_out/n${N}_bench.log
 python - <<PY
+import json as _j
+try:
+    _d = _j.loads([x for x in open("gpurun_out/n${N}_bench.log") if x.startswith("{")][-1]); print("host phases", _d.get("host_phase_ms_per_step"))
+except Exception as _e: print(_e)
 import json
 try:
     l = [x for x in open("gpurun_out/n${N}_bench.log") if x.startswith("{")][-1]; d = json.loads(l); e = d.get("e2e", {})
