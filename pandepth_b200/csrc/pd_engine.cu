@@ -198,17 +198,19 @@ int run_batch(pd_engine *e, int32_t tid, uint32_t n, const int32_t *pos, const u
         int rc = ensure_cut(e, cb, (size_t)nseg + 1); if (rc) return rc;
         pdk::CutArgs c{pos, n, (int32_t)seg_a, nseg, cb.lo, cb.hi, (int64_t)e->org[tid]};
         const int32_t ncoarse = (nseg + pdk::CUT_COARSE - 1) / pdk::CUT_COARSE;
+        // a batch whose arrays are ordered by the main stream cannot be cut before that stream gets there anyway: its cut
+        // kernels run in line (two cross-stream hops per batch saved); the side stream is for batches that are complete already
+        const bool side = input_ready != nullptr || ready_now;
+        cudaStream_t cs = side ? e->cut_stream : e->stream;
         if (input_ready) CK(cudaStreamWaitEvent(e->cut_stream, input_ready, 0));
-        else if (!ready_now) { CK(cudaEventRecord(e->cut_input, e->stream)); CK(cudaStreamWaitEvent(e->cut_stream, e->cut_input, 0)); }
-        if (cb.used) CK(cudaStreamWaitEvent(e->cut_stream, cb.released, 0));      // the tile kernel that last read these arrays
-        rc = launch_on(e, e->cut_stream, K_CUT, [&] {
-            pdk::k_cut_coarse<<<(ncoarse + pdk::CUT_THREADS - 1) / pdk::CUT_THREADS, pdk::CUT_THREADS, 0, e->cut_stream>>>(c, cb.coarse, ncoarse);
-            pdk::k_cut<<<(nseg + 1 + pdk::CUT_THREADS - 1) / pdk::CUT_THREADS, pdk::CUT_THREADS, 0, e->cut_stream>>>(c, cb.coarse, ncoarse);
+        if (side && cb.used) CK(cudaStreamWaitEvent(e->cut_stream, cb.released, 0));      // the tile kernel that last read these arrays
+        rc = launch_on(e, cs, K_CUT, [&] {
+            pdk::k_cut_coarse<<<(ncoarse + pdk::CUT_THREADS - 1) / pdk::CUT_THREADS, pdk::CUT_THREADS, 0, cs>>>(c, cb.coarse, ncoarse);
+            pdk::k_cut<<<(nseg + 1 + pdk::CUT_THREADS - 1) / pdk::CUT_THREADS, pdk::CUT_THREADS, 0, cs>>>(c, cb.coarse, ncoarse);
         });
         if (rc) return rc;
         e->stats.kernel_launches++;
-        CK(cudaEventRecord(cb.ready, e->cut_stream));
-        CK(cudaStreamWaitEvent(e->stream, cb.ready, 0));
+        if (side) { CK(cudaEventRecord(cb.ready, e->cut_stream)); CK(cudaStreamWaitEvent(e->stream, cb.ready, 0)); }
         if (e->org[tid] != 0 && seg_a == 0) {
             // range sharding: reads that start more than HALO bases left of the owned range are seen by no segment; the ones
             // among them that reach into the range are the first lo[0] reads of the batch (a device-side count, usually 0)

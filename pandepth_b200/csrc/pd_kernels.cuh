@@ -619,7 +619,7 @@ struct ScatterArgs {
     uint32_t xflags; int32_t min_mapq;
     int32_t shift;     // contig coordinate of delta[0] (range sharding); runs are clipped to [0, contig_len) after the shift
     const uint32_t *n_dev;   // non-null: only reads [0, *n_dev) (a device-side count: the reads left of a sorted batch's first cut)
-    int *delta_used;         // with n_dev: set when anything was scattered (the engine then runs the scan at finalize)
+    int *delta_used;         // non-null (n_dev mode): set when a run end was scattered (the engine then runs the scan at finalize)
     int64_t stripe_lo, stripe_hi;   // only run ends at delta indices in [stripe_lo, stripe_hi) are applied by this launch (striped
                                     // scatter: one launch per L2-sized stripe of the delta array; 0 / INT64_MAX = everything)
 };
@@ -641,6 +641,7 @@ __device__ __forceinline__ void scatter_one(const ScatterArgs &a, uint32_t i)
         if (s >= e) return;
         if (s >= slo && s < shi) red_add_u32(a.delta + s, 1u);
         if (e >= slo && e < shi) red_add_u32(a.delta + e, 0xffffffffu);
+        if (a.delta_used) *a.delta_used = 1;                   // (n_dev mode) something was scattered: the scan has to run at finalize
     };
     for (uint32_t k = 0; k < nops; ++k) {
         const uint32_t w = __ldcs(a.cigar + c0 + k);
@@ -657,8 +658,11 @@ __device__ __forceinline__ void scatter_one(const ScatterArgs &a, uint32_t i)
 __global__ void __launch_bounds__(256) k_delta_scatter(ScatterArgs a)
 {
     if (a.n_dev) {                                              // grid-stride over a device-side count (usually zero)
+        // Range sharding: the reads left of the first segment's look-back.  Only those that reach into the owned range scatter
+        // anything (none of them for reads shorter than HALO) -- and only then is the flag raised: raising it for every batch
+        // with such reads cost ranks > 0 a whole-range scan, a 4 B/base clear and a reduce without partials per step (4.6 of
+        // 11.7 ms at cfg5 on 2 GPUs, seen as all-reduce wait on rank 0).
         const uint32_t n = min(*a.n_dev, a.n);
-        if (n && a.delta_used && blockIdx.x == 0 && threadIdx.x == 0) *a.delta_used = 1;
         for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) scatter_one(a, i);
         return;
     }
