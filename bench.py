@@ -544,12 +544,14 @@ def ours(args):
         value = R_total * args.steps / (ms_dev * 1e-3) / 1e6
         # dram traffic of one k_tile_accumulate launch from the committed ncu --set full capture (same workload only)
         traffic = None
+        traffic_src = None
         try:
             import glob
             for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json"))):
                 tj = json.load(open(f))["kernels"].get("k_tile_accumulate")
                 if tj and args.genome == 3.0e9 and coverage == 50.0 and world == 1:
                     traffic = tj["dram_bytes_per_launch"]
+                    traffic_src = f"profiles/{os.path.basename(f)}: dram__bytes_read.sum + dram__bytes_write.sum of one launch, committed ncu --set full capture of this workload (not measured by this run)"
         except Exception:
             traffic = None
         cfg = "cfg2" if world == 1 else "cfg5"
@@ -565,7 +567,7 @@ def ours(args):
                        "l2": "inputs (8 B/read) and the depth array (4 B/base) are far larger than the 126 MB L2; no flush needed",
                        "timing": "CUDA events on the engine's stream, max over ranks"},
             "roofline": {"bound": "hbm", "kernel": "k_tile_accumulate", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak if peak else None, "traffic": traffic,
+                         "frac": achieved / peak if peak else None, "traffic": traffic, "traffic_source": traffic_src,
                          "algorithmic_bytes_per_launch": alg_per_launch, "avg_launch_ms": avg_ms, "launches": kt["launches"],
                          "peak_source": peak_src,
                          "kernel_share_of_step": kt["ms"] / ms_dev if ms_dev else None},
