@@ -22,10 +22,17 @@ B="python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline"
 ( timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_bgzf_decode -s 12 -c 1 -f -o gpurun_out/prof_r02_bgzf_A python tools/bench_bgzf.py /tmp/cA.bam --steps 1 --no-feed ) > gpurun_out/z_ncu_bgzf_A.log 2>&1
 ( timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_bgzf_decode -s 12 -c 1 -f -o gpurun_out/prof_r02_bgzf_B python tools/bench_bgzf.py /tmp/cB.bam --steps 1 --no-feed ) > gpurun_out/z_ncu_bgzf_B.log 2>&1
 ( timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_tile_accumulate -s 3 -c 1 -f -o gpurun_out/prof_r02_tile_mixed python tools/bench_variants.py --steps 1 --only mixed ) > gpurun_out/z_ncu_tile_mixed.log 2>&1
+# compute-sanitizer over the kernels this round changed: tile kernel with the multi-op queue and the filter bitmap (smoke: mixed CIGARs,
+# flag + mapq arrays), the K-decoder inflate kernels, the striped scatter
+( timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python __graft_entry__.py smoke ) > gpurun_out/z_san_memcheck_smoke.log 2>&1; echo "rc=$?" >> gpurun_out/z_san_memcheck_smoke.log
+( timeout 600 compute-sanitizer --tool racecheck --error-exitcode 9 python __graft_entry__.py smoke ) > gpurun_out/z_san_racecheck_smoke.log 2>&1; echo "rc=$?" >> gpurun_out/z_san_racecheck_smoke.log
+( timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_bgzf_gpu.py -x -q -k "fixtures or literal_dominated or few_blocks" ) > gpurun_out/z_san_memcheck_bgzf.log 2>&1; echo "rc=$?" >> gpurun_out/z_san_memcheck_bgzf.log
+( timeout 900 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_bgzf_gpu.py -x -q -k "literal_dominated" ) > gpurun_out/z_san_racecheck_bgzf.log 2>&1; echo "rc=$?" >> gpurun_out/z_san_racecheck_bgzf.log
+( timeout 900 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_engine_gpu.py -x -q -k "striped or (fixtures and mix)" ) > gpurun_out/z_san_racecheck_engine.log 2>&1; echo "rc=$?" >> gpurun_out/z_san_racecheck_engine.log
 ( REPS=2 timeout 900 bash tools/bench_cli.sh 3000 A ) > gpurun_out/z_cli_3000_A.log 2>&1
 ( REPS=2 THREADS=16 timeout 900 bash tools/bench_cli.sh 3000 A -w 100 ) > gpurun_out/z_cli_3000_A_w100.log 2>&1
 ( REPS=2 THREADS=16 timeout 900 bash tools/bench_cli.sh 100 B ) > gpurun_out/z_cli_100_B.log 2>&1
-for f in z_smoke z_pytest_gpu z_variants z_delta_path z_windows z_cli_3000_A z_cli_3000_A_w100 z_cli_100_B; do echo "== $f"; tail -n 14 gpurun_out/$f.log | cut -c1-900; done
+for f in z_smoke z_pytest_gpu z_san_memcheck_smoke z_san_racecheck_smoke z_san_memcheck_bgzf z_san_racecheck_bgzf z_san_racecheck_engine z_variants z_delta_path z_windows z_cli_3000_A z_cli_3000_A_w100 z_cli_100_B; do echo "== $f"; tail -n 14 gpurun_out/$f.log | cut -c1-900; done
 python - <<'PY'
 import json
 for f in ("z_bench_ref", "z_bench", "z_bench_B"):
