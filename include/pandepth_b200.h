@@ -41,6 +41,8 @@ enum {
 #define PD_SORTED 1u   /* records are sorted by pos within each tid (coordinate-sorted BAM order): enables the tile path */
 #define PD_DEVICE 2u   /* every pointer argument is a device pointer on the engine's GPU */
 #define PD_ASYNC  4u   /* host buffers are pinned and stay valid until pd_sync(): copies are not waited for */
+#define PD_CRC    16u  /* pd_push_bgzf: every payload is followed in `bytes` by its 8-byte BGZF trailer (CRC32, ISIZE): the engine verifies the
+                          CRC32 of every inflated block on the device, like bgzf_read_block does; a mismatch is PD_ERR_ARG */
 #define PD_READY  8u   /* with PD_DEVICE: the arrays are complete NOW (not merely ordered by the engine's stream), so the engine may
                           index the batch on a side stream while earlier batches are still being accumulated */
 
@@ -103,7 +105,7 @@ int pd_push(pd_engine *e, int64_t n_reads, const int32_t *tid, const int32_t *po
  * Returns PD_ERR_FALLBACK when the chunk holds something the device path does not handle -- a record that does not start
  * on a BGZF block boundary (writers other than htslib, reads larger than a block) or a CIGAR kept in the CG tag.  Depth
  * accumulated by earlier chunks stays in the engine: the caller resets it and feeds the file through pd_push_contig.
- * A block that does not inflate to its ISIZE is PD_ERR_ARG. */
+ * A block that does not inflate to its ISIZE -- or, with PD_CRC, to bytes with another CRC32 than its trailer says -- is PD_ERR_ARG. */
 typedef struct pd_bgzf_block { uint64_t in_off; uint32_t in_len; uint32_t out_len; } pd_bgzf_block;
 #ifndef PD_BGZF_DEPTH
 #define PD_BGZF_DEPTH 6   /* PD_ASYNC: `bytes` of a call is no longer read once this many later pd_push_bgzf calls have returned */

@@ -392,6 +392,7 @@ int bz_finish(pd_engine *e, BzSlot &s)
     CK(cudaEventSynchronize(s.decoded));
     const uint32_t n_reads = s.h_totals[0], n_cigar = s.h_totals[1], fl = s.h_totals[2];
     if (fl & pdk::BZ_INFLATE) { bz_cancel(e); return fail(e, PD_ERR_ARG, "pd_push_bgzf: a BGZF block does not inflate to its ISIZE (corrupt or truncated block)"); }
+    if (fl & pdk::BZ_CRC) { bz_cancel(e); return fail(e, PD_ERR_ARG, "pd_push_bgzf: BGZF block CRC mismatch (corrupt block)"); }
     if (fl & (pdk::BZ_MALFORMED | pdk::BZ_STRADDLE | pdk::BZ_CG_TAG)) {
         bz_cancel(e);
         return fail(e, PD_ERR_FALLBACK, (fl & pdk::BZ_CG_TAG) ? "pd_push_bgzf: a CIGAR may live in the CG tag (host path needed)"
@@ -770,7 +771,7 @@ int pd_push_bgzf(pd_engine *e, const uint8_t *bytes, size_t n_bytes, const pd_bg
     if (!e) return PD_ERR_ARG;
     if (n_blocks < 0 || (n_blocks > 0 && (!bytes || !blocks)) || n_blocks > 0x7fffffffll) return fail(e, PD_ERR_ARG, "pd_push_bgzf: bad arguments");
     CK(cudaSetDevice(e->device));
-    const bool dev = (flags & PD_DEVICE) != 0;
+    const bool dev = (flags & PD_DEVICE) != 0, crc = (flags & PD_CRC) != 0;
     int rc = PD_OK;
     if (n_blocks > 0) {
         BzSlot &s = e->bz[e->bz_next];
@@ -781,7 +782,8 @@ int pd_push_bgzf(pd_engine *e, const uint8_t *bytes, size_t n_bytes, const pd_bg
         for (int64_t b = 0; b < n_blocks; b++) {
             const pd_bgzf_block &k = blocks[b];
             if (k.in_off > n_bytes || k.in_len > n_bytes - k.in_off || k.out_len > 65536u) return fail(e, PD_ERR_ARG, "pd_push_bgzf: block outside the buffer or ISIZE > 64 KB");
-            lo = std::min<uint64_t>(lo, k.in_off); hi = std::max<uint64_t>(hi, k.in_off + k.in_len);
+            lo = std::min<uint64_t>(lo, k.in_off); hi = std::max<uint64_t>(hi, k.in_off + k.in_len + (crc ? 8u : 0u));
+            if (crc && (uint64_t)k.in_off + k.in_len + 8u > n_bytes) return fail(e, PD_ERR_ARG, "pd_push_bgzf: PD_CRC needs the 8-byte trailer behind every payload inside the buffer");
             out_total += k.out_len;
         }
         if (out_total > 0xf0000000ull) return fail(e, PD_ERR_ARG, "pd_push_bgzf: chunk inflates to more than 3.75 GB; pass smaller chunks");
@@ -805,7 +807,7 @@ int pd_push_bgzf(pd_engine *e, const uint8_t *bytes, size_t n_bytes, const pd_bg
         if (s.out_used) CK(cudaStreamWaitEvent(s.stream, s.consumed, 0));     // the slot's previous arrays have been accumulated
         CK(cudaMemsetAsync(s.d_ticket, 0, 4, s.stream));
         pdk::BzArgs a{d_in, s.d_out, s.d_blk, (uint32_t)n_blocks, first_skip, e->n_targets, e->xflags, e->min_mapq,
-                      s.st_pos, s.st_tid, s.st_coff, s.st_cig, s.d_sum, s.d_ticket};
+                      s.st_pos, s.st_tid, s.st_coff, s.st_cig, s.d_sum, s.d_ticket, crc ? 1u : 0u};
         // literal-dominated streams (BAMs with SEQ + QUAL inflate by less than 4x): K decoders per warp, symbol loop in lockstep
         int K = out_total < 4 * (hi - lo) ? e->bz_lit_k : 1;
         if (e->bz_force_k) K = e->bz_force_k;

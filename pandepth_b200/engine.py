@@ -7,7 +7,7 @@ from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 
-PD_SORTED, PD_DEVICE, PD_ASYNC, PD_READY = 1, 2, 4, 8
+PD_SORTED, PD_DEVICE, PD_ASYNC, PD_READY, PD_CRC = 1, 2, 4, 8, 16
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 

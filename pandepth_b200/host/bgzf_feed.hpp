@@ -196,7 +196,7 @@ inline BgzfFeedResult bgzf_feed_file(pd_engine *eng, std::mutex *eng_mu, const s
             int rc;
             {
                 std::lock_guard<std::mutex> g(emu);
-                rc = state.load() == 1 ? pd_push_bgzf(eng, buf, got, blocks.data(), (int64_t)blocks.size(), j == 0 ? first_skip : 0u, PD_ASYNC) : PD_OK;
+                rc = state.load() == 1 ? pd_push_bgzf(eng, buf, got, blocks.data(), (int64_t)blocks.size(), j == 0 ? first_skip : 0u, PD_ASYNC | PD_CRC) : PD_OK;
                 ++push_seq;
                 in_flight.emplace_back(push_seq, id);
                 // the engine has finished reading the bytes of a chunk once PD_BGZF_DEPTH later pushes have returned

@@ -84,7 +84,7 @@ int main(int argc, char **argv)
     std::vector<BgzfSummary> sum(nb);
     uint32_t ticket = 0;
     BzArgs a{data.data(), out.data(), blk.data(), (uint32_t)nb, skip0, (int32_t)n_ref, xflags, min_mapq,
-             st_pos.data(), st_tid.data(), st_coff.data(), st_cigv.data(), sum.data(), &ticket};
+             st_pos.data(), st_tid.data(), st_coff.data(), st_cigv.data(), sum.data(), &ticket, 1u /* verify the CRC32 behind every payload */};
     if (K == 2) emu::launch(1, 32 * std::min(warps, 4u), k_bgzf_decode_multi<2, 4>, a);
     else if (K == 4) emu::launch(1, 32 * std::min(warps, 2u), k_bgzf_decode_multi<4, 2>, a);
     else if (K == 8) emu::launch(1, 32, k_bgzf_decode_multi<8, 1>, a);

@@ -47,8 +47,10 @@ def _chunks(data, per_chunk, first=None):
     return out
 
 
-def _decode_depth(data, tlen, xflags, q, per_chunk=1 << 30, flags=0, order=None, hint=None):
+def _decode_depth(data, tlen, xflags, q, per_chunk=1 << 30, flags=0, order=None, hint=None, crc=True):
     import pandepth_b200 as pd
+    if crc:
+        flags |= pd.PD_CRC                      # the buffers are whole files: every payload has its trailer behind it
     buf = np.frombuffer(data, np.uint8)
     ch = _chunks(data, per_chunk)
     if order == "reverse":
@@ -291,3 +293,35 @@ def test_device_decode_literal_dominated_bam_with_k_decoders(K, tmp_path, monkey
     got, _ = _decode_depth(data, tlen, 1796, -1, per_chunk=5, flags=pd.PD_ASYNC)
     _assert_depth(got, want, f"flavour B, K={K}")
     assert sum(int(g.sum(dtype=np.uint64)) for g in got) == 150 * len(recs)
+
+
+def test_crc32_catches_a_flipped_byte_that_keeps_the_stream_valid(mixed):
+    """A stored (level 0) block with one payload byte changed -- the low byte of a record's pos -- inflates to its ISIZE and
+    still parses as records, so only the CRC32 of the trailer can tell.  With PD_CRC the engine reports the mismatch (the
+    reference, through htslib's bgzf_read_block, fails on such a file too); without the flag the changed depth comes out."""
+    import pandepth_b200 as pd
+    data, tlen, rec = mixed
+    raw, first, recs, _ = bu.bam_payload(data)
+    good = bu.rewrite_bgzf(raw, bu.record_cuts(raw, first, recs, max_block=15000), level=0)
+    want = model.accumulate(tlen, rec, 1796, -1)
+    got, _ = _decode_depth(good, tlen, 1796, -1)
+    _assert_depth(got, want, "stored blocks, CRC verified")
+    # flip one byte of the compressed file: a stored payload byte IS the inflated byte
+    tab = bu.block_table(good)
+    blk = tab[tab.size // 2]
+    r = next(x for x in recs if x > first + 40000)                 # some record well inside the file
+    bad = bytearray(good)
+    # find the record's position inside its block: blocks hold raw[cuts[i]:cuts[i+1]] back to back
+    acc = 0
+    for b in tab:
+        if acc + int(b["out_len"]) > r + 8:
+            off = int(b["in_off"]) + 5 + (r + 8 - acc)            # 5 = stored-block header (BFINAL/BTYPE byte, LEN, NLEN)
+            break
+        acc += int(b["out_len"])
+    assert bad[off] == raw[r + 8]
+    bad[off] ^= 0x01
+    with pytest.raises(pd.PDError) as ei:
+        _decode_depth(bytes(bad), tlen, 1796, -1)
+    assert ei.value.code == 1 and "CRC" in str(ei.value)
+    got2, _ = _decode_depth(bytes(bad), tlen, 1796, -1, crc=False)  # without the check: silently different depth
+    assert any(not np.array_equal(g, w) for g, w in zip(got2, want) if w.size)
