@@ -30,6 +30,10 @@ namespace pdh {
 
 // Pinned buffers for compressed pieces; kept for the life of the process (a second file or bench step reuses them).
 struct ChunkPool {
+    // Upper bound on the pinned bytes of this pool (0 = none).  Pinned memory costs ~0.3 ms per MB to allocate and about as much
+    // again when the process exits -- paid on every run of the command line (measured: 23 x 81 MB for a 5 GB BAM with SEQ+QUAL
+    // = 0.6 s + ~1.5 s of a 3.75 s run), and once in a long-lived caller (bench.py's end-to-end arm, a service).
+    size_t max_bytes = 0;
     struct Buf { uint8_t *p = nullptr; size_t cap = 0; };
     std::vector<Buf> bufs; std::vector<int> free_ids;
     std::mutex mu; std::condition_variable cv;
@@ -114,6 +118,8 @@ inline BgzfFeedResult bgzf_feed_file(pd_engine *eng, std::mutex *eng_mu, const s
     const uint64_t span = file_size > data_start ? file_size - data_start : 0;
     // small inputs: more, smaller pieces (pinned memory costs ~0.3 ms per MB to allocate and as much again to release at exit)
     if (!getenv("PANDEPTH_BGZF_PIECE_MB")) piece = std::min<size_t>(piece, std::max<size_t>(8u << 20, (size_t)(span / (4 * (uint64_t)std::max(1, threads)))));
+    if (pool.max_bytes && !getenv("PANDEPTH_BGZF_PIECE_MB"))   // the pool holds threads + PD_BGZF_DEPTH + 1 buffers of piece + 68 KB
+        piece = std::min<size_t>(piece, std::max<size_t>(4u << 20, pool.max_bytes / (size_t)(std::max(1, threads) + PD_BGZF_DEPTH + 1)));
     piece = std::max<size_t>(piece, 1u << 17);
     const size_t n_pieces = (size_t)((span + piece - 1) / piece);
     if (n_pieces == 0) { close(fd); res.status = 1; return res; }

@@ -411,6 +411,8 @@ struct Feeder {
             eng_ok = true;
         }
         const auto t0 = std::chrono::steady_clock::now();
+        // one run per process: bound the pinned pool (PANDEPTH_PINNED_MB, default 512 MB; 0 = unbounded)
+        { const char *pm = getenv("PANDEPTH_PINNED_MB"); chunk_pool.max_bytes = (size_t)((pm ? atof(pm) : 512.0) * 1048576.0); }
         const BgzfFeedResult r = bgzf_feed_file(eng, &eng_mu, input, std::max(1, o.threads), chunk_pool, strict_eof);
         ns_decode += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
         n_push += r.pieces;

@@ -502,6 +502,7 @@ std::vector<pd_engine *> feed_multi_gpu(const Options &o, const std::string &pat
                 if (f_beg == UINT64_MAX) { res[k].status = 1; return; }     // no read at or behind my first base
             }
             const bool last = k + 1 == K;
+            { const char *pm = getenv("PANDEPTH_PINNED_MB"); pools[k].max_bytes = (size_t)((pm ? atof(pm) : 512.0) * 1048576.0); }
             res[k] = bgzf_feed_file(eng[k], nullptr, path, thr, pools[k], true, f_beg, UINT64_MAX, last ? INT32_MAX : t1, last ? INT32_MAX : (int32_t)end[k][(size_t)t1]);
         });
     for (auto &t : th) t.join();
