@@ -787,11 +787,11 @@ int pd_push_bgzf(pd_engine *e, const uint8_t *bytes, size_t n_bytes, const pd_bg
             out_total += k.out_len;
         }
         if (out_total > 0xf0000000ull) return fail(e, PD_ERR_ARG, "pd_push_bgzf: chunk inflates to more than 3.75 GB; pass smaller chunks");
-        rc = bz_ensure(e, s, (size_t)(hi - lo), out_total + 8ull * (uint64_t)n_blocks, (uint32_t)n_blocks, dev); if (rc) return rc;
+        rc = bz_ensure(e, s, (size_t)(hi - lo), out_total + 32ull * (uint64_t)n_blocks, (uint32_t)n_blocks, dev); if (rc) return rc;
         uint64_t oo = 0;
         for (int64_t b = 0; b < n_blocks; b++) {
             s.h_blk[b] = pdk::BgzfBlockDesc{blocks[b].in_off - lo, blocks[b].in_len, blocks[b].out_len, oo};
-            oo += (blocks[b].out_len + 7u) & ~7u;                 // every block's output starts 8-byte aligned
+            oo += (blocks[b].out_len + 31u) & ~31u;               // every block's output starts on a 32-byte boundary (whole sectors for the CRC)
         }
         s.n_blocks = (uint32_t)n_blocks;
         const uint8_t *d_in = dev ? bytes + lo : s.d_in;

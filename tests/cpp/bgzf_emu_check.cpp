@@ -76,14 +76,15 @@ int main(int argc, char **argv)
 
     // ---- device structures ----
     std::vector<BgzfBlockDesc> blk(nb); uint64_t oo = 0;
-    for (size_t b = 0; b < nb; b++) { blk[b] = BgzfBlockDesc{blocks[b0 + b].in_off, blocks[b0 + b].in_len, blocks[b0 + b].out_len, oo}; oo += (blocks[b0 + b].out_len + 7u) & ~7u; }
-    std::vector<uint8_t> out(oo + 64, 0xAB);
+    for (size_t b = 0; b < nb; b++) { blk[b] = BgzfBlockDesc{blocks[b0 + b].in_off, blocks[b0 + b].in_len, blocks[b0 + b].out_len, oo}; oo += (blocks[b0 + b].out_len + 31u) & ~31u; }
+    std::vector<uint8_t> out_store(oo + 64 + 32, 0xAB);
+    uint8_t *const out = out_store.data() + ((32 - ((uintptr_t)out_store.data() & 31)) & 31);     // 32-byte aligned like the engine's buffer
     const size_t st_rec = oo / 32 + 2 * nb + 64, st_cig = oo / 4 + nb + 64, n_rec = oo / 36 + 64;
     std::vector<int32_t> st_pos(st_rec), st_tid(st_rec), pos(n_rec + 1), tid(n_rec + 1);
     std::vector<uint32_t> st_coff(st_rec), st_cigv(st_cig), coff(n_rec + 1), cig(oo / 4 + 64), r0(nb), c0(nb), totals(4);
     std::vector<BgzfSummary> sum(nb);
     uint32_t ticket = 0;
-    BzArgs a{data.data(), out.data(), blk.data(), (uint32_t)nb, skip0, (int32_t)n_ref, xflags, min_mapq,
+    BzArgs a{data.data(), out, blk.data(), (uint32_t)nb, skip0, (int32_t)n_ref, xflags, min_mapq,
              st_pos.data(), st_tid.data(), st_coff.data(), st_cigv.data(), sum.data(), &ticket, 1u /* verify the CRC32 behind every payload */};
     if (K == 2) emu::launch(1, 32 * std::min(warps, 4u), k_bgzf_decode_multi<2, 4>, a);
     else if (K == 4) emu::launch(1, 32 * std::min(warps, 2u), k_bgzf_decode_multi<4, 2>, a);
@@ -104,11 +105,11 @@ int main(int argc, char **argv)
     for (size_t b = 0; b < nb; b++) {
         std::vector<uint8_t> want(blk[b].out_len);
         if (!zlib_raw(data.data() + blk[b].in_off, blk[b].in_len, want.data(), blk[b].out_len)) { printf("block %zu: zlib rejects\n", b); bad++; continue; }
-        if (memcmp(want.data(), out.data() + blk[b].out_off, blk[b].out_len) != 0) {
+        if (memcmp(want.data(), out + blk[b].out_off, blk[b].out_len) != 0) {
             size_t d = 0; while (want[d] == out[blk[b].out_off + d]) d++;
             printf("block %zu: inflated bytes differ at %zu of %u\n", b, d, blk[b].out_len); bad++;
         }
-        for (size_t x = blk[b].out_len; x < ((blk[b].out_len + 7u) & ~7u); x++) if (out[blk[b].out_off + x] != 0xAB) { printf("block %zu: wrote past its output\n", b); bad++; break; }
+        for (size_t x = blk[b].out_len; x < ((blk[b].out_len + 31u) & ~31u); x++) if (out[blk[b].out_off + x] != 0xAB) { printf("block %zu: wrote past its output\n", b); bad++; break; }
         const uint32_t sk = b == 0 ? skip0 : 0;
         uint32_t n = 0, nc = 0, fl = 0; int32_t ft = INT32_MIN, fp = 0, lt = INT32_MIN, lp = INT32_MIN;
         const int64_t used = walk_bam_block(want.data() + sk, blk[b].out_len - sk, [&](int32_t t, int32_t p, uint16_t flag, uint8_t mapq, uint32_t ncg, const uint8_t *cg) {

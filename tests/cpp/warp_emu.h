@@ -139,6 +139,8 @@ inline uintptr_t shared_base() { return (((uintptr_t)&anchor) - (uintptr_t)(512u
 inline uint32_t emu_shared_addr(const void *p) { return (uint32_t)((uintptr_t)p - emu::shared_base()); }
 inline const void *emu_shared_ptr(uint32_t sa) { return (const void *)(emu::shared_base() + sa); }
 #define __align__(n) __attribute__((aligned(n)))
+struct uint4 { uint32_t x, y, z, w; };
+inline uint32_t min(uint32_t a, uint32_t b) { return a < b ? a : b; }
 inline uint32_t atomicAdd(uint32_t *p, uint32_t v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
