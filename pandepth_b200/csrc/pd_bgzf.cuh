@@ -366,7 +366,7 @@ __device__ __forceinline__ int bz_inflate(const uint8_t *in, uint32_t in_len, ui
 
 // ---------------------------------------------------------------------------------------------------------------
 // CRC32 of an inflated block (zlib's: reflected 0xEDB88320), by the whole warp -- what bgzf_read_block verifies on the host.
-// The block is cut into 32 stripes of S bytes (the last ones may be short or empty); lane i computes the CRC32 of its stripe
+// The block is cut into 64 stripes of S bytes (the last ones may be short or empty); lane i computes the CRC32 of its two stripes
 // byte by byte through a 1 KB table in shared memory, and the stripes' CRCs are combined with the linear-algebra identity
 // behind zlib's crc32_combine:
 //     crc(A || B) = x^(8 |B|) * crc(A)  (mod P)  xor  crc(B)
@@ -410,39 +410,46 @@ __device__ __forceinline__ void bz_crc_table_init(uint32_t *tab, int tid, int nt
 
 __device__ __forceinline__ uint32_t bz_crc32_warp(const uint8_t *out, uint32_t len, const uint32_t *tab, int lane)
 {
-    // stripes of S bytes, S a multiple of 32, left-aligned: lane i owns [i S, min((i + 1) S, len)).  `out` is 32-byte aligned
-    // (the engine places every block's output on a 32-byte boundary), so a lane reads whole 32-byte sectors, each exactly
-    // once -- word loads walked every sector eight times through an L1 that 48 resident warps leave no room in, and made
-    // the check L2-bandwidth bound (+27 % on match-dominated files instead of the ~3 % its instructions cost).
-    const uint32_t S = (((len + 31u) >> 5) + 31u) & ~31u;
-    const uint32_t b0 = (uint32_t)lane * S, b1 = min(b0 + S, len);
-    uint32_t c = 0xffffffffu;
-    auto word = [&](uint32_t w) {
-        c = tab[(c ^ w) & 0xffu] ^ (c >> 8); w >>= 8;
-        c = tab[(c ^ w) & 0xffu] ^ (c >> 8); w >>= 8;
-        c = tab[(c ^ w) & 0xffu] ^ (c >> 8); w >>= 8;
-        c = tab[(c ^ w) & 0xffu] ^ (c >> 8);
-    };
-    if (b0 < len) {
-        uint32_t i = b0;
-        if ((((uintptr_t)out) & 31u) == 0) {
-            for (; i + 32 <= b1; i += 32) {
-                const uint4 u = *reinterpret_cast<const uint4 *>(out + i), v = *reinterpret_cast<const uint4 *>(out + i + 16);
-                word(u.x); word(u.y); word(u.z); word(u.w); word(v.x); word(v.y); word(v.z); word(v.w);
-            }
+    // 64 stripes of S bytes, S a multiple of 32, left-aligned: stripe j = [j S, min((j + 1) S, len)); lane i owns stripes 2i and
+    // 2i + 1 and walks them TOGETHER -- two independent table chains per lane: a single byte-serial chain (lookup -> xor ->
+    // lookup) left the warp waiting on shared-memory latency for 2 K steps per block.  `out` is 32-byte aligned (the engine
+    // places every block's output on a 32-byte boundary), so a lane reads whole 32-byte sectors, each exactly once -- word
+    // loads walked every sector eight times through an L1 that 48 resident warps leave no room in (L2-bandwidth bound).
+    const uint32_t S = (((len + 63u) >> 6) + 31u) & ~31u;
+    const uint32_t a0 = 2u * (uint32_t)lane * S, a1 = min(a0 + S, len), b0 = a0 + S, b1 = min(b0 + S, len);
+    uint32_t ca = 0xffffffffu, cb = 0xffffffffu;
+    auto step2 = [&](uint32_t wa, uint32_t wb) {               // one word of either stripe
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            ca = tab[(ca ^ wa) & 0xffu] ^ (ca >> 8); wa >>= 8;
+            cb = tab[(cb ^ wb) & 0xffu] ^ (cb >> 8); wb >>= 8;
         }
-        for (; i < b1; i++) c = tab[(c ^ out[i]) & 0xffu] ^ (c >> 8);       // the block's tail (and everything, for an unaligned buffer)
-        c = ~c;
-    } else c = 0u;                                             // crc32 of an empty stripe is 0 (and contributes nothing)
-    // weight of this stripe: x^(8 * bytes behind it) = x^(8 rem) * (x^(8 S))^(nfull - 1 - lane) for the full stripes, 1 for the last one
-    const uint32_t nfull = len / S, rem = len - nfull * S;
-    uint32_t pw = 1u << 31;
-    if ((uint32_t)lane < nfull) {
-        uint32_t sq = bz_crc_xpow8n(S);
-        pw = bz_crc_xpow8n(rem);
-        for (uint32_t k = nfull - 1u - (uint32_t)lane; k; k >>= 1) { if (k & 1u) pw = bz_crc_mulmod(sq, pw); if (k > 1u) sq = bz_crc_mulmod(sq, sq); }
+    };
+    uint32_t i = a0, j = b0;
+    if ((((uintptr_t)out) & 31u) == 0) {
+        for (; j + 32 <= b1; i += 32, j += 32) {               // stripe 2i + 1 is never longer than stripe 2i
+            const uint4 u = *reinterpret_cast<const uint4 *>(out + i), x = *reinterpret_cast<const uint4 *>(out + j);
+            step2(u.x, x.x); step2(u.y, x.y); step2(u.z, x.z); step2(u.w, x.w);
+            const uint4 v = *reinterpret_cast<const uint4 *>(out + i + 16), y = *reinterpret_cast<const uint4 *>(out + j + 16);
+            step2(v.x, y.x); step2(v.y, y.y); step2(v.z, y.z); step2(v.w, y.w);
+        }
     }
-    uint32_t t = bz_crc_mulmod(pw, c);
+    for (; i < a1; i++) ca = tab[(ca ^ out[i]) & 0xffu] ^ (ca >> 8);        // what is left of either stripe (everything, for an unaligned buffer)
+    for (; j < b1; j++) cb = tab[(cb ^ out[j]) & 0xffu] ^ (cb >> 8);
+    ca = a0 < len ? ~ca : 0u;                                  // crc32 of an empty stripe is 0 (and contributes nothing)
+    cb = b0 < len ? ~cb : 0u;
+    // weight of a stripe: x^(8 * bytes behind it) = x^(8 rem) * (x^(8 S))^(nfull - 1 - j) for the full stripes, 1 for the last one
+    const uint32_t nfull = len / S, rem = len - nfull * S;
+    const uint32_t xs = bz_crc_xpow8n(S), xr = bz_crc_xpow8n(rem);
+    auto weight = [&](uint32_t stripe) {
+        if (stripe >= nfull) return 1u << 31;
+        uint32_t pw = xr, sq = xs;
+        for (uint32_t k = nfull - 1u - stripe; k; k >>= 1) { if (k & 1u) pw = bz_crc_mulmod(sq, pw); if (k > 1u) sq = bz_crc_mulmod(sq, sq); }
+        return pw;
+    };
+    const uint32_t wb_ = weight(2u * (uint32_t)lane + 1u);
+    const uint32_t wa_ = (2u * (uint32_t)lane + 1u < nfull) ? bz_crc_mulmod(xs, wb_) : weight(2u * (uint32_t)lane);   // one stripe further from the end
+    uint32_t t = bz_crc_mulmod(wa_, ca) ^ bz_crc_mulmod(wb_, cb);
 #pragma unroll
     for (int o = 16; o; o >>= 1) t ^= __shfl_xor_sync(0xffffffffu, t, o);
     return t;

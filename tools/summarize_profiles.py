@@ -76,7 +76,8 @@ for rep in sorted(f for f in os.listdir(G) if f.startswith(f"prof_{tag}_") and f
         t = vals["gpu__time_duration.sum"][0] * US[vals["gpu__time_duration.sum"][1]]
         T.append(f"   {'dram traffic (read+write)':34s} {tr / 1e6:18.1f} MB   -> {tr / t / 1e9:8.1f} GB/s under ncu"); T.append("")
         short = r[kn].split("(")[0].replace("void ", "").split("<")[0]
-        traffic[short] = {"dram_bytes_per_launch": tr, "duration_s_under_ncu": t, "report": rep}
+        key = short if short not in traffic else short + ":" + rep[len(f"prof_{tag}_"):-len(".ncu-rep")]     # e.g. k_tile_accumulate:tile_mixed
+        traffic[key] = {"dram_bytes_per_launch": tr, "duration_s_under_ncu": t, "report": rep}
 open(os.path.join(P, f"{tag}_ncu_full_summary.txt"), "w").write("\n".join(T) + "\n")
 json.dump({"note": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full; cfg2 launch = one 333,333,333-base contig / 111,111,111 reads",
            "kernels": traffic}, open(os.path.join(P, f"{tag}_traffic.json"), "w"), indent=1)
