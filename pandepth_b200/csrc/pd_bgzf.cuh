@@ -399,13 +399,28 @@ __host__ __device__ __forceinline__ uint32_t bz_crc_xpow8n(uint32_t n)          
     return p;
 }
 
-__device__ __forceinline__ void bz_crc_table_init(uint32_t *tab, int tid, int nthreads)   // tab[256], by the whole CTA (then a barrier)
+// tab[0..255]: the byte table; tab[256 + k] = x^(2^k) mod P, k < 32 (the powers every stripe weight is a product of: with them
+// x^(8 n) costs popcount(n) multiplications instead of a square-and-multiply chain per block -- those chains were half of
+// the check's instructions).  By the whole CTA, then a barrier.
+constexpr int BZ_CRC_TAB_WORDS = 256 + 32;
+__device__ __forceinline__ void bz_crc_table_init(uint32_t *tab, int tid, int nthreads)
 {
     for (int i = tid; i < 256; i += nthreads) {
         uint32_t c = (uint32_t)i;
         for (int k = 0; k < 8; k++) c = (c & 1u) ? (c >> 1) ^ BZ_CRC_POLY : c >> 1;
         tab[i] = c;
     }
+    if (tid == 0) {
+        uint32_t p = 0x40000000u;                              // x^1
+        for (int k = 0; k < 32; k++) { tab[256 + k] = p; p = bz_crc_mulmod(p, p); }
+    }
+}
+
+__device__ __forceinline__ uint32_t bz_crc_xpow8n_tab(uint32_t n, const uint32_t *tab)     // x^(8 n) mod P, n < 2^28
+{
+    uint32_t p = 1u << 31;
+    for (int k = 3; n; n >>= 1, k++) if (n & 1u) p = bz_crc_mulmod(tab[256 + k], p);
+    return p;
 }
 
 __device__ __forceinline__ uint32_t bz_crc32_warp(const uint8_t *out, uint32_t len, const uint32_t *tab, int lane)
@@ -440,15 +455,11 @@ __device__ __forceinline__ uint32_t bz_crc32_warp(const uint8_t *out, uint32_t l
     cb = b0 < len ? ~cb : 0u;
     // weight of a stripe: x^(8 * bytes behind it) = x^(8 rem) * (x^(8 S))^(nfull - 1 - j) for the full stripes, 1 for the last one
     const uint32_t nfull = len / S, rem = len - nfull * S;
-    const uint32_t xs = bz_crc_xpow8n(S), xr = bz_crc_xpow8n(rem);
-    auto weight = [&](uint32_t stripe) {
-        if (stripe >= nfull) return 1u << 31;
-        uint32_t pw = xr, sq = xs;
-        for (uint32_t k = nfull - 1u - stripe; k; k >>= 1) { if (k & 1u) pw = bz_crc_mulmod(sq, pw); if (k > 1u) sq = bz_crc_mulmod(sq, sq); }
-        return pw;
+    auto weight = [&](uint32_t stripe) {                       // bytes behind a full stripe: rem + (nfull - 1 - stripe) S
+        return stripe >= nfull ? 1u << 31 : bz_crc_xpow8n_tab(rem + (nfull - 1u - stripe) * S, tab);
     };
     const uint32_t wb_ = weight(2u * (uint32_t)lane + 1u);
-    const uint32_t wa_ = (2u * (uint32_t)lane + 1u < nfull) ? bz_crc_mulmod(xs, wb_) : weight(2u * (uint32_t)lane);   // one stripe further from the end
+    const uint32_t wa_ = (2u * (uint32_t)lane + 1u < nfull) ? bz_crc_mulmod(bz_crc_xpow8n_tab(S, tab), wb_) : weight(2u * (uint32_t)lane);   // one stripe further from the end
     uint32_t t = bz_crc_mulmod(wa_, ca) ^ bz_crc_mulmod(wb_, cb);
 #pragma unroll
     for (int o = 16; o; o >>= 1) t ^= __shfl_xor_sync(0xffffffffu, t, o);
@@ -563,7 +574,7 @@ __global__ void __launch_bounds__(BZ_WPC * 32, PD_BZ_K1_CTAS) k_bgzf_decode(BzAr
     __shared__ uint16_t lit_raw[(BZ_WPC + 1) << BZ_LIT_BITS];
     __shared__ BzTables tabs[BZ_WPC];
     __shared__ uint32_t rec_offs[BZ_WPC][32];
-    __shared__ uint32_t crc_tab[256];
+    __shared__ uint32_t crc_tab[BZ_CRC_TAB_WORDS];
     bz_crc_table_init(crc_tab, (int)threadIdx.x, (int)blockDim.x);
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -842,7 +853,7 @@ __global__ void __launch_bounds__(WPC * 32, PD_BZ_MULTI_CTAS) k_bgzf_decode_mult
     __shared__ uint16_t lit_raw[(WPC * K << LB) + (1 << BZ_LIT_BITS)];   // + 2 KB: the tables start at a 2 KB boundary of the shared window
     __shared__ BzTables tabs[WPC][K];
     __shared__ uint32_t rec_offs[WPC][32];
-    __shared__ uint32_t crc_tab[256];
+    __shared__ uint32_t crc_tab[BZ_CRC_TAB_WORDS];
     bz_crc_table_init(crc_tab, (int)threadIdx.x, (int)blockDim.x);
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

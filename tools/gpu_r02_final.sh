@@ -15,7 +15,7 @@ oracle/_ref/bamgen -P -q -o /tmp/cB.bam -c $(python -c "print(','.join(f'chr{i+1
 ( timeout 600 python tools/bench_bgzf.py /tmp/cA.bam --steps 5 ) > gpurun_out/z_bgzf_A.log 2>&1
 ( timeout 600 python tools/bench_bgzf.py /tmp/cB.bam --steps 5 ) > gpurun_out/z_bgzf_B.log 2>&1
 B="python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline"
-( timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches.csv $B ) > gpurun_out/z_ncu_launch.log 2>&1
+( timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:^k_(cut|tile|fill|reduce|scan|delta|bgzf|filter)" -c 200 --csv --log-file gpurun_out/launches.csv $B ) > gpurun_out/z_ncu_launch.log 2>&1
 ( timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_bgzf_A.csv python tools/bench_bgzf.py /tmp/cA.bam --steps 1 --no-feed ) > gpurun_out/z_ncu_launch_A.log 2>&1
 ( timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_bgzf_B.csv python tools/bench_bgzf.py /tmp/cB.bam --steps 1 --no-feed ) > gpurun_out/z_ncu_launch_B.log 2>&1
 ( timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_tile_accumulate -s 9 -c 1 -f -o gpurun_out/prof_r02_tile $B ) > gpurun_out/z_ncu_tile.log 2>&1
