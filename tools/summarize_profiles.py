@@ -7,7 +7,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G = os.path.join(ROOT, "gpurun_out"); P = os.path.join(ROOT, "profiles"); os.makedirs(P, exist_ok=True)
 
 # ---- launch lists --------------------------------------------------------------------------------------------
-LISTS = [("launches.csv", "launches", "python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline (cfg2: 3 Gb x 50x), first 200 launches"),
+LISTS = [("launches.csv", "launches", "python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline (cfg2: 3 Gb x 50x), the engine's kernels only (-k regex: torch launches ~2x10^4 kernels to generate the input)"),
          ("launches_bgzf_A.csv", "launches_bgzf_A", "python tools/bench_bgzf.py cA.bam --steps 1 --no-feed (flavour A: 100 M SEQ-less reads, compressed file resident in HBM)"),
          ("launches_bgzf_B.csv", "launches_bgzf_B", "python tools/bench_bgzf.py cB.bam --steps 1 --no-feed (flavour B: 20 M reads with SEQ+QUAL, compressed file resident in HBM)")]
 for fname, out, what in LISTS:
@@ -23,7 +23,7 @@ for fname, out, what in LISTS:
         name = r[kn].split("(")[0].replace("void ", "")
         v = float(r[mv].replace(",", "")) * {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(r[mu], 1.0)
         a = agg.setdefault(name, [0, 0.0]); a[0] += 1; a[1] += v; tot += v
-    ours = {k: v for k, v in agg.items() if k.startswith("pdk::")}; tot_o = sum(v[1] for v in ours.values()) or 1.0
+    ours = {k: v for k, v in agg.items() if k.startswith("pdk::") or k.startswith("k_")}; tot_o = sum(v[1] for v in ours.values()) or 1.0
     L = [f"# ncu launch list, {tag}: {what}",
          "# ncu --metrics gpu__time_duration.sum --clock-control none -c N --csv ...",
          "# per-launch times under ncu are cold-cache and serialised: compare SHARES, not absolutes.",
