@@ -97,7 +97,7 @@ inline BgzfFeedResult bgzf_feed_file(pd_engine *eng, std::mutex *eng_mu, const s
     const uint64_t true_size = (uint64_t)st.st_size;
     const uint64_t file_size = std::min<uint64_t>(true_size, range_end);      // blocks starting at or after this offset belong to someone else
     // piece size from the compression ratio of the first blocks: ~384 MB inflated, at most 96 MB compressed.  Measured on B200 through
-    // this feeder (gpurun_out/k_*feed*): flavour A (10^9 reads, 2.1 GB) 9 / 18 / 37 / 74 MB pieces -> 294 / 288 / 298 / 311 ms;
+    // this feeder (profiles/r02_bgzf_sweeps.txt): flavour A (10^9 reads, 2.1 GB) 9 / 18 / 37 / 74 MB pieces -> 294 / 288 / 298 / 311 ms;
     // flavour B (33 M reads, 5.4 GB) 48 / 96 / 192 MB -> 182 / 177 / 204 ms
     double ratio = 4.0;
     {
