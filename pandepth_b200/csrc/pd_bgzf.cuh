@@ -313,13 +313,17 @@ __device__ __forceinline__ int bz_inflate(const uint8_t *in, uint32_t in_len, ui
                             if (e < 0x1000u) {
                                 op[1] = (uint8_t)e; wnd1 >>= (e >> 8); used += e >> 8;
                                 e = bz_lds_u16(lit_sa | (wnd1 & 0x7feu));
-                                if (e < 0x1000u) { op[2] = (uint8_t)e; used += e >> 8; o += 3; }
-                                else o += 2;
+                                if (e < 0x1000u) { op[2] = (uint8_t)e; used += e >> 8; o += 3; br.drop(used); continue; }
+                                o += 2;
                             } else o += 1;
                             br.drop(used);
-                            continue;
+                            // e is the entry of the symbol BEHIND the literals (at most 20 of the window's 32 bits are used, so its
+                            // 10 lookup bits were valid): a length code or the end of the block -- taken from here instead of being
+                            // looked up twice more (match-dominated streams alternate literal / match: a fifth of their instructions)
                         }
-                        int s = bz_symbol(br, T.lit_cnt, T.lit_sym, lit_fast, BZ_LIT_BITS);
+                        int s;
+                        if (e == BZ_MISS) s = bz_symbol(br, T.lit_cnt, T.lit_sym, lit_fast, BZ_LIT_BITS);     // code longer than the table
+                        else { br.drop(bz_entry_len(e)); s = bz_entry_sym(e); }
                         if (s < 0) { cmd = 3; break; }
                         if (s < 256) { if (o >= out_cap) { cmd = 3; break; } out[o++] = (uint8_t)s; continue; }
                         if (s == 256) { cmd = 2; break; }
@@ -486,9 +490,32 @@ __device__ __forceinline__ void bz_walk_block(const BzArgs &a, uint32_t b, const
     bool chain_end = (flags != 0) || p > len;
     if (p > len) flags |= BZ_MALFORMED;
     while (!chain_end) {
-        // lane 0 follows the block_size chain for up to 32 records
         uint32_t nrec = 0;
-        if (lane == 0) {
+        p = __shfl_sync(FULLM, p, 0);
+        // Speculation: records of one size follow each other in most blocks (always in files of fixed-length reads).  Lane i
+        // guesses that record i starts i * (4 + block_size of the first record) behind it and reads the size there; the leading
+        // lanes that all found that same size have their records' true offsets -- two dependent loads for up to 32 records where
+        // following the chain costs one L2 round trip per record (17 % of this kernel's stall samples on SEQ-less files).
+        bool spec = false;
+        if (p + 4 <= len) {
+            const uint32_t bs0 = bz_ld32(out + p);
+            if (bs0 >= 32 && bs0 <= (1u << 30)) {
+                const uint64_t step = 4ull + bs0, pi = (uint64_t)p + (uint64_t)lane * step;
+                const bool fits = pi + step <= (uint64_t)len;
+                const uint32_t bsi = fits ? bz_ld32(out + pi) : 0u;
+                const unsigned same = __ballot_sync(FULLM, fits && bsi == bs0);
+                const uint32_t nsame = same == FULLM ? 32u : (uint32_t)(__ffs((int)~same) - 1);
+                if (nsame >= 2u) {
+                    if ((uint32_t)lane < nsame) rec_off[lane] = (uint32_t)pi;
+                    nrec = nsame;
+                    p += (uint32_t)(nsame * step);
+                    if (p + 4 > len) nrec |= 0x400u;                                  // end of the block reached
+                    spec = true;
+                }
+            }
+        }
+        // otherwise lane 0 follows the block_size chain for up to 32 records
+        if (!spec && lane == 0) {
             while (nrec < 32 && p + 4 <= len) {
                 const uint32_t bs = bz_ld32(out + p);
                 if (bs < 32 || bs > (1u << 30)) { nrec |= 0x100u; break; }       // malformed
@@ -498,7 +525,7 @@ __device__ __forceinline__ void bz_walk_block(const BzArgs &a, uint32_t b, const
             }
             if (!(nrec & 0x300u) && p + 4 > len) nrec |= 0x400u;                 // end of the block reached
         }
-        nrec = __shfl_sync(FULLM, nrec, 0);
+        if (!spec) nrec = __shfl_sync(FULLM, nrec, 0);                            // (warp-uniform branch)
         if (nrec & 0x100u) flags |= BZ_MALFORMED;
         if (nrec & 0x700u) chain_end = true;
         nrec &= 0xffu;
