@@ -12,7 +12,7 @@ oracle/_ref/bamgen -P -q -o /tmp/cB.bam -c $(python -c "print(','.join(f'chr{i+1
 ( timeout 900 python bench.py --steps 20 --warmup 5 ) > gpurun_out/u_bench.log 2>&1
 ( timeout 900 python bench.py --flavour B --bam-mb 100 --steps 3 --warmup 3 --no-e2e-arrays ) > gpurun_out/u_bench_B.log 2>&1
 # many contigs: 50 000 x 20 kb, 2 M reads (uniform generator writes sorted reads over all contigs)
-oracle/_ref/bamgen -o /tmp/many.bam -c $(python -c "print(','.join(f's{i}:20000' for i in range(50000)))") -n 2000000 -s 5 -l 100 > gpurun_out/u_many_gen.log 2>&1
+( python tools/make_many_contigs.py /tmp/many.sam 50000 20000 2000000 && oracle/_ref/bamgen -I /tmp/many.sam -o /tmp/many.bam ) > gpurun_out/u_many_gen.log 2>&1
 for rep in 1 2; do ( /usr/bin/time -f "wall %e s" env PANDEPTH_TIMING=1 pandepth_b200/bin/pandepth -i /tmp/many.bam -o /tmp/many_out -t 16 ) >> gpurun_out/u_many_cli.log 2>&1; done
 ( /usr/bin/time -f "wall %e s" env PANDEPTH_GPU_DECODE=0 PANDEPTH_TIMING=1 pandepth_b200/bin/pandepth -i /tmp/many.bam -o /tmp/many_out_h -t 16 ) >> gpurun_out/u_many_cli_host.log 2>&1
 cmp <(zcat /tmp/many_out.chr.stat.gz) <(zcat /tmp/many_out_h.chr.stat.gz) && echo "many contigs: device decode == host decode" | tee -a gpurun_out/u_many_cli.log
