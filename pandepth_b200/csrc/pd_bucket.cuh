@@ -1,0 +1,186 @@
+// pd_bucket.cuh -- the unsorted path at scale: expand -> bucket -> tile (sm_100a).
+//
+// Role in the reference: the same walk as everywhere (filter :732-733, CIGAR switch :735-760), for input that is not in
+// coordinate order (unsorted SAM/BAM streams :4679-4710, out-of-order batches).  `k_delta_scatter` turns every run end into
+// a global reduction at a random address; measured on B200 those run at ~25 G/s wherever their lines live (the L2's atomic
+// units are the limit), i.e. 3.7 % of the HBM roofline for 111 M shuffled reads.  The fix is fewer global reductions: bring
+// the batch into *bucket* order and let the tile kernel, which accumulates in shared memory, do the rest.
+//
+//   k_expand_runs     filter + CIGAR walk of every read -> aligned runs (start, len) relative to the owned range, clipped to it
+//                     (one run per read for single-op input); runs are appended with warp-aggregated cursor bumps
+//   k_bucket_hist     histogram of the runs over coarse buckets of 2^19 bases (shared-memory pre-aggregation per CTA)
+//   k_bucket_scan     exclusive scan of the <= 4096 coarse counts (one CTA)
+//   k_bucket_scatter  runs -> coarse-bucket order (a CTA reserves, per coarse bucket, a range for its tile's runs)
+//   k_bucket_fine     one CTA per coarse bucket: counts its runs over 2048 fine buckets of 256 bases (= the tile kernel's
+//                     look-back), scans them in shared memory, publishes the fine offsets and scatters the runs -> fine order
+//   k_bucket_cuts     lo[] / hi[] of every 2048-base segment straight from the fine offsets (no searches)
+//
+// Runs inside a fine bucket stay in arbitrary order: `k_tile_accumulate` only needs every run that starts in
+// [s0 - 256, s0 + 2048) inside [lo[j], hi[j + 1]) -- its table updates are atomic, order-free -- so it is launched with
+// TileArgs::unordered (the sortedness checks off).  Every pass moves whole arrays with coalesced reads; the scattered
+// writes go out in short bursts per bucket.  Traffic: 16 B/read (expand) + 24 B/run (coarse) + 20 B/run (fine) + the
+// tile kernel's 8 B/run + 4 B/base.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pdk {
+
+constexpr int BK_COARSE_SHIFT = 19;                 // coarse bucket = 2^19 bases
+constexpr int BK_FINE_SHIFT = 8;                    // fine bucket = 256 bases = HALO
+constexpr int BK_FINE = 1 << (BK_COARSE_SHIFT - BK_FINE_SHIFT);   // 2048 fine buckets per coarse bucket
+constexpr int BK_MAX_COARSE = 4096;                 // 2^31 bases
+constexpr int BK_TILE = 4096;                       // runs per CTA tile in the coarse passes
+static_assert(HALO == (1 << BK_FINE_SHIFT) && SEG == 8 * HALO, "fine buckets are the tile kernel's look-back; eight of them make a segment");
+
+struct ExpandArgs {
+    const int32_t *pos; const uint32_t *cigar; const uint32_t *cigar_off;
+    const uint16_t *flag; const uint8_t *mapq;
+    uint32_t n; int32_t contig_len; int32_t shift;
+    uint32_t xflags; int32_t min_mapq;
+    int32_t *run_pos; uint32_t *run_cig;            // out: start (>= 0, < contig_len) and (len << 4 | M)
+    uint32_t *n_runs; uint32_t cap;                 // cursor (never passes cap: a batch has at most one run per CIGAR word)
+    uint32_t *delta; int *delta_used;               // contig base of the delta array: runs of 2^28 bases or more (no CIGAR word holds them) go there
+};
+
+__global__ void __launch_bounds__(256) k_expand_runs(ExpandArgs a)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    bool live = i < a.n;
+    if (live && a.flag && (a.flag[i] & a.xflags)) live = false;
+    if (live && a.mapq && (int)a.mapq[i] < a.min_mapq) live = false;
+    int32_t p = live ? __ldcs(a.pos + i) : -1;
+    if (p < 0) live = false;
+    uint32_t c0 = i, nops = live ? 1u : 0u;
+    if (live && a.cigar_off) { c0 = a.cigar_off[i]; nops = a.cigar_off[i + 1] - c0; }
+    const int64_t clen = a.contig_len;
+    int64_t q = (int64_t)p - a.shift, rs = 0, re = 0; bool open = false;
+    // every lane walks its ops; an emission is a warp-uniform step (lanes without a run to emit sit it out), so the cursor is
+    // bumped once per warp and step
+    const uint32_t max_ops = __reduce_max_sync(0xffffffffu, nops);
+    for (uint32_t k = 0; k <= max_ops; ++k) {
+        bool emit = false; int64_t es = 0, ee = 0;
+        if (k < nops) {
+            const uint32_t w = __ldcs(a.cigar + c0 + k);
+            const uint32_t op = w & 15u; const int64_t n = w >> 4;
+            if (is_match_op(op)) {
+                if (open && re == q) re = q + n;
+                else { if (open) { emit = true; es = rs; ee = re; } rs = q; re = q + n; open = true; }
+                q += n;
+            } else if (is_skip_op(op)) q += n;
+        } else if (k == nops && open) { emit = true; es = rs; ee = re; open = false; }
+        if (emit) { if (es < 0) es = 0; if (ee > clen) ee = clen; if (es >= ee) emit = false; }
+        if (emit && ee - es >= (1ll << 28)) {                    // does not fit a (len << 4 | op) word: straight to the delta array
+            red_add_u32(a.delta + es, 1u); red_add_u32(a.delta + ee, 0xffffffffu); *a.delta_used = 1;
+            emit = false;
+        }
+        const unsigned em = __ballot_sync(0xffffffffu, emit);
+        if (em) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(a.n_runs, (uint32_t)__popc(em));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (emit) {
+                const uint32_t at = base + (uint32_t)__popc(em & ((1u << lane) - 1u));
+                if (at < a.cap) { a.run_pos[at] = (int32_t)es; a.run_cig[at] = (uint32_t)(ee - es) << 4; }
+            }
+        }
+    }
+}
+
+// coarse histogram: hist[b] += runs with (pos >> 19) == b
+__global__ void __launch_bounds__(256) k_bucket_hist(const int32_t *__restrict__ pos, const uint32_t *__restrict__ n_runs, uint32_t *__restrict__ hist, int n_coarse)
+{
+    __shared__ uint32_t h[BK_MAX_COARSE];
+    for (int i = threadIdx.x; i < n_coarse; i += blockDim.x) h[i] = 0;
+    __syncthreads();
+    const uint32_t n = *n_runs;
+    for (uint32_t i = blockIdx.x * BK_TILE + threadIdx.x, e = min(n, (blockIdx.x + 1u) * BK_TILE); i < e; i += blockDim.x)
+        atomicAdd(&h[(uint32_t)pos[i] >> BK_COARSE_SHIFT], 1u);
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_coarse; i += blockDim.x) if (h[i]) atomicAdd(&hist[i], h[i]);
+}
+
+// base[b] = exclusive prefix of hist (base[n_coarse] = total); cursor[b] = 0.  One CTA of 1024 threads, <= 4096 bins.
+__global__ void __launch_bounds__(1024) k_bucket_scan(const uint32_t *__restrict__ hist, uint32_t *__restrict__ base, uint32_t *__restrict__ cursor, int n_coarse)
+{
+    __shared__ uint32_t part[1024];
+    const int t = threadIdx.x;
+    uint32_t v[4], s = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { const int i = t * 4 + k; v[k] = i < n_coarse ? hist[i] : 0u; s += v[k]; }
+    part[t] = s;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) { const uint32_t y = t >= o ? part[t - o] : 0u; __syncthreads(); part[t] += y; __syncthreads(); }
+    uint32_t ex = part[t] - s;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { const int i = t * 4 + k; if (i < n_coarse) { base[i] = ex; cursor[i] = 0; } ex += v[k]; }
+    if (t == 1023) base[n_coarse] = part[1023];
+}
+
+// runs -> coarse order.  A CTA counts its tile per coarse bucket, reserves a range per bucket with ONE global atomic, and
+// places its runs inside the reserved ranges with shared-memory cursors.
+__global__ void __launch_bounds__(256) k_bucket_scatter(const int32_t *__restrict__ pos, const uint32_t *__restrict__ cig, const uint32_t *__restrict__ n_runs,
+                                                        const uint32_t *__restrict__ base, uint32_t *__restrict__ cursor, int n_coarse,
+                                                        int32_t *__restrict__ out_pos, uint32_t *__restrict__ out_cig)
+{
+    __shared__ uint32_t h[BK_MAX_COARSE];
+    for (int i = threadIdx.x; i < n_coarse; i += blockDim.x) h[i] = 0;
+    __syncthreads();
+    const uint32_t n = *n_runs;
+    const uint32_t t0 = blockIdx.x * BK_TILE, t1 = min(n, t0 + BK_TILE);
+    for (uint32_t i = t0 + threadIdx.x; i < t1; i += blockDim.x) atomicAdd(&h[(uint32_t)pos[i] >> BK_COARSE_SHIFT], 1u);
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_coarse; i += blockDim.x) { const uint32_t c = h[i]; h[i] = c ? base[i] + atomicAdd(&cursor[i], c) : 0u; }
+    __syncthreads();
+    for (uint32_t i = t0 + threadIdx.x; i < t1; i += blockDim.x) {
+        const int32_t p = pos[i];
+        const uint32_t at = atomicAdd(&h[(uint32_t)p >> BK_COARSE_SHIFT], 1u);
+        out_pos[at] = p; out_cig[at] = cig[i];
+    }
+}
+
+// one CTA per coarse bucket: fine order inside it + the fine offsets (fine_off[b * 2048 + f] = first run of fine bucket f)
+__global__ void __launch_bounds__(512) k_bucket_fine(const int32_t *__restrict__ pos, const uint32_t *__restrict__ cig, const uint32_t *__restrict__ base,
+                                                     uint32_t *__restrict__ fine_off, int32_t *__restrict__ out_pos, uint32_t *__restrict__ out_cig)
+{
+    __shared__ uint32_t h[BK_FINE];
+    __shared__ uint32_t part[512];
+    const uint32_t b = blockIdx.x, r0 = base[b], r1 = base[b + 1];
+    const int t = threadIdx.x;
+    for (int i = t; i < BK_FINE; i += 512) h[i] = 0;
+    __syncthreads();
+    for (uint32_t i = r0 + t; i < r1; i += 512) atomicAdd(&h[((uint32_t)pos[i] >> BK_FINE_SHIFT) & (BK_FINE - 1)], 1u);
+    __syncthreads();
+    // exclusive scan of 2048 counts by 512 threads (4 each)
+    uint32_t v[4], s = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { v[k] = h[t * 4 + k]; s += v[k]; }
+    part[t] = s;
+    __syncthreads();
+    for (int o = 1; o < 512; o <<= 1) { const uint32_t y = t >= o ? part[t - o] : 0u; __syncthreads(); part[t] += y; __syncthreads(); }
+    uint32_t ex = r0 + part[t] - s;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { h[t * 4 + k] = ex; fine_off[(size_t)b * BK_FINE + t * 4 + k] = ex; ex += v[k]; }
+    __syncthreads();
+    for (uint32_t i = r0 + t; i < r1; i += 512) {
+        const int32_t p = pos[i];
+        const uint32_t at = atomicAdd(&h[((uint32_t)p >> BK_FINE_SHIFT) & (BK_FINE - 1)], 1u);
+        out_pos[at] = p; out_cig[at] = cig[i];
+    }
+}
+
+// lo[j] = first run with pos >= s0_j - 256, hi[j] = first run with pos >= s0_j (nseg + 1 entries), from the fine offsets
+__global__ void __launch_bounds__(256) k_bucket_cuts(const uint32_t *__restrict__ fine_off, const uint32_t *__restrict__ n_runs, uint32_t n_fine_total,
+                                                     int32_t seg0, int32_t nseg, uint32_t *__restrict__ lo, uint32_t *__restrict__ hi)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j > nseg) return;
+    const uint32_t total = *n_runs;
+    const int64_t f = (int64_t)(seg0 + j) * 8;                   // first fine bucket of segment j
+    auto off = [&](int64_t k) { return k <= 0 ? 0u : (k >= (int64_t)n_fine_total ? total : fine_off[k]); };
+    if (j < nseg) lo[j] = off(f - 1);
+    hi[j] = off(f);
+}
+
+}  // namespace pdk

@@ -12,6 +12,7 @@
 #include "../../include/pandepth_b200.h"
 #include "pd_kernels.cuh"
 #include "pd_bgzf.cuh"
+#include "pd_bucket.cuh"
 
 #include <nvtx3/nvToolsExt.h>      // header-only NVTX v3: ranges show up in nsys / ncu timelines, no-ops without a tool attached
 
@@ -34,9 +35,9 @@ static_assert(PAD_ELEMS % pdk::SCAN_TILE == 0 && PAD_ELEMS % pdk::REDUCE_CHUNK =
 constexpr int64_t HOST_CHUNK_READS = 8 << 20;            // staging chunk for host-resident pushes
 constexpr int N_SLOTS = 2;
 
-enum KernelId { K_CUT = 0, K_TILE, K_SCATTER, K_SCAN, K_FILL, K_REDUCE, K_WINDOWS, K_BGZF, K_BGZF_PACK, K_FILTER, K_COUNT };
+enum KernelId { K_CUT = 0, K_TILE, K_SCATTER, K_SCAN, K_FILL, K_REDUCE, K_WINDOWS, K_BGZF, K_BGZF_PACK, K_FILTER, K_BUCKET, K_COUNT };
 const char *const kKernelNames[K_COUNT] = {"k_cut", "k_tile_accumulate", "k_delta_scatter", "k_scan_add",
-                                           "k_fill_untouched", "k_reduce_units", "k_reduce_windows", "k_bgzf_decode", "k_bgzf_pack", "k_filter_bits"};
+                                           "k_fill_untouched", "k_reduce_units", "k_reduce_windows", "k_bgzf_decode", "k_bgzf_pack", "k_filter_bits", "k_bucket"};
 
 struct Slot {
     int32_t *pos = nullptr; uint32_t *cigar = nullptr; uint32_t *cigar_off = nullptr;
@@ -97,6 +98,11 @@ struct pd_engine {
     BzSlot bz[N_BZ]; int bz_next = 0;
     int32_t bz_prog_tid = -1, bz_prog_pos = -1;   // first record of the last block (with records) of the last chunk that was planned
     uint8_t *d_owned = nullptr;
+    // unsorted path at scale (pd_bucket.cuh): runs in two ping-pong arrays, coarse / fine bucket tables
+    int32_t *bk_pos[2] = {nullptr, nullptr}; uint32_t *bk_cig[2] = {nullptr, nullptr}; size_t bk_cap = 0;
+    uint32_t *bk_tab = nullptr;      // [0] run cursor, [1] overflow flag (unused), then hist[4096], base[4097], cursor[4096]
+    uint32_t *bk_fine = nullptr; size_t bk_fine_cap = 0;
+    uint64_t bucket_min_reads = 262144;   // smaller unsorted batches scatter directly (PANDEPTH_BUCKET_MIN_READS; 0 = never bucket)
     uint32_t *d_pass_bits = nullptr; size_t bits_cap = 0;   // record filter of the current batch, one bit per read (k_filter_bits)
     int bz_grid = 148 * 4, bz_grid_k2 = 148 * 6, bz_grid_k4 = 148 * 6, bz_grid_k8 = 148 * 6;
     uint64_t scatter_stripe = 32ull << 20;          // elements (128 MB of deltas) per stripe of a striped scatter (PANDEPTH_SCATTER_STRIPE_MB)
@@ -182,7 +188,7 @@ int ensure_cut(pd_engine *e, pd_engine::CutBuf &c, size_t nseg)
 // ordered by the main stream (a caller's device batch), unless ready_now says they are complete already (PD_READY).
 int run_batch(pd_engine *e, int32_t tid, uint32_t n, const int32_t *pos, const uint16_t *flag, const uint8_t *mapq,
               const uint32_t *cigar_off, const uint32_t *cigar, bool sorted, int64_t seg_a, int64_t seg_b,
-              cudaEvent_t input_ready = nullptr, bool ready_now = false)
+              cudaEvent_t input_ready = nullptr, bool ready_now = false, uint64_t n_cigar_words = 0)
 {
     const uint64_t off = e->off[tid];
     if (e->delta_stale) {            // a batch after a scan (rare): both paths may write deltas, so the consumed ones go first
@@ -234,7 +240,7 @@ int run_batch(pd_engine *e, int32_t tid, uint32_t n, const int32_t *pos, const u
                         e->d_depth + off, e->d_delta + off, e->d_seg_state + off / pdk::SEG, e->xflags, e->min_mapq,
                         e->d_flags, e->d_flags + 1,
                         e->hint_on ? 1u : 0u, e->hint_min_dep, e->hint_mask, e->d_part_cov + off / pdk::SEG, e->d_part_sum + off / pdk::SEG,
-                        e->tile_resident_warps, (int32_t)e->org[tid]};
+                        e->tile_resident_warps, (int32_t)e->org[tid], 0u};
         const size_t smem = (size_t)pdk::WPC * (pdk::TILE_SMEM_WORDS + (has_off ? pdk::TILE_QUEUE_WORDS : 0)) * 4;
         const unsigned grid = (nseg + pdk::WPC - 1) / pdk::WPC, blk = pdk::WPC * 32;
         rc = launch(e, K_TILE, [&] {
@@ -244,6 +250,67 @@ int run_batch(pd_engine *e, int32_t tid, uint32_t n, const int32_t *pos, const u
         if (rc) return rc;
         CK(cudaEventRecord(cb.released, e->stream)); cb.used = true;
         e->stats.tile_path_batches++;
+    } else if (e->bucket_min_reads && (uint64_t)n >= e->bucket_min_reads) {
+        // ---- expand -> bucket -> tile (pd_bucket.cuh): the batch is brought into 256-base bucket order on the device and
+        // accumulated by the tile kernel in shared memory instead of 2 n global reductions at random addresses ----
+        uint64_t cap = n;
+        if (cigar_off) {
+            cap = n_cigar_words;
+            if (!cap) {                                          // a device batch: the number of CIGAR words is cigar_off[n]
+                uint32_t last = 0;
+                CK(cudaMemcpyAsync(&last, cigar_off + n, 4, cudaMemcpyDeviceToHost, e->stream));
+                CK(cudaStreamSynchronize(e->stream));
+                uint32_t first = 0;
+                CK(cudaMemcpyAsync(&first, cigar_off, 4, cudaMemcpyDeviceToHost, e->stream));
+                CK(cudaStreamSynchronize(e->stream));
+                cap = (uint64_t)last - first;
+            }
+            if (cap < n) cap = n;
+        }
+        if (cap > 0xfffffff0ull) return fail(e, PD_ERR_ARG, "pd_push_contig: an unsorted batch with more than 2^32 CIGAR words; push smaller batches");
+        if (cap > e->bk_cap) {
+            CK(cudaStreamSynchronize(e->stream));
+            for (int k = 0; k < 2; k++) { cudaFree(e->bk_pos[k]); cudaFree(e->bk_cig[k]); e->bk_pos[k] = nullptr; e->bk_cig[k] = nullptr; }
+            const size_t c = (size_t)cap + (size_t)cap / 8 + 4096;
+            for (int k = 0; k < 2; k++) { CK(cudaMalloc(&e->bk_pos[k], c * 4)); CK(cudaMalloc(&e->bk_cig[k], c * 4)); }
+            e->bk_cap = c; e->stats.hbm_bytes_allocated += c * 16;
+        }
+        const int n_coarse = (int)(((uint64_t)e->elen[tid] + (1u << pdk::BK_COARSE_SHIFT) - 1) >> pdk::BK_COARSE_SHIFT);
+        const size_t n_fine = (size_t)n_coarse * pdk::BK_FINE;
+        if (!e->bk_tab) CK(cudaMalloc(&e->bk_tab, (2 + 3 * (pdk::BK_MAX_COARSE + 1)) * 4));
+        if (n_fine > e->bk_fine_cap) {
+            if (e->bk_fine) { CK(cudaStreamSynchronize(e->stream)); cudaFree(e->bk_fine); e->bk_fine = nullptr; }
+            CK(cudaMalloc(&e->bk_fine, n_fine * 4)); e->bk_fine_cap = n_fine;
+        }
+        uint32_t *d_nruns = e->bk_tab, *d_hist = e->bk_tab + 2, *d_base = d_hist + (pdk::BK_MAX_COARSE + 1), *d_cursor = d_base + (pdk::BK_MAX_COARSE + 1);
+        CK(cudaMemsetAsync(e->bk_tab, 0, (2 + (pdk::BK_MAX_COARSE + 1)) * 4, e->stream));      // cursor, flag, hist
+        const int32_t nseg = (int32_t)(e->elen[tid] / pdk::SEG) + 1;
+        pd_engine::CutBuf &cb = e->cut[e->cut_next]; e->cut_next ^= 1;
+        int rc = ensure_cut(e, cb, (size_t)nseg + 1); if (rc) return rc;
+        if (cb.used) CK(cudaStreamWaitEvent(e->stream, cb.released, 0));
+        pdk::ExpandArgs x{pos, cigar, cigar_off, flag, mapq, n, (int32_t)e->elen[tid], (int32_t)e->org[tid], e->xflags, e->min_mapq,
+                          e->bk_pos[0], e->bk_cig[0], d_nruns, (uint32_t)cap, e->d_delta + off, e->d_flags + 1};
+        const unsigned tiles = (unsigned)((cap + pdk::BK_TILE - 1) / pdk::BK_TILE);
+        rc = launch(e, K_BUCKET, [&] {
+            pdk::k_expand_runs<<<(n + 255) / 256, 256, 0, e->stream>>>(x);
+            pdk::k_bucket_hist<<<tiles, 256, 0, e->stream>>>(e->bk_pos[0], d_nruns, d_hist, n_coarse);
+            pdk::k_bucket_scan<<<1, 1024, 0, e->stream>>>(d_hist, d_base, d_cursor, n_coarse);
+            pdk::k_bucket_scatter<<<tiles, 256, 0, e->stream>>>(e->bk_pos[0], e->bk_cig[0], d_nruns, d_base, d_cursor, n_coarse, e->bk_pos[1], e->bk_cig[1]);
+            pdk::k_bucket_fine<<<(unsigned)n_coarse, 512, 0, e->stream>>>(e->bk_pos[1], e->bk_cig[1], d_base, e->bk_fine, e->bk_pos[0], e->bk_cig[0]);
+            pdk::k_bucket_cuts<<<(unsigned)((nseg + 1 + 255) / 256), 256, 0, e->stream>>>(e->bk_fine, d_nruns, (uint32_t)n_fine, 0, nseg, cb.lo, cb.hi);
+        });
+        if (rc) return rc;
+        e->stats.kernel_launches += 5;
+        pdk::TileArgs t{e->bk_pos[0], e->bk_cig[0], nullptr, nullptr, nullptr, nullptr, cb.lo, cb.hi, (uint32_t)cap, 0, nseg, (int32_t)e->elen[tid],
+                        e->d_depth + off, e->d_delta + off, e->d_seg_state + off / pdk::SEG, e->xflags, e->min_mapq,
+                        e->d_flags, e->d_flags + 1,
+                        e->hint_on ? 1u : 0u, e->hint_min_dep, e->hint_mask, e->d_part_cov + off / pdk::SEG, e->d_part_sum + off / pdk::SEG,
+                        e->tile_resident_warps, 0, 1u};
+        const size_t smem = (size_t)pdk::WPC * pdk::TILE_SMEM_WORDS * 4;
+        rc = launch(e, K_TILE, [&] { pdk::k_tile_accumulate<false, false><<<(nseg + pdk::WPC - 1) / pdk::WPC, pdk::WPC * 32, smem, e->stream>>>(t); });
+        if (rc) return rc;
+        CK(cudaEventRecord(cb.released, e->stream)); cb.used = true;
+        e->stats.delta_path_batches++;
     } else {
         pdk::ScatterArgs s{pos, cigar, cigar_off, flag, mapq, n, (int32_t)e->elen[tid], e->d_delta + off, e->xflags, e->min_mapq,
                            (int32_t)e->org[tid], nullptr, nullptr, 0, INT64_MAX};
@@ -531,6 +598,7 @@ void pd_destroy(pd_engine *e)
         if (s.stream) cudaStreamDestroy(s.stream);
     }
     cudaFree(e->d_owned); cudaFree(e->d_org); cudaFree(e->d_pass_bits);
+    cudaFree(e->bk_pos[0]); cudaFree(e->bk_pos[1]); cudaFree(e->bk_cig[0]); cudaFree(e->bk_cig[1]); cudaFree(e->bk_tab); cudaFree(e->bk_fine);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     delete e;
@@ -626,6 +694,7 @@ pd_engine *pd_create_ranges(int device, int n_targets, const uint32_t *target_le
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pdk::k_bgzf_decode_multi<8, 1>, 1 * 32, 0) == cudaSuccess && n_sm > 0 && per_sm > 0)
             e->bz_grid_k8 = n_sm * per_sm;
         if (const char *fk = getenv("PANDEPTH_BGZF_K")) { const int v = atoi(fk); if (v == 1 || v == 2 || v == 4 || v == 8) e->bz_force_k = v; }
+        if (const char *v = getenv("PANDEPTH_BUCKET_MIN_READS")) e->bucket_min_reads = (uint64_t)std::max<long long>(0, atoll(v));
         if (const char *v = getenv("PANDEPTH_SCATTER_STRIPE_MB")) { const double mb = atof(v); if (mb >= 0.001) e->scatter_stripe = std::max<uint64_t>(256, (uint64_t)(mb * 262144.0)); }
         if (const char *v = getenv("PANDEPTH_SCATTER_STRIPE_MIN_READS")) e->scatter_stripe_min_reads = (uint64_t)std::max<long long>(1, atoll(v));
         if (const char *fk = getenv("PANDEPTH_BGZF_LIT_K")) { const int v = atoi(fk); if (v == 1 || v == 2 || v == 4 || v == 8) e->bz_lit_k = v; }
@@ -732,7 +801,7 @@ int pd_push_contig(pd_engine *e, int32_t tid, int64_t n_reads, const int32_t *po
         // cigar offsets on the device are absolute: rebase the cigar pointer instead of rewriting them
         const uint32_t *d_cig = cigar_off ? s.cigar - cg0 : s.cigar;
         rc = run_batch(e, tid, (uint32_t)n, s.pos, flag ? s.flag : nullptr, mapq ? s.mapq : nullptr,
-                       cigar_off ? s.cigar_off : nullptr, d_cig, sorted, seg_a, seg_b, s.copied);
+                       cigar_off ? s.cigar_off : nullptr, d_cig, sorted, seg_a, seg_b, s.copied, false, cigar_off ? (uint64_t)ncig : 0);
         if (rc) return rc;
         CK(cudaEventRecord(s.consumed, e->stream));
         s.used = true;

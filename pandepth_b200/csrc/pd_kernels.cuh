@@ -209,6 +209,8 @@ struct TileArgs {
     uint32_t *part_cov; unsigned long long *part_sum;     // contig base, one entry per segment
     int32_t pf_dist;      // PD_PREFETCH: segments between a warp's own segment and the one whose reads it prefetches
     int32_t shift;        // contig coordinate of depth[0] (range sharding: this engine owns [shift, shift + contig_len) of the contig)
+    uint32_t unordered;   // the reads of [lo[j], hi[j+1]) are those of segment j's window but in no particular order (bucketed
+                          // unsorted batches, pd_bucket.cuh): the sortedness checks are off, the window check stays
 };
 
 constexpr int TILE_UNROLL = PD_TILE_UNROLL;   // 32-read chunks whose loads are issued together (memory-level parallelism)
@@ -401,7 +403,7 @@ __global__ void __launch_bounds__(WPC * 32, TILE_MIN_CTAS) k_tile_accumulate(Til
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int32_t r = __shfl_sync(FULL, pv[u], (lane + 31) & 31);
-                bad |= pv[u] < (lane == 0 ? prev_last : r);
+                bad |= !a.unordered && pv[u] < (lane == 0 ? prev_last : r);
                 if (PD_TILE_AGG) eqm |= (uint32_t)(pv[u] == r && lane != 0) << u;
                 prev_last = r;                                 // meaningful in lane 0 only
             }

@@ -216,6 +216,69 @@ def test_striped_scatter_applies_every_run_end_once(monkeypatch):
             assert eng.stats()["kernel_launches"] >= 15
 
 
+@pytest.mark.parametrize("seed", [5, 6])
+def test_bucketed_unsorted_path_matches_oracle(seed, monkeypatch):
+    """Unsorted batches at scale go expand -> bucket -> tile (pd_bucket.cuh) instead of global reductions; forced here for
+    small batches.  Mixed CIGARs (far N skips, clips, I/D/=/X/P), the device-side filter, pile-ups, reads over the contig
+    ends, several contigs (one of a single base), two unsorted batches on top of each other and on top of a sorted one,
+    and range-sharded engines whose ranges start inside a contig."""
+    import pandepth_b200 as pd
+    from pandepth_b200.shard import assign_ranges
+    monkeypatch.setenv("PANDEPTH_BUCKET_MIN_READS", "1")
+    rng = np.random.default_rng(seed)
+    lens = [700_001, 1, 90_000, 2_500]
+    names = [f"c{i}" for i in range(len(lens))]
+    rows = []
+    for t, ln in enumerate(lens):
+        n = 0 if ln < 10 else ln // 3
+        starts = rng.integers(-100, ln, n)
+        starts[rng.integers(0, max(1, n), n // 12)] = ln // 2                    # a pile-up
+        for p in starts.tolist():
+            k = rng.integers(0, 10)
+            cs = ("150M", "150M", "150M", f"{rng.integers(1, 40)}S{rng.integers(1, 120)}M", f"{rng.integers(1, 80)}M{rng.integers(1, 6000)}N{rng.integers(1, 80)}M",
+                  f"{rng.integers(1, 60)}={rng.integers(1, 9)}I{rng.integers(1, 60)}X{rng.integers(1, 30)}D{rng.integers(1, 60)}M2H", f"3D{rng.integers(1, 100)}M1P{rng.integers(1, 100)}M",
+                  f"{rng.integers(1, 900)}M", "20M", "*")[k]
+            if p + 1 < 1:
+                continue
+            rows.append((int(rng.choice([0, 0, 16, 1024, 256, 4])), t, p + 1, int(rng.integers(0, 61)), cs))
+    rec = model.records_from_tuples(rows, names)
+    tlen = np.array(lens, np.uint32)
+    perm = rng.permutation(rec.n)
+    for xflags, q in ((1796, -1), (0, 25)):
+        want = model.accumulate(tlen, rec, xflags, q)
+        with _engine(tlen, xflags=xflags, min_mapq=q) as eng:                    # one unsorted batch per contig
+            _push_all(eng, rec.select(perm), False, 1)
+            eng.finalize()
+            _check_depth(eng, tlen, want)
+        with _engine(tlen, xflags=xflags, min_mapq=q) as eng:                    # three unsorted pieces + nothing else: additive
+            _push_all(eng, rec.select(perm), False, 3)
+            eng.finalize()
+            _check_depth(eng, tlen, want)
+        half = rec.n // 2
+        with _engine(tlen, xflags=xflags, min_mapq=q) as eng:                    # a sorted batch first, unsorted on top of it
+            eng.set_reduce_hint(1, 0xFFFFFFFF)
+            _push_all(eng, rec.select(np.arange(0, half)), True, 2)
+            _push_all(eng, rec.select(rng.permutation(np.arange(half, rec.n))), False, 2)
+            eng.finalize()
+            _check_depth(eng, tlen, want)
+            it = np.arange(len(lens), dtype=np.int32)[tlen > 1]
+            cov, tot = eng.reduce(it, np.zeros(it.size, np.int32), tlen[it].astype(np.int32), 1, 0xFFFFFFFF)
+            assert [int(x) for x in tot] == [int(want[t].sum(dtype=np.uint64)) for t in it]
+    # range sharding: three engines, every one fed everything unsorted
+    beg, end = assign_ranges(lens, 3)
+    want = model.accumulate(tlen, rec)
+    total = [np.zeros(int(n), np.uint64) for n in lens]
+    for r in range(3):
+        with pd.Engine(tlen, own_beg=beg[r], own_end=end[r]) as eng:
+            _push_all(eng, rec.select(perm), False, 2)
+            eng.finalize()
+            for t, ln in enumerate(lens):
+                if ln:
+                    total[t] += eng.depth(t)
+    for t in range(len(lens)):
+        assert np.array_equal(total[t].astype(np.uint32), want[t]), f"range-sharded bucketed path, contig {t}"
+
+
 def test_other_read_lengths_and_no_common_span():
     """Read lengths above the modelled span (L > HALO) and batches with no dominant span fall back to corrections."""
     rng = np.random.default_rng(9)
