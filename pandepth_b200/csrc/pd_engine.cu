@@ -240,7 +240,7 @@ int run_batch(pd_engine *e, int32_t tid, uint32_t n, const int32_t *pos, const u
                         e->d_depth + off, e->d_delta + off, e->d_seg_state + off / pdk::SEG, e->xflags, e->min_mapq,
                         e->d_flags, e->d_flags + 1,
                         e->hint_on ? 1u : 0u, e->hint_min_dep, e->hint_mask, e->d_part_cov + off / pdk::SEG, e->d_part_sum + off / pdk::SEG,
-                        e->tile_resident_warps, (int32_t)e->org[tid], 0u};
+                        e->tile_resident_warps, (int32_t)e->org[tid], 0u, nullptr};
         const size_t smem = (size_t)pdk::WPC * (pdk::TILE_SMEM_WORDS + (has_off ? pdk::TILE_QUEUE_WORDS : 0)) * 4;
         const unsigned grid = (nseg + pdk::WPC - 1) / pdk::WPC, blk = pdk::WPC * 32;
         rc = launch(e, K_TILE, [&] {
@@ -305,7 +305,7 @@ int run_batch(pd_engine *e, int32_t tid, uint32_t n, const int32_t *pos, const u
                         e->d_depth + off, e->d_delta + off, e->d_seg_state + off / pdk::SEG, e->xflags, e->min_mapq,
                         e->d_flags, e->d_flags + 1,
                         e->hint_on ? 1u : 0u, e->hint_min_dep, e->hint_mask, e->d_part_cov + off / pdk::SEG, e->d_part_sum + off / pdk::SEG,
-                        e->tile_resident_warps, 0, 1u};
+                        e->tile_resident_warps, 0, 1u, d_nruns};
         const size_t smem = (size_t)pdk::WPC * pdk::TILE_SMEM_WORDS * 4;
         rc = launch(e, K_TILE, [&] { pdk::k_tile_accumulate<false, false><<<(nseg + pdk::WPC - 1) / pdk::WPC, pdk::WPC * 32, smem, e->stream>>>(t); });
         if (rc) return rc;

@@ -211,6 +211,7 @@ struct TileArgs {
     int32_t shift;        // contig coordinate of depth[0] (range sharding: this engine owns [shift, shift + contig_len) of the contig)
     uint32_t unordered;   // the reads of [lo[j], hi[j+1]) are those of segment j's window but in no particular order (bucketed
                           // unsorted batches, pd_bucket.cuh): the sortedness checks are off, the window check stays
+    const uint32_t *n_dev;   // non-null: the number of reads lives on the device (`n` is only an upper bound)
 };
 
 constexpr int TILE_UNROLL = PD_TILE_UNROLL;   // 32-read chunks whose loads are issued together (memory-level parallelism)
@@ -243,6 +244,7 @@ __global__ void __launch_bounds__(WPC * 32, TILE_MIN_CTAS) k_tile_accumulate(Til
     const int j = blockIdx.x * WPC + warp;
     if (j >= a.nseg) return;
     const uint32_t i_lo = a.lo[j], i_hi = a.hi[j + 1];        // hi[] holds lower_bound(s0_j): nseg+1 entries
+    const uint32_t n_all = a.n_dev ? __ldg(a.n_dev) : a.n;
 #if PD_PREFETCH
     // the reads of segment j + pf_dist (the segment that takes this warp's place when it retires) are pulled into L2 now,
     // so that warp finds them there instead of in DRAM: one 128-byte line (32 reads) per lane and instruction
@@ -250,7 +252,7 @@ __global__ void __launch_bounds__(WPC * 32, TILE_MIN_CTAS) k_tile_accumulate(Til
         const int jp = j + a.pf_dist;
         if (jp < a.nseg) {
             const uint32_t plo = a.lo[jp], phi = a.hi[jp + 1];
-            if (plo < phi && phi <= a.n && phi - plo <= 32u * 32u * 8u) {
+            if (plo < phi && phi <= n_all && phi - plo <= 32u * 32u * 8u) {
                 for (uint32_t q = (plo & ~31u) + lane * 32; q < phi; q += 32 * 32) {
                     asm volatile("prefetch.global.L2 [%0];" :: "l"(a.pos + q));
                     asm volatile("prefetch.global.L2 [%0];" :: "l"((HAS_OFF ? a.cigar_off : a.cigar) + q));
@@ -266,10 +268,10 @@ __global__ void __launch_bounds__(WPC * 32, TILE_MIN_CTAS) k_tile_accumulate(Til
     // of lo are before the window, the read at hi is beyond it, and the next window starts inside ours.  The loads are
     // issued here and checked at the very end, off the critical path.
     int32_t chk_l = INT32_MIN, chk_r = INT32_MAX; uint32_t chk_n = 0;
-    bool bad = i_lo > i_hi || i_hi > a.n;
+    bool bad = i_lo > i_hi || i_hi > n_all;
     if (lane == 0 && !bad) {
         if (i_lo > 0) chk_l = ldg_i32(a.pos + i_lo - 1);
-        if (i_hi < a.n) chk_r = ldg_i32(a.pos + i_hi);
+        if (i_hi < n_all) chk_r = ldg_i32(a.pos + i_hi);
         if (j + 1 < a.nseg) chk_n = a.lo[j + 1];
     }
     const int64_t shift = a.shift;
