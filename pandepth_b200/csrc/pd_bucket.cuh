@@ -7,7 +7,7 @@
 // the batch into *bucket* order and let the tile kernel, which accumulates in shared memory, do the rest.
 //
 //   k_expand_runs     filter + CIGAR walk of every read -> aligned runs (start, len) relative to the owned range, clipped to it
-//                     (one run per read for single-op input); runs are appended with warp-aggregated cursor bumps
+//                     (one run per read for single-op input), written into the slots of the read's own CIGAR words
 //   k_bucket_hist     histogram of the runs over coarse buckets of 2^19 bases (shared-memory pre-aggregation per CTA)
 //   k_bucket_scan     exclusive scan of the <= 4096 coarse counts (one CTA)
 //   k_bucket_scatter  runs -> coarse-bucket order (a CTA reserves, per coarse bucket, a range for its tile's runs)
@@ -30,7 +30,8 @@ constexpr int BK_COARSE_SHIFT = 19;                 // coarse bucket = 2^19 base
 constexpr int BK_FINE_SHIFT = 8;                    // fine bucket = 256 bases = HALO
 constexpr int BK_FINE = 1 << (BK_COARSE_SHIFT - BK_FINE_SHIFT);   // 2048 fine buckets per coarse bucket
 constexpr int BK_MAX_COARSE = 4096;                 // 2^31 bases
-constexpr int BK_TILE = 4096;                       // runs per CTA tile in the coarse passes
+constexpr int BK_TILE = 65536;                      // slots per CTA tile in the coarse passes: a CTA bumps every coarse cursor it meets once, so
+                                                    // small tiles mean many global atomics on few addresses (4096-slot tiles: most of an 11.5 ms pass)
 static_assert(HALO == (1 << BK_FINE_SHIFT) && SEG == 8 * HALO, "fine buckets are the tile kernel's look-back; eight of them make a segment");
 
 struct ExpandArgs {
@@ -38,65 +39,62 @@ struct ExpandArgs {
     const uint16_t *flag; const uint8_t *mapq;
     uint32_t n; int32_t contig_len; int32_t shift;
     uint32_t xflags; int32_t min_mapq;
-    int32_t *run_pos; uint32_t *run_cig;            // out: start (>= 0, < contig_len) and (len << 4 | M)
-    uint32_t *n_runs; uint32_t cap;                 // cursor (never passes cap: a batch has at most one run per CIGAR word)
+    int32_t *run_pos; uint32_t *run_cig;            // out: start (>= 0, < contig_len) and (len << 4 | M); run_pos = -1: empty slot
+    uint32_t cap;                                   // slots: n for single-op batches, the batch's CIGAR words otherwise
     uint32_t *delta; int *delta_used;               // contig base of the delta array: runs of 2^28 bases or more (no CIGAR word holds them) go there
 };
 
+// No cursor, no atomics: read i owns the slots of its own CIGAR words (slot i for a single-op batch) -- a run consumes at
+// least one word, so its runs fit -- and marks the slots it does not fill as empty; the bucket passes skip those.
+// (A first version appended runs through one global cursor: 3.5 M same-address atomics, most of an 11.5 ms pass.)
 __global__ void __launch_bounds__(256) k_expand_runs(ExpandArgs a)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    bool live = i < a.n;
-    if (live && a.flag && (a.flag[i] & a.xflags)) live = false;
+    if (i >= a.n) return;
+    bool live = true;
+    if (a.flag && (a.flag[i] & a.xflags)) live = false;
     if (live && a.mapq && (int)a.mapq[i] < a.min_mapq) live = false;
-    int32_t p = live ? __ldcs(a.pos + i) : -1;
+    const int32_t p = __ldcs(a.pos + i);
     if (p < 0) live = false;
-    uint32_t c0 = i, nops = live ? 1u : 0u;
-    if (live && a.cigar_off) { c0 = a.cigar_off[i]; nops = a.cigar_off[i + 1] - c0; }
+    uint32_t c0 = i, nops = 1, slot = i;
+    if (a.cigar_off) { c0 = a.cigar_off[i]; nops = a.cigar_off[i + 1] - c0; slot = c0 - a.cigar_off[0]; }
+    const uint32_t slot_end = slot + nops;
     const int64_t clen = a.contig_len;
     int64_t q = (int64_t)p - a.shift, rs = 0, re = 0; bool open = false;
-    // every lane walks its ops; an emission is a warp-uniform step (lanes without a run to emit sit it out), so the cursor is
-    // bumped once per warp and step
-    const uint32_t max_ops = __reduce_max_sync(0xffffffffu, nops);
-    for (uint32_t k = 0; k <= max_ops; ++k) {
-        bool emit = false; int64_t es = 0, ee = 0;
-        if (k < nops) {
+    auto emit = [&]() {
+        int64_t es = rs < 0 ? 0 : rs, ee = re > clen ? clen : re;
+        if (es >= ee) return;
+        if (ee - es >= (1ll << 28)) {                            // does not fit a (len << 4 | op) word: straight to the delta array
+            red_add_u32(a.delta + es, 1u); red_add_u32(a.delta + ee, 0xffffffffu); *a.delta_used = 1;
+            return;
+        }
+        if (slot < a.cap) { a.run_pos[slot] = (int32_t)es; a.run_cig[slot] = (uint32_t)(ee - es) << 4; }
+        slot++;
+    };
+    if (live) {
+        for (uint32_t k = 0; k < nops; ++k) {
             const uint32_t w = __ldcs(a.cigar + c0 + k);
             const uint32_t op = w & 15u; const int64_t n = w >> 4;
-            if (is_match_op(op)) {
-                if (open && re == q) re = q + n;
-                else { if (open) { emit = true; es = rs; ee = re; } rs = q; re = q + n; open = true; }
+            if (is_match_op(op)) {                               // :745-752  adjacent M/=/X merge into one run
+                if (open && re == q) re = q + n; else { if (open) emit(); rs = q; re = q + n; open = true; }
                 q += n;
-            } else if (is_skip_op(op)) q += n;
-        } else if (k == nops && open) { emit = true; es = rs; ee = re; open = false; }
-        if (emit) { if (es < 0) es = 0; if (ee > clen) ee = clen; if (es >= ee) emit = false; }
-        if (emit && ee - es >= (1ll << 28)) {                    // does not fit a (len << 4 | op) word: straight to the delta array
-            red_add_u32(a.delta + es, 1u); red_add_u32(a.delta + ee, 0xffffffffu); *a.delta_used = 1;
-            emit = false;
+            } else if (is_skip_op(op)) q += n;                   // :754-757
         }
-        const unsigned em = __ballot_sync(0xffffffffu, emit);
-        if (em) {
-            uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(a.n_runs, (uint32_t)__popc(em));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (emit) {
-                const uint32_t at = base + (uint32_t)__popc(em & ((1u << lane) - 1u));
-                if (at < a.cap) { a.run_pos[at] = (int32_t)es; a.run_cig[at] = (uint32_t)(ee - es) << 4; }
-            }
-        }
+        if (open) emit();
     }
+    for (; slot < slot_end && slot < a.cap; slot++) a.run_pos[slot] = -1;
 }
 
 // coarse histogram: hist[b] += runs with (pos >> 19) == b
-__global__ void __launch_bounds__(256) k_bucket_hist(const int32_t *__restrict__ pos, const uint32_t *__restrict__ n_runs, uint32_t *__restrict__ hist, int n_coarse)
+__global__ void __launch_bounds__(256) k_bucket_hist(const int32_t *__restrict__ pos, uint32_t n, uint32_t *__restrict__ hist, int n_coarse)
 {
     __shared__ uint32_t h[BK_MAX_COARSE];
     for (int i = threadIdx.x; i < n_coarse; i += blockDim.x) h[i] = 0;
     __syncthreads();
-    const uint32_t n = *n_runs;
-    for (uint32_t i = blockIdx.x * BK_TILE + threadIdx.x, e = min(n, (blockIdx.x + 1u) * BK_TILE); i < e; i += blockDim.x)
-        atomicAdd(&h[(uint32_t)pos[i] >> BK_COARSE_SHIFT], 1u);
+    for (uint32_t i = blockIdx.x * BK_TILE + threadIdx.x, e = min(n, (blockIdx.x + 1u) * BK_TILE); i < e; i += blockDim.x) {
+        const int32_t p = pos[i];
+        if (p >= 0) atomicAdd(&h[(uint32_t)p >> BK_COARSE_SHIFT], 1u);
+    }
     __syncthreads();
     for (int i = threadIdx.x; i < n_coarse; i += blockDim.x) if (h[i]) atomicAdd(&hist[i], h[i]);
 }
@@ -120,21 +118,21 @@ __global__ void __launch_bounds__(1024) k_bucket_scan(const uint32_t *__restrict
 
 // runs -> coarse order.  A CTA counts its tile per coarse bucket, reserves a range per bucket with ONE global atomic, and
 // places its runs inside the reserved ranges with shared-memory cursors.
-__global__ void __launch_bounds__(256) k_bucket_scatter(const int32_t *__restrict__ pos, const uint32_t *__restrict__ cig, const uint32_t *__restrict__ n_runs,
+__global__ void __launch_bounds__(256) k_bucket_scatter(const int32_t *__restrict__ pos, const uint32_t *__restrict__ cig, uint32_t n,
                                                         const uint32_t *__restrict__ base, uint32_t *__restrict__ cursor, int n_coarse,
                                                         int32_t *__restrict__ out_pos, uint32_t *__restrict__ out_cig)
 {
     __shared__ uint32_t h[BK_MAX_COARSE];
     for (int i = threadIdx.x; i < n_coarse; i += blockDim.x) h[i] = 0;
     __syncthreads();
-    const uint32_t n = *n_runs;
     const uint32_t t0 = blockIdx.x * BK_TILE, t1 = min(n, t0 + BK_TILE);
-    for (uint32_t i = t0 + threadIdx.x; i < t1; i += blockDim.x) atomicAdd(&h[(uint32_t)pos[i] >> BK_COARSE_SHIFT], 1u);
+    for (uint32_t i = t0 + threadIdx.x; i < t1; i += blockDim.x) { const int32_t p = pos[i]; if (p >= 0) atomicAdd(&h[(uint32_t)p >> BK_COARSE_SHIFT], 1u); }
     __syncthreads();
     for (int i = threadIdx.x; i < n_coarse; i += blockDim.x) { const uint32_t c = h[i]; h[i] = c ? base[i] + atomicAdd(&cursor[i], c) : 0u; }
     __syncthreads();
     for (uint32_t i = t0 + threadIdx.x; i < t1; i += blockDim.x) {
         const int32_t p = pos[i];
+        if (p < 0) continue;                                     // an empty slot
         const uint32_t at = atomicAdd(&h[(uint32_t)p >> BK_COARSE_SHIFT], 1u);
         out_pos[at] = p; out_cig[at] = cig[i];
     }
@@ -171,7 +169,7 @@ __global__ void __launch_bounds__(512) k_bucket_fine(const int32_t *__restrict__
 }
 
 // lo[j] = first run with pos >= s0_j - 256, hi[j] = first run with pos >= s0_j (nseg + 1 entries), from the fine offsets
-__global__ void __launch_bounds__(256) k_bucket_cuts(const uint32_t *__restrict__ fine_off, const uint32_t *__restrict__ n_runs, uint32_t n_fine_total,
+__global__ void __launch_bounds__(256) k_bucket_cuts(const uint32_t *__restrict__ fine_off, const uint32_t *__restrict__ n_runs /* = &base[n_coarse] */, uint32_t n_fine_total,
                                                      int32_t seg0, int32_t nseg, uint32_t *__restrict__ lo, uint32_t *__restrict__ hi)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;

@@ -282,20 +282,21 @@ int run_batch(pd_engine *e, int32_t tid, uint32_t n, const int32_t *pos, const u
             if (e->bk_fine) { CK(cudaStreamSynchronize(e->stream)); cudaFree(e->bk_fine); e->bk_fine = nullptr; }
             CK(cudaMalloc(&e->bk_fine, n_fine * 4)); e->bk_fine_cap = n_fine;
         }
-        uint32_t *d_nruns = e->bk_tab, *d_hist = e->bk_tab + 2, *d_base = d_hist + (pdk::BK_MAX_COARSE + 1), *d_cursor = d_base + (pdk::BK_MAX_COARSE + 1);
-        CK(cudaMemsetAsync(e->bk_tab, 0, (2 + (pdk::BK_MAX_COARSE + 1)) * 4, e->stream));      // cursor, flag, hist
+        uint32_t *d_hist = e->bk_tab + 2, *d_base = d_hist + (pdk::BK_MAX_COARSE + 1), *d_cursor = d_base + (pdk::BK_MAX_COARSE + 1);
+        const uint32_t *d_nruns = d_base + n_coarse;             // total number of runs = base[n_coarse], known on the device only
+        CK(cudaMemsetAsync(e->bk_tab, 0, (2 + (pdk::BK_MAX_COARSE + 1)) * 4, e->stream));      // hist
         const int32_t nseg = (int32_t)(e->elen[tid] / pdk::SEG) + 1;
         pd_engine::CutBuf &cb = e->cut[e->cut_next]; e->cut_next ^= 1;
         int rc = ensure_cut(e, cb, (size_t)nseg + 1); if (rc) return rc;
         if (cb.used) CK(cudaStreamWaitEvent(e->stream, cb.released, 0));
         pdk::ExpandArgs x{pos, cigar, cigar_off, flag, mapq, n, (int32_t)e->elen[tid], (int32_t)e->org[tid], e->xflags, e->min_mapq,
-                          e->bk_pos[0], e->bk_cig[0], d_nruns, (uint32_t)cap, e->d_delta + off, e->d_flags + 1};
+                          e->bk_pos[0], e->bk_cig[0], (uint32_t)cap, e->d_delta + off, e->d_flags + 1};
         const unsigned tiles = (unsigned)((cap + pdk::BK_TILE - 1) / pdk::BK_TILE);
         rc = launch(e, K_BUCKET, [&] {
             pdk::k_expand_runs<<<(n + 255) / 256, 256, 0, e->stream>>>(x);
-            pdk::k_bucket_hist<<<tiles, 256, 0, e->stream>>>(e->bk_pos[0], d_nruns, d_hist, n_coarse);
+            pdk::k_bucket_hist<<<tiles, 256, 0, e->stream>>>(e->bk_pos[0], (uint32_t)cap, d_hist, n_coarse);
             pdk::k_bucket_scan<<<1, 1024, 0, e->stream>>>(d_hist, d_base, d_cursor, n_coarse);
-            pdk::k_bucket_scatter<<<tiles, 256, 0, e->stream>>>(e->bk_pos[0], e->bk_cig[0], d_nruns, d_base, d_cursor, n_coarse, e->bk_pos[1], e->bk_cig[1]);
+            pdk::k_bucket_scatter<<<tiles, 256, 0, e->stream>>>(e->bk_pos[0], e->bk_cig[0], (uint32_t)cap, d_base, d_cursor, n_coarse, e->bk_pos[1], e->bk_cig[1]);
             pdk::k_bucket_fine<<<(unsigned)n_coarse, 512, 0, e->stream>>>(e->bk_pos[1], e->bk_cig[1], d_base, e->bk_fine, e->bk_pos[0], e->bk_cig[0]);
             pdk::k_bucket_cuts<<<(unsigned)((nseg + 1 + 255) / 256), 256, 0, e->stream>>>(e->bk_fine, d_nruns, (uint32_t)n_fine, 0, nseg, cb.lo, cb.hi);
         });

@@ -255,10 +255,11 @@ def test_bucketed_unsorted_path_matches_oracle(seed, monkeypatch):
             eng.finalize()
             _check_depth(eng, tlen, want)
         half = rec.n // 2
+        first_half = rec.select(perm[:half])
         with _engine(tlen, xflags=xflags, min_mapq=q) as eng:                    # a sorted batch first, unsorted on top of it
             eng.set_reduce_hint(1, 0xFFFFFFFF)
-            _push_all(eng, rec.select(np.arange(0, half)), True, 2)
-            _push_all(eng, rec.select(rng.permutation(np.arange(half, rec.n))), False, 2)
+            _push_all(eng, first_half.select(_sorted_order(first_half)), True, 2)
+            _push_all(eng, rec.select(perm[half:]), False, 2)
             eng.finalize()
             _check_depth(eng, tlen, want)
             it = np.arange(len(lens), dtype=np.int32)[tlen > 1]
