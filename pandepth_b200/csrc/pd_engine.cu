@@ -102,7 +102,10 @@ struct pd_engine {
     int32_t *bk_pos[2] = {nullptr, nullptr}; uint32_t *bk_cig[2] = {nullptr, nullptr}; size_t bk_cap = 0;
     uint32_t *bk_tab = nullptr;      // [0] run cursor, [1] overflow flag (unused), then hist[4096], base[4097], cursor[4096]
     uint32_t *bk_fine = nullptr; size_t bk_fine_cap = 0;
-    uint64_t bucket_min_reads = 262144;   // smaller unsorted batches scatter directly (PANDEPTH_BUCKET_MIN_READS; 0 = never bucket)
+    uint64_t bucket_min_reads = 0;   // unsorted batches of at least this many reads go expand -> bucket -> tile (PANDEPTH_BUCKET_MIN_READS);
+                                     // 0 = never, the default: measured on B200 the two wide bucket passes (636 coarse, 2048 fine buckets)
+                                     // write 4-byte pieces of more open sectors than the L2 holds and take 10.8 ms per 111 M reads, against
+                                     // 7.85 + 0.48 ms for scatter + scan (profiles/r02_delta_path.txt); needs staged, narrower passes
     uint32_t *d_pass_bits = nullptr; size_t bits_cap = 0;   // record filter of the current batch, one bit per read (k_filter_bits)
     int bz_grid = 148 * 4, bz_grid_k2 = 148 * 6, bz_grid_k4 = 148 * 6, bz_grid_k8 = 148 * 6;
     uint64_t scatter_stripe = 32ull << 20;          // elements (128 MB of deltas) per stripe of a striped scatter (PANDEPTH_SCATTER_STRIPE_MB)
@@ -265,8 +268,8 @@ int run_batch(pd_engine *e, int32_t tid, uint32_t n, const int32_t *pos, const u
                 CK(cudaStreamSynchronize(e->stream));
                 cap = (uint64_t)last - first;
             }
-            if (cap < n) cap = n;
         }
+        if (cap == 0) { e->stats.delta_path_batches++; e->stats.reads_pushed += n; e->finalized = false; e->pushed_since_reset = true; return PD_OK; }   // no CIGAR word, no run
         if (cap > 0xfffffff0ull) return fail(e, PD_ERR_ARG, "pd_push_contig: an unsorted batch with more than 2^32 CIGAR words; push smaller batches");
         if (cap > e->bk_cap) {
             CK(cudaStreamSynchronize(e->stream));
