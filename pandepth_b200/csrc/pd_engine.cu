@@ -299,8 +299,8 @@ int run_batch(pd_engine *e, int32_t tid, uint32_t n, const int32_t *pos, const u
             pdk::k_expand_runs<<<(n + 255) / 256, 256, 0, e->stream>>>(x);
             pdk::k_bucket_hist<<<tiles, 256, 0, e->stream>>>(e->bk_pos[0], (uint32_t)cap, d_hist, n_coarse);
             pdk::k_bucket_scan<<<1, 1024, 0, e->stream>>>(d_hist, d_base, d_cursor, n_coarse);
-            pdk::k_bucket_scatter<<<tiles, 256, 0, e->stream>>>(e->bk_pos[0], e->bk_cig[0], (uint32_t)cap, d_base, d_cursor, n_coarse, e->bk_pos[1], e->bk_cig[1]);
-            pdk::k_bucket_fine<<<(unsigned)n_coarse, 512, 0, e->stream>>>(e->bk_pos[1], e->bk_cig[1], d_base, e->bk_fine, e->bk_pos[0], e->bk_cig[0]);
+            pdk::k_bucket_scatter<<<(unsigned)((cap + pdk::BK_STAGE - 1) / pdk::BK_STAGE), 256, pdk::BK_SCATTER_SMEM, e->stream>>>(e->bk_pos[0], e->bk_cig[0], (uint32_t)cap, d_base, d_cursor, n_coarse, e->bk_pos[1], e->bk_cig[1]);
+            pdk::k_bucket_fine<<<(unsigned)n_coarse, 512, pdk::BK_FINE_SMEM, e->stream>>>(e->bk_pos[1], e->bk_cig[1], d_base, e->bk_fine, e->bk_pos[0], e->bk_cig[0]);
             pdk::k_bucket_cuts<<<(unsigned)((nseg + 1 + 255) / 256), 256, 0, e->stream>>>(e->bk_fine, d_nruns, (uint32_t)n_fine, 0, nseg, cb.lo, cb.hi);
         });
         if (rc) return rc;
@@ -683,6 +683,8 @@ pd_engine *pd_create_ranges(int device, int n_targets, const uint32_t *target_le
         if ((ce = cudaFuncSetAttribute(pdk::k_tile_accumulate<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return bail("cudaFuncSetAttribute", ce);
         if ((ce = cudaFuncSetAttribute(pdk::k_tile_accumulate<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_off)) != cudaSuccess) return bail("cudaFuncSetAttribute", ce);
         if ((ce = cudaFuncSetAttribute(pdk::k_tile_accumulate<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_off)) != cudaSuccess) return bail("cudaFuncSetAttribute", ce);
+        if ((ce = cudaFuncSetAttribute(pdk::k_bucket_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pdk::BK_SCATTER_SMEM)) != cudaSuccess) return bail("cudaFuncSetAttribute", ce);
+        if ((ce = cudaFuncSetAttribute(pdk::k_bucket_fine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pdk::BK_FINE_SMEM)) != cudaSuccess) return bail("cudaFuncSetAttribute", ce);
     }
     {
         int n_sm = 0, per_sm = 0;
