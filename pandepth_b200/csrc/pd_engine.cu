@@ -102,10 +102,10 @@ struct pd_engine {
     int32_t *bk_pos[2] = {nullptr, nullptr}; uint32_t *bk_cig[2] = {nullptr, nullptr}; size_t bk_cap = 0;
     uint32_t *bk_tab = nullptr;      // [0] run cursor, [1] overflow flag (unused), then hist[4096], base[4097], cursor[4096]
     uint32_t *bk_fine = nullptr; size_t bk_fine_cap = 0;
-    uint64_t bucket_min_reads = 0;   // unsorted batches of at least this many reads go expand -> bucket -> tile (PANDEPTH_BUCKET_MIN_READS);
-                                     // 0 = never, the default: measured on B200 the two wide bucket passes (636 coarse, 2048 fine buckets)
-                                     // write 4-byte pieces of more open sectors than the L2 holds and take 10.8 ms per 111 M reads, against
-                                     // 7.85 + 0.48 ms for scatter + scan (profiles/r02_delta_path.txt); needs staged, narrower passes
+    uint64_t bucket_min_reads = 1u << 20;   // unsorted batches of at least this many reads go expand -> bucket -> tile (PANDEPTH_BUCKET_MIN_READS;
+                                     // 0 = never).  Measured on B200, 111 M shuffled reads over 333 Mb (profiles/r02_delta_path.txt): scatter + scan
+                                     // 7.85 + 0.48 ms; bucket passes placing runs straight into global memory 10.8-11.5 ms (+ 0.45 ms tile);
+                                     // staged in shared memory and written out in bursts 4.89 ms (+ 0.45): 1.56x faster than the scatter
     uint32_t *d_pass_bits = nullptr; size_t bits_cap = 0;   // record filter of the current batch, one bit per read (k_filter_bits)
     int bz_grid = 148 * 4, bz_grid_k2 = 148 * 6, bz_grid_k4 = 148 * 6, bz_grid_k8 = 148 * 6;
     uint64_t scatter_stripe = 32ull << 20;          // elements (128 MB of deltas) per stripe of a striped scatter (PANDEPTH_SCATTER_STRIPE_MB)
