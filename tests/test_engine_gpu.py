@@ -216,7 +216,7 @@ def test_striped_scatter_applies_every_run_end_once(monkeypatch):
             assert eng.stats()["kernel_launches"] >= 15
 
 
-@pytest.mark.parametrize("seed", [5, 6])
+@pytest.mark.parametrize("seed", [5])
 def test_bucketed_unsorted_path_matches_oracle(seed, monkeypatch):
     """Unsorted batches at scale go expand -> bucket -> tile (pd_bucket.cuh) instead of global reductions; forced here for
     small batches.  Mixed CIGARs (far N skips, clips, I/D/=/X/P), the device-side filter, pile-ups, reads over the contig
@@ -226,11 +226,11 @@ def test_bucketed_unsorted_path_matches_oracle(seed, monkeypatch):
     from pandepth_b200.shard import assign_ranges
     monkeypatch.setenv("PANDEPTH_BUCKET_MIN_READS", "1")
     rng = np.random.default_rng(seed)
-    lens = [700_001, 1, 90_000, 2_500]
+    lens = [700_001, 1, 90_000, 2_500]                                           # contig 0 spans two coarse buckets (2^19 bases each)
     names = [f"c{i}" for i in range(len(lens))]
     rows = []
     for t, ln in enumerate(lens):
-        n = 0 if ln < 10 else ln // 3
+        n = 0 if ln < 10 else ln // 6                                            # (every read is its own tiny batch below: keep the count moderate)
         starts = rng.integers(-100, ln, n)
         starts[rng.integers(0, max(1, n), n // 12)] = ln // 2                    # a pile-up
         for p in starts.tolist():
