@@ -270,7 +270,7 @@ int run_batch(pd_engine *e, int32_t tid, uint32_t n, const int32_t *pos, const u
             }
         }
         if (cap == 0) { e->stats.delta_path_batches++; e->stats.reads_pushed += n; e->finalized = false; e->pushed_since_reset = true; return PD_OK; }   // no CIGAR word, no run
-        if (cap > 0xfffffff0ull) return fail(e, PD_ERR_ARG, "pd_push_contig: an unsorted batch with more than 2^32 CIGAR words; push smaller batches");
+        if (cap > 0xffff0000ull) return fail(e, PD_ERR_ARG, "pd_push_contig: an unsorted batch with more than 2^32 - 2^16 CIGAR words; push smaller batches");   // (tile arithmetic of the bucket passes is 32-bit)
         if (cap > e->bk_cap) {
             CK(cudaStreamSynchronize(e->stream));
             for (int k = 0; k < 2; k++) { cudaFree(e->bk_pos[k]); cudaFree(e->bk_cig[k]); e->bk_pos[k] = nullptr; e->bk_cig[k] = nullptr; }
