@@ -21,7 +21,9 @@
 // writes go out in short bursts per bucket.  Traffic: 16 B/read (expand) + 24 B/run (coarse) + 20 B/run (fine) + the
 // tile kernel's 8 B/run + 4 B/base.
 #pragma once
+#ifndef PD_WARP_EMU              // tests/cpp/bucket_emu_check.cpp runs these kernels on the CPU (tests/cpp/warp_emu.h)
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 
 namespace pdk {
@@ -145,7 +147,11 @@ __global__ void __launch_bounds__(256) k_bucket_scatter(const int32_t *__restric
                                                         const uint32_t *__restrict__ base, uint32_t *__restrict__ cursor, int n_coarse,
                                                         int32_t *__restrict__ out_pos, uint32_t *__restrict__ out_cig)
 {
+#ifndef PD_WARP_EMU
     extern __shared__ uint32_t bk_sm[];
+#else
+    uint32_t *bk_sm = emu::dyn_smem();
+#endif
     uint32_t *cnt = bk_sm, *start = cnt + BK_MAX_COARSE, *gbase = start + BK_MAX_COARSE, *part = gbase + BK_MAX_COARSE;
     int32_t *st_pos = reinterpret_cast<int32_t *>(part + 256); uint32_t *st_cig = reinterpret_cast<uint32_t *>(st_pos + BK_STAGE);
     const uint32_t t0 = blockIdx.x * BK_STAGE, t1 = min(n, t0 + BK_STAGE);
@@ -178,7 +184,11 @@ constexpr size_t BK_FINE_SMEM = (4 * BK_FINE + 512 + 2 * BK_STAGE) * 4;
 __global__ void __launch_bounds__(512) k_bucket_fine(const int32_t *__restrict__ pos, const uint32_t *__restrict__ cig, const uint32_t *__restrict__ base,
                                                      uint32_t *__restrict__ fine_off, int32_t *__restrict__ out_pos, uint32_t *__restrict__ out_cig)
 {
+#ifndef PD_WARP_EMU
     extern __shared__ uint32_t bk_sm[];
+#else
+    uint32_t *bk_sm = emu::dyn_smem();
+#endif
     uint32_t *gcur = bk_sm, *cnt = gcur + BK_FINE, *start = cnt + BK_FINE, *cur = start + BK_FINE, *part = cur + BK_FINE;
     int32_t *st_pos = reinterpret_cast<int32_t *>(part + 512); uint32_t *st_cig = reinterpret_cast<uint32_t *>(st_pos + BK_STAGE);
     const uint32_t b = blockIdx.x, r0 = base[b], r1 = base[b + 1];

@@ -40,7 +40,7 @@ struct Barrier {
 };
 
 struct Warp { Barrier bar{32}; uint64_t slot[32]; };
-struct Cta { Barrier bar; std::vector<Warp> warps; explicit Cta(int threads) : bar(threads), warps((size_t)(threads + 31) / 32) {} };
+struct Cta { Barrier bar; std::vector<Warp> warps; std::vector<uint32_t> dyn; explicit Cta(int threads) : bar(threads), warps((size_t)(threads + 31) / 32), dyn(64 * 1024) {} };   // dyn: 256 KB of "dynamic shared memory"
 
 static thread_local Warp *tl_warp = nullptr;
 static thread_local Cta *tl_cta = nullptr;
@@ -64,6 +64,8 @@ void launch(unsigned grid, unsigned block, K kernel, A args)
         for (auto &x : th) x.join();
     }
 }
+
+inline uint32_t *dyn_smem() { return tl_cta->dyn.data(); }
 
 template <typename T> inline T exchange(T v, int src)
 {
@@ -141,6 +143,8 @@ inline const void *emu_shared_ptr(uint32_t sa) { return (const void *)(emu::shar
 #define __align__(n) __attribute__((aligned(n)))
 struct uint4 { uint32_t x, y, z, w; };
 inline uint32_t min(uint32_t a, uint32_t b) { return a < b ? a : b; }
+inline int min(int a, int b) { return a < b ? a : b; }
+template <typename T> inline T __ldcs(const T *p) { return *p; }
 inline uint32_t atomicAdd(uint32_t *p, uint32_t v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
