@@ -11,7 +11,9 @@
 //
 // All arithmetic is integer (uint32 modular depth, uint64 sums); no tensor cores are involved.
 #pragma once
+#ifndef PD_WARP_EMU              // tests/cpp/tile_emu_check.cpp runs k_cut / k_filter_bits / k_tile_accumulate on the CPU (tests/cpp/warp_emu.h)
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 
 namespace pdk {
@@ -54,16 +56,25 @@ __device__ __forceinline__ uint32_t ldg_u32(const uint32_t *p) { return __ldg(p)
 
 __device__ __forceinline__ void red_add_u32(uint32_t *addr, uint32_t v)
 {
+#ifndef PD_WARP_EMU
     asm volatile("red.global.add.u32 [%0], %1;" ::"l"(addr), "r"(v) : "memory");
+#else
+    atomicAdd(addr, v);
+#endif
 }
 
 // one Kogge-Stone step of a warp inclusive scan: t += (lane >= o) ? shfl_up(t, o) : 0, using the predicate shfl.up
 // itself produces (2 instructions instead of shuffle + compare + select + add)
 __device__ __forceinline__ uint32_t scan_step_up(uint32_t t, int o)
 {
+#ifndef PD_WARP_EMU
     asm volatile("{ .reg .u32 y; .reg .pred p;\n\t"
                  "shfl.sync.up.b32 y|p, %0, %1, 0, 0xffffffff;\n\t"
                  "@p add.u32 %0, %0, y; }" : "+r"(t) : "r"(o));
+#else
+    const uint32_t y = __shfl_up_sync(0xffffffffu, t, (unsigned)o);
+    if (emu::tl_lane >= o) t += y;
+#endif
     return t;
 }
 
@@ -71,11 +82,15 @@ __device__ __forceinline__ uint32_t scan_step_up(uint32_t t, int o)
 // compare / add / conditional-move chain, three instructions per element)
 __device__ __forceinline__ uint32_t nonzero4(const uint4 v)
 {
+#ifndef PD_WARP_EMU
     uint32_t r;
     asm("{ .reg .u32 a, b, c, d;\n\t"
         "min.u32 a, %1, 1; min.u32 b, %2, 1; min.u32 c, %3, 1; min.u32 d, %4, 1;\n\t"
         "add.u32 a, a, b; add.u32 c, c, d; add.u32 %0, a, c; }" : "=r"(r) : "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
     return r;
+#else
+    return (v.x != 0) + (v.y != 0) + (v.z != 0) + (v.w != 0);
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -227,19 +242,27 @@ constexpr int TILE_UNROLL = PD_TILE_UNROLL;   // 32-read chunks whose loads are 
 // TMA 1-D bulk copy shared::cta -> global of one segment (8 KB), issued by one lane; `add` folds into what is there
 __device__ __forceinline__ void bulk_flush_segment(uint32_t *gdst, const uint32_t *ssrc, bool add)
 {
+#ifndef PD_WARP_EMU
     const uint32_t sa = (uint32_t)__cvta_generic_to_shared(ssrc);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the generic-proxy stores of the scan are visible to the async proxy
     if (add) asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.u32 [%0], [%1], %2;" :: "l"(gdst), "r"(sa), "n"(SEG * 4) : "memory");
     else asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(gdst), "r"(sa), "n"(SEG * 4) : "memory");
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory may be reused / the CTA may retire
+#else
+    for (int i = 0; i < SEG; i++) { if (add) gdst[i] += ssrc[i]; else gdst[i] = ssrc[i]; }
+#endif
 }
 
 template <bool HAS_OFF, bool HAS_FILTER>
 __global__ void __launch_bounds__(WPC * 32, TILE_MIN_CTAS) k_tile_accumulate(TileArgs a)
 {
     constexpr int U = HAS_OFF ? (TILE_UNROLL > 8 ? 8 : TILE_UNROLL) : TILE_UNROLL;   // offsets cost two more registers per chunk
+#ifndef PD_WARP_EMU
     extern __shared__ __align__(16) uint32_t smem[];
+#else
+    uint32_t *smem = emu::dyn_smem();
+#endif
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int j = blockIdx.x * WPC + warp;
     if (j >= a.nseg) return;
@@ -254,8 +277,10 @@ __global__ void __launch_bounds__(WPC * 32, TILE_MIN_CTAS) k_tile_accumulate(Til
             const uint32_t plo = a.lo[jp], phi = a.hi[jp + 1];
             if (plo < phi && phi <= n_all && phi - plo <= 32u * 32u * 8u) {
                 for (uint32_t q = (plo & ~31u) + lane * 32; q < phi; q += 32 * 32) {
+#ifndef PD_WARP_EMU
                     asm volatile("prefetch.global.L2 [%0];" :: "l"(a.pos + q));
                     asm volatile("prefetch.global.L2 [%0];" :: "l"((HAS_OFF ? a.cigar_off : a.cigar) + q));
+#endif
                 }
             }
         }
@@ -611,6 +636,7 @@ __global__ void __launch_bounds__(WPC * 32, TILE_MIN_CTAS) k_tile_accumulate(Til
     if (lane == 0 && (bad || (int64_t)chk_l - shift >= hbase || (int64_t)chk_r - shift < send || chk_n > i_hi)) atomicOr(a.err, ERR_UNSORTED);
 }
 
+#ifndef PD_WARP_EMU              // (the emulated build stops here: cut, filter and tile kernels)
 // ---------------------------------------------------------------------------------------------------------------
 // k_delta_scatter: unsorted or long-span batches.  One thread per read; every aligned run becomes +1 at its start
 // and -1 at its end in the global delta array (red.global.add.u32).
@@ -1070,5 +1096,7 @@ __global__ void __launch_bounds__(256) k_reduce_windows(WindowArgs a)
         }
     }
 }
+
+#endif  // PD_WARP_EMU
 
 }  // namespace pdk
