@@ -11,7 +11,7 @@
 //
 // All arithmetic is integer (uint32 modular depth, uint64 sums); no tensor cores are involved.
 #pragma once
-#ifndef PD_WARP_EMU              // tests/cpp/tile_emu_check.cpp runs k_cut / k_filter_bits / k_tile_accumulate on the CPU (tests/cpp/warp_emu.h)
+#ifndef PD_WARP_EMU              // tests/cpp/{tile,reduce}_emu_check.cpp run these kernels on the CPU (tests/cpp/warp_emu.h)
 #include <cuda_runtime.h>
 #endif
 #include <stdint.h>
@@ -636,7 +636,6 @@ __global__ void __launch_bounds__(WPC * 32, TILE_MIN_CTAS) k_tile_accumulate(Til
     if (lane == 0 && (bad || (int64_t)chk_l - shift >= hbase || (int64_t)chk_r - shift < send || chk_n > i_hi)) atomicOr(a.err, ERR_UNSORTED);
 }
 
-#ifndef PD_WARP_EMU              // (the emulated build stops here: cut, filter and tile kernels)
 // ---------------------------------------------------------------------------------------------------------------
 // k_delta_scatter: unsorted or long-span batches.  One thread per read; every aligned run becomes +1 at its start
 // and -1 at its end in the global delta array (red.global.add.u32).
@@ -785,7 +784,9 @@ __global__ void __launch_bounds__(SCAN_THREADS, PD_SCAN_MIN_CTAS) k_scan_add(uin
                 unsigned long long d = 0;
                 uint32_t status = 2, val = 0;
                 if (idx >= 0) {
-#if PD_SCAN_POLL_LD
+#if defined(PD_WARP_EMU)
+                    do { d = __atomic_load_n(desc + idx, __ATOMIC_ACQUIRE); status = (uint32_t)(d >> 32); } while (status == 0);
+#elif PD_SCAN_POLL_LD
                     do { asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(d) : "l"(desc + idx) : "memory"); status = (uint32_t)(d >> 32); } while (status == 0);
 #else
                     do { d = atomicAdd(desc + idx, 0ull); status = (uint32_t)(d >> 32); } while (status == 0);
@@ -857,7 +858,7 @@ static_assert(REDUCE_CHUNK % SEG == 0 && REDUCE_CHUNK / SEG == 4, "a reduce chun
 
 struct ReduceArgs {
     const uint32_t *depth;           // array base
-    const uint64_t *contig_off;      // per tid, element offset (multiple of SCAN_TILE, hence of SEG)
+    const uint64_t *contig_off;      // per tid, element offset (multiple of REDUCE_CHUNK and SCAN_TILE: pd_engine.cu PAD_ELEMS)
     const uint32_t *contig_len;      // per tid
     const int32_t *tid; const int32_t *start0; const int32_t *end0;
     const uint64_t *unit_prefix;     // n_iv+1: units before interval i; unit c of an interval is its part inside the
@@ -1096,7 +1097,5 @@ __global__ void __launch_bounds__(256) k_reduce_windows(WindowArgs a)
         }
     }
 }
-
-#endif  // PD_WARP_EMU
 
 }  // namespace pdk
