@@ -179,7 +179,7 @@ int ensure_cut(pd_engine *e, pd_engine::CutBuf &c, size_t nseg)
 {
     if (!c.ready) { CK(cudaEventCreateWithFlags(&c.ready, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&c.released, cudaEventDisableTiming)); }
     if (nseg <= c.cap) return PD_OK;
-    if (c.lo) { CK(cudaStreamSynchronize(e->stream)); CK(cudaStreamSynchronize(e->cut_stream)); cudaFree(c.lo); cudaFree(c.hi); cudaFree(c.coarse); c.lo = c.hi = c.coarse = nullptr; }
+    if (c.lo) { CK(cudaStreamSynchronize(e->stream)); CK(cudaStreamSynchronize(e->cut_stream)); cudaFree(c.lo); cudaFree(c.hi); cudaFree(c.coarse); c.lo = c.hi = c.coarse = nullptr; c.cap = 0; }
     size_t cap = nseg + nseg / 4 + 1024;
     CK(cudaMalloc(&c.lo, cap * 4)); CK(cudaMalloc(&c.hi, cap * 4)); CK(cudaMalloc(&c.coarse, (cap / pdk::CUT_COARSE + 2) * 4));
     c.cap = cap;
@@ -232,7 +232,7 @@ int run_batch(pd_engine *e, int32_t tid, uint32_t n, const int32_t *pos, const u
             // the record filter as one bit per read (the tile kernel reads a word per 32-read chunk)
             const size_t n_words = (size_t)n / 32 + 34;
             if (n_words > e->bits_cap) {
-                if (e->d_pass_bits) { CK(cudaStreamSynchronize(e->stream)); cudaFree(e->d_pass_bits); e->d_pass_bits = nullptr; }
+                if (e->d_pass_bits) { CK(cudaStreamSynchronize(e->stream)); cudaFree(e->d_pass_bits); e->d_pass_bits = nullptr; e->bits_cap = 0; }
                 const size_t cap = n_words + n_words / 4 + 1024;
                 CK(cudaMalloc(&e->d_pass_bits, cap * 4)); e->bits_cap = cap;
             }
@@ -274,6 +274,7 @@ int run_batch(pd_engine *e, int32_t tid, uint32_t n, const int32_t *pos, const u
         if (cap > e->bk_cap) {
             CK(cudaStreamSynchronize(e->stream));
             for (int k = 0; k < 2; k++) { cudaFree(e->bk_pos[k]); cudaFree(e->bk_cig[k]); e->bk_pos[k] = nullptr; e->bk_cig[k] = nullptr; }
+            e->bk_cap = 0;                                       // (a failed allocation below must not leave a capacity over null pointers)
             const size_t c = (size_t)cap + (size_t)cap / 8 + 4096;
             for (int k = 0; k < 2; k++) { CK(cudaMalloc(&e->bk_pos[k], c * 4)); CK(cudaMalloc(&e->bk_cig[k], c * 4)); }
             e->bk_cap = c; e->stats.hbm_bytes_allocated += c * 16;
@@ -282,7 +283,7 @@ int run_batch(pd_engine *e, int32_t tid, uint32_t n, const int32_t *pos, const u
         const size_t n_fine = (size_t)n_coarse * pdk::BK_FINE;
         if (!e->bk_tab) CK(cudaMalloc(&e->bk_tab, (2 + 3 * (pdk::BK_MAX_COARSE + 1)) * 4));
         if (n_fine > e->bk_fine_cap) {
-            if (e->bk_fine) { CK(cudaStreamSynchronize(e->stream)); cudaFree(e->bk_fine); e->bk_fine = nullptr; }
+            if (e->bk_fine) { CK(cudaStreamSynchronize(e->stream)); cudaFree(e->bk_fine); e->bk_fine = nullptr; e->bk_fine_cap = 0; }
             CK(cudaMalloc(&e->bk_fine, n_fine * 4)); e->bk_fine_cap = n_fine;
         }
         uint32_t *d_hist = e->bk_tab + 2, *d_base = d_hist + (pdk::BK_MAX_COARSE + 1), *d_cursor = d_base + (pdk::BK_MAX_COARSE + 1);
@@ -350,7 +351,7 @@ int ensure_slot(pd_engine *e, Slot &s, size_t reads, size_t ncig, bool need_off,
     if (reads > s.cap_reads) {
         if (s.used) CK(cudaEventSynchronize(s.consumed));
         cudaFree(s.pos); cudaFree(s.cigar_off); cudaFree(s.flag); cudaFree(s.mapq);
-        s.pos = nullptr; s.cigar_off = nullptr; s.flag = nullptr; s.mapq = nullptr;
+        s.pos = nullptr; s.cigar_off = nullptr; s.flag = nullptr; s.mapq = nullptr; s.cap_reads = 0;
         size_t cap = reads + reads / 8 + 1024;
         CK(cudaMalloc(&s.pos, cap * 4)); CK(cudaMalloc(&s.cigar_off, (cap + 1) * 4));
         CK(cudaMalloc(&s.flag, cap * 2)); CK(cudaMalloc(&s.mapq, cap));
@@ -359,7 +360,7 @@ int ensure_slot(pd_engine *e, Slot &s, size_t reads, size_t ncig, bool need_off,
     }
     if (ncig > s.cap_cigar) {
         if (s.used) CK(cudaEventSynchronize(s.consumed));
-        cudaFree(s.cigar); s.cigar = nullptr;
+        cudaFree(s.cigar); s.cigar = nullptr; s.cap_cigar = 0;
         size_t cap = ncig + ncig / 8 + 1024;
         CK(cudaMalloc(&s.cigar, cap * 4));
         s.cap_cigar = cap;
@@ -386,7 +387,7 @@ int bz_grow(pd_engine *e, T *&p, size_t &cap, size_t need, size_t *cap_out = nul
 {
     (void)cap_out;
     if (need <= cap) return PD_OK;
-    if (p) { CK(cudaDeviceSynchronize()); cudaFree(p); p = nullptr; }
+    if (p) { CK(cudaDeviceSynchronize()); cudaFree(p); p = nullptr; cap = 0; }
     const size_t c = need + need / 4 + 1024;
     CK(cudaMalloc(&p, c * sizeof(T)));
     e->stats.hbm_bytes_allocated += c * sizeof(T);
@@ -409,14 +410,14 @@ int bz_ensure(pd_engine *e, BzSlot &s, size_t in_bytes, uint64_t out_total, uint
     if (n_blocks > s.blk_cap) {
         if (s.d_blk) CK(cudaDeviceSynchronize());
         cudaFree(s.d_blk); cudaFree(s.d_sum); cudaFree(s.d_r0); cudaFree(s.d_c0);
-        s.d_blk = nullptr; s.d_sum = nullptr; s.d_r0 = s.d_c0 = nullptr;
+        s.d_blk = nullptr; s.d_sum = nullptr; s.d_r0 = s.d_c0 = nullptr; s.blk_cap = 0;
         const size_t c = (size_t)n_blocks + n_blocks / 4 + 256;
         CK(cudaMalloc(&s.d_blk, c * sizeof(pdk::BgzfBlockDesc))); CK(cudaMalloc(&s.d_sum, c * sizeof(pdk::BgzfSummary)));
         CK(cudaMalloc(&s.d_r0, c * 4)); CK(cudaMalloc(&s.d_c0, c * 4));
         s.blk_cap = c;
     }
     if (n_blocks > s.h_blk_cap) {
-        if (s.h_blk) { cudaFreeHost(s.h_blk); cudaFreeHost(s.h_sum); s.h_blk = nullptr; s.h_sum = nullptr; }
+        if (s.h_blk) { cudaFreeHost(s.h_blk); cudaFreeHost(s.h_sum); s.h_blk = nullptr; s.h_sum = nullptr; s.h_blk_cap = 0; }
         const size_t c = (size_t)n_blocks + n_blocks / 4 + 256;
         CK(cudaHostAlloc(&s.h_blk, c * sizeof(pdk::BgzfBlockDesc), cudaHostAllocDefault));
         CK(cudaHostAlloc(&s.h_sum, c * sizeof(pdk::BgzfSummary), cudaHostAllocDefault));
@@ -426,7 +427,7 @@ int bz_ensure(pd_engine *e, BzSlot &s, size_t in_bytes, uint64_t out_total, uint
     const size_t st_rec = (size_t)(out_total / 32) + 2ull * n_blocks + 64, st_cig = (size_t)(out_total / 4) + n_blocks + 64;
     const size_t n_rec = (size_t)(out_total / 36) + 64, n_cig = (size_t)(out_total / 4) + 64;
     if (st_rec > s.st_rec_cap) {
-        size_t c0 = s.st_rec_cap, c1 = s.st_rec_cap, c2 = s.st_rec_cap;
+        size_t c0 = s.st_rec_cap, c1 = s.st_rec_cap, c2 = s.st_rec_cap; s.st_rec_cap = 0;      // (restored below only if all three grew)
         rc = bz_grow(e, s.st_pos, c0, st_rec); if (rc) return rc;
         rc = bz_grow(e, s.st_tid, c1, st_rec); if (rc) return rc;
         rc = bz_grow(e, s.st_coff, c2, st_rec); if (rc) return rc;
@@ -434,7 +435,7 @@ int bz_ensure(pd_engine *e, BzSlot &s, size_t in_bytes, uint64_t out_total, uint
     }
     rc = bz_grow(e, s.st_cig, s.st_cig_cap, st_cig); if (rc) return rc;
     if (n_rec + 1 > s.rec_cap) {
-        size_t c0 = s.rec_cap, c1 = s.rec_cap, c2 = s.rec_cap;
+        size_t c0 = s.rec_cap, c1 = s.rec_cap, c2 = s.rec_cap; s.rec_cap = 0;
         rc = bz_grow(e, s.pos, c0, n_rec + 1); if (rc) return rc;
         rc = bz_grow(e, s.tid, c1, n_rec + 1); if (rc) return rc;
         rc = bz_grow(e, s.coff, c2, n_rec + 1); if (rc) return rc;
@@ -965,7 +966,7 @@ int pd_finalize(pd_engine *e)
 static int ensure_todo(pd_engine *e, size_t n)
 {
     if (n <= e->todo_cap) return PD_OK;
-    if (e->d_todo) { CK(cudaStreamSynchronize(e->stream)); cudaFree(e->d_todo); e->d_todo = nullptr; }
+    if (e->d_todo) { CK(cudaStreamSynchronize(e->stream)); cudaFree(e->d_todo); e->d_todo = nullptr; e->todo_cap = 0; }
     const size_t cap = n + n / 4 + 1024;
     CK(cudaMalloc(&e->d_todo, cap * 4));
     e->todo_cap = cap;
@@ -975,7 +976,7 @@ static int ensure_todo(pd_engine *e, size_t n)
 static int ensure_red(pd_engine *e, size_t bytes)
 {
     if (bytes <= e->red_cap) return PD_OK;
-    if (e->d_red) { CK(cudaStreamSynchronize(e->stream)); cudaFree(e->d_red); e->d_red = nullptr; }
+    if (e->d_red) { CK(cudaStreamSynchronize(e->stream)); cudaFree(e->d_red); e->d_red = nullptr; e->red_cap = 0; }
     size_t cap = bytes + bytes / 4 + 4096;
     CK(cudaMalloc(&e->d_red, cap));
     e->red_cap = cap;
