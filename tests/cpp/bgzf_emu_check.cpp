@@ -8,6 +8,7 @@
 #include "pd_bgzf.cuh"
 #include "pd_inflate.cuh"
 #include <zlib.h>
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <tuple>
@@ -144,6 +145,38 @@ int main(int argc, char **argv)
             if (memcmp(cig.data(), w_cig.data(), w_cig.size() * 4)) { printf("cigar[] differs\n"); bad++; }
         }
     }
-    printf("%s: %zu blocks, %zu records kept, %zu cigar words, flags %x: %s\n", argv[1], nb, w_pos.size(), w_cig.size(), flags_or, bad ? "MISMATCH" : "ok");
+    // ---- k_delta_scatter_multi over the dense arrays (the path of blocks with a contig change or records out of order): contig
+    // table from the BAM header; contig 0 is owned in part (range sharding), the last of three or more contigs not at all ----
+    uint64_t multi_bases = 0;
+    if (!bad && !(flags_or & BZ_MALFORMED) && n_ref) {
+        std::vector<uint32_t> tlen(n_ref), org(n_ref, 0); std::vector<uint64_t> toff(n_ref); std::vector<uint8_t> owned(n_ref, 1);
+        size_t hq = 8 + inf_le32(head.data() + 4) + 4; uint64_t total = 0;
+        for (uint32_t r = 0; r < n_ref; r++) { const uint32_t ln = inf_le32(head.data() + hq); tlen[r] = inf_le32(head.data() + hq + 4 + ln); hq += 8 + ln; }
+        if (tlen[0] >= 8) { org[0] = tlen[0] / 4; tlen[0] /= 2; }
+        if (n_ref >= 3) owned[n_ref - 1] = 0;
+        for (uint32_t r = 0; r < n_ref; r++) { toff[r] = total; total += ((uint64_t)tlen[r] + 1 + 8191) / 8192 * 8192; }
+        if (total <= (64u << 20)) {
+            std::vector<uint32_t> delta(total, 0), want(total, 0);
+            const uint32_t n = totals[0];
+            ScatterMultiArgs m{tid.data(), pos.data(), cig.data(), coff.data(), n, toff.data(), tlen.data(), org.data(), owned.data(), (int32_t)n_ref, delta.data()};
+            const unsigned grid = (n + 255) / 256;
+            for (unsigned b = 0; b < grid; b++) for (unsigned t = 0; t < 256; t++) { threadIdx.x = t; blockIdx.x = b; blockDim.x = 256; gridDim.x = grid; k_delta_scatter_multi(m); }
+            for (size_t i = 0; i < w_pos.size(); i++) {                              // PanDepth.cpp:735-760 on the walked records
+                const int32_t t = w_tid[i];
+                if (!owned[t] || w_pos[i] < 0) continue;
+                int64_t x = (int64_t)w_pos[i] - org[t];
+                for (uint32_t k = w_coff[i]; k < w_coff[i + 1]; k++) {
+                    const uint32_t op = w_cig[k] & 15u; const int64_t len = w_cig[k] >> 4;
+                    if (op == 0 || op == 7 || op == 8) { for (int64_t y = std::max<int64_t>(x, 0); y < std::min<int64_t>(x + len, tlen[t]); y++) want[toff[t] + (uint64_t)y]++; x += len; }
+                    else if (op == 2 || op == 3) x += len;
+                }
+            }
+            uint32_t run = 0; size_t nd = 0; multi_bases = total;
+            for (uint64_t i = 0; i < total; i++) { run += delta[i]; if (run != want[i]) nd++; }
+            if (nd || run) { printf("k_delta_scatter_multi: %zu bases differ from the walk (residue %u)\n", nd, run); bad++; }
+        }
+    }
+    printf("%s: %zu blocks, %zu records kept, %zu cigar words, flags %x, scatter_multi over %llu bases: %s\n", argv[1], nb, w_pos.size(), w_cig.size(), flags_or,
+           (unsigned long long)multi_bases, bad ? "MISMATCH" : "ok");
     return bad ? 1 : 0;
 }
