@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(256) k_expand_runs(ExpandArgs a)
         int64_t es = rs < 0 ? 0 : rs, ee = re > clen ? clen : re;
         if (es >= ee) return;
         if (ee - es >= (1ll << 28)) {                            // does not fit a (len << 4 | op) word: straight to the delta array
-            red_add_u32(a.delta + es, 1u); red_add_u32(a.delta + ee, 0xffffffffu); *a.delta_used = 1;
+            red_add_u32(a.delta + es, 1u); red_add_u32(a.delta + ee, 0xffffffffu); raise_flag(a.delta_used);
             return;
         }
         if (slot < a.cap) { a.run_pos[slot] = (int32_t)es; a.run_cig[slot] = (uint32_t)(ee - es) << 4; }

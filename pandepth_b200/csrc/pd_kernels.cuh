@@ -63,6 +63,17 @@ __device__ __forceinline__ void red_add_u32(uint32_t *addr, uint32_t v)
 #endif
 }
 
+// many threads may raise the same host-visible flag with the same value: a plain store on the device; the emulated build makes it
+// an atomic store so that ThreadSanitizer (tests/test_emu_tsan_cpu.py) reports only races that matter
+__device__ __forceinline__ void raise_flag(int *p)
+{
+#ifndef PD_WARP_EMU
+    *p = 1;
+#else
+    __atomic_store_n(p, 1, __ATOMIC_RELAXED);
+#endif
+}
+
 // one Kogge-Stone step of a warp inclusive scan: t += (lane >= o) ? shfl_up(t, o) : 0, using the predicate shfl.up
 // itself produces (2 instructions instead of shuffle + compare + select + add)
 __device__ __forceinline__ uint32_t scan_step_up(uint32_t t, int o)
@@ -362,7 +373,7 @@ __global__ void __launch_bounds__(WPC * 32, TILE_MIN_CTAS) k_tile_accumulate(Til
                     if (owner && e > far_w) {
                         red_add_u32(a.delta + hbase + max(rs, far_w), 1u);
                         red_add_u32(a.delta + hbase + e, 0xffffffffu);
-                        if (!far_flagged) { *a.delta_used = 1; far_flagged = true; }
+                        if (!far_flagged) { raise_flag(a.delta_used); far_flagged = true; }
                     }
                 }
                 open = false;
@@ -484,7 +495,7 @@ __global__ void __launch_bounds__(WPC * 32, TILE_MIN_CTAS) k_tile_accumulate(Til
                     if ((w >= (uint32_t)HALO || own_halo) && e > far_w) {           // rare: run longer than HALO, applied by its owner
                         red_add_u32(a.delta + hbase + far_w, cnt);
                         red_add_u32(a.delta + hbase + e, 0u - cnt);
-                        if (!far_flagged) { *a.delta_used = 1; far_flagged = true; }
+                        if (!far_flagged) { raise_flag(a.delta_used); far_flagged = true; }
                     }
                 }
             }
@@ -670,7 +681,7 @@ __device__ __forceinline__ void scatter_one(const ScatterArgs &a, uint32_t i)
         if (s >= e) return;
         if (s >= slo && s < shi) red_add_u32(a.delta + s, 1u);
         if (e >= slo && e < shi) red_add_u32(a.delta + e, 0xffffffffu);
-        if (a.delta_used) *a.delta_used = 1;                   // (n_dev mode) something was scattered: the scan has to run at finalize
+        if (a.delta_used) raise_flag(a.delta_used);                 // (n_dev mode) something was scattered: the scan has to run at finalize
     };
     for (uint32_t k = 0; k < nops; ++k) {
         const uint32_t w = __ldcs(a.cigar + c0 + k);

@@ -14,13 +14,7 @@
 #include <random>
 #include <utility>
 
-// the few things pd_bucket.cuh takes from pd_kernels.cuh
-namespace pdk {
-constexpr int SEG = 2048, HALO = 256;
-inline bool is_match_op(uint32_t op) { return (0x181u >> op) & 1u; }
-inline bool is_skip_op(uint32_t op) { return (0x00cu >> op) & 1u; }
-inline void red_add_u32(uint32_t *addr, uint32_t v) { __atomic_fetch_add(addr, v, __ATOMIC_SEQ_CST); }
-}
+#include "pd_kernels.cuh"
 #include "pd_bucket.cuh"
 using namespace pdk;
 
