@@ -2,6 +2,7 @@
 //   reduce_emu_check scatter  <contig_len> <reads> <seed> <shift> <style 0|1|2>   k_delta_scatter (whole / striped / device-side count) + k_scan_add
 //   reduce_emu_check reduce   <contig_len> <intervals> <seed> <min_dep> <mask>    k_fill_untouched + k_reduce_units_part + k_reduce_units (with and without partials)
 //   reduce_emu_check windows  <contig_len> <win> <start0> <min_dep> <mask> <seed> k_reduce_windows (every width class of the kernel)
+//   reduce_emu_check sweep    <contig_len> <first win> <last win> <mask> <seed>   the same for every width of a range (start, -d vary with the width)
 // Each is compared with the plain loops of the reference: PanDepth.cpp:732-760 (walk), :295-348 (StatChrDepthWin / LowMEM), :4366-4381
 // (mode-6 windows).  Two contigs share the arrays at 8192-aligned offsets, like the engine's layout.
 #define PD_WARP_EMU 1
@@ -204,6 +205,12 @@ int main(int argc, char **argv)
     const std::string mode = argv[1];
     if (mode == "scatter") return check_scatter(atoi(argv[2]), (uint32_t)atoi(argv[3]), (uint64_t)atoll(argv[4]), atoi(argv[5]), atoi(argv[6])) ? 1 : 0;
     if (mode == "reduce") return check_reduce(atoi(argv[2]), (uint32_t)atoi(argv[3]), (uint64_t)atoll(argv[4]), (uint32_t)strtoul(argv[5], nullptr, 0), (uint32_t)strtoul(argv[6], nullptr, 0)) ? 1 : 0;
+    if (mode == "sweep") {                                   // every width in [lo, hi]: sweep <len> <lo> <hi> <mask> <seed>
+        int bad = 0;
+        for (int64_t w = atoll(argv[3]); w <= atoll(argv[4]); w++)
+            bad += check_windows(atoll(argv[2]) + (w % 3), w, (w % 8 == 0) ? 0 : (w % 8 == 4) ? 64 : w % 41, (w % 4 == 2) ? 3u : 1u, (uint32_t)strtoul(argv[5], nullptr, 0), (uint64_t)atoll(argv[6]) + (uint64_t)w);
+        return bad ? 1 : 0;
+    }
     if (mode == "windows" && argc >= 8)
         return check_windows(atoll(argv[2]), atoll(argv[3]), atoll(argv[4]), (uint32_t)strtoul(argv[5], nullptr, 0), (uint32_t)strtoul(argv[6], nullptr, 0), (uint64_t)atoll(argv[7])) ? 1 : 0;
     return 2;

@@ -66,3 +66,10 @@ WIDTHS = (1, 7, 31, 32, 33, 64, 100, 128, 129, 149, 150, 160, 161, 200, 512, 513
 def test_fixed_windows_every_width_class(mask, min_dep, start0, checker):
     for k, win in enumerate(WIDTHS):
         _ok(checker, "windows", 50_001 if k % 2 else 49_152, win, start0, min_dep, mask, 7 + k)
+
+
+@pytest.mark.parametrize("first,last,mask", [(32, 170, "0x3ffff"), (1, 40, "0xffffffff"), (500, 520, "0x3ffff")])
+def test_fixed_windows_every_width_of_a_range(first, last, mask, checker):
+    """every width of the 4-window-group branch (multiples of 4 on aligned starts take its 128-bit form, the others the 5-load form; -d 3 on
+    widths = 2 mod 4), the lane-per-window branch and the edge of the 32-bit lane-strided branch"""
+    _ok(checker, "sweep", 12_001, first, last, mask, 5)
