@@ -29,6 +29,7 @@ int main(int argc, char **argv)
     // k_delta_scatter in the engine: tests/test_engine_gpu.py); reads over the end of the range / contig are clipped
     for (auto &p : pos) p = shift + (int32_t)(rng() % (uint64_t)(clen + 200 + (shift ? HALO : 0))) - (shift ? HALO : 0);
     for (uint32_t i = 0; i < n / 10; i++) pos[rng() % n] = shift + clen / 2;       // a pile-up
+    for (auto &p : pos) if (p < 0) p = 0;                                          // (a range that starts less than HALO into the contig; pos -1 means unmapped)
     std::sort(pos.begin(), pos.end());
     std::vector<uint16_t> flag(n); std::vector<uint8_t> mapq(n); std::vector<uint32_t> off(n + 1, 0), cig;
     auto W = [](uint32_t len, uint32_t op) { return len << 4 | op; };

@@ -38,6 +38,8 @@ def checker(tmp_path_factory):
     (4_000, 30_000, 6, 1, 0, 0),            # 15,000 reads per segment: the ring wraps many times
     (2_047, 50, 7, 0, 1, 0),                # one partial segment
     (2_048, 0, 7, 0, 1, 0),                 # an empty batch
+    (257, 31_289, 8, 0, 1, 255),            # a range that starts 255 bases into the contig: the halo of segment 0 is cut at the contig start
+    (1, 512, 9, 1, 0, 0),                   # a one-base contig
 ])
 def test_tile_kernels_match_a_host_walk(clen, reads, seed, has_off, has_filter, shift, checker):
     r = subprocess.run([checker, str(clen), str(reads), str(seed), str(has_off), str(has_filter), str(shift)], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
