@@ -5,7 +5,8 @@
 // queues them, and the result is compared with a plain host walk:
 //   * the bucketed runs are the expected multiset of (start, len) runs, nothing lost, nothing invented;
 //   * they are in fine-bucket (256-base) order, fine_off[] points at every bucket's first run;
-//   * lo[j] / hi[j] equal the lower bounds of s0_j - 256 / s0_j over the sorted starts -- what k_cut computes for sorted input.
+//   * lo[j] / hi[j] equal the lower bounds of s0_j - 256 / s0_j over the sorted starts -- what k_cut computes for sorted input;
+//   * k_tile_accumulate over the bucketed runs (unordered mode) gives the depth of the expected runs, base by base.
 #define PD_WARP_EMU 1
 #include "warp_emu.h"
 #include <algorithm>
@@ -98,6 +99,23 @@ int main(int argc, char **argv)
         const uint32_t wl = (uint32_t)(std::lower_bound(starts.begin(), starts.end(), (int32_t)std::max<int64_t>(s0 - HALO, INT32_MIN)) - starts.begin());
         const uint32_t wh = (uint32_t)(std::lower_bound(starts.begin(), starts.end(), (int32_t)std::min<int64_t>(s0, INT32_MAX)) - starts.begin());
         if ((j < nseg && lo[j] != wl) || hi[j] != wh) { printf("segment %d: cuts %u/%u, expected %u/%u\n", j, lo[j], hi[j], wl, wh); bad++; }
+    }
+    // ---- and the tile kernel over the bucketed runs (unordered = 1, device-side run count), as the engine launches it: per-base depth
+    // (+ the far-run deltas of expand and tile, prefix-summed as k_scan_add would) equals the depth the expected runs give ----
+    if (!bad) {
+        const size_t tot = ((size_t)clen + 1 + 8191) / 8192 * 8192;
+        std::vector<uint32_t> depth(tot, 0xcccccccc), dl(tot, 0), part_cov(nseg + 1, 0), wantd((size_t)clen, 0);
+        std::vector<unsigned long long> part_sum(nseg + 1, 0); std::vector<uint8_t> seg_state(nseg + 1, 0);
+        for (size_t b = 0; b < (size_t)clen + 1 && b < delta.size(); b++) dl[b] = delta[b];          // what k_expand_runs scattered itself (runs >= 2^28: none here)
+        int flags_dev[2] = {0, 0};
+        TileArgs t{pa.data(), ca.data(), nullptr, nullptr, nullptr, nullptr, lo.data(), hi.data(), cap, 0, nseg, clen, depth.data(), dl.data(), seg_state.data(), xflags, min_mapq,
+                   &flags_dev[0], &flags_dev[1], 1u, 1u, 0xffffffffu, part_cov.data(), part_sum.data(), 24, 0, 1u, base.data() + n_coarse};
+        run((unsigned)((nseg + WPC - 1) / WPC), WPC * 32, [&] { k_tile_accumulate<false, false>(t); });
+        for (auto &r : want) for (uint32_t b = 0; b < (r.second >> 4); b++) wantd[(size_t)r.first + b]++;
+        if (flags_dev[0]) { printf("the tile kernel reported err bits %x on bucketed runs\n", flags_dev[0]); bad++; }
+        uint32_t acc = 0; size_t nd = 0;
+        for (size_t b = 0; b < (size_t)clen; b++) { acc += dl[b]; const uint32_t d = (seg_state[b / SEG] ? depth[b] : 0u) + acc; if (d != wantd[b]) nd++; }
+        if (nd) { printf("depth over the bucketed runs differs on %zu bases\n", nd); bad++; }
     }
     printf("bucket_emu_check: contig %d, %u reads (%u CIGAR words), shift %d: %zu runs in %d coarse / %zu fine buckets, %d segments: %s\n",
            clen, n, cap, shift, want.size(), n_coarse, n_fine, nseg, bad ? "MISMATCH" : "ok");
