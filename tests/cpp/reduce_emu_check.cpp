@@ -99,6 +99,7 @@ static int check_scatter(int32_t clen, uint32_t n, uint64_t seed, int32_t shift,
     if (nbad) { printf("%zu elements differ, first at %zu: got %u want %u\n", nbad, first, depth[first], before[first] + want[first]); bad++; }
     printf("reduce_emu_check scatter: contigs %d + %d, %u reads, shift %d, style %d, %llu scan tiles: %s\n", lens[0], lens[1], n, shift, style,
            (unsigned long long)n_tiles, bad ? "MISMATCH" : "ok");
+    std::free(depth); std::free(delta);
     return bad;
 }
 
