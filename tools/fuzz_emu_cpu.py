@@ -4,7 +4,10 @@ source on the CPU, on random shapes biased to the edges (contig lengths and read
 2^19; ranges that start inside a contig; empty / one-read / piled-up batches; window widths around every branch of the window
 reducer; random BAMs from oracle/_ref/bamgen through the inflate kernels with K = 1/2/4/8 decoders per warp).
 
-    python tools/fuzz_emu_cpu.py [--seconds 600] [--seed 1] [--only tile|bucket|scatter|reduce|windows|bgzf]
+    python tools/fuzz_emu_cpu.py [--seconds 600] [--seed 1] [--only tile|bucket|scatter|reduce|windows|bgzf|corrupt] [--sanitize]
+
+--sanitize builds the checkers with -fsanitize=address,undefined; `--only corrupt` feeds the inflate / record-walk kernels bit-flipped BAMs
+(any checker verdict is fine there; a sanitizer report, a crash or a hang is a failure).
 
 Prints every failing command line (nothing is expected to fail) and a summary.  The pytest suite runs fixed cases of the same
 checkers (tests/test_{tile,bucket,reduce,bgzf}_emu_cpu.py); this is the long-running version.
@@ -15,21 +18,24 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BAMGEN = os.path.join(ROOT, "oracle", "_ref", "bamgen")
 
 
-def build(tmp):
+def build(tmp, sanitize=False):
     exe = {}
+    san = ["-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined"] if sanitize else ["-O2"]
     for name, libs in (("tile", []), ("bucket", []), ("reduce", []), ("bgzf", ["-lz"])):
         exe[name] = os.path.join(tmp, name + "_emu_check")
-        subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", "-I" + os.path.join(ROOT, "pandepth_b200", "csrc"), "-I" + os.path.join(ROOT, "tests", "cpp"),
+        subprocess.run(["g++", *san, "-std=c++17", "-pthread", "-I" + os.path.join(ROOT, "pandepth_b200", "csrc"), "-I" + os.path.join(ROOT, "tests", "cpp"),
                         os.path.join(ROOT, "tests", "cpp", name + "_emu_check.cpp"), *libs, "-o", exe[name]], check=True)
     return exe
 
 
 def main():
     ap = argparse.ArgumentParser(); ap.add_argument("--seconds", type=float, default=600); ap.add_argument("--seed", type=int, default=1); ap.add_argument("--only", default="")
+    ap.add_argument("--sanitize", action="store_true")
     a = ap.parse_args()
     rnd = random.Random(a.seed)
     tmp = tempfile.mkdtemp(prefix="pd_fuzz_emu_")
-    exe = build(tmp)
+    exe = build(tmp, a.sanitize)
+    env = dict(os.environ, ASAN_OPTIONS="detect_leaks=0:abort_on_error=0", UBSAN_OPTIONS="print_stacktrace=1")
     kinds = ["tile", "tile", "bucket", "scatter", "reduce", "windows"] + (["bgzf", "bgzf"] if os.path.exists(BAMGEN) else [])
     if a.only:
         kinds = [a.only]
@@ -51,6 +57,17 @@ def main():
             ln = rnd.choice([1, 31, 32, 33, 127, 128, 640, rr(1, 40000)])
             cmd = [exe["reduce"], "windows", ln, rnd.choice([1, 2, 31, 32, 36, 100, 128, 132, 160, 161, 512, 513, rr(1, 3000)]), rnd.choice([0, 0, 4, 64, rr(0, ln + 2)]),
                    rnd.choice([1, 1, 2, 7]), rnd.choice(["0xffffffff", "0x3ffff"]), seed]
+        elif kind == "corrupt":
+            bam = os.path.join(tmp, "f.bam"); src = os.path.join(tmp, "src%d.bam" % rr(3))
+            if not os.path.exists(src):
+                gen = [BAMGEN, "-o", src, "-c", "c1:200000,c2:1,c3:150000,c4:900,c5:30000", "-n", str(rnd.choice([80, 500, 12000])), "-s", str(rr(1, 10**6)), "-l", "100"]
+                gen += rnd.choice([["-m", "mixed"], ["-q"], []])
+                subprocess.run(gen, check=True, capture_output=True)
+            d = bytearray(open(src, "rb").read())
+            for _ in range(rnd.choice([1, 1, 2, 5])):
+                d[rr(200, len(d) - 28)] ^= 1 << rr(8)               # behind the BAM header block, in front of the EOF block
+            open(bam, "wb").write(d); gen = ["bit flips in", src]
+            cmd = [exe["bgzf"], bam, rnd.choice([1, 2, 3]), 1796, -1, rnd.choice([1, 2]), 0, rnd.choice([1, 2, 4, 8])]
         else:
             bam = os.path.join(tmp, "f.bam")
             contigs = ",".join(f"c{i}:{rnd.choice([1, 2, 100, 900, 30000, 200000, 1000000])}" for i in range(rnd.choice([1, 1, 2, 5, 40])))
@@ -62,16 +79,17 @@ def main():
             cmd = [exe["bgzf"], bam, rnd.choice([1, 2, 5, 9]), rnd.choice([0, 1796, 4, 1024]), rnd.choice([-1, 0, 20, 60]), rnd.choice([1, 2, 3, 4]), rnd.choice([0, 0, 1, 3]), rnd.choice([1, 1, 2, 4, 8])]
         cmd = [str(c) for c in cmd]
         try:
-            r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+            r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
             out = [l for l in r.stdout.strip().splitlines() if "checking" not in l]
-            ok = r.returncode == 0 and out and all(l.endswith(": ok") or "nothing to check" in l for l in out)
+            clean = "Sanitizer" not in r.stderr and "runtime error" not in r.stderr and r.returncode >= 0
+            ok = clean and (kind == "corrupt" or (r.returncode == 0 and out and all(l.endswith(": ok") or "nothing to check" in l for l in out)))
             tail = r.stdout[-600:] + r.stderr[-300:]
         except subprocess.TimeoutExpired:
             ok, tail = False, "timeout"
         runs[kind] = runs.get(kind, 0) + 1
         if not ok:
             fails += 1
-            if kind == "bgzf":
+            if kind in ("bgzf", "corrupt"):
                 keep = os.path.join(tmp, f"fail{fails}.bam"); os.replace(cmd[1], keep); cmd[1] = keep; print("generated by:", " ".join(gen))
             print("FAIL", " ".join(cmd), "\n", tail, flush=True)
     print(f"{sum(runs.values())} runs {runs}, {fails} failures, {time.time() - t0:.0f} s, seed {a.seed}")
