@@ -49,8 +49,8 @@ enum {
 /* Create an engine on CUDA device `device` for the BAM header's targets (sam_hdr_t::target_len,
  * read at PanDepth.cpp:684).  `owned` (nullable) selects the contigs this engine accumulates (multi-GPU
  * contig sharding, the reference's ChrNumVer bins :4479-4503); pushes for other tids are ignored.
- * xflags / min_mapq are -x / -q (In3str1v::flags, ::InInt; defaults 1796 / -1).  NULL on failure
- * (pd_last_error(NULL) has the reason). */
+ * xflags / min_mapq are -x / -q (In3str1v::flags, ::InInt; defaults 1796 / -1).  Contigs may be up to 2^31 - 8192 bases long
+ * (BAM positions are int32).  NULL on failure (pd_last_error(NULL) has the reason). */
 pd_engine *pd_create(int device, int n_targets, const uint32_t *target_len, const uint8_t *owned,
                      uint32_t xflags, int min_mapq);
 /* Range sharding ("genomic ranges are independent if reads overlapping a boundary are fed to both

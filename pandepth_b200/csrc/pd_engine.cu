@@ -633,7 +633,8 @@ pd_engine *pd_create_ranges(int device, int n_targets, const uint32_t *target_le
     e->off.assign(n_targets, 0);
     uint64_t total = 0;
     for (int t = 0; t < n_targets; ++t) {
-        if (e->tlen[t] > 0x7fffffffu) { g_create_error = "pd_create: contig longer than 2^31-1"; delete e; return nullptr; }
+        // (segment arithmetic of the tile kernel is 32-bit up to one segment + halo beyond the contig end)
+        if (e->tlen[t] > 0x7fffe000u) { g_create_error = "pd_create: contig longer than 2^31 - 8192 bases"; delete e; return nullptr; }
         const uint32_t b = std::min(own_beg[t], e->tlen[t]), z = std::min(own_end[t], e->tlen[t]);
         if (z <= b) continue;                                  // nothing of this contig is owned: pushes for it are ignored
         e->owned[t] = 1; e->org[t] = b; e->elen[t] = z - b;
