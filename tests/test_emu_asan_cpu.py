@@ -65,6 +65,7 @@ def test_inflate_and_record_walk_stay_inside_their_buffers_on_corrupt_files(tmp_
     for K in (1, 2, 4, 8):
         _run(exe, m, 8, 1796, -1, 2, 0, K)
         _run(exe, b, 8, 1796, -1, 2, 0, K)
+    _run(exe, m, 8, 1796, 300, 2, 0, 1)           # a filter nothing passes: empty dense arrays
     rnd = random.Random(20)
     c = str(tmp_path / "corrupt.bam")
     for k in range(12):
